@@ -1,0 +1,122 @@
+/* lc3b - batched LC3 codec engine for NVIDIA B200 (sm_100a): public C ABI.
+ *
+ * Drop-in boundary for ONE path of ninjasource/lc3-codec: Lc3Decoder::decode_frame /
+ * Lc3Encoder::encode_frame, batched over many independent streams ("stream" plays the
+ * role of the reference's channel_index).  The reference has no FFI layer; each entry
+ * point below names the inherent method it replaces (paths relative to the reference
+ * root).  Plain pointers and sizes only - no C++/torch types.
+ *
+ * Ownership mirrors the reference's preallocated-buffer style: the caller allocates the
+ * device workspace (size from *_workspace_bytes) and all I/O buffers; the library
+ * allocates nothing on the device after init and never frees caller memory.
+ *
+ * Threading: a handle is not thread-safe (the reference takes &mut self); calls are
+ * asynchronous on the caller's CUDA stream and ordered within it; frames of a stream
+ * must be submitted in order; different handles are independent.
+ *
+ * There is no CPU fallback: every entry point that does work requires a CUDA device.
+ */
+#ifndef LC3B_H
+#define LC3B_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes (never unwinds across the boundary) */
+enum {
+    LC3B_OK = 0,
+    LC3B_ERR_BITS_PER_SAMPLE = 1, /* Lc3DecoderError::Only16BitsPerAudioSampleSupported, src/decoder/lc3_decoder.rs:80 */
+    LC3B_ERR_INVALID_ARG = 2,     /* where the reference panics (bad channel index :228, wrong slice length asserts) */
+    LC3B_ERR_CUDA = 3,            /* a CUDA runtime call failed; lc3b_last_cuda_error() has the code */
+    LC3B_ERR_WORKSPACE = 4        /* workspace too small or misaligned */
+};
+
+/* SamplingFrequency, src/common/config.rs:2 (44.1 kHz shares every size with 48 kHz, :48-49) */
+enum { LC3B_HZ8000 = 0, LC3B_HZ16000 = 1, LC3B_HZ24000 = 2, LC3B_HZ32000 = 3, LC3B_HZ44100 = 4, LC3B_HZ48000 = 5 };
+/* FrameDuration, src/common/config.rs:12 */
+enum { LC3B_7P5MS = 0, LC3B_10MS = 1 };
+
+/* Lc3Config, src/common/config.rs:18-39 */
+typedef struct lc3b_config {
+    int32_t fs_ind, fs, ne, nb, nf, z, n_ms;
+} lc3b_config;
+
+/* Lc3Config::new, src/common/config.rs:42.  Returns LC3B_ERR_INVALID_ARG for unknown enums. */
+int lc3b_config_new(int sampling_frequency, int frame_duration, lc3b_config* out);
+
+int lc3b_last_cuda_error(void);
+const char* lc3b_version(void);
+
+/* ------------------------------------------------------------------ decoder */
+typedef struct lc3b_decoder lc3b_decoder;
+
+/* Lc3Decoder::calc_working_buffer_lengths, src/decoder/lc3_decoder.rs:236.
+ * max_nbytes: largest frame length (bytes) that will ever be submitted (<= 400). */
+int lc3b_decoder_workspace_bytes(int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                                 size_t* device_bytes);
+
+/* Lc3Decoder::new, src/decoder/lc3_decoder.rs:181.  `dev_workspace` is device memory of at least
+ * `device_bytes`, 256-byte aligned; it is zero-filled and initialised here (plc_seed = 24607, alpha = 1,
+ * packet_loss_concealment.rs:31-33) on `cuda_stream`. */
+int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                      int device, void* dev_workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* One Lc3Decoder::decode_frame (src/decoder/lc3_decoder.rs:217) per stream, for all streams of the handle.
+ *   frames        device, stream-major: frame of stream s at frames + s*frame_stride
+ *   frame_nbytes  device int32[n_streams] or NULL.  NULL: every frame is `nbytes` long.  Otherwise the per-stream
+ *                 `buf_in.len()`; 0 hands the decoder an empty slice, which the reference conceals (:138-141).
+ *   nbytes        frame length when frame_nbytes is NULL, and upper bound otherwise (<= max_nbytes, <= frame_stride)
+ *   pcm_out       device, int16, stream s at pcm_out + s*pcm_stride (elements); nf samples are written
+ *   status_out    device int32[n_streams] or NULL: 0 = decoded, 1 = concealed (an extension: the reference hides it)
+ * Returns LC3B_ERR_BITS_PER_SAMPLE when bits_per_sample != 16, like the reference; nothing is launched then. */
+int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                       int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
+                       void* cuda_stream);
+
+/* Same call with HOST buffers (what a caller of the reference holds): copies frames host->device, decodes, copies
+ * PCM device->host, all on `cuda_stream`, using staging areas inside the workspace.  Asynchronous when the host
+ * buffers are pinned.  status_out (host, nullable) as above. */
+int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                            int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
+                            void* cuda_stream);
+
+/* Inspection (parity gate i): when set, every decode also writes, per stream, a record of
+ * LC3B_TRACE_WORDS int32 (layout below) and the entropy-decoded integer spectrum x[0..ne).  Device pointers,
+ * NULL to disable.  trace: [n_streams][LC3B_TRACE_WORDS], x: [n_streams][ne]. */
+int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x);
+
+/* Spectrum handed to the IMDCT by the last decode (after SNS, or the concealed one): device f32 [n_streams][ne],
+ * copied into `out` (device) on `cuda_stream`.  For stage-level parity tests. */
+int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream);
+
+/* Profiling hook: which kernels lc3b_decode_frames launches (bit 0 = entropy kernel, bit 1 = synthesis kernel;
+ * default 3).  Lets bench.py time each kernel alone with CUDA events; results are only meaningful with mask 3. */
+int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask);
+
+void lc3b_decoder_destroy(lc3b_decoder* h);
+
+/* Self-test hooks: the engine's own f32 transcendentals (csrc/lc3b_math.cuh, msun-style) evaluated
+ * on the host (no GPU needed) or on the device, so tests can compare them with the oracle's.
+ * which: 0 powf(x,y) 1 log2f 2 log10f 3 exp2f 4 asinf 5 exp2_raw(fast-math) 6 powi(x,(int)y).
+ * Host variant: x, y, out are host arrays.  Device variant: device arrays, runs on cuda_stream. */
+int lc3b_selftest_math_host(int which, const float* x, const float* y, float* out, int n);
+int lc3b_selftest_math_device(int which, const float* x, const float* y, float* out, int n, void* cuda_stream);
+
+/* trace record layout (int32 words) */
+enum {
+    LC3B_TR_OK = 0, LC3B_TR_BW, LC3B_TR_LASTNZ, LC3B_TR_LSB_MODE, LC3B_TR_GG_IND, LC3B_TR_NUM_TNS,
+    LC3B_TR_RC_ORDER_IN0, LC3B_TR_RC_ORDER_IN1, LC3B_TR_IND_LF, LC3B_TR_IND_HF, LC3B_TR_LS_INDA, LC3B_TR_LS_INDB,
+    LC3B_TR_IDX_A, LC3B_TR_IDX_B, LC3B_TR_SUBMODE_LSB, LC3B_TR_SUBMODE_MSB, LC3B_TR_G_IND, LC3B_TR_PITCH_PRESENT,
+    LC3B_TR_LTPF_ACTIVE, LC3B_TR_PITCH_INDEX, LC3B_TR_NOISE_FACTOR, LC3B_TR_RC_ORDER0, LC3B_TR_RC_ORDER1,
+    LC3B_TR_RC_I0 /* 16 words */, LC3B_TR_NRES = LC3B_TR_RC_I0 + 16, LC3B_TR_SEED, LC3B_TR_IS_ZERO,
+    LC3B_TRACE_WORDS = 48
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC3B_H */

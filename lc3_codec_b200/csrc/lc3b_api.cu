@@ -1,0 +1,384 @@
+// lc3b engine: C ABI (include/lc3b.h) - configuration, workspace carving, launch sequencing.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "lc3b_common.cuh"
+#include "lc3b_math.cuh"
+#include "lc3_tables.h"
+
+namespace lc3b {
+
+static thread_local int g_last_cuda_error = 0;
+static int cuda_fail(cudaError_t e) {
+    g_last_cuda_error = (int)e;
+    return LC3B_ERR_CUDA;
+}
+#define CU(x)                                      \
+    do {                                           \
+        cudaError_t _e = (x);                      \
+        if (_e != cudaSuccess) return cuda_fail(_e); \
+    } while (0)
+
+// common/config.rs:42-100
+static bool make_config(int sf, int fd, lc3b_config* c) {
+    static const int FS_IND[6] = {0, 1, 2, 3, 4, 4};
+    static const int FS[6] = {8000, 16000, 24000, 32000, 44100, 48000};
+    static const int NF75[6] = {60, 120, 180, 240, 360, 360};
+    static const int NF10[6] = {80, 160, 240, 320, 480, 480};
+    if (sf < 0 || sf > 5 || fd < 0 || fd > 1) return false;
+    c->fs_ind = FS_IND[sf];
+    c->fs = FS[sf];
+    c->n_ms = fd;
+    if (fd == LC3B_7P5MS) {
+        c->nf = NF75[sf];
+        c->ne = c->nf == 360 ? 300 : c->nf;
+        c->nb = sf == LC3B_HZ8000 ? 60 : 64;
+        c->z = 7 * c->nf / 30;
+    } else {
+        c->nf = NF10[sf];
+        c->ne = c->nf == 480 ? 400 : c->nf;
+        c->nb = 64;
+        c->z = 3 * c->nf / 8;
+    }
+    return true;
+}
+
+// The LC3 tables are device-qualified in this build, so the per-config float tables that depend on them
+// (window, band edges, LTPF coefficient products) are produced by a tiny init kernel (init_tables_kernel).
+struct Carve {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+struct Layout {
+    size_t dcfg, win, dtw, ftw, spec, xq, ola, ltpf_y, ltpf_xtail, side, sstate, stage_in, stage_out, stage_len,
+        stage_status, total;
+};
+
+static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
+    Carve cv;
+    Layout L;
+    const size_t ns = (size_t)n_streams, nblk = (ns + 31) / 32;
+    const int blocks = c.n_ms == LC3B_10MS ? 2 : 3;
+    L.dcfg = cv.take(sizeof(DevConfig));
+    L.win = cv.take(sizeof(float) * 2 * c.nf);
+    L.dtw = cv.take(sizeof(float2) * (c.nf / 2));
+    L.ftw = cv.take(sizeof(float2) * (c.nf / 2));
+    L.spec = cv.take(sizeof(float) * 2 * ns * c.ne);
+    L.xq = cv.take(sizeof(int32_t) * nblk * c.ne * 32);
+    L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
+    L.ltpf_y = cv.take(sizeof(float) * ns * blocks * c.nf);
+    L.ltpf_xtail = cv.take(sizeof(float) * ns * 16);
+    L.side = cv.take(sizeof(int32_t) * ns * SIDE_WORDS);
+    L.sstate = cv.take(sizeof(int32_t) * ns * SS_WORDS);
+    L.stage_in = cv.take(ns * (size_t)max_nbytes);
+    L.stage_out = cv.take(sizeof(int16_t) * ns * c.nf);
+    L.stage_len = cv.take(sizeof(int32_t) * ns);
+    L.stage_status = cv.take(sizeof(int32_t) * ns);
+    L.total = cv.off;
+    return L;
+}
+
+// ---------------------------------------------------------------- device-side table construction
+// Runs once per handle.  Twiddles are computed in f64 and narrowed, like the reference
+// (dct_iv.rs:30-35, kissfft.rs:19-29); the window is folded with the 1/sqrt(2 nf) gain.
+__global__ void init_tables_kernel(DevConfig* cfg, float* win, float2* dtw, float2* ftw) {
+    const int nf = cfg->nf, N = nf / 2;
+    const float* w;
+    if (cfg->n_ms == LC3B_7P5MS) {
+        w = nf == 60 ? LC3T_W_N60_7P5MS : nf == 120 ? LC3T_W_N120_7P5MS : nf == 180 ? LC3T_W_N180_7P5MS
+            : nf == 240 ? LC3T_W_N240_7P5MS : LC3T_W_N360_7P5MS;
+    } else {
+        w = nf == 80 ? LC3T_W_N80_10MS : nf == 160 ? LC3T_W_N160_10MS : nf == 240 ? LC3T_W_N240_10MS
+            : nf == 320 ? LC3T_W_N320_10MS : LC3T_W_N480_10MS;
+    }
+    const float gain = 1.0f / sqrtf(2.0f * (float)nf);
+    for (int m = threadIdx.x; m < 2 * nf; m += blockDim.x) win[m] = gain * w[2 * nf - 1 - m];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double t = -M_PI * (double)(8 * i + 1) / (8.0 * (double)N * 2.0);
+        dtw[i] = make_float2((float)cos(t), (float)sin(t));
+        const double ph = -2.0 * M_PI * (double)i / (double)N;
+        ftw[i] = make_float2((float)cos(ph), (float)sin(ph));
+    }
+    if (threadIdx.x == 0) {
+        const uint16_t* bi;
+        if (cfg->n_ms == LC3B_7P5MS) {
+            bi = cfg->fs_ind == 0 ? LC3T_I_8000_7P5MS : cfg->fs_ind == 1 ? LC3T_I_16000_7P5MS
+                 : cfg->fs_ind == 2 ? LC3T_I_24000_7P5MS : cfg->fs_ind == 3 ? LC3T_I_32000_7P5MS : LC3T_I_48000_7P5MS;
+        } else {
+            bi = cfg->fs_ind == 0 ? LC3T_I_8000_10MS : cfg->fs_ind == 1 ? LC3T_I_16000_10MS
+                 : cfg->fs_ind == 2 ? LC3T_I_24000_10MS : cfg->fs_ind == 3 ? LC3T_I_32000_10MS : LC3T_I_48000_10MS;
+        }
+        for (int b = 0; b <= cfg->nb; b++) cfg->band_idx[b] = bi[b];
+        for (int b = cfg->nb + 1; b < 65; b++) cfg->band_idx[b] = cfg->ne;
+        // LTPF coefficient products (long_term_post_filter.rs:204-240), 44.1 kHz uses the 48 kHz tables truncated
+        static const float GAINS[4] = {0.4f, 0.35f, 0.3f, 0.25f};
+        for (int g = 0; g < 4; g++) {
+            for (int k = 0; k < 12; k++) cfg->ltpf_num[g][k] = 0.0f;
+            for (int fr = 0; fr < 4; fr++) for (int k = 0; k < 16; k++) cfg->ltpf_den[g][fr][k] = 0.0f;
+            for (int k = 0; k <= cfg->ltpf_l_num; k++) {
+                float tab;
+                switch (cfg->fs) {
+                    case 8000: tab = LC3T_TAB_LTPF_NUM_8000[g][k]; break;
+                    case 16000: tab = LC3T_TAB_LTPF_NUM_16000[g][k]; break;
+                    case 24000: tab = LC3T_TAB_LTPF_NUM_24000[g][k]; break;
+                    case 32000: tab = LC3T_TAB_LTPF_NUM_32000[g][k]; break;
+                    default: tab = LC3T_TAB_LTPF_NUM_48000[g][k]; break;
+                }
+                cfg->ltpf_num[g][k] = xm(xm(0.85f, GAINS[g]), tab);
+            }
+            for (int fr = 0; fr < 4; fr++) {
+                for (int k = 0; k <= cfg->ltpf_l_den; k++) {
+                    float tab;
+                    switch (cfg->fs) {
+                        case 8000: tab = LC3T_TAB_LTPF_DEN_8000[fr][k]; break;
+                        case 16000: tab = LC3T_TAB_LTPF_DEN_16000[fr][k]; break;
+                        case 24000: tab = LC3T_TAB_LTPF_DEN_24000[fr][k]; break;
+                        case 32000: tab = LC3T_TAB_LTPF_DEN_32000[fr][k]; break;
+                        default: tab = LC3T_TAB_LTPF_DEN_48000[fr][k]; break;
+                    }
+                    cfg->ltpf_den[g][fr][k] = xm(GAINS[g], tab);
+                }
+            }
+        }
+    }
+}
+
+__global__ void init_streams_kernel(int32_t* sstate, int n_streams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    int32_t* ss = sstate + (size_t)s * SS_WORDS;
+    ss[SS_SLOT] = 0;
+    ss[SS_PLC_LOST] = 0;
+    ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f);     // packet_loss_concealment.rs:31-33
+    ss[SS_PLC_SEED] = 24607;
+    ss[SS_LTPF_PREV] = 4 << 8;
+    ss[SS_LTPF_PINT] = 0;
+    ss[SS_LTPF_PFR] = 0;
+    ss[SS_LTPF_BLK] = 0;
+}
+
+static void fill_host_config(const lc3b_config& c, DevConfig* d) {
+    memset(d, 0, sizeof(*d));
+    d->fs_ind = c.fs_ind; d->fs = c.fs; d->ne = c.ne; d->nb = c.nb; d->nf = c.nf; d->z = c.z; d->n_ms = c.n_ms;
+    static const int NBITS_BW[5] = {0, 1, 2, 2, 3};           // side_info_reader.rs:11
+    d->nbits_bw = NBITS_BW[c.fs_ind];
+    int lg = 0;
+    while ((1 << lg) < c.ne / 2) lg++;                        // ((ne/2) as f32).log2().ceil(), side_info_reader.rs:50
+    d->lastnz_bits = lg;
+    d->n_fft = c.nf / 2;
+    // Stockham stage radices: 4s, then 2, 3s, 5s
+    int n = d->n_fft, i = 0;
+    while (n % 4 == 0) { d->fft_radix[i++] = 4; n /= 4; }
+    while (n % 2 == 0) { d->fft_radix[i++] = 2; n /= 2; }
+    while (n % 3 == 0) { d->fft_radix[i++] = 3; n /= 3; }
+    while (n % 5 == 0) { d->fft_radix[i++] = 5; n /= 5; }
+    switch (c.fs) {                                            // long_term_post_filter.rs:104-134
+        case 8000: case 16000: d->ltpf_l_den = 4; break;
+        case 24000: d->ltpf_l_den = 6; break;
+        case 32000: d->ltpf_l_den = 8; break;
+        case 44100: d->ltpf_l_den = 11; break;
+        default: d->ltpf_l_den = 12; break;
+    }
+    d->ltpf_l_num = d->ltpf_l_den - 2;
+    if (c.n_ms == LC3B_10MS) { d->ltpf_blocks = 2; d->ltpf_norm = c.nf / 4; } else { d->ltpf_blocks = 3; d->ltpf_norm = c.nf / 3; }
+    d->ltpf_s2p5 = c.fs == 44100 ? 48000 / 400 : c.fs / 400;
+    for (int k = 0; k < 400; k++) d->gg_table[k] = powf_msun(10.0f, xd((float)(k - 245), 28.0f));   // global_gain.rs:19-20
+    const float step = (float)(M_PI / 17.0);                   // temporal_noise_shaping.rs:38-45
+    for (int k = 0; k < 17; k++) d->tns_sin[k] = (float)sin((double)xm(step, (float)(k - 8)));
+}
+
+__host__ __device__ inline float math_dispatch(int which, float x, float y) {
+    switch (which) {
+        case 0: return powf_msun(x, y);
+        case 1: return log2f_msun(x);
+        case 2: return log10f_msun(x);
+        case 3: return exp2f_msun(x);
+        case 4: return asinf_msun(x);
+        case 5: return exp2_raw_fm(x);
+        default: return powi_nt(x, (int32_t)y);
+    }
+}
+__global__ void math_kernel(int which, const float* x, const float* y, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = math_dispatch(which, x[i], y ? y[i] : 0.0f);
+}
+
+}  // namespace lc3b
+
+using namespace lc3b;
+
+struct lc3b_decoder {
+    DecoderState st;
+    int stage_mask;
+};
+
+extern "C" {
+
+const char* lc3b_version(void) { return "lc3b 0.1 (sm_100a)"; }
+int lc3b_last_cuda_error(void) { return g_last_cuda_error; }
+
+int lc3b_config_new(int sampling_frequency, int frame_duration, lc3b_config* out) {
+    if (!out || !make_config(sampling_frequency, frame_duration, out)) return LC3B_ERR_INVALID_ARG;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_workspace_bytes(int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                                 size_t* device_bytes) {
+    lc3b_config c;
+    if (!device_bytes || n_streams <= 0 || max_nbytes <= 0 || max_nbytes > MAX_NBYTES ||
+        !make_config(sampling_frequency, frame_duration, &c))
+        return LC3B_ERR_INVALID_ARG;
+    *device_bytes = make_layout(c, n_streams, max_nbytes).total;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                      int device, void* dev_workspace, size_t workspace_bytes, void* cuda_stream) {
+    lc3b_config c;
+    if (!out || !dev_workspace || n_streams <= 0 || max_nbytes <= 0 || max_nbytes > MAX_NBYTES ||
+        !make_config(sampling_frequency, frame_duration, &c))
+        return LC3B_ERR_INVALID_ARG;
+    const Layout L = make_layout(c, n_streams, max_nbytes);
+    if (workspace_bytes < L.total || ((uintptr_t)dev_workspace & 255) != 0) return LC3B_ERR_WORKSPACE;
+    CU(cudaSetDevice(device));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    uint8_t* base = (uint8_t*)dev_workspace;
+    lc3b_decoder* h = (lc3b_decoder*)calloc(1, sizeof(lc3b_decoder));
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    DecoderState& st = h->st;
+    st.cfg = c;
+    st.n_streams = n_streams;
+    st.n_blocks32 = (n_streams + 31) / 32;
+    st.max_nbytes = max_nbytes;
+    st.device = device;
+    st.dcfg = (DevConfig*)(base + L.dcfg);
+    st.win = (float*)(base + L.win);
+    st.dtw = (float2*)(base + L.dtw);
+    st.ftw = (float2*)(base + L.ftw);
+    st.spec = (float*)(base + L.spec);
+    st.xq = (int32_t*)(base + L.xq);
+    st.ola = (float*)(base + L.ola);
+    st.ltpf_y = (float*)(base + L.ltpf_y);
+    st.ltpf_xtail = (float*)(base + L.ltpf_xtail);
+    st.side = (int32_t*)(base + L.side);
+    st.sstate = (int32_t*)(base + L.sstate);
+    st.stage_in = base + L.stage_in;
+    st.stage_out = (int16_t*)(base + L.stage_out);
+    st.stage_len = (int32_t*)(base + L.stage_len);
+    st.stage_status = (int32_t*)(base + L.stage_status);
+    st.trace = nullptr;
+    st.trace_x = nullptr;
+
+    DevConfig hc;
+    fill_host_config(c, &hc);
+    cudaError_t e = cudaMemsetAsync(dev_workspace, 0, L.total, stream);   // the reference is handed zeroed buffers
+    if (e == cudaSuccess) e = cudaMemcpyAsync(st.dcfg, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);               // hc is a stack object
+    if (e == cudaSuccess) {
+        init_tables_kernel<<<1, 256, 0, stream>>>(st.dcfg, st.win, st.dtw, st.ftw);
+        init_streams_kernel<<<(n_streams + 255) / 256, 256, 0, stream>>>(st.sstate, n_streams);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        free(h);
+        return cuda_fail(e);
+    }
+    h->stage_mask = 3;
+    *out = h;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask) {
+    if (!h || mask < 1 || mask > 3) return LC3B_ERR_INVALID_ARG;
+    h->stage_mask = mask;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x) {
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    h->st.trace = trace;
+    h->st.trace_x = x;
+    return LC3B_OK;
+}
+
+int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                       int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
+                       void* cuda_stream) {
+    if (!h || !frames || !pcm_out) return LC3B_ERR_INVALID_ARG;
+    if (bits_per_sample != 16) return LC3B_ERR_BITS_PER_SAMPLE;                       // lc3_decoder.rs:80
+    const DecoderState& st = h->st;
+    if (nbytes < 0 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
+        return LC3B_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (h->stage_mask & 1) CU(launch_entropy(st, frames, frame_nbytes, nbytes, frame_stride, status_out, stream));
+    if (h->stage_mask & 2) CU(launch_synth(st, pcm_out, pcm_stride, stream));
+    return LC3B_OK;
+}
+
+int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                            int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
+                            void* cuda_stream) {
+    if (!h || !frames || !pcm_out) return LC3B_ERR_INVALID_ARG;
+    if (bits_per_sample != 16) return LC3B_ERR_BITS_PER_SAMPLE;
+    const DecoderState& st = h->st;
+    if (nbytes < 0 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
+        return LC3B_ERR_INVALID_ARG;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const size_t ns = (size_t)st.n_streams;
+    // frames: one strided copy packs the rows to pitch `nbytes`
+    CU(cudaMemcpy2DAsync(st.stage_in, (size_t)nbytes, frames, frame_stride, (size_t)nbytes, ns, cudaMemcpyHostToDevice, stream));
+    if (frame_nbytes) CU(cudaMemcpyAsync(st.stage_len, frame_nbytes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, stream));
+    CU(launch_entropy(st, st.stage_in, frame_nbytes ? st.stage_len : nullptr, nbytes, (size_t)nbytes,
+                      status_out ? st.stage_status : nullptr, stream));
+    CU(launch_synth(st, st.stage_out, (size_t)st.cfg.nf, stream));
+    CU(cudaMemcpy2DAsync(pcm_out, pcm_stride * sizeof(int16_t), st.stage_out, (size_t)st.cfg.nf * sizeof(int16_t),
+                         (size_t)st.cfg.nf * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, stream));
+    if (status_out) CU(cudaMemcpyAsync(status_out, st.stage_status, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, stream));
+    return LC3B_OK;
+}
+
+int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream) {
+    if (!h || !out) return LC3B_ERR_INVALID_ARG;
+    // the slot differs per stream; gather on the device
+    extern void lc3b_gather_spectrum(const DecoderState&, float*, cudaStream_t);
+    lc3b_gather_spectrum(h->st, out, (cudaStream_t)cuda_stream);
+    CU(cudaGetLastError());
+    return LC3B_OK;
+}
+
+void lc3b_decoder_destroy(lc3b_decoder* h) { free(h); }
+
+int lc3b_selftest_math_host(int which, const float* x, const float* y, float* out, int n) {
+    if (!x || !out || n < 0 || which < 0 || which > 6) return LC3B_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++) out[i] = lc3b::math_dispatch(which, x[i], y ? y[i] : 0.0f);
+    return LC3B_OK;
+}
+
+int lc3b_selftest_math_device(int which, const float* x, const float* y, float* out, int n, void* cuda_stream) {
+    if (!x || !out || n < 0 || which < 0 || which > 6) return LC3B_ERR_INVALID_ARG;
+    lc3b::math_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(which, x, y, out, n);
+    CU(cudaGetLastError());
+    return LC3B_OK;
+}
+
+}  // extern "C"
+
+namespace lc3b {
+__global__ void gather_spectrum_kernel(const float* spec, const int32_t* side, float* out, int n_streams, int ne) {
+    const int s = blockIdx.x;
+    const int slot = side[(size_t)s * SIDE_WORDS + SD_SLOT];
+    const float* sp = spec + ((size_t)slot * n_streams + s) * ne;
+    for (int k = threadIdx.x; k < ne; k += blockDim.x) out[(size_t)s * ne + k] = sp[k];
+}
+}  // namespace lc3b
+
+void lc3b_gather_spectrum(const lc3b::DecoderState& st, float* out, cudaStream_t stream) {
+    lc3b::gather_spectrum_kernel<<<st.n_streams, 128, 0, stream>>>(st.spec, st.side, out, st.n_streams, st.cfg.ne);
+}

@@ -1,0 +1,93 @@
+// lc3b engine: shared declarations (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lc3b.h"
+
+#if defined(__CUDACC__)
+#define LC3_TABLE(T) static __device__ const T
+#else
+#define LC3_TABLE(T) static const T
+#endif
+
+namespace lc3b {
+
+constexpr int MAX_NE = 400;
+constexpr int MAX_NF = 480;
+constexpr int MAX_NBYTES = 400;      // LC3 frames are at most 400 bytes
+constexpr int SIDE_WORDS = 16;       // entropy -> synthesis hand-off record, int32 words per stream
+
+// hand-off record written by the entropy kernel for the synthesis kernel
+enum {
+    SD_OK = 0,          // 1: frame decoded; 0: conceal (lc3_decoder.rs:138-141)
+    SD_LTPF_ACTIVE,     // LongTermPostFilterInfo.is_active
+    SD_PITCH_INDEX,
+    SD_NBITS,           // buf_in.len() * 8
+    SD_PLC_SEED,        // PLC LCG state BEFORE this frame's ne steps (concealed frames)
+    SD_PLC_ALPHA,       // f32 bits: alpha to apply (concealed frames)
+    SD_SLOT,            // which of the two spectrum slots holds the spectrum to transform
+};
+
+// Everything a kernel needs to know about the (fs, duration) configuration; lives in the workspace.
+struct DevConfig {
+    int32_t fs_ind, fs, ne, nb, nf, z, n_ms;
+    int32_t nbits_bw, lastnz_bits;       // side-info field widths
+    int32_t n_fft;                       // nf / 2
+    int32_t fft_radix[8];                // Stockham stage radices, product = n_fft, 0-terminated
+    int32_t ltpf_l_den, ltpf_l_num, ltpf_blocks, ltpf_norm, ltpf_s2p5;
+    int32_t band_idx[65];                // I_fs
+    float gg_table[400];                 // 10^(i/28), i = index - 245  (global_gain.rs:19-20)
+    float tns_sin[17];                   // sin(pi/17 * (i - 8)) (temporal_noise_shaping.rs:44)
+    float ltpf_num[4][12];               // 0.85 * gain * TAB_LTPF_NUM[gain_ind][k]  (long_term_post_filter.rs:232-236)
+    float ltpf_den[4][4][16];            // gain * TAB_LTPF_DEN[pitch_frac][k], first index = gain_ind
+    // per-config float tables appended after this struct in the workspace:
+    //   win  [2*nf]   gain * w[2nf-1-m]   (modified_dct.rs:89 and :131-134 folded together)
+    //   dtw  [n_fft]  DCT-IV twiddles exp(-i*pi*(8n+1)/(8*nf)) as float2 (dct_iv.rs:30-35)
+    //   ftw  [n_fft]  FFT twiddles exp(-2*pi*i*k/n_fft) as float2 (kissfft.rs:19-29)
+};
+
+struct DecoderState {
+    // configuration
+    lc3b_config cfg;
+    int n_streams, n_blocks32, max_nbytes, device;
+    // device pointers (carved from the caller's workspace)
+    DevConfig* dcfg;
+    float* win;          // [2*nf]
+    float2* dtw;         // [n_fft]
+    float2* ftw;         // [n_fft]
+    float* spec;         // [2][n_streams][ne]  double-buffered spectrum; the valid slot doubles as PLC "last good"
+    int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (private to the entropy kernel)
+    float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)
+    float* ltpf_y;       // [n_streams][blocks*nf]  x_hat_ltpf_mem (long_term_post_filter.rs:30)
+    float* ltpf_xtail;   // [n_streams][16]  last samples of x_hat_mem (only l_num <= 10 are ever read back)
+    int32_t* side;       // [n_streams][SIDE_WORDS]
+    int32_t* sstate;     // [n_streams][8]  per-stream scalars, see SS_* below
+    uint8_t* stage_in;   // [n_streams][max_nbytes] staging for the host-buffer entry point
+    int16_t* stage_out;  // [n_streams][nf]
+    int32_t* stage_len;  // [n_streams]
+    int32_t* stage_status;  // [n_streams]
+    // optional inspection outputs (caller-owned device memory)
+    int32_t* trace;
+    int32_t* trace_x;
+};
+
+// per-stream persistent scalars
+enum {
+    SS_SLOT = 0,        // index of the spectrum slot that holds the last good spectrum
+    SS_PLC_LOST,        // num_lost_frames (packet_loss_concealment.rs:11)
+    SS_PLC_ALPHA,       // f32 bits
+    SS_PLC_SEED,        // plc_seed
+    SS_LTPF_PREV,       // bit0 = ltpf_active_prev, bits 8.. = previous gain code (0..3 table row, 4 = zero gain)
+    SS_LTPF_PINT,       // p_int_mem
+    SS_LTPF_PFR,        // p_fr_mem
+    SS_LTPF_BLK,        // block_start_index / nf
+    SS_WORDS = 8
+};
+
+cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                           size_t frame_stride, int32_t* status_out, cudaStream_t stream);
+cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream);
+cudaError_t launch_init_state(const DecoderState& st, cudaStream_t stream);
+
+}  // namespace lc3b

@@ -1,0 +1,651 @@
+// lc3b engine, decoder kernel 1 of 2: bitstream -> shaped spectrum, one THREAD per frame.
+//
+// Replaces, per stream, the first half of DecoderChannel::decode (src/decoder/lc3_decoder.rs:73-135):
+//   side_info_reader::read            src/decoder/side_info_reader.rs:29
+//   arithmetic_codec::decode          src/decoder/arithmetic_codec.rs:109 (range decoder, TNS data, spectral tuples,
+//                                     residual / lsb-mode bits, noise-filling seed, zero-frame flag)
+//   residual_spectrum::decode         src/decoder/residual_spectrum.rs:13
+//   noise_filling::apply_noise_filling src/decoder/noise_filling.rs:18
+//   global_gain::apply_global_gain    src/decoder/global_gain.rs:15
+//   temporal_noise_shaping            src/decoder/temporal_noise_shaping.rs:24
+//   spectral_noise_shaping::decode    src/decoder/spectral_noise_shaping.rs:21
+// Everything here is a serial recurrence per frame (range state, context chain, LCG, lattice), so the
+// parallel axis is frames: lane = frame, a warp = 32 consecutive streams, all lanes walk the same line
+// index k so that the per-line traffic is coalesced:
+//   * the frame bytes of the CTA are staged once into shared memory (rows padded to an odd word count);
+//   * pass 1 (entropy) writes integers to a lane-interleaved scratch  xq[warp][k][lane]  (128 B per warp store);
+//   * pass 2 (dequantise + noise fill + gain + TNS lattice + SNS gain) streams them back, and hands the
+//     f32 spectrum to a 32x33 shared tile per warp that is flushed as 128-byte row segments into the
+//     stream-major spectrum slot  spec[slot][stream][k].
+// The spectrum slot written is the stream's INACTIVE one; it becomes the active slot (= PLC "last good",
+// packet_loss_concealment.rs:50) only if the frame decoded without error, so concealment needs no copy.
+// All f32 arithmetic uses contraction-proof ops in the reference's order: the spectrum is bit-exact.
+#include "lc3b_common.cuh"
+#include "lc3b_math.cuh"
+#include "lc3_tables.h"
+
+namespace lc3b {
+
+struct EntropyParams {
+    const DevConfig* cfg;
+    const uint8_t* frames;
+    const int32_t* frame_nbytes;
+    int nbytes;
+    size_t frame_stride;
+    int n_streams;
+    float* spec;          // [2][n_streams][ne]
+    int32_t* xq;          // [n_blocks32][ne][32]
+    int32_t* side;        // [n_streams][SIDE_WORDS]
+    int32_t* sstate;      // [n_streams][SS_WORDS]
+    int32_t* status_out;  // nullable
+    int32_t* trace;       // nullable
+    int32_t* trace_x;     // nullable
+    int row_pitch;        // bytes per staged frame row in shared memory
+};
+
+// ---------------------------------------------------------------- bit reader over one staged frame (buffer_reader.rs)
+struct Reader {
+    const uint8_t* buf;   // shared-memory row
+    int len;              // buf_in.len()
+    int head;             // head_byte_cursor
+    int tail;             // tail_bit_cursor
+
+    __device__ __forceinline__ bool head_byte(uint32_t& out) {          // :42
+        if (head >= len) return false;
+        out = buf[head++];
+        return true;
+    }
+    __device__ __forceinline__ bool tail_bool(int& bit) {               // :98
+        int byte_index = tail >> 3, bit_index = tail & 7;
+        if (len - head - byte_index + 2 < 0) return false;
+        int from = len - byte_index - 1;
+        if (from < 0) return false;                                     // the reference would panic; needs len < 3
+        bit = (buf[from] >> bit_index) & 1;
+        tail += 1;
+        return true;
+    }
+    __device__ __forceinline__ bool tail_uint(int num_bits, uint32_t& out) {   // :63
+        int byte_index = tail >> 3, bit_index = tail & 7;
+        int add_bytes = (num_bits > 8 - bit_index && num_bits < 8) ? 2 : 1;
+        int num_bytes = (num_bits >> 3) + add_bytes;
+        if (len - head - byte_index - num_bytes < 0) return false;
+        // same value as the reference's big-endian load + shifts: bits [bit_index, bit_index + num_bits)
+        // of the little-endian number formed by the bytes counted from the tail
+        int last = len - byte_index - 1;
+        uint64_t v = 0;
+        for (int i = 0; i < num_bytes; i++) v |= (uint64_t)buf[last - i] << (8 * i);
+        out = (uint32_t)((v >> bit_index) & ((1ull << num_bits) - 1ull));
+        tail += num_bits;
+        return true;
+    }
+};
+
+struct AcState { uint32_t low, range; };
+
+// arithmetic_codec.rs:67-97.  `tab` holds cum | freq << 16 per symbol.
+__device__ __forceinline__ bool ac_decode(Reader& rd, AcState& st, const uint32_t* __restrict__ tab, int nsym, int& sym) {
+    uint32_t tmp = st.range >> 10;
+    if (st.low >= (tmp << 10)) return false;                            // AcRangeFlOutOfRange
+    uint32_t q = st.low / tmp;                                          // largest val with tmp*cum[val] <= low
+    int val;
+    if (nsym == 17) {
+        val = ((tab[16] & 0xffffu) <= q) ? 16 : 0;
+        if (val == 0) {
+            if ((tab[8] & 0xffffu) <= q) val = 8;
+            if ((tab[val + 4] & 0xffffu) <= q) val += 4;
+            if ((tab[val + 2] & 0xffffu) <= q) val += 2;
+            if ((tab[val + 1] & 0xffffu) <= q) val += 1;
+        }
+    } else {                                                            // 8 symbols (TNS order)
+        val = 0;
+        if ((tab[4] & 0xffffu) <= q) val = 4;
+        if ((tab[val + 2] & 0xffffu) <= q) val += 2;
+        if ((tab[val + 1] & 0xffffu) <= q) val += 1;
+    }
+    uint32_t e = tab[val];
+    st.low -= tmp * (e & 0xffffu);
+    st.range = tmp * (e >> 16);
+    while (st.range < 0x10000u) {
+        uint32_t b;
+        if (!rd.head_byte(b)) return false;
+        st.low = ((st.low << 8) & 0x00ffffffu) + b;
+        st.range <<= 8;
+    }
+    sym = val;
+    return true;
+}
+
+// mpvq_deenum, spectral_noise_shaping.rs:155-235.  y lives in shared memory (per-thread column).
+__device__ void mpvq_deenum(int dim_in, int k_val_in, int ls_ind, uint32_t mpvq_ind, float* y, int ystride) {
+    for (int i = 0; i < dim_in; i++) y[i * ystride] = 0.0f;
+    int leading_sign = ls_ind == 0 ? 1 : -1;
+    int k_max_local = k_val_in;
+    uint32_t ind = mpvq_ind;
+    for (int pos = 0; pos < dim_in; pos++) {
+        const uint32_t* h_row = LC3T_MPVQ_OFFSETS[dim_in - 1 - pos];
+        int k_delta;
+        if (ind != 0) {
+            int k_acc = k_max_local;
+            uint32_t off = h_row[k_acc];
+            bool wrap_flag = ind < off;
+            uint32_t ul_diff = 0;
+            if (!wrap_flag) ul_diff = ind - off;
+            while (wrap_flag) {
+                k_acc -= 1;
+                wrap_flag = ind < h_row[k_acc];
+                if (!wrap_flag) ul_diff = ind - h_row[k_acc];
+            }
+            ind = ul_diff;
+            k_delta = k_max_local - k_acc;
+        } else {
+            y[pos * ystride] = (float)(leading_sign < 0 ? -k_max_local : k_max_local);
+            break;
+        }
+        if (k_delta != 0) {
+            y[pos * ystride] = (float)(leading_sign < 0 ? -k_delta : k_delta);
+            leading_sign = (ind & 1) ? -1 : 1;
+            ind >>= 1;
+            k_max_local -= k_delta;
+        }
+    }
+}
+
+struct SideInfoD {
+    int bw, lastnz, lsb_mode, gg_ind, num_tns, rc_in0, rc_in1;
+    int ind_lf, ind_hf, ls_inda, ls_indb, idx_a, idx_b, submode_lsb, submode_msb, g_ind;
+    int pitch_present, ltpf_active, pitch_index, noise_factor;
+};
+
+// side_info_reader.rs:29-200
+__device__ bool read_side_info(Reader& rd, const DevConfig& c, SideInfoD& s) {
+    uint32_t v;
+    int b;
+    s.bw = 0;
+    if (c.nbits_bw > 0) {
+        if (!rd.tail_uint(c.nbits_bw, v)) return false;
+        if ((uint32_t)c.fs_ind < v) return false;
+        s.bw = (int)v;
+    }
+    if (!rd.tail_uint(c.lastnz_bits, v)) return false;
+    s.lastnz = (int)((v + 1) << 1);
+    if (s.lastnz > c.ne) return false;
+    if (!rd.tail_bool(s.lsb_mode)) return false;
+    if (!rd.tail_uint(8, v)) return false;
+    s.gg_ind = (int)v;
+    s.num_tns = s.bw < 3 ? 1 : 2;
+    s.rc_in0 = s.rc_in1 = 0;
+    if (!rd.tail_bool(s.rc_in0)) return false;
+    if (s.num_tns == 2 && !rd.tail_bool(s.rc_in1)) return false;
+    if (!rd.tail_bool(s.pitch_present)) return false;
+    // read_sns_vq :127
+    if (!rd.tail_uint(5, v)) return false;
+    s.ind_lf = (int)v;
+    if (!rd.tail_uint(5, v)) return false;
+    s.ind_hf = (int)v;
+    if (!rd.tail_bool(s.submode_msb)) return false;
+    if (!rd.tail_uint(s.submode_msb == 0 ? 1 : 2, v)) return false;
+    int g_ind = (int)v;
+    if (!rd.tail_bool(s.ls_inda)) return false;
+    if (s.submode_msb == 0) {
+        if (!rd.tail_uint(25, v)) return false;
+        if (v >= 33460056u) return false;
+        int idx_bor = (int)(v / 2390004u);
+        s.idx_a = (int)(v - (uint32_t)idx_bor * 2390004u);
+        s.submode_lsb = 0;
+        int t = idx_bor - 2;
+        if (t < 0) s.submode_lsb = 1;
+        int u = t + s.submode_lsb * 2;
+        if (s.submode_lsb != 0) { g_ind = (g_ind << 1) + u; s.idx_b = 0; s.ls_indb = 0; }
+        else { s.idx_b = u >> 1; s.ls_indb = u & 1; }
+    } else {
+        s.ls_indb = 0; s.idx_b = 0; s.submode_lsb = 0;
+        if (!rd.tail_uint(24, v)) return false;
+        if (v >= 16708096u) return false;
+        if (v >= 15158272u) {
+            v -= 15158272u;
+            s.submode_lsb = 1;
+            g_ind = (g_ind << 1) + (int)(v & 1);
+            s.idx_a = (int)(v >> 1);
+        } else s.idx_a = (int)v;
+    }
+    s.g_ind = g_ind;
+    s.ltpf_active = 0;
+    s.pitch_index = 0;
+    if (s.pitch_present) {
+        if (!rd.tail_bool(s.ltpf_active)) return false;
+        if (!rd.tail_uint(9, v)) return false;
+        s.pitch_index = (int)v;
+    }
+    if (!rd.tail_uint(3, v)) return false;
+    s.noise_factor = (int)v;
+    return true;
+}
+
+// One step of the inverse TNS lattice (temporal_noise_shaping.rs:58-71) with the state in registers.
+__device__ __forceinline__ float tns_lattice(float x, float (&st)[8], const float (&rc)[8], int order) {
+    float t = x;
+#pragma unroll
+    for (int j = 7; j >= 0; j--) {
+        if (j < order) {
+            t = xs(t, xm(rc[j], st[j]));
+            if (j + 1 < order) st[j + 1] = xa(xm(rc[j], t), st[j]);
+        }
+    }
+    st[0] = t;
+    return t;
+}
+
+constexpr int ENT_THREADS = 128;
+
+// shared-memory carve-up (bytes), T = ENT_THREADS
+//   lookup  4096            AC_SPEC_LOOKUP
+//   spec_cf 64*17*4         cum | freq << 16
+//   tns_cf  (2*8 + 8*17)*4  order tables then coef tables
+//   lev     7*T*4           lsb-mode save_lev flags, one bit per tuple
+//   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
+//   tile    (T/32)*32*33*4  per-warp transpose tile for the spectrum write-out
+//   rows    T*row_pitch     staged frame bytes
+__host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
+    return 4096 + 64 * 17 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 16 * ENT_THREADS * 4 +
+           (ENT_THREADS / 32) * 32 * 33 * 4 + (size_t)ENT_THREADS * row_pitch;
+}
+
+template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
+__global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_lookup = smem;
+    uint32_t* s_spec_cf = (uint32_t*)(smem + 4096);
+    uint32_t* s_tns_cf = s_spec_cf + 64 * 17;
+    uint32_t* s_lev = s_tns_cf + (2 * 8 + 8 * 17);
+    float* s_scf = (float*)(s_lev + 7 * ENT_THREADS);
+    float* s_tile = s_scf + 16 * ENT_THREADS;
+    uint8_t* s_rows = (uint8_t*)(s_tile + (ENT_THREADS / 32) * 32 * 33);
+
+    const DevConfig& c = *p.cfg;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int stream0 = blockIdx.x * ENT_THREADS;
+    const int stream = stream0 + tid;
+    const bool live = stream < p.n_streams;
+    const int ne = c.ne;
+
+    // ---- stage tables and frame bytes
+    for (int i = tid; i < 4096 / 4; i += ENT_THREADS) ((uint32_t*)s_lookup)[i] = ((const uint32_t*)LC3T_AC_SPEC_LOOKUP)[i];
+    for (int i = tid; i < 64 * 17; i += ENT_THREADS)
+        s_spec_cf[i] = (uint32_t)(uint16_t)(&LC3T_AC_SPEC_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_SPEC_FREQ[0][0])[i] << 16);
+    for (int i = tid; i < 2 * 8; i += ENT_THREADS)
+        s_tns_cf[i] = (uint32_t)(uint16_t)(&LC3T_AC_TNS_ORDER_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_TNS_ORDER_FREQ[0][0])[i] << 16);
+    for (int i = tid; i < 8 * 17; i += ENT_THREADS)
+        s_tns_cf[16 + i] = (uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_FREQ[0][0])[i] << 16);
+    for (int i = tid; i < 7 * ENT_THREADS; i += ENT_THREADS) s_lev[i] = 0;
+    {
+        const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
+        const int nb = p.nbytes;
+        for (int i = tid; i < n_rows * nb; i += ENT_THREADS) {
+            int r = i / nb, b = i - r * nb;
+            s_rows[r * p.row_pitch + b] = p.frames[(size_t)(stream0 + r) * p.frame_stride + b];
+        }
+    }
+    __syncthreads();
+
+    // ---- per-frame serial decode (pass 1)
+    Reader rd;
+    rd.buf = s_rows + tid * p.row_pitch;
+    rd.len = live ? (p.frame_nbytes ? p.frame_nbytes[stream] : p.nbytes) : 0;
+    if (rd.len > p.nbytes) rd.len = p.nbytes;
+    if (rd.len < 0) rd.len = 0;
+    rd.head = 0;
+    rd.tail = 0;
+    const int nbits = rd.len * 8;
+    int32_t* xq = p.xq + ((size_t)(stream >> 5) * ne) * 32 + lane;   // element k at xq[k * 32]
+
+    SideInfoD si;
+    bool ok = live && read_side_info(rd, c, si);
+    int rc_order0 = 0, rc_order1 = 0;
+    int rc_i[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) rc_i[i] = 0;
+    AcState ac{0, 0x00ffffffu};
+    uint32_t seed_acc = 0;     // sum |x_k| * k, wrapping (arithmetic_codec.rs:140-145)
+    int nres = 0;
+
+    if (ok) {                                                          // ac_dec_init :57
+        if (rd.head + 2 < rd.len) {
+            ac.low = ((uint32_t)rd.buf[0] << 16) | ((uint32_t)rd.buf[1] << 8) | rd.buf[2];
+            rd.head = 3;
+        } else ok = false;
+    }
+    if (ok) {                                                          // decode_tns_data :307
+        const int max_bits = c.n_ms == LC3B_7P5MS ? 360 : 480;
+        const int w = nbits < max_bits ? 1 : 0;
+        rc_order0 = si.rc_in0;
+        rc_order1 = si.rc_in1;
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            int& ord = f == 0 ? rc_order0 : rc_order1;
+            if (ok && f < si.num_tns && ord > 0) {
+                int o;
+                ok = ac_decode(rd, ac, s_tns_cf + w * 8, 8, o);
+                if (ok) {
+                    ord = o + 1;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (ok && k < ord) {
+                            int sym;
+                            ok = ac_decode(rd, ac, s_tns_cf + 16 + k * 17, 17, sym);
+                            rc_i[f * 8 + k] = sym;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (ok) {                                                          // decode_spectral_data :211
+        const int rate_flag = nbits > (160 + c.fs_ind * 160) ? 512 : 0;
+        int ctx = 0;
+        const int ntup = si.lastnz >> 1;
+        for (int k = 0; k < ntup && ok; k++) {
+            int t = ctx + rate_flag + ((k * 2) > (ne / 2) ? 256 : 0);
+            int xa_ = 0, xb_ = 0, sym = 0, lev = 0, bit;
+            while (lev < 14) {
+                int pki = s_lookup[t + min(lev, 3) * 1024];
+                if (!ac_decode(rd, ac, s_spec_cf + pki * 17, 17, sym)) { ok = false; break; }
+                if (sym < 16) break;
+                if (!si.lsb_mode || lev > 0) {
+                    if (!rd.tail_bool(bit)) { ok = false; break; }
+                    xa_ += bit << lev;
+                    if (!rd.tail_bool(bit)) { ok = false; break; }
+                    xb_ += bit << lev;
+                }
+                lev++;
+            }
+            if (!ok) break;
+            if (si.lsb_mode && lev > 0) s_lev[(k >> 5) * ENT_THREADS + tid] |= 1u << (k & 31);   // save_lev[k], QUIRK (i)
+            const int a = sym & 3, b = sym >> 2;                        // QUIRK (ii): sym may be 16 when lev == 14
+            xa_ += a << lev;
+            xb_ += b << lev;
+            if (xa_ > 0) {
+                if (!rd.tail_bool(bit)) { ok = false; break; }
+                if (bit) xa_ = -xa_;
+            }
+            if (xb_ > 0) {
+                if (!rd.tail_bool(bit)) { ok = false; break; }
+                if (bit) xb_ = -xb_;
+            }
+            xq[(2 * k) * 32] = xa_;
+            xq[(2 * k + 1) * 32] = xb_;
+            seed_acc += (uint32_t)abs(xa_) * (uint32_t)(2 * k) + (uint32_t)abs(xb_) * (uint32_t)(2 * k + 1);
+            const int l = min(lev, 3);
+            t = (l <= 1) ? 1 + (a + b) * (l + 1) : 12 + l;
+            ctx = (ctx & 15) * 16 + t;
+        }
+    }
+    if (ok) {                                                          // calc_num_residual_bits :390
+        const int nbits_side = rd.tail - 8;
+        const int nbits_ari = (rd.head + 1 - 3) * 8 + 25 - (31 - __clz(ac.range));
+        if (nbits < nbits_side + nbits_ari) ok = false;                 // NegativeResidualNumBits
+        nres = nbits - nbits_side - nbits_ari;
+    }
+    if (ok && si.lsb_mode) {                                           // decode_residual_bits (lsb branch) :193-207
+        // QUIRK (i): flags were stored per TUPLE index but are consumed per LINE index k = 0, 2, 4, ...
+        int left = nres;
+        bool stop = false;
+        for (int k = 0; k < si.lastnz && !stop; k += 2) {
+            if (!((s_lev[(k >> 5) * ENT_THREADS + tid] >> (k & 31)) & 1u)) continue;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {                               // read_res_bit :346
+                if (stop) break;
+                if (left == 0) { stop = true; break; }
+                int bit;
+                if (!rd.tail_bool(bit)) { ok = false; stop = true; break; }
+                left--;
+                if (bit) {
+                    const int idx = k + j;
+                    int v = xq[idx * 32];
+                    if (v > 0) { v += 1; seed_acc += (uint32_t)idx; }
+                    else if (v < 0) { v -= 1; seed_acc += (uint32_t)idx; }
+                    else {
+                        if (left == 0) { stop = true; break; }
+                        if (!rd.tail_bool(bit)) { ok = false; stop = true; break; }
+                        left--;
+                        v = bit ? -1 : 1;
+                        seed_acc += (uint32_t)idx;
+                    }
+                    xq[idx * 32] = v;
+                }
+            }
+        }
+    }
+
+    // ---- pass 2: dequantise, noise fill, gain, TNS, SNS; spectrum -> inactive slot
+    int slot = 0;
+    if (live) slot = p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
+    const int new_slot = slot ^ 1;
+    float* s_y = s_scf + tid;                                          // PVQ vector / scale factors, stride T
+    bool is_zero_frame = false;
+    float gg = 0.0f, nf_level = 0.0f;
+    float rc0[8], rc1[8];
+    int bw_stop = 0, nf_start = 0, tns_s0 = 0, tns_e0 = 0, tns_e1 = 0;
+    int lastnz = 0;
+    if (ok) {
+        lastnz = si.lastnz;
+        const int x0 = xq[0], x1 = xq[32];
+        is_zero_frame = si.lastnz == 2 && x0 == 0 && x1 == 0 && si.gg_ind == 0;
+        {                                                              // global_gain.rs:15-25
+            const int fs = c.fs_ind + 1;
+            const int gg_off = -min(nbits / (10 * fs), 115) - 105 - 5 * fs;
+            gg = c.gg_table[si.gg_ind + gg_off + 245];
+        }
+        nf_level = xd(xs(8.0f, (float)si.noise_factor), 16.0f);
+        const bool d10 = c.n_ms == LC3B_10MS;
+        bw_stop = d10 ? 80 * (si.bw + 1) : 60 * (si.bw + 1);
+        nf_start = d10 ? 24 : 18;
+        // temporal_noise_shaping.rs:83-138 band split
+        tns_s0 = d10 ? 12 : 9;
+        if (si.bw < 3) { tns_e0 = bw_stop; tns_e1 = bw_stop; }
+        else { tns_e0 = bw_stop / 2; tns_e1 = bw_stop; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {                                   // QUIRK: index 0 -> rc = 0.0
+            rc0[i] = rc_i[i] != 0 ? c.tns_sin[rc_i[i]] : 0.0f;
+            rc1[i] = rc_i[8 + i] != 0 ? c.tns_sin[rc_i[8 + i]] : 0.0f;
+        }
+        // spectral_noise_shaping.rs:21-98: stage 1 + PVQ shape + DCT rotation -> 16 scale factors in s_y
+        const int shape_j = (si.submode_msb << 1) + si.submode_lsb;
+        const float* gains;
+        constexpr int YS = ENT_THREADS;
+        switch (shape_j) {
+            case 0: {
+                mpvq_deenum(10, 10, si.ls_inda, (uint32_t)si.idx_a, s_y, YS);
+                // second call writes z[0..6) which the reference copies to y[10..16)
+                mpvq_deenum(6, 1, si.ls_indb, (uint32_t)si.idx_b, s_y + 10 * YS, YS);
+                gains = LC3T_SNS_VQ_REG_ADJ_GAINS;
+                break;
+            }
+            case 1:
+                mpvq_deenum(10, 10, si.ls_inda, (uint32_t)si.idx_a, s_y, YS);
+                for (int i = 10; i < 16; i++) s_y[i * YS] = 0.0f;
+                gains = LC3T_SNS_VQ_REG_LF_ADJ_GAINS;
+                break;
+            case 2: mpvq_deenum(16, 8, si.ls_inda, (uint32_t)si.idx_a, s_y, YS); gains = LC3T_SNS_VQ_NEAR_ADJ_GAINS; break;
+            default: mpvq_deenum(16, 6, si.ls_inda, (uint32_t)si.idx_a, s_y, YS); gains = LC3T_SNS_VQ_FAR_ADJ_GAINS; break;
+        }
+        float y[16];
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) { y[i] = s_y[i * YS]; sum = xa(sum, xm(y[i], y[i])); }
+        const float y_norm = sqrtf(sum);
+        float g = gains[si.g_ind];
+        if (y_norm != 0.0f) g = xd(g, y_norm);
+        for (int n = 0; n < 16; n++) {
+            float factor = 0.0f;
+#pragma unroll
+            for (int col = 0; col < 16; col++) factor = xa(factor, xm(y[col], LC3T_D[n][col]));
+            const float st1 = n < 8 ? LC3T_LFCB[si.ind_lf][n] : LC3T_HFCB[si.ind_hf][n - 8];
+            s_y[n * YS] = xa(st1, xm(g, factor));
+        }
+    }
+
+    // scale-factor interpolation (spectral_noise_shaping.rs:85-98) evaluated per band on demand
+    auto scf_at = [&](int n) { return s_y[n * ENT_THREADS]; };
+    auto interp64 = [&](int j) -> float {
+        if (j < 2) return scf_at(0);
+        if (j >= 62) {
+            const float d = xs(scf_at(15), scf_at(14));
+            return xa(scf_at(15), xm(j == 62 ? 0.125f : 0.375f, d));
+        }
+        const int n = (j - 2) >> 2, r = (j - 2) & 3;
+        const float fn = scf_at(n), d = xs(scf_at(n + 1), fn);
+        const float w = r == 0 ? 0.125f : r == 1 ? 0.375f : r == 2 ? 0.625f : 0.875f;
+        return xa(fn, xm(w, d));
+    };
+    const int nb = c.nb, n2 = 64 - nb;
+    auto band_gain = [&](int b) -> float {                             // :100-123 incl. the nb < 64 folding
+        float s;
+        if (n2 != 0) s = b < n2 ? xd(xa(interp64(2 * b), interp64(2 * b + 1)), 2.0f) : interp64(b + n2);
+        else s = interp64(b);
+        return exp2_raw_fm(s);
+    };
+
+    float* tile = s_tile + wid * 32 * 33;
+    float* out_base = p.spec + ((size_t)new_slot * p.n_streams + (size_t)(stream0 + wid * 32)) * ne;
+    const int rows_valid = min(32, p.n_streams - (stream0 + wid * 32));
+
+    const bool any_ok = __any_sync(0xffffffffu, ok);
+    if (any_ok) {
+        float st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int32_t win[W + 1];                 // win[0] = x[k], win[j] = x[k + j]
+        int last_nz = -1000;
+        int nf_state = (int)(seed_acc & 0xffffu);
+        int res_used = 0;
+        int band = 0;
+        float gband = ok ? band_gain(0) : 0.0f;
+        auto fetch = [&](int j) -> int32_t { return (ok && j < lastnz) ? xq[j * 32] : 0; };
+#pragma unroll
+        for (int j = 0; j <= W; j++) win[j] = 0;
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            win[j + 1] = fetch(j);
+            if (win[j + 1] != 0 && j < bw_stop) last_nz = j;
+        }
+        for (int k = 0; k < ne; k++) {
+#pragma unroll
+            for (int j = 0; j < W; j++) win[j] = win[j + 1];
+            {
+                const int j = k + W;
+                win[W] = j < ne ? fetch(j) : 0;
+                if (win[W] != 0 && j < bw_stop) last_nz = j;
+            }
+            const int32_t xi = win[0];
+            float v = (float)xi;
+            if (ok) {
+                if (!si.lsb_mode && xi != 0 && res_used < nres) {       // residual_spectrum.rs:13-39
+                    int bit = 0;
+                    rd.tail_bool(bit);                                  // cannot fail here, see DESIGN.md
+                    res_used++;
+                    if (bit) v = xi > 0 ? xa(v, 0.3125f) : xa(v, 0.1875f);
+                    else v = xi > 0 ? xs(v, 0.1875f) : xs(v, 0.3125f);
+                }
+                if (!is_zero_frame && k >= nf_start && k < bw_stop && last_nz < k - W) {   // noise_filling.rs:37-55
+                    nf_state = (13849 + nf_state * 31821) & 0xFFFF;
+                    v = nf_state < 0x8000 ? nf_level : -nf_level;
+                }
+                v = xm(v, gg);
+                if (k >= tns_s0 && k < tns_e1) {                        // QUIRK: lattice state carries across filters
+                    if (k < tns_e0) { if (rc_order0 > 0) v = tns_lattice(v, st, rc0, rc_order0); }
+                    else if (rc_order1 > 0 && si.num_tns == 2) v = tns_lattice(v, st, rc1, rc_order1);
+                }
+                while (k >= c.band_idx[band + 1] && band + 1 < nb) { band++; gband = band_gain(band); }
+                v = xm(v, gband);
+            }
+            // transpose through the warp tile, flush every 32 lines
+            tile[(k & 31) * 33 + lane] = v;
+            if ((k & 31) == 31 || k == ne - 1) {
+                __syncwarp();
+                const int k0 = k & ~31, cnt = (k & 31) + 1;
+                for (int r = 0; r < rows_valid; r++) {
+                    const bool row_ok = __shfl_sync(0xffffffffu, (int)ok, r);
+                    if (row_ok && lane < cnt) out_base[(size_t)r * ne + k0 + lane] = tile[lane * 33 + r];
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    // ---- hand-off record, slot flip, status, inspection
+    if (live) {
+        int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+        sd[SD_OK] = ok;
+        sd[SD_LTPF_ACTIVE] = ok ? si.ltpf_active : 0;
+        sd[SD_PITCH_INDEX] = ok ? si.pitch_index : 0;
+        sd[SD_NBITS] = nbits;
+        sd[SD_SLOT] = ok ? new_slot : slot;
+        if (ok) p.sstate[(size_t)stream * SS_WORDS + SS_SLOT] = new_slot;
+        if (p.status_out) p.status_out[stream] = ok ? 0 : 1;
+        if (p.trace) {
+            int32_t* tr = p.trace + (size_t)stream * LC3B_TRACE_WORDS;
+            for (int i = 0; i < LC3B_TRACE_WORDS; i++) tr[i] = 0;
+            tr[LC3B_TR_OK] = ok;
+            if (ok) {
+                tr[LC3B_TR_BW] = si.bw; tr[LC3B_TR_LASTNZ] = si.lastnz; tr[LC3B_TR_LSB_MODE] = si.lsb_mode;
+                tr[LC3B_TR_GG_IND] = si.gg_ind; tr[LC3B_TR_NUM_TNS] = si.num_tns; tr[LC3B_TR_RC_ORDER_IN0] = si.rc_in0;
+                tr[LC3B_TR_RC_ORDER_IN1] = si.rc_in1; tr[LC3B_TR_IND_LF] = si.ind_lf; tr[LC3B_TR_IND_HF] = si.ind_hf;
+                tr[LC3B_TR_LS_INDA] = si.ls_inda; tr[LC3B_TR_LS_INDB] = si.ls_indb; tr[LC3B_TR_IDX_A] = si.idx_a;
+                tr[LC3B_TR_IDX_B] = si.idx_b; tr[LC3B_TR_SUBMODE_LSB] = si.submode_lsb; tr[LC3B_TR_SUBMODE_MSB] = si.submode_msb;
+                tr[LC3B_TR_G_IND] = si.g_ind; tr[LC3B_TR_PITCH_PRESENT] = si.pitch_present; tr[LC3B_TR_LTPF_ACTIVE] = si.ltpf_active;
+                tr[LC3B_TR_PITCH_INDEX] = si.pitch_index; tr[LC3B_TR_NOISE_FACTOR] = si.noise_factor;
+                tr[LC3B_TR_RC_ORDER0] = rc_order0; tr[LC3B_TR_RC_ORDER1] = rc_order1;
+#pragma unroll
+                for (int i = 0; i < 16; i++) tr[LC3B_TR_RC_I0 + i] = rc_i[i];
+                // residual_bits.len(): bits actually consumed in the non-lsb branch, 0 in lsb mode (:160-209)
+                int n_nonzero_used = 0;
+                if (!si.lsb_mode) {
+                    int cnt = 0;
+                    for (int k = 0; k < si.lastnz && cnt < nres; k++) if (xq[k * 32] != 0) cnt++;
+                    n_nonzero_used = cnt;
+                }
+                tr[LC3B_TR_NRES] = n_nonzero_used;
+                tr[LC3B_TR_SEED] = (int32_t)(seed_acc & 0xffffu);
+                tr[LC3B_TR_IS_ZERO] = is_zero_frame;
+            }
+        }
+        if (p.trace_x) {
+            int32_t* tx = p.trace_x + (size_t)stream * ne;
+            for (int k = 0; k < ne; k++) tx[k] = (ok && k < si.lastnz) ? xq[k * 32] : 0;
+        }
+    }
+}
+
+cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                           size_t frame_stride, int32_t* status_out, cudaStream_t stream) {
+    EntropyParams p;
+    p.cfg = st.dcfg;
+    p.frames = frames;
+    p.frame_nbytes = frame_nbytes;
+    p.nbytes = nbytes;
+    p.frame_stride = frame_stride;
+    p.n_streams = st.n_streams;
+    p.spec = st.spec;
+    p.xq = st.xq;
+    p.side = st.side;
+    p.sstate = st.sstate;
+    p.status_out = status_out;
+    p.trace = st.trace;
+    p.trace_x = st.trace_x;
+    int words = (nbytes + 3) / 4 + 1;
+    if ((words & 1) == 0) words++;                 // odd word pitch: lanes land on distinct banks
+    p.row_pitch = words * 4;
+    const size_t smem = entropy_smem_bytes(p.row_pitch);
+    const int grid = (st.n_streams + ENT_THREADS - 1) / ENT_THREADS;
+    cudaError_t e;
+    if (st.cfg.n_ms == LC3B_10MS) {
+        e = cudaFuncSetAttribute(entropy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        entropy_kernel<3><<<grid, ENT_THREADS, smem, stream>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(entropy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        entropy_kernel<2><<<grid, ENT_THREADS, smem, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace lc3b

@@ -1,0 +1,368 @@
+// lc3b engine, decoder kernel 2 of 2: shaped spectrum -> PCM, one WARP per frame.
+//
+// Replaces, per stream, the second half of DecoderChannel::decode (src/decoder/lc3_decoder.rs:134-153):
+//   PacketLossConcealment::save / load_into   src/decoder/packet_loss_concealment.rs:50,63
+//   ModDiscreteCosTrans::run                  src/decoder/modified_dct.rs:76 (DCT-IV via N = nf/2 complex FFT,
+//                                             src/common/dct_iv.rs:49, src/common/kissfft.rs:78; window; overlap-add)
+//   LongTermPostFilter::run                   src/decoder/long_term_post_filter.rs:252 (five transition cases)
+//   output_scaling::scale_and_round           src/decoder/output_scaling.rs:13
+// Data-parallel work: 32 lanes walk the frame's lines/samples, all global traffic is stream-major and
+// coalesced (spectrum 4*ne B in, overlap memory 4*(nf-z) B in/out, LTPF history 4*nf B out, PCM 2*nf B out).
+// The FFT is a shared-memory Stockham autosort with radix-2/3/4/5 butterflies (a different factor order than
+// kissfft: the PCM contract is +-1 LSB, not bit equality).  The LTPF recursion only reaches back
+// p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are computed in parallel per step.
+#include "lc3b_common.cuh"
+#include "lc3b_math.cuh"
+
+namespace lc3b {
+
+struct SynthParams {
+    const DevConfig* cfg;
+    const float* win;
+    const float2* dtw;
+    const float2* ftw;
+    const float* spec;
+    float* ola;
+    float* ltpf_y;
+    float* ltpf_xtail;
+    const int32_t* side;
+    int32_t* sstate;
+    int16_t* pcm_out;
+    size_t pcm_stride;
+    int n_streams;
+    int hist_len;        // ltpf_blocks * nf
+    int smem_per_warp;   // bytes
+};
+
+constexpr int SYN_WARPS = 4;
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+template <int R>
+__device__ __forceinline__ void dft(float2 (&v)[R]);
+template <>
+__device__ __forceinline__ void dft<2>(float2 (&v)[2]) {
+    float2 a = v[0], b = v[1];
+    v[0] = caddf(a, b);
+    v[1] = csubf(a, b);
+}
+template <>
+__device__ __forceinline__ void dft<3>(float2 (&v)[3]) {
+    const float S = -0.86602540378443864676f;          // -sin(2 pi / 3)
+    float2 t = caddf(v[1], v[2]);
+    float2 d = csubf(v[1], v[2]);
+    float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
+    float2 r = make_float2(-S * d.y, S * d.x);         // -i * sin * d  (forward transform)
+    v[0] = caddf(v[0], t);
+    v[1] = caddf(m, r);
+    v[2] = csubf(m, r);
+}
+template <>
+__device__ __forceinline__ void dft<4>(float2 (&v)[4]) {
+    float2 a = caddf(v[0], v[2]), b = csubf(v[0], v[2]);
+    float2 c = caddf(v[1], v[3]), d = csubf(v[1], v[3]);
+    float2 dj = make_float2(d.y, -d.x);                // -i * d
+    v[0] = caddf(a, c);
+    v[1] = caddf(b, dj);
+    v[2] = csubf(a, c);
+    v[3] = csubf(b, dj);
+}
+template <>
+__device__ __forceinline__ void dft<5>(float2 (&v)[5]) {
+    const float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
+    const float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
+    float2 a1 = caddf(v[1], v[4]), b1 = csubf(v[1], v[4]);
+    float2 a2 = caddf(v[2], v[3]), b2 = csubf(v[2], v[3]);
+    float2 m1 = make_float2(v[0].x + C1 * a1.x + C2 * a2.x, v[0].y + C1 * a1.y + C2 * a2.y);
+    float2 m2 = make_float2(v[0].x + C2 * a1.x + C1 * a2.x, v[0].y + C2 * a1.y + C1 * a2.y);
+    // forward transform: X[k] = m - i*(S..)*b ; -i*(x+iy) = (y, -x)
+    float2 n1 = make_float2(S1 * b1.y + S2 * b2.y, -(S1 * b1.x + S2 * b2.x));
+    float2 n2 = make_float2(S2 * b1.y - S1 * b2.y, -(S2 * b1.x - S1 * b2.x));
+    v[0] = make_float2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
+    v[1] = caddf(m1, n1);
+    v[4] = csubf(m1, n1);
+    v[2] = caddf(m2, n2);
+    v[3] = csubf(m2, n2);
+}
+
+// one Stockham stage: N/R butterflies spread over the warp
+template <int R>
+__device__ __forceinline__ void fft_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ ftw,
+                                          int N, int Ns, int lane) {
+    const int nbf = N / R;
+    const int tw_step = N / (Ns * R);
+    for (int j = lane; j < nbf; j += 32) {
+        const int k = j % Ns;
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            v[t] = x[j + t * nbf];
+            if (t > 0) v[t] = cmulf(v[t], ftw[k * t * tw_step]);
+        }
+        dft<R>(v);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; t++) y[base + t * Ns] = v[t];
+    }
+}
+
+__global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const DevConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int stream = blockIdx.x * SYN_WARPS + wid;
+    if (stream >= p.n_streams) return;
+    const int nf = c.nf, ne = c.ne, z = c.z, N = c.n_fft, h = nf / 2;
+
+    uint8_t* base = smem + (size_t)wid * p.smem_per_warp;
+    float2* bufA = (float2*)base;                 // N complex
+    float2* bufB = bufA + N;                      // N complex
+    float* X = (float*)(bufB + N);                // nf floats: spectrum in, then DCT-IV output, then time samples
+    float* Y = X + nf;                            // hist_len floats: LTPF circular history (only touched when filtering)
+
+    const int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+    int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
+    const int ok = sd[SD_OK];
+    const int slot = sd[SD_SLOT];
+    const int nbits = sd[SD_NBITS];
+    const float* sp = p.spec + ((size_t)slot * p.n_streams + stream) * ne;
+
+    // ---- spectrum load, with concealment (packet_loss_concealment.rs:63-85) when the frame was bad
+    if (ok) {
+        for (int k = lane; k < nf; k += 32) X[k] = k < ne ? sp[k] : 0.0f;
+        if (lane == 0) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
+    } else {
+        int lost = ss[SS_PLC_LOST];
+        float alpha = u2f((uint32_t)ss[SS_PLC_ALPHA]);
+        uint32_t seed = (uint32_t)ss[SS_PLC_SEED];
+        __syncwarp();                                            // every lane has read the state before any lane updates it
+        if (lost >= 4) alpha = xm(alpha, lost < 8 ? 0.9f : 0.85f);
+        // lane's first line is k = lane: LCG advanced lane+1 times; then jump 32 steps at a time
+        uint32_t s = seed;
+        for (int i = 0; i <= lane; i++) s = (16831u + s * 12821u) & 0xFFFFu;
+        uint32_t a32 = 1, c32 = 0;                               // composition of 32 LCG steps
+        for (int i = 0; i < 32; i++) { c32 = (16831u + c32 * 12821u) & 0xFFFFu; a32 = (a32 * 12821u) & 0xFFFFu; }
+        for (int k = lane; k < nf; k += 32) {
+            float v = 0.0f;
+            if (k < ne) {
+                const float lg = sp[k];
+                v = s < 0x8000u ? xm(lg, alpha) : xm(lg, -alpha);
+                if (k == ne - 1) ss[SS_PLC_SEED] = (int32_t)s;
+                s = (a32 * s + c32) & 0xFFFFu;
+            }
+            X[k] = v;
+        }
+        if (lane == 0) { ss[SS_PLC_LOST] = lost + 1; ss[SS_PLC_ALPHA] = (int32_t)f2u(alpha); }
+    }
+    __syncwarp();
+
+    // ---- DCT-IV: pre-twiddle, N-point FFT, post-twiddle (dct_iv.rs:49-67)
+    for (int n = lane; n < N; n += 32) bufA[n] = cmulf(p.dtw[n], make_float2(X[2 * n], X[nf - 1 - 2 * n]));
+    __syncwarp();
+    {
+        float2 *src = bufA, *dst = bufB;
+        int Ns = 1;
+        for (int sidx = 0; sidx < 8 && c.fft_radix[sidx] != 0; sidx++) {
+            const int R = c.fft_radix[sidx];
+            switch (R) {
+                case 2: fft_stage<2>(src, dst, p.ftw, N, Ns, lane); break;
+                case 3: fft_stage<3>(src, dst, p.ftw, N, Ns, lane); break;
+                case 4: fft_stage<4>(src, dst, p.ftw, N, Ns, lane); break;
+                default: fft_stage<5>(src, dst, p.ftw, N, Ns, lane); break;
+            }
+            Ns *= R;
+            float2* t = src; src = dst; dst = t;
+            __syncwarp();
+        }
+        for (int n = lane; n < N; n += 32) {
+            const float2 v = cmulf(p.dtw[n], src[n]);
+            X[2 * n] = v.x * 2.0f;
+            X[nf - 1 - 2 * n] = -v.y * 2.0f;
+        }
+    }
+    __syncwarp();
+
+    // ---- unfold + window + overlap-add (modified_dct.rs:97-151); t[m] below is the reference's t_hat_mdct[m] / gain
+    auto t_at = [&](int m) -> float {
+        if (m < h) return X[h + m];
+        if (m < nf) return -X[nf - 1 - (m - h)];
+        if (m < nf + h) return -X[h - 1 - (m - nf)];
+        return -X[m - 3 * h];
+    };
+    float* ola = p.ola + (size_t)stream * (nf - z);
+    float* T = (float*)bufA;                       // reuse: nf output samples + (nf - z) new overlap memory fit in 2N complex
+    for (int n = lane; n < nf; n += 32) {
+        float o;
+        if (n < nf - z) o = ola[n] + t_at(z + n) * p.win[z + n];
+        else o = t_at(nf + (n - (nf - z))) * p.win[nf + (n - (nf - z))];
+        T[n] = o;
+    }
+    __syncwarp();                                  // all reads of the old X-derived values for the first half are done
+    for (int n = lane; n < nf - z; n += 32) ola[n] = t_at(nf + z + n) * p.win[nf + z + n];
+    __syncwarp();
+    for (int n = lane; n < nf; n += 32) X[n] = T[n];   // X = x_hat (input of the post filter)
+    __syncwarp();
+
+    // ---- long term post filter (long_term_post_filter.rs:252-343)
+    const int active = sd[SD_LTPF_ACTIVE];
+    const int prev = ss[SS_LTPF_PREV];
+    const int prev_active = prev & 1, prev_code = prev >> 8;
+    const int blocks = c.ltpf_blocks, l_num = c.ltpf_l_num, l_den = c.ltpf_l_den, norm = c.ltpf_norm, s2p5 = c.ltpf_s2p5;
+    const int blk = ss[SS_LTPF_BLK] * nf;
+    int p_int = 0, p_fr = 0, code = 4;
+    if (active) {                                  // compute_filter_parameters :164-190, compute_gains_params :142-161
+        const int pi = sd[SD_PITCH_INDEX];
+        int pit;
+        double pfr;
+        if (pi >= 440) { pit = pi - 283; pfr = 0.0; }
+        else if (pi >= 380) { pit = pi / 2 - 63; pfr = (double)(2 * pi - 4 * pit - 252); }
+        else { pit = pi / 4 + 32; pfr = (double)(pi + 128 - 4 * pit); }
+        const double pitch = (double)pit + pfr / 4.0;
+        const double pitch_fs = pitch * (8000.0 * ceil((double)c.fs / 8000.0) / 12800.0);
+        const int p_up = (int)((pitch_fs * 4.0) + 0.5);
+        p_int = p_up / 4;
+        p_fr = p_up - 4 * p_int;
+        const int t_nbits = c.n_ms == LC3B_7P5MS ? (int)round((double)nbits * 10.0 / 7.5) : nbits;
+        const int sf = c.fs_ind * 80;
+        code = t_nbits < 320 + sf ? 0 : t_nbits < 400 + sf ? 1 : t_nbits < 480 + sf ? 2 : t_nbits < 560 + sf ? 3 : 4;
+    }
+    const int p_int_mem = ss[SS_LTPF_PINT], p_fr_mem = ss[SS_LTPF_PFR];
+    float* yhist = p.ltpf_y + (size_t)stream * p.hist_len;
+    float* xtail = p.ltpf_xtail + (size_t)stream * 16;
+
+    if (!active && !prev_active) {                 // case 1: pass-through, history only
+        for (int n = lane; n < nf; n += 32) yhist[blk + n] = X[n];
+    } else {
+        // coefficient sets: current (c_num, c_den) and previous (c_num_mem, c_den_mem); code 4 = all zero
+        auto cnum = [&](int cd, int k) -> float { return cd < 4 ? c.ltpf_num[cd][k] : 0.0f; };
+        auto cden = [&](int cd, int fr, int k) -> float { return cd < 4 ? c.ltpf_den[cd][fr][k] : 0.0f; };
+        const int cur_code = active ? code : 4;     // inactive: zeroed coefficients (:196-201)
+        const int mem_code = prev_active ? prev_code : 4;
+        for (int n = lane; n < p.hist_len; n += 32) Y[n] = yhist[n];
+        __syncwarp();
+        auto wrapi = [&](int idx) -> int { return idx < 0 ? idx + p.hist_len : idx; };   // :244-250
+        auto x_at = [&](int pos) -> float {          // x_hat_mem[wrap(pos)], pos relative to buffer start
+            const int rel = pos - blk;               // >= -l_num
+            return rel >= 0 ? X[rel] : xtail[16 + rel];
+        };
+        // compute_filter / compute_filter_mem :380-415
+        auto filt = [&](int start, int pint, int cd, int fr) -> float {
+            float out = 0.0f;
+            for (int k = 0; k <= l_num; k++) out = xa(out, xm(cnum(cd, k), x_at(start - k)));
+            const int sden = start - pint + l_den / 2;
+            for (int k = 0; k <= l_den; k++) out = xs(out, xm(cden(cd, fr, k), Y[wrapi(sden - k)]));
+            return out;
+        };
+        const float fnorm = (float)norm;
+        // run `body(n)` for n in [n0, n1) in dependency-safe chunks: outputs reach back at least `reach` samples
+        auto chunked = [&](int n0, int n1, int reach, auto body) {
+            const int C = reach < 32 ? reach : 32;
+            for (int s = n0; s < n1; s += C) {
+                const int n = s + lane;
+                if (lane < C && n < n1) body(n);
+                __syncwarp();
+            }
+        };
+        const int reach_cur = active ? p_int - l_den / 2 : 32;
+        const int reach_mem = prev_active ? p_int_mem - l_den / 2 : 32;
+        auto deactivate_first = [&]() {              // :417-424
+            chunked(0, s2p5, reach_mem, [&](int n) {
+                float fo = filt(blk + n, p_int_mem, mem_code, p_fr_mem);
+                fo = xm(fo, xs(1.0f, xd((float)n, fnorm)));
+                Y[blk + n] = xs(X[n], fo);
+            });
+        };
+        auto plain_from = [&](int n0) {
+            chunked(n0, nf, reach_cur, [&](int n) { Y[blk + n] = xs(X[n], filt(blk + n, p_int, cur_code, p_fr)); });
+        };
+        if (active && !prev_active) {                // case 2
+            chunked(0, s2p5, reach_cur, [&](int n) {
+                float fo = filt(blk + n, p_int, cur_code, p_fr);
+                fo = xm(fo, xd((float)n, fnorm));
+                Y[blk + n] = xs(X[n], fo);
+            });
+            plain_from(s2p5);
+        } else if (!active && prev_active) {         // case 3
+            deactivate_first();
+            for (int n = s2p5 + lane; n < nf; n += 32) Y[blk + n] = X[n];
+        } else if (p_int == p_int_mem && p_fr == p_fr_mem) {   // case 4
+            plain_from(0);
+        } else {                                     // case 5
+            deactivate_first();
+            // activate_first_2p5ms_from_mem :345-378: numerator taps read a frozen copy of y[blk-l_num .. blk+norm)
+            float* scratch = (float*)bufB;
+            for (int i = lane; i < l_num + norm; i += 32) {
+                int src;
+                if (blk < l_num) src = i < l_num ? blocks * nf - l_num + i : i - l_num;
+                else src = blk - l_num + i;
+                scratch[i] = Y[src];
+            }
+            __syncwarp();
+            chunked(0, s2p5, reach_cur, [&](int n) {
+                float fo = 0.0f;
+                for (int k = 0; k <= l_num; k++) fo = xa(fo, xm(cnum(cur_code, k), scratch[l_num + n - k]));
+                const int sden = blk + n - p_int + l_den / 2;
+                for (int k = 0; k <= l_den; k++) fo = xs(fo, xm(cden(cur_code, p_fr, k), Y[wrapi(sden - k)]));
+                fo = xm(fo, xd((float)n, fnorm));
+                Y[blk + n] = xs(scratch[n + l_num], fo);
+            });
+            plain_from(s2p5);
+        }
+        __syncwarp();
+        for (int n = lane; n < nf; n += 32) { const float v = Y[blk + n]; yhist[blk + n] = v; X[n] = v; }
+    }
+    __syncwarp();
+    // x tail for the next frame: last 16 samples of this frame's x_hat (the filter INPUT).  X may hold the
+    // filter output by now; T (bufA) still holds the input (case 5's scratch lives in bufB).
+    if (lane < 16) xtail[lane] = T[nf - 16 + lane];
+    if (lane == 0) {
+        ss[SS_LTPF_PREV] = (active ? 1 : 0) | ((active ? code : 4) << 8);
+        ss[SS_LTPF_PINT] = p_int;
+        ss[SS_LTPF_PFR] = p_fr;
+        int nb = ss[SS_LTPF_BLK] + 1;                // :334-337
+        if (nb * nf > (blocks - 1) * nf) nb = 0;
+        ss[SS_LTPF_BLK] = nb;
+    }
+
+    // ---- output_scaling.rs:13-26: round half away from zero, saturate
+    int16_t* out = p.pcm_out + (size_t)stream * p.pcm_stride;
+    for (int n = lane; n < nf; n += 32) {
+        const float v = X[n];
+        int32_t q = v > 0.0f ? cast_i32(xa(v, 0.5f)) : cast_i32(xs(v, 0.5f));
+        q = q > 32767 ? 32767 : q < -32768 ? -32768 : q;
+        out[n] = (int16_t)q;
+    }
+}
+
+cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream) {
+    SynthParams p;
+    p.cfg = st.dcfg;
+    p.win = st.win;
+    p.dtw = st.dtw;
+    p.ftw = st.ftw;
+    p.spec = st.spec;
+    p.ola = st.ola;
+    p.ltpf_y = st.ltpf_y;
+    p.ltpf_xtail = st.ltpf_xtail;
+    p.side = st.side;
+    p.sstate = st.sstate;
+    p.pcm_out = pcm_out;
+    p.pcm_stride = pcm_stride;
+    p.n_streams = st.n_streams;
+    const int nf = st.cfg.nf, N = nf / 2;
+    const int blocks = st.cfg.n_ms == LC3B_10MS ? 2 : 3;
+    p.hist_len = blocks * nf;
+    size_t per_warp = (size_t)2 * N * sizeof(float2) + (size_t)nf * 4 + (size_t)p.hist_len * 4;
+    per_warp = (per_warp + 15) & ~(size_t)15;
+    p.smem_per_warp = (int)per_warp;
+    const size_t smem = per_warp * SYN_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (st.n_streams + SYN_WARPS - 1) / SYN_WARPS;
+    synth_kernel<<<grid, SYN_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace lc3b

@@ -1,0 +1,91 @@
+"""ctypes binding of liblc3b.so (include/lc3b.h).  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "liblc3b.so"
+
+
+class SamplingFrequency(enum.IntEnum):      # src/common/config.rs:2
+    Hz8000 = 0
+    Hz16000 = 1
+    Hz24000 = 2
+    Hz32000 = 3
+    Hz44100 = 4
+    Hz48000 = 5
+
+    @staticmethod
+    def from_hz(hz: int) -> "SamplingFrequency":
+        return {8000: SamplingFrequency.Hz8000, 16000: SamplingFrequency.Hz16000, 24000: SamplingFrequency.Hz24000,
+                32000: SamplingFrequency.Hz32000, 44100: SamplingFrequency.Hz44100, 48000: SamplingFrequency.Hz48000}[hz]
+
+
+class FrameDuration(enum.IntEnum):          # src/common/config.rs:12
+    SevenPointFiveMs = 0
+    TenMs = 1
+
+    @staticmethod
+    def from_ms(ms: float) -> "FrameDuration":
+        return FrameDuration.TenMs if float(ms) == 10.0 else FrameDuration.SevenPointFiveMs
+
+
+class Lc3bError(RuntimeError):
+    """A non-zero status from the C ABI (LC3B_ERR_*)."""
+
+    def __init__(self, code: int, what: str):
+        names = {1: "LC3B_ERR_BITS_PER_SAMPLE", 2: "LC3B_ERR_INVALID_ARG", 3: "LC3B_ERR_CUDA", 4: "LC3B_ERR_WORKSPACE"}
+        extra = f" (cudaError {lib().lc3b_last_cuda_error()})" if code == 3 else ""
+        super().__init__(f"{what}: {names.get(code, code)}{extra}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("fs_ind", "fs", "ne", "nb", "nf", "z", "n_ms")]
+
+
+EXPORTS = ["lc3b_config_new", "lc3b_last_cuda_error", "lc3b_version", "lc3b_decoder_workspace_bytes",
+           "lc3b_decoder_init", "lc3b_decode_frames", "lc3b_decode_frames_host", "lc3b_decoder_set_trace",
+           "lc3b_decoder_get_spectrum", "lc3b_decoder_set_stage_mask", "lc3b_decoder_destroy", "lc3b_selftest_math_host",
+           "lc3b_selftest_math_device"]
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _SO
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not _SO.exists():
+            raise ImportError(f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a).  lc3_codec_b200 has no CPU fallback.")
+        L = C.CDLL(str(_SO))
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.lc3b_version.restype = C.c_char_p
+        L.lc3b_config_new.argtypes = [i32, i32, C.POINTER(Config)]
+        L.lc3b_decoder_workspace_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
+        L.lc3b_decoder_init.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, sz, vp]
+        L.lc3b_decode_frames.argtypes = [vp, i32, vp, vp, i32, sz, vp, sz, vp, vp]
+        L.lc3b_decode_frames_host.argtypes = [vp, i32, vp, vp, i32, sz, vp, sz, vp, vp]
+        L.lc3b_decoder_set_trace.argtypes = [vp, vp, vp]
+        L.lc3b_decoder_get_spectrum.argtypes = [vp, vp, vp]
+        L.lc3b_decoder_set_stage_mask.argtypes = [vp, i32]
+        L.lc3b_decoder_destroy.argtypes = [vp]
+        L.lc3b_decoder_destroy.restype = None
+        L.lc3b_selftest_math_host.argtypes = [i32, vp, vp, vp, i32]
+        L.lc3b_selftest_math_device.argtypes = [i32, vp, vp, vp, i32, vp]
+        _lib = L
+    return _lib
+
+
+def config(sampling_frequency: int, frame_duration: int) -> Config:
+    c = Config()
+    rc = lib().lc3b_config_new(int(sampling_frequency), int(frame_duration), C.byref(c))
+    if rc:
+        raise Lc3bError(rc, "lc3b_config_new")
+    return c

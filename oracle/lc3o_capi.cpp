@@ -316,7 +316,7 @@ void lc3o_encode_streams(int nthreads, int n_streams, int n_frames, const int32_
 
 void lc3o_decode_streams(int nthreads, int n_streams, int n_frames, int sf, int fd, const uint8_t* bytes, int nbytes,
                          const int32_t* nbytes_per_frame /*nullable*/, int16_t* pcm, int32_t* trace /*nullable*/,
-                         int32_t* x_out /*nullable*/) {
+                         int32_t* x_out /*nullable*/, float* spec_out /*nullable: spectrum handed to the IMDCT*/) {
     Config c = make_config((SamplingFrequency)sf, (FrameDuration)fd);
     parallel_for(nthreads, n_streams, [=](int s) {
         DecoderChannel d;
@@ -326,6 +326,7 @@ void lc3o_decode_streams(int nthreads, int n_streams, int n_frames, int sf, int 
             int len = nbytes_per_frame ? nbytes_per_frame[fi] : nbytes;
             d.decode(16, bytes + fi * nbytes, len, pcm + fi * c.nf, c.nf);
             if (trace) fill_trace(d, trace + fi * TR_WORDS, x_out ? x_out + fi * c.ne : nullptr, c.ne);
+            if (spec_out) std::memcpy(spec_out + fi * c.ne, d.spec.data(), sizeof(float) * c.ne);
         }
     });
 }

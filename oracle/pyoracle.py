@@ -88,14 +88,15 @@ def encode_streams(pcm: np.ndarray, fs: int, ms: float, nbytes: int, nthreads: i
 
 def decode_streams(frames: np.ndarray, fs: int, ms: float, nbytes_per_frame: np.ndarray | None = None,
                    nthreads: int | None = None, trace: bool = False):
-    """bytes [n_streams, n_frames, nbytes] u8 -> pcm [n_streams, n_frames, nf] i16 (+ trace, x) via the oracle decoder."""
+    """bytes [n_streams, n_frames, nbytes] u8 -> pcm [n_streams, n_frames, nf] i16 (+ trace, x, spectrum) via the oracle decoder."""
     frames = np.ascontiguousarray(frames, np.uint8)
     s, f, nb = frames.shape
     cfg = config(fs, ms)
     pcm = np.zeros((s, f, cfg["nf"]), np.int16)
     tr = np.zeros((s, f, TRACE_WORDS), np.int32) if trace else None
     xo = np.zeros((s, f, cfg["ne"]), np.int32) if trace else None
+    sp = np.zeros((s, f, cfg["ne"]), np.float32) if trace else None
     npf = None if nbytes_per_frame is None else np.ascontiguousarray(nbytes_per_frame, np.int32)
     lib().lc3o_decode_streams(C.c_int(nthreads or ncores()), s, f, SF[fs], FD[ms], p(frames), nb, p(npf), p(pcm), p(tr),
-                              p(xo))
-    return (pcm, tr, xo) if trace else pcm
+                              p(xo), p(sp))
+    return (pcm, tr, xo, sp) if trace else pcm
