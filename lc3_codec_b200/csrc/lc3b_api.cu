@@ -333,13 +333,18 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const size_t ns = (size_t)st.n_streams;
     // frames: one strided copy packs the rows to pitch `nbytes`
-    CU(cudaMemcpy2DAsync(st.stage_in, (size_t)nbytes, frames, frame_stride, (size_t)nbytes, ns, cudaMemcpyHostToDevice, stream));
+    // (a pitched copy of many short rows is far slower than one linear copy, so the dense case takes the linear path)
+    if (frame_stride == (size_t)nbytes) CU(cudaMemcpyAsync(st.stage_in, frames, ns * (size_t)nbytes, cudaMemcpyHostToDevice, stream));
+    else CU(cudaMemcpy2DAsync(st.stage_in, (size_t)nbytes, frames, frame_stride, (size_t)nbytes, ns, cudaMemcpyHostToDevice, stream));
     if (frame_nbytes) CU(cudaMemcpyAsync(st.stage_len, frame_nbytes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, stream));
     CU(launch_entropy(st, st.stage_in, frame_nbytes ? st.stage_len : nullptr, nbytes, (size_t)nbytes,
                       status_out ? st.stage_status : nullptr, stream));
     CU(launch_synth(st, st.stage_out, (size_t)st.cfg.nf, stream));
-    CU(cudaMemcpy2DAsync(pcm_out, pcm_stride * sizeof(int16_t), st.stage_out, (size_t)st.cfg.nf * sizeof(int16_t),
-                         (size_t)st.cfg.nf * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, stream));
+    if (pcm_stride == (size_t)st.cfg.nf)
+        CU(cudaMemcpyAsync(pcm_out, st.stage_out, ns * (size_t)st.cfg.nf * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
+    else
+        CU(cudaMemcpy2DAsync(pcm_out, pcm_stride * sizeof(int16_t), st.stage_out, (size_t)st.cfg.nf * sizeof(int16_t),
+                             (size_t)st.cfg.nf * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, stream));
     if (status_out) CU(cudaMemcpyAsync(status_out, st.stage_status, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, stream));
     return LC3B_OK;
 }

@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
         // QUIRK (i): flags were stored per TUPLE index but are consumed per LINE index k = 0, 2, 4, ...
         int left = nres;
         bool stop = false;
-        for (int k = 0; k < si.lastnz && !stop; k += 2) {
+        // save_lev[] is only ever written for tuple indices < lastnz/2 and is zero beyond, so the walk can stop there.
+        for (int k = 0; k < (si.lastnz >> 1) && !stop; k += 2) {
             if (!((s_lev[(k >> 5) * ENT_THREADS + tid] >> (k & 31)) & 1u)) continue;
 #pragma unroll
             for (int j = 0; j < 2; j++) {                               // read_res_bit :346
@@ -506,7 +507,9 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     };
 
     float* tile = s_tile + wid * 32 * 33;
-    float* out_base = p.spec + ((size_t)new_slot * p.n_streams + (size_t)(stream0 + wid * 32)) * ne;
+    // streams of one warp may sit in different slots (a slot only flips on a good frame): address rows per stream
+    float* out_base = p.spec + (size_t)(stream0 + wid * 32) * ne;
+    const size_t slot_stride = (size_t)p.n_streams * ne;
     const int rows_valid = min(32, p.n_streams - (stream0 + wid * 32));
 
     const bool any_ok = __any_sync(0xffffffffu, ok);
@@ -563,7 +566,8 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
                 const int k0 = k & ~31, cnt = (k & 31) + 1;
                 for (int r = 0; r < rows_valid; r++) {
                     const bool row_ok = __shfl_sync(0xffffffffu, (int)ok, r);
-                    if (row_ok && lane < cnt) out_base[(size_t)r * ne + k0 + lane] = tile[lane * 33 + r];
+                    const int row_slot = __shfl_sync(0xffffffffu, new_slot, r);
+                    if (row_ok && lane < cnt) out_base[row_slot * slot_stride + (size_t)r * ne + k0 + lane] = tile[lane * 33 + r];
                 }
                 __syncwarp();
             }

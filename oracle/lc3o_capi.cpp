@@ -7,6 +7,7 @@
 #include "lc3o.h"
 
 using namespace lc3o;
+namespace lc3o { extern thread_local int g_fail_line; }
 
 // Per-frame inspection record shared with the CUDA engine (include/lc3b.h: LC3B_TRACE_*).
 enum {
@@ -49,6 +50,7 @@ static void parallel_for(int nthreads, int n, F f) {
 extern "C" {
 
 int lc3o_trace_words() { return TR_WORDS; }
+int lc3o_last_fail_line() { return lc3o::g_fail_line; }
 
 void lc3o_config(int sf, int fd, int32_t* out7) {
     Config c = make_config((SamplingFrequency)sf, (FrameDuration)fd);

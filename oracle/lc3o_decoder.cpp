@@ -4,11 +4,15 @@
 
 namespace lc3o {
 
+// diagnostics only: source line of the last decode error on this thread (which reference error variant fired)
+thread_local int g_fail_line = 0;
+#define FAIL() (g_fail_line = __LINE__, false)
+
 // ================================================================== buffer_reader.rs
 // buffer_reader.rs:42-50
 bool BufferReader::read_head_byte(const uint8_t* buf, int64_t len, uint8_t* out) {
     if (head_byte_cursor < len) { *out = buf[head_byte_cursor++]; return true; }
-    return false;
+    return FAIL();
 }
 // buffer_reader.rs:52-60
 bool BufferReader::read_head_u24(const uint8_t* buf, int64_t len, uint32_t* out) {
@@ -18,7 +22,7 @@ bool BufferReader::read_head_u24(const uint8_t* buf, int64_t len, uint32_t* out)
         head_byte_cursor += 3;
         return true;
     }
-    return false;
+    return FAIL();
 }
 // buffer_reader.rs:63-96: big-endian load of the 1..4 bytes that hold the field, then shifts.
 // The bounds test involves the HEAD cursor (tail reads may not cross into consumed head bytes).
@@ -28,7 +32,7 @@ bool BufferReader::read_tail_usize(const uint8_t* buf, int64_t len, int num_bits
     int bits_left = 8 - bit_index;
     int add_bytes = (num_bits > bits_left && num_bits < 8) ? 2 : 1;
     int num_bytes = num_bits / 8 + add_bytes;
-    if ((int32_t)len - (int32_t)head_byte_cursor - (int32_t)byte_index - (int32_t)num_bytes < 0) return false;
+    if ((int32_t)len - (int32_t)head_byte_cursor - (int32_t)byte_index - (int32_t)num_bytes < 0) return FAIL();
     int64_t from = len - byte_index - num_bytes;
     const uint8_t* s = buf + from;
     uint32_t value;
@@ -50,9 +54,9 @@ bool BufferReader::read_tail_usize(const uint8_t* buf, int64_t len, int num_bits
 bool BufferReader::read_tail_bool(const uint8_t* buf, int64_t len, bool* out) {
     int64_t byte_index = tail_bit_cursor / 8;
     int bit_index = (int)(tail_bit_cursor % 8);
-    if ((int32_t)len - (int32_t)head_byte_cursor - (int32_t)byte_index + 2 < 0) return false;
+    if ((int32_t)len - (int32_t)head_byte_cursor - (int32_t)byte_index + 2 < 0) return FAIL();
     int64_t from = len - byte_index - 1;
-    if (from < 0) return false;   // the reference would panic (index out of range); unreachable for nbytes >= 20
+    if (from < 0) return FAIL();   // the reference would panic (index out of range); unreachable for nbytes >= 20
     uint8_t byte = buf[from];
     byte = (uint8_t)(byte << (7 - bit_index));
     byte >>= 7;
@@ -73,20 +77,20 @@ static int lastnz_bits(int ne) {
 static bool read_sns_vq(const uint8_t* buf, int64_t len, BufferReader& rd, SnsVq* o) {
     uint64_t v;
     bool b;
-    if (!rd.read_tail_usize(buf, len, 5, &v)) return false;
+    if (!rd.read_tail_usize(buf, len, 5, &v)) return FAIL();
     o->ind_lf = (int)v;
-    if (!rd.read_tail_usize(buf, len, 5, &v)) return false;
+    if (!rd.read_tail_usize(buf, len, 5, &v)) return FAIL();
     o->ind_hf = (int)v;
-    if (!rd.read_tail_bool(buf, len, &b)) return false;
+    if (!rd.read_tail_bool(buf, len, &b)) return FAIL();
     o->submode_msb = b;
-    if (!rd.read_tail_usize(buf, len, o->submode_msb == 0 ? 1 : 2, &v)) return false;
+    if (!rd.read_tail_usize(buf, len, o->submode_msb == 0 ? 1 : 2, &v)) return FAIL();
     int g_ind = (int)v;
-    if (!rd.read_tail_bool(buf, len, &b)) return false;
+    if (!rd.read_tail_bool(buf, len, &b)) return FAIL();
     o->ls_inda = b;
     if (o->submode_msb == 0) {
-        if (!rd.read_tail_usize(buf, len, 25, &v)) return false;
+        if (!rd.read_tail_usize(buf, len, 25, &v)) return FAIL();
         int64_t tmp = (int64_t)v;
-        if (tmp >= 33460056) return false;                     // PlcTriggerSns1OutOfRange
+        if (tmp >= 33460056) return FAIL();                     // PlcTriggerSns1OutOfRange
         int64_t idx_bor_gain_lsb = tmp / 2390004;
         o->idx_a = (int)(tmp - idx_bor_gain_lsb * 2390004);
         o->submode_lsb = 0;
@@ -105,9 +109,9 @@ static bool read_sns_vq(const uint8_t* buf, int64_t len, BufferReader& rd, SnsVq
         o->ls_indb = 0;
         o->idx_b = 0;
         o->submode_lsb = 0;
-        if (!rd.read_tail_usize(buf, len, 24, &v)) return false;
+        if (!rd.read_tail_usize(buf, len, 24, &v)) return FAIL();
         int64_t tmp = (int64_t)v;
-        if (tmp >= 16708096) return false;                     // PlcTriggerSns2OutOfRange
+        if (tmp >= 16708096) return FAIL();                     // PlcTriggerSns2OutOfRange
         if (tmp >= 15158272) {
             tmp -= 15158272;
             o->submode_lsb = 1;
@@ -129,37 +133,37 @@ bool read_side_info(const uint8_t* buf, int64_t len, BufferReader& rd, int fs_in
     int nbits_bw = NBITS_BW_TABLE[fs_ind];
     int p_bw = 0;
     if (nbits_bw > 0) {
-        if (!rd.read_tail_usize(buf, len, nbits_bw, &v)) return false;
-        if ((uint64_t)fs_ind < v) return false;                // BandwidthIdxOutOfRange
+        if (!rd.read_tail_usize(buf, len, nbits_bw, &v)) return FAIL();
+        if ((uint64_t)fs_ind < v) return FAIL();                // BandwidthIdxOutOfRange
         p_bw = (int)v;
     }
-    if (!rd.read_tail_usize(buf, len, lastnz_bits(ne), &v)) return false;
+    if (!rd.read_tail_usize(buf, len, lastnz_bits(ne), &v)) return FAIL();
     int lastnz = (int)((v + 1) << 1);
-    if (lastnz > ne) return false;                             // LastNonZeroTupleGreaterThanYLen
-    if (!rd.read_tail_bool(buf, len, &b)) return false;
+    if (lastnz > ne) return FAIL();                             // LastNonZeroTupleGreaterThanYLen
+    if (!rd.read_tail_bool(buf, len, &b)) return FAIL();
     o->lsb_mode = b;
-    if (!rd.read_tail_usize(buf, len, 8, &v)) return false;
+    if (!rd.read_tail_usize(buf, len, 8, &v)) return FAIL();
     o->global_gain_index = (int)v;
     o->num_tns_filters = p_bw < 3 ? 1 : 2;
     o->rc_order_ari_input[0] = o->rc_order_ari_input[1] = 0;
     for (int f = 0; f < o->num_tns_filters; f++) {
-        if (!rd.read_tail_bool(buf, len, &b)) return false;
+        if (!rd.read_tail_bool(buf, len, &b)) return FAIL();
         o->rc_order_ari_input[f] = b;
     }
     bool pitch_present;
-    if (!rd.read_tail_bool(buf, len, &pitch_present)) return false;
-    if (!read_sns_vq(buf, len, rd, &o->sns_vq)) return false;
+    if (!rd.read_tail_bool(buf, len, &pitch_present)) return FAIL();
+    if (!read_sns_vq(buf, len, rd, &o->sns_vq)) return FAIL();
     // side_info_reader.rs:105-125
     o->ltpf.pitch_present = pitch_present;
     o->ltpf.is_active = false;
     o->ltpf.pitch_index = 0;
     if (pitch_present) {
-        if (!rd.read_tail_bool(buf, len, &b)) return false;
+        if (!rd.read_tail_bool(buf, len, &b)) return FAIL();
         o->ltpf.is_active = b;
-        if (!rd.read_tail_usize(buf, len, 9, &v)) return false;
+        if (!rd.read_tail_usize(buf, len, 9, &v)) return FAIL();
         o->ltpf.pitch_index = (int)v;
     }
-    if (!rd.read_tail_usize(buf, len, 3, &v)) return false;
+    if (!rd.read_tail_usize(buf, len, 3, &v)) return FAIL();
     o->noise_factor = (int)v;
     o->bandwidth = p_bw;   // 0..4 by construction (p_bw <= fs_ind <= 4)
     o->lastnz = lastnz;
@@ -174,7 +178,7 @@ static bool ac_decode(const uint8_t* buf, int64_t len, BufferReader& rd, AcState
                       const int16_t* freq, int n_sym, int* out) {
     uint32_t tmp = st.range >> 10;
     uint32_t limit = tmp << 10;
-    if (st.low >= limit) return false;                         // AcRangeFlOutOfRange
+    if (st.low >= limit) return FAIL();                         // AcRangeFlOutOfRange
     int val = n_sym - 1;
     while (st.low < tmp * (uint32_t)(int32_t)cum[val]) val--;
     st.low -= tmp * (uint32_t)(int32_t)cum[val];
@@ -183,7 +187,7 @@ static bool ac_decode(const uint8_t* buf, int64_t len, BufferReader& rd, AcState
         st.low <<= 8;
         st.low &= 0x00ffffff;
         uint8_t byte;
-        if (!rd.read_head_byte(buf, len, &byte)) return false;
+        if (!rd.read_head_byte(buf, len, &byte)) return FAIL();
         st.low += byte;
         st.range <<= 8;
     }
@@ -203,12 +207,12 @@ static bool decode_tns_data(const uint8_t* buf, int64_t len, BufferReader& rd, c
         if (tns_order[f] > 0) {
             int order;
             if (!ac_decode(buf, len, rd, st, LC3T_AC_TNS_ORDER_CUMFREQ[w], LC3T_AC_TNS_ORDER_FREQ[w], 8, &order))
-                return false;
+                return FAIL();
             tns_order[f] = order + 1;
             for (int k = 0; k < tns_order[f]; k++) {
                 if (!ac_decode(buf, len, rd, st, LC3T_AC_TNS_COEF_CUMFREQ[k], LC3T_AC_TNS_COEF_FREQ[k], 17,
                                &tns_idx[f * 8 + k]))
-                    return false;
+                    return FAIL();
             }
         }
     }
@@ -228,12 +232,12 @@ static bool decode_spectral_data(const uint8_t* buf, int64_t len, BufferReader& 
         while (lev < 14) {
             int pki = LC3T_AC_SPEC_LOOKUP[t + (lev < 3 ? lev : 3) * 1024];
             if (!ac_decode(buf, len, rd, st, LC3T_AC_SPEC_CUMFREQ[pki], LC3T_AC_SPEC_FREQ[pki], 17, &sym))
-                return false;
+                return FAIL();
             if (sym < 16) break;
             if (!si.lsb_mode || lev > 0) {
-                if (!rd.read_tail_bool(buf, len, &bit)) return false;
+                if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
                 xa += (int32_t)bit << lev;
-                if (!rd.read_tail_bool(buf, len, &bit)) return false;
+                if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
                 xb += (int32_t)bit << lev;
             }
             lev++;
@@ -245,11 +249,11 @@ static bool decode_spectral_data(const uint8_t* buf, int64_t len, BufferReader& 
         xa += (int32_t)a << lev;
         xb += (int32_t)b << lev;
         if (xa > 0) {
-            if (!rd.read_tail_bool(buf, len, &bit)) return false;
+            if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
             if (bit) xa = -xa;
         }
         if (xb > 0) {
-            if (!rd.read_tail_bool(buf, len, &bit)) return false;
+            if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
             if (bit) xb = -xb;
         }
         x[2 * k] = xa;
@@ -266,7 +270,7 @@ static bool read_res_bit(int32_t* x, BufferReader& rd, const uint8_t* buf, int64
                          bool* cont) {
     if (*nres == 0) { *cont = false; return true; }
     bool bit;
-    if (!rd.read_tail_bool(buf, len, &bit)) return false;
+    if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
     *nres -= 1;
     if (bit) {
         int32_t& v = x[idx];
@@ -274,7 +278,7 @@ static bool read_res_bit(int32_t* x, BufferReader& rd, const uint8_t* buf, int64
         else if (v < 0) v -= 1;
         else {
             if (*nres == 0) { *cont = false; return true; }
-            if (!rd.read_tail_bool(buf, len, &bit)) return false;
+            if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
             *nres -= 1;
             v = bit ? -1 : 1;
         }
@@ -290,13 +294,13 @@ bool arithmetic_decode(const uint8_t* buf, int64_t len, BufferReader& rd, int fs
                        FrameDuration n_ms, int32_t* x, ArithmeticData* out) {
     int nbits = (int)len * 8;
     AcState st;
-    if (!rd.read_head_u24(buf, len, &st.low)) return false;    // ac_dec_init :57
+    if (!rd.read_head_u24(buf, len, &st.low)) return FAIL();    // ac_dec_init :57
     st.range = 0x00ffffff;
-    if (!decode_tns_data(buf, len, rd, si, st, nbits, n_ms, out->rc_i, out->rc_order)) return false;
+    if (!decode_tns_data(buf, len, rd, si, st, nbits, n_ms, out->rc_i, out->rc_order)) return FAIL();
 
     int32_t save_lev[400];
     std::memset(save_lev, 0, sizeof(save_lev));
-    if (!decode_spectral_data(buf, len, rd, si, nbits, fs_ind, ne, st, x, save_lev)) return false;
+    if (!decode_spectral_data(buf, len, rd, si, nbits, fs_ind, ne, st, x, save_lev)) return FAIL();
     for (int k = si.lastnz; k < 400; k++) x[k] = 0;            // x is [i32; MAX_LEN_SPECTRAL]
 
     // decode_residual_bits :160-209 with calc_num_residual_bits :390-407
@@ -304,7 +308,7 @@ bool arithmetic_decode(const uint8_t* buf, int64_t len, BufferReader& rd, int fs
     // f64 log2 + floor of an integer in [1, 2^24): exact integer log2.  range == 0 cannot reach here
     // (the renormalisation loop above would have run out of bytes first).
     int64_t nbits_ari = (rd.head_byte_cursor + 1 - 3) * 8 + 25 - (int64_t)ilog2_u32(st.range);
-    if ((int64_t)nbits < nbits_side + nbits_ari) return false; // NegativeResidualNumBits
+    if ((int64_t)nbits < nbits_side + nbits_ari) return FAIL(); // NegativeResidualNumBits
     int64_t nres = nbits - nbits_side - nbits_ari;
     out->residual_bits.clear();
     if (!si.lsb_mode) {
@@ -312,8 +316,8 @@ bool arithmetic_decode(const uint8_t* buf, int64_t len, BufferReader& rd, int fs
             if (x[k] != 0) {
                 if ((int64_t)out->residual_bits.size() == nres) break;
                 bool bit;
-                if (!rd.read_tail_bool(buf, len, &bit)) return false;
-                if (out->residual_bits.size() >= 480) return false;   // heapless::Vec<bool,480> overflow
+                if (!rd.read_tail_bool(buf, len, &bit)) return FAIL();
+                if (out->residual_bits.size() >= 480) return FAIL();   // heapless::Vec<bool,480> overflow
                 out->residual_bits.push_back(bit);
             }
         }
@@ -321,9 +325,9 @@ bool arithmetic_decode(const uint8_t* buf, int64_t len, BufferReader& rd, int fs
         for (int k = 0; k < si.lastnz; k += 2) {
             if (save_lev[k] > 0) {
                 bool cont;
-                if (!read_res_bit(x, rd, buf, len, k, &nres, &cont)) return false;
+                if (!read_res_bit(x, rd, buf, len, k, &nres, &cont)) return FAIL();
                 if (!cont) break;
-                if (!read_res_bit(x, rd, buf, len, k + 1, &nres, &cont)) return false;
+                if (!read_res_bit(x, rd, buf, len, k + 1, &nres, &cont)) return FAIL();
                 if (!cont) break;
             }
         }
