@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: the named workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident loop only (for ncu captures; not a bench value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -222,6 +223,11 @@ def main():
         ms_total = timed(step_dev, args.steps, args.warmup)
     clocks = clk.summary()
     fps = world * S * args.steps / (ms_total * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": fps, "unit": "frames/s", "ms_per_step": ms_total / args.steps}))
+        return
 
     # ---- per-kernel time, each kernel alone (profiling hook), same inputs
     k_steps = max(20, min(args.steps, 100))
