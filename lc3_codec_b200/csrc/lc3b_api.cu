@@ -57,7 +57,7 @@ struct Carve {
 };
 
 struct Layout {
-    size_t dcfg, win, dtw, ftw, spec, xq, ola, ltpf_y, ltpf_xtail, side, sstate, stage_in, stage_out, stage_len,
+    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, ola, ltpf_y, ltpf_xtail, side, sstate, stage_in, stage_out, stage_len,
         stage_status, total;
 };
 
@@ -70,6 +70,7 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
     L.win = cv.take(sizeof(float) * 2 * c.nf);
     L.dtw = cv.take(sizeof(float2) * (c.nf / 2));
     L.ftw = cv.take(sizeof(float2) * (c.nf / 2));
+    L.sym_lut = cv.take(64 * 1024);
     L.spec = cv.take(sizeof(float) * 2 * ns * c.ne);
     L.xq = cv.take(sizeof(int32_t) * nblk * c.ne * 32);
     L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
@@ -147,6 +148,16 @@ __global__ void init_tables_kernel(DevConfig* cfg, float* win, float2* dtw, floa
                 }
             }
         }
+    }
+}
+
+// symbol for every (probability model, quotient): largest val with cum[val] <= q (arithmetic_codec.rs:82-85)
+__global__ void init_sym_lut_kernel(uint8_t* lut) {
+    const int pki = blockIdx.x;
+    for (int q = threadIdx.x; q < 1024; q += blockDim.x) {
+        int val = 16;
+        while (LC3T_AC_SPEC_CUMFREQ[pki][val] > q) val--;
+        lut[pki * 1024 + q] = (uint8_t)val;
     }
 }
 
@@ -262,6 +273,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     st.win = (float*)(base + L.win);
     st.dtw = (float2*)(base + L.dtw);
     st.ftw = (float2*)(base + L.ftw);
+    st.sym_lut = base + L.sym_lut;
     st.spec = (float*)(base + L.spec);
     st.xq = (int32_t*)(base + L.xq);
     st.ola = (float*)(base + L.ola);
@@ -283,6 +295,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);               // hc is a stack object
     if (e == cudaSuccess) {
         init_tables_kernel<<<1, 256, 0, stream>>>(st.dcfg, st.win, st.dtw, st.ftw);
+        init_sym_lut_kernel<<<64, 256, 0, stream>>>(st.sym_lut);
         init_streams_kernel<<<(n_streams + 255) / 256, 256, 0, stream>>>(st.sstate, n_streams);
         e = cudaGetLastError();
     }

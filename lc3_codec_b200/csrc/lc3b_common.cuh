@@ -56,6 +56,7 @@ struct DecoderState {
     float* win;          // [2*nf]
     float2* dtw;         // [n_fft]
     float2* ftw;         // [n_fft]
+    uint8_t* sym_lut;    // [64][1024] arithmetic-decoder symbol for (pki, quotient), built at init
     float* spec;         // [2][n_streams][ne]  double-buffered spectrum; the valid slot doubles as PLC "last good"
     int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (private to the entropy kernel)
     float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)

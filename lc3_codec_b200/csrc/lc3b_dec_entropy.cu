@@ -40,6 +40,7 @@ struct EntropyParams {
     int32_t* status_out;  // nullable
     int32_t* trace;       // nullable
     int32_t* trace_x;     // nullable
+    const uint8_t* sym_lut;   // [64][1024] symbol for (pki, floor(low / (range >> 10)))
     int row_pitch;        // bytes per staged frame row in shared memory
 };
 
@@ -49,32 +50,44 @@ struct Reader {
     int len;              // buf_in.len()
     int head;             // head_byte_cursor
     int tail;             // tail_bit_cursor
+    uint64_t tw;          // window of not-yet-consumed tail bits, LSB = next bit; (tail + tw_n) % 8 == 0 always
+    int tw_n;             // valid bits in tw
 
+    __device__ __forceinline__ void refill() {                         // up to 4 more bytes, counted from the end
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = len - 1 - ((tail + tw_n) >> 3);
+            const uint32_t byte = idx >= 0 ? buf[idx] : 0u;
+            tw |= (uint64_t)byte << tw_n;
+            tw_n += 8;
+        }
+    }
     __device__ __forceinline__ bool head_byte(uint32_t& out) {          // :42
         if (head >= len) return false;
         out = buf[head++];
         return true;
     }
     __device__ __forceinline__ bool tail_bool(int& bit) {               // :98
-        int byte_index = tail >> 3, bit_index = tail & 7;
+        const int byte_index = tail >> 3;
         if (len - head - byte_index + 2 < 0) return false;
-        int from = len - byte_index - 1;
-        if (from < 0) return false;                                     // the reference would panic; needs len < 3
-        bit = (buf[from] >> bit_index) & 1;
+        if (byte_index >= len) return false;                            // the reference would panic; needs len < 3
+        if (tw_n == 0) refill();
+        bit = (int)(tw & 1u);
+        tw >>= 1;
+        tw_n -= 1;
         tail += 1;
         return true;
     }
     __device__ __forceinline__ bool tail_uint(int num_bits, uint32_t& out) {   // :63
-        int byte_index = tail >> 3, bit_index = tail & 7;
-        int add_bytes = (num_bits > 8 - bit_index && num_bits < 8) ? 2 : 1;
-        int num_bytes = (num_bits >> 3) + add_bytes;
+        const int byte_index = tail >> 3, bit_index = tail & 7;
+        const int add_bytes = (num_bits > 8 - bit_index && num_bits < 8) ? 2 : 1;
+        const int num_bytes = (num_bits >> 3) + add_bytes;
         if (len - head - byte_index - num_bytes < 0) return false;
-        // same value as the reference's big-endian load + shifts: bits [bit_index, bit_index + num_bits)
-        // of the little-endian number formed by the bytes counted from the tail
-        int last = len - byte_index - 1;
-        uint64_t v = 0;
-        for (int i = 0; i < num_bytes; i++) v |= (uint64_t)buf[last - i] << (8 * i);
-        out = (uint32_t)((v >> bit_index) & ((1ull << num_bits) - 1ull));
+        // same value as the reference's big-endian load + shifts: the next num_bits bits, LSB first
+        if (tw_n < num_bits) refill();
+        out = (uint32_t)(tw & ((1ull << num_bits) - 1ull));
+        tw >>= num_bits;
+        tw_n -= num_bits;
         tail += num_bits;
         return true;
     }
@@ -82,11 +95,33 @@ struct Reader {
 
 struct AcState { uint32_t low, range; };
 
-// arithmetic_codec.rs:67-97.  `tab` holds cum | freq << 16 per symbol.
+// q = floor(low / tmp) for low < 2^24, 64 <= tmp < 2^14: the float quotient is within 1 of the truth, fix it up exactly
+__device__ __forceinline__ uint32_t exact_quotient(uint32_t low, uint32_t tmp) {
+    uint32_t q = (uint32_t)__fdividef((float)low, (float)tmp);
+    int32_t r = (int32_t)(low - q * tmp);
+    if (r < 0) q -= 1;
+    else if ((uint32_t)r >= tmp) q += 1;
+    return q;
+}
+
+__device__ __forceinline__ bool ac_finish(Reader& rd, AcState& st, uint32_t tmp, uint32_t e) {
+    st.low -= tmp * (e & 0xffffu);
+    st.range = tmp * (e >> 16);
+    while (st.range < 0x10000u) {
+        uint32_t b;
+        if (!rd.head_byte(b)) return false;
+        st.low = ((st.low << 8) & 0x00ffffffu) + b;
+        st.range <<= 8;
+    }
+    return true;
+}
+
+// arithmetic_codec.rs:67-97.  `tab` holds cum | freq << 16 per symbol; the reference scans from the top for the
+// largest val with tmp * cum[val] <= low, i.e. cum[val] <= floor(low / tmp).
 __device__ __forceinline__ bool ac_decode(Reader& rd, AcState& st, const uint32_t* __restrict__ tab, int nsym, int& sym) {
-    uint32_t tmp = st.range >> 10;
+    const uint32_t tmp = st.range >> 10;
     if (st.low >= (tmp << 10)) return false;                            // AcRangeFlOutOfRange
-    uint32_t q = st.low / tmp;                                          // largest val with tmp*cum[val] <= low
+    const uint32_t q = exact_quotient(st.low, tmp);
     int val;
     if (nsym == 17) {
         val = ((tab[16] & 0xffffu) <= q) ? 16 : 0;
@@ -102,17 +137,19 @@ __device__ __forceinline__ bool ac_decode(Reader& rd, AcState& st, const uint32_
         if ((tab[val + 2] & 0xffffu) <= q) val += 2;
         if ((tab[val + 1] & 0xffffu) <= q) val += 1;
     }
-    uint32_t e = tab[val];
-    st.low -= tmp * (e & 0xffffu);
-    st.range = tmp * (e >> 16);
-    while (st.range < 0x10000u) {
-        uint32_t b;
-        if (!rd.head_byte(b)) return false;
-        st.low = ((st.low << 8) & 0x00ffffffu) + b;
-        st.range <<= 8;
-    }
     sym = val;
-    return true;
+    return ac_finish(rd, st, tmp, tab[val]);
+}
+
+// Spectral symbols: same search answered by a 64 x 1024 byte table (symbol for every quotient), see init_sym_lut_kernel.
+__device__ __forceinline__ bool ac_decode_spec(Reader& rd, AcState& st, const uint32_t* __restrict__ tab,
+                                               const uint8_t* __restrict__ lut, int& sym) {
+    const uint32_t tmp = st.range >> 10;
+    if (st.low >= (tmp << 10)) return false;
+    const uint32_t q = exact_quotient(st.low, tmp);                     // < 1024 by the test above
+    const int val = __ldg(lut + q);
+    sym = val;
+    return ac_finish(rd, st, tmp, tab[val]);
 }
 
 // mpvq_deenum, spectral_noise_shaping.rs:155-235.  y lives in shared memory (per-thread column).
@@ -244,10 +281,12 @@ constexpr int ENT_THREADS = 128;
 //   lev     7*T*4           lsb-mode save_lev flags, one bit per tuple
 //   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
 //   tile    (T/32)*32*33*4  per-warp transpose tile for the spectrum write-out
+//   ring    16*T*4          per-thread prefetch ring for pass 2 (cp.async from the xq scratch)
+//   band    68*4            I_fs band edges
 //   rows    T*row_pitch     staged frame bytes
 __host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
     return 4096 + 64 * 17 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 16 * ENT_THREADS * 4 +
-           (ENT_THREADS / 32) * 32 * 33 * 4 + (size_t)ENT_THREADS * row_pitch;
+           (ENT_THREADS / 32) * 32 * 33 * 4 + 16 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 
 template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
@@ -259,7 +298,9 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     uint32_t* s_lev = s_tns_cf + (2 * 8 + 8 * 17);
     float* s_scf = (float*)(s_lev + 7 * ENT_THREADS);
     float* s_tile = s_scf + 16 * ENT_THREADS;
-    uint8_t* s_rows = (uint8_t*)(s_tile + (ENT_THREADS / 32) * 32 * 33);
+    int32_t* s_ring = (int32_t*)(s_tile + (ENT_THREADS / 32) * 32 * 33);
+    int32_t* s_band = s_ring + 16 * ENT_THREADS;
+    uint8_t* s_rows = (uint8_t*)(s_band + 68);
 
     const DevConfig& c = *p.cfg;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -277,6 +318,7 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     for (int i = tid; i < 8 * 17; i += ENT_THREADS)
         s_tns_cf[16 + i] = (uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_FREQ[0][0])[i] << 16);
     for (int i = tid; i < 7 * ENT_THREADS; i += ENT_THREADS) s_lev[i] = 0;
+    for (int i = tid; i < 65; i += ENT_THREADS) s_band[i] = p.cfg->band_idx[i];
     {
         const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
         const int nb = p.nbytes;
@@ -295,6 +337,8 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     if (rd.len < 0) rd.len = 0;
     rd.head = 0;
     rd.tail = 0;
+    rd.tw = 0;
+    rd.tw_n = 0;
     const int nbits = rd.len * 8;
     int32_t* xq = p.xq + ((size_t)(stream >> 5) * ne) * 32 + lane;   // element k at xq[k * 32]
 
@@ -340,16 +384,18 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
         }
     }
     if (ok) {                                                          // decode_spectral_data :211
+        // One arithmetic symbol per iteration for every lane (escape or final), instead of a per-tuple inner loop:
+        // lanes sit at different tuples/levels but all execute the same decode, which keeps the warp converged.
         const int rate_flag = nbits > (160 + c.fs_ind * 160) ? 512 : 0;
         int ctx = 0;
         const int ntup = si.lastnz >> 1;
-        for (int k = 0; k < ntup && ok; k++) {
+        int k = 0, lev = 0, xa_ = 0, xb_ = 0;
+        while (k < ntup) {
             int t = ctx + rate_flag + ((k * 2) > (ne / 2) ? 256 : 0);
-            int xa_ = 0, xb_ = 0, sym = 0, lev = 0, bit;
-            while (lev < 14) {
-                int pki = s_lookup[t + min(lev, 3) * 1024];
-                if (!ac_decode(rd, ac, s_spec_cf + pki * 17, 17, sym)) { ok = false; break; }
-                if (sym < 16) break;
+            const int pki = s_lookup[t + min(lev, 3) * 1024];
+            int sym, bit;
+            if (!ac_decode_spec(rd, ac, s_spec_cf + pki * 17, p.sym_lut + pki * 1024, sym)) { ok = false; break; }
+            if (sym >= 16) {                                            // escape: two more magnitude bits
                 if (!si.lsb_mode || lev > 0) {
                     if (!rd.tail_bool(bit)) { ok = false; break; }
                     xa_ += bit << lev;
@@ -357,10 +403,10 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
                     xb_ += bit << lev;
                 }
                 lev++;
+                if (lev < 14) continue;                                 // QUIRK (ii): at lev == 14 the tuple ends with sym == 16
             }
-            if (!ok) break;
             if (si.lsb_mode && lev > 0) s_lev[(k >> 5) * ENT_THREADS + tid] |= 1u << (k & 31);   // save_lev[k], QUIRK (i)
-            const int a = sym & 3, b = sym >> 2;                        // QUIRK (ii): sym may be 16 when lev == 14
+            const int a = sym & 3, b = sym >> 2;
             xa_ += a << lev;
             xb_ += b << lev;
             if (xa_ > 0) {
@@ -377,6 +423,10 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
             const int l = min(lev, 3);
             t = (l <= 1) ? 1 + (a + b) * (l + 1) : 12 + l;
             ctx = (ctx & 15) * 16 + t;
+            k++;
+            lev = 0;
+            xa_ = 0;
+            xb_ = 0;
         }
     }
     if (ok) {                                                          // calc_num_residual_bits :390
@@ -521,20 +571,35 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
         int res_used = 0;
         int band = 0;
         float gband = ok ? band_gain(0) : 0.0f;
-        auto fetch = [&](int j) -> int32_t { return (ok && j < lastnz) ? xq[j * 32] : 0; };
+        // The integers come back from the lane-interleaved scratch through a 16-slot per-thread ring filled by
+        // cp.async PF lines ahead, so the L2 round trip never sits on the serial per-line chain.
+        constexpr int PF = 12;
+        int32_t* ring = s_ring + tid;                                  // slot e at ring[(e & 15) * ENT_THREADS]
+        const int n_valid = ok ? lastnz : 0;                           // lines >= lastnz are zero and never fetched
+        auto issue = [&](int e) {
+            if (e < n_valid) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (e & 15) * ENT_THREADS);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(xq + e * 32));
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
 #pragma unroll
         for (int j = 0; j <= W; j++) win[j] = 0;
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            win[j + 1] = fetch(j);
+            win[j + 1] = j < n_valid ? xq[j * 32] : 0;
             if (win[j + 1] != 0 && j < bw_stop) last_nz = j;
         }
+        for (int e = W; e < W + PF; e++) issue(e);
+        int next_edge = s_band[1];
         for (int k = 0; k < ne; k++) {
 #pragma unroll
             for (int j = 0; j < W; j++) win[j] = win[j + 1];
             {
                 const int j = k + W;
-                win[W] = j < ne ? fetch(j) : 0;
+                issue(j + PF);
+                asm volatile("cp.async.wait_group %0;\n" ::"n"(PF));
+                win[W] = j < n_valid ? ring[(j & 15) * ENT_THREADS] : 0;
                 if (win[W] != 0 && j < bw_stop) last_nz = j;
             }
             const int32_t xi = win[0];
@@ -556,7 +621,7 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
                     if (k < tns_e0) { if (rc_order0 > 0) v = tns_lattice(v, st, rc0, rc_order0); }
                     else if (rc_order1 > 0 && si.num_tns == 2) v = tns_lattice(v, st, rc1, rc_order1);
                 }
-                while (k >= c.band_idx[band + 1] && band + 1 < nb) { band++; gband = band_gain(band); }
+                while (k >= next_edge && band + 1 < nb) { band++; next_edge = s_band[band + 1]; gband = band_gain(band); }
                 v = xm(v, gband);
             }
             // transpose through the warp tile, flush every 32 lines
@@ -634,6 +699,7 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
     p.status_out = status_out;
     p.trace = st.trace;
     p.trace_x = st.trace_x;
+    p.sym_lut = st.sym_lut;
     int words = (nbytes + 3) / 4 + 1;
     if ((words & 1) == 0) words++;                 // odd word pitch: lanes land on distinct banks
     p.row_pitch = words * 4;
