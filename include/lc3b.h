@@ -99,6 +99,35 @@ int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask);
 
 void lc3b_decoder_destroy(lc3b_decoder* h);
 
+/* ------------------------------------------------------------------ encoder */
+typedef struct lc3b_encoder lc3b_encoder;
+
+/* Lc3Encoder::calc_working_buffer_lengths, src/encoder/lc3_encoder.rs:194.  8 kHz returns LC3B_ERR_INVALID_ARG:
+ * Lc3Encoder::new panics there (BandwidthDetector::new indexes a table with fs_ind - 1, bandwidth_detector.rs:42-56). */
+int lc3b_encoder_workspace_bytes(int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                                 size_t* device_bytes);
+
+/* Lc3Encoder::new, src/encoder/lc3_encoder.rs:117: zeroed working memory, t_prev = 17 (long_term_post_filter.rs:85),
+ * attack_pos_last = -1 (attack_detector.rs:38). */
+int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                      int device, void* dev_workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* One Lc3Encoder::encode_frame (src/encoder/lc3_encoder.rs:175) per stream.
+ *   pcm_in      device int16, stream s at pcm_in + s*pcm_stride (elements), nf samples each (`samples_in`)
+ *   frames_out  device, stream s at frames_out + s*frame_stride, `nbytes` bytes each (`buf_out`, buf_out.len() = nbytes)
+ * The reference's encode cannot fail (Lc3EncoderError is empty, :30); wrong slice lengths panic there and are
+ * LC3B_ERR_INVALID_ARG here (nbytes < 20 underflows the bit budget, spectral_quantization.rs:133). */
+int lc3b_encode_frames(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride, uint8_t* frames_out, int nbytes,
+                       size_t frame_stride, void* cuda_stream);
+/* Same with HOST buffers (pinned => asynchronous). */
+int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride, uint8_t* frames_out, int nbytes,
+                            size_t frame_stride, void* cuda_stream);
+/* Test hook: device copies of the last encode's intermediates (any pointer may be NULL): xf [S][ne] f32 (quantiser
+ * input, after SNS and TNS), e_b [S][64] f32, hand [S][8] i32 (near_nyquist, attack, pitch_index, pitch_present,
+ * ltpf_active, nbits_ltpf), xq [S][ne] i16. */
+int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* hand, int16_t* xq, void* cuda_stream);
+void lc3b_encoder_destroy(lc3b_encoder* h);
+
 /* Self-test hooks: the engine's own f32 transcendentals (csrc/lc3b_math.cuh, msun-style) evaluated
  * on the host (no GPU needed) or on the device, so tests can compare them with the oracle's.
  * which: 0 powf(x,y) 1 log2f 2 log10f 3 exp2f 4 asinf 5 exp2_raw(fast-math) 6 powi(x,(int)y).

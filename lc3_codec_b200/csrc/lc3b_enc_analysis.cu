@@ -1,0 +1,515 @@
+// lc3b engine, encoder kernel 1 of 2: PCM -> MDCT spectrum, band energies, attack flag, LTPF parameters.
+// One WARP per frame.  Compiled with -fmad=false: every expression below rounds exactly like the reference's f32 code.
+//
+// Replaces, per stream, the first half of EncoderChannel::encode (src/encoder/lc3_encoder.rs:63-90):
+//   ModDiscreteCosTrans::run     src/encoder/modified_dct.rs:108 (time buffer :126, window+fold :73, DCT-IV
+//                                src/common/dct_iv.rs:49 over src/common/kissfft.rs:78, energies :140, near-Nyquist :154)
+//   AttackDetector::run          src/encoder/attack_detector.rs:45
+//   LongTermPostFilter::run      src/encoder/long_term_post_filter.rs:139 (resampler, 50 Hz high-pass, pitch detection,
+//                                pitch-lag parameter, activation bit)
+// Parallelisation never reassociates a sum: each lane owns whole outputs (one band energy, one resampled sample, one
+// correlation lag, one butterfly) and accumulates them in the reference's order; only truly serial recurrences (the
+// biquad, the block-energy envelope, the decision logic) run on lane 0.  The FFT is kissfft's own decimation-in-time
+// schedule (same factor order 4,4,..,2,3,5, same butterflies, same twiddle products) executed level by level with
+// the butterflies of a level spread over the lanes, so the spectrum is bit-identical to the reference's.
+#include "lc3b_enc_common.cuh"
+#include "lc3b_math.cuh"
+#include "lc3_tables.h"
+
+namespace lc3b {
+
+struct AnalysisParams {
+    const EncConfig* cfg;
+    const float* win;
+    const float2* dtw;
+    const float2* ftw;
+    const int32_t* perm;
+    const int16_t* pcm;
+    size_t pcm_stride;
+    int nbytes;
+    int n_streams;
+    int16_t* thist;
+    int16_t* xs_hist;
+    float* x12;
+    float* x6;
+    int32_t* estate;
+    float* xf;
+    float* e_b;
+    int32_t* ehand;
+    int smem_per_warp, wk_floats, cx_c2;
+};
+
+constexpr int ANA_WARPS = 4;
+
+struct C2 { float r, i; };
+__device__ __forceinline__ C2 cmul(C2 a, C2 b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }   // complex.rs:16-24
+__device__ __forceinline__ C2 cadd(C2 a, C2 b) { return {a.r + b.r, a.i + b.i}; }
+__device__ __forceinline__ C2 csub(C2 a, C2 b) { return {a.r - b.r, a.i - b.i}; }
+__device__ __forceinline__ C2 ld(const float2* p, int i) { float2 v = p[i]; return {v.x, v.y}; }
+__device__ __forceinline__ C2 lds(const C2* p, int i) { return p[i]; }
+
+// kissfft.rs:133-256, one butterfly (index u of a block `f` with sub-length m) per call
+__device__ __forceinline__ void bfly2(C2* f, const float2* tw, int fs, int m, int u) {
+    C2 t = cmul(f[m + u], ld(tw, u * fs));
+    f[m + u] = csub(f[u], t);
+    f[u] = cadd(f[u], t);
+}
+__device__ __forceinline__ void bfly4(C2* f, const float2* tw, int fs, int m, int u) {
+    const int m2 = 2 * m, m3 = 3 * m;
+    C2 s0 = cmul(f[u + m], ld(tw, u * fs));
+    C2 s1 = cmul(f[u + m2], ld(tw, u * fs * 2));
+    C2 s2 = cmul(f[u + m3], ld(tw, u * fs * 3));
+    C2 s5 = csub(f[u], s1);
+    C2 f0 = cadd(f[u], s1);
+    C2 s3 = cadd(s0, s2);
+    C2 s4 = csub(s0, s2);
+    f[u + m2] = csub(f0, s3);
+    f[u] = cadd(f0, s3);
+    f[u + m] = {s5.r + s4.i, s5.i - s4.r};             // forward transform (inverse == false)
+    f[u + m3] = {s5.r - s4.i, s5.i + s4.r};
+}
+__device__ __forceinline__ void bfly3(C2* f, const float2* tw, int fs, int m, int u) {
+    const int m2 = 2 * m;
+    const C2 epi3 = ld(tw, fs * m);
+    C2 s1 = cmul(f[u + m], ld(tw, u * fs));
+    C2 s2 = cmul(f[u + m2], ld(tw, u * fs * 2));
+    C2 s3 = cadd(s1, s2);
+    C2 s0 = csub(s1, s2);
+    C2 fi = f[u];
+    C2 fm = {fi.r - (s3.r * 0.5f), fi.i - (s3.i * 0.5f)};
+    s0.r *= epi3.i;
+    s0.i *= epi3.i;
+    f[u] = cadd(fi, s3);
+    f[u + m2] = {fm.r + s0.i, fm.i - s0.r};
+    f[u + m] = {fm.r - s0.i, fm.i + s0.r};
+}
+__device__ __forceinline__ void bfly5(C2* f, const float2* tw, int fs, int m, int u) {
+    const C2 ya = ld(tw, fs * m), yb = ld(tw, fs * 2 * m);
+    const int m1 = m, m2 = 2 * m, m3 = 3 * m, m4 = 4 * m;
+    C2 s0 = f[u];
+    C2 s1 = cmul(f[u + m1], ld(tw, u * fs));
+    C2 s2 = cmul(f[u + m2], ld(tw, u * 2 * fs));
+    C2 s3 = cmul(f[u + m3], ld(tw, u * 3 * fs));
+    C2 s4 = cmul(f[u + m4], ld(tw, u * 4 * fs));
+    C2 s7 = cadd(s1, s4), s10 = csub(s1, s4), s8 = cadd(s2, s3), s9 = csub(s2, s3);
+    C2 f0;
+    f0.r = s0.r + (s7.r + s8.r);
+    f0.i = s0.i + (s7.i + s8.i);
+    f[u] = f0;
+    C2 s5 = {s0.r + (s7.r * ya.r) + (s8.r * yb.r), s0.i + (s7.i * ya.r) + (s8.i * yb.r)};
+    C2 s6 = {(s10.i * ya.i) + (s9.i * yb.i), -(s10.r * ya.i) - (s9.r * yb.i)};
+    f[u + m1] = csub(s5, s6);
+    f[u + m4] = cadd(s5, s6);
+    C2 s11 = {s0.r + (s7.r * yb.r) + (s8.r * ya.r), s0.i + (s7.i * yb.r) + (s8.i * ya.r)};
+    C2 s12 = {-(s10.i * yb.i) + (s9.i * ya.i), (s10.r * yb.i) - (s9.r * ya.i)};
+    f[u + m2] = cadd(s11, s12);
+    f[u + m3] = csub(s11, s12);
+}
+
+__global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int stream = blockIdx.x * ANA_WARPS + wid;
+    if (stream >= p.n_streams) return;
+    const int nf = c.nf, ne = c.ne, z = c.z, N = c.n_fft, half = nf / 2;
+
+    uint8_t* base = smem + (size_t)wid * p.smem_per_warp;
+    float* wk = (float*)base;                       // max(nf, 320) floats
+    C2* cx = (C2*)(wk + p.wk_floats);               // max(N, 215) complex; later r6[98] + rw6[98] + r12[233]
+    float* x12 = (float*)(cx + p.cx_c2);            // x12_len floats
+    float* x6 = x12 + c.x12_len;                    // 178 floats
+    int16_t* tb = (int16_t*)(x6 + 178);             // 2*nf
+    int16_t* xs = tb + 2 * nf;                      // x_s_ext_len (<= 540)
+
+    const int16_t* in = p.pcm + (size_t)stream * p.pcm_stride;
+    int16_t* thist = p.thist + (size_t)stream * (nf - z);
+    int32_t* es = p.estate + (size_t)stream * ES_WORDS;
+
+    // ---- update_time_buffer (modified_dct.rs:126-138)
+    for (int n = lane; n < nf - z; n += 32) tb[n] = thist[n];
+    for (int n = lane; n < nf; n += 32) tb[nf - z + n] = in[n];
+    for (int n = lane; n < z; n += 32) tb[2 * nf - z + n] = 0;
+    __syncwarp();
+    for (int n = lane; n < nf - z; n += 32) thist[n] = tb[nf + n];
+    // ---- window + fold (:73-97)
+    {
+        const int mid = 3 * half;
+        for (int i = lane; i < half; i += 32) {
+            const int a = mid - 1 - i, b = mid + i;
+            wk[i] = -((float)tb[a] * p.win[a]) - ((float)tb[b] * p.win[b]);
+            const int a2 = i, b2 = nf - 1 - i;
+            wk[half + i] = ((float)tb[a2] * p.win[a2]) - ((float)tb[b2] * p.win[b2]);
+        }
+    }
+    __syncwarp();
+    // ---- DCT-IV (dct_iv.rs:49-67): pre-twiddle straight into kissfft's leaf order, levels innermost first
+    for (int o = lane; o < N; o += 32) {
+        const int n = p.perm[o];
+        cx[o] = cmul(ld(p.dtw, n), C2{wk[2 * n], wk[nf - 2 * n - 1]});
+    }
+    __syncwarp();
+    for (int lv = c.n_levels - 1; lv >= 0; lv--) {
+        const int pp = c.fac_p[lv], m = c.fac_m[lv], fs = c.fac_stride[lv];
+        const int nbf = N / pp;
+        for (int b = lane; b < nbf; b += 32) {
+            const int blk = b / m, u = b - blk * m;
+            C2* f = cx + blk * (pp * m);
+            switch (pp) {
+                case 2: bfly2(f, p.ftw, fs, m, u); break;
+                case 3: bfly3(f, p.ftw, fs, m, u); break;
+                case 4: bfly4(f, p.ftw, fs, m, u); break;
+                default: bfly5(f, p.ftw, fs, m, u); break;
+            }
+        }
+        __syncwarp();
+    }
+    {
+        const float gain = 1.0f / sqrtf(2.0f * (float)nf);
+        for (int n = lane; n < N; n += 32) {
+            const C2 v = cmul(ld(p.dtw, n), cx[n]);
+            const float a = v.r * 2.0f, b = -v.i * 2.0f;
+            wk[2 * n] = a * gain;
+            wk[nf - 2 * n - 1] = b * gain;
+        }
+    }
+    __syncwarp();
+    // ---- band energies (:140-152, divide inside the sum) and near-Nyquist flag (:154-178)
+    float* e_b = p.e_b + (size_t)stream * 64;
+    float* ebs = (float*)cx;                        // staging of the energies for the serial sums below
+    for (int b = lane; b < c.nb; b += 32) {
+        const int from = c.band_idx[b], to = c.band_idx[b + 1];
+        const float width = (float)(to - from);
+        float e = 0.0f;
+        for (int k = from; k < to; k++) e += wk[k] * wk[k] / width;
+        e_b[b] = e;
+        ebs[b] = e;
+    }
+    for (int k = lane; k < ne; k += 32) p.xf[(size_t)stream * ne + k] = wk[k];
+    __syncwarp();
+    int near_nyquist = 0;
+    if (c.fs <= 32000 && lane == 0) {
+        const int nn_idx = c.n_ms == LC3B_7P5MS ? c.nb - 4 : c.nb - 2;
+        float lo = 0.0f, hi = 0.0f;
+        for (int n = 0; n < c.nb; n++) { if (n < nn_idx) lo += ebs[n]; else hi += ebs[n]; }
+        near_nyquist = hi > 30.0f * lo;
+    }
+    near_nyquist = __shfl_sync(0xffffffffu, near_nyquist, 0);
+    __syncwarp();
+
+    const int16_t* x = tb + (nf - z);               // this frame's input samples
+
+    // ---- attack detector (attack_detector.rs:45-105)
+    int attack_detected = 0;
+    {
+        bool active;
+        if (c.fs < 32000) active = false;
+        else if (c.n_ms == LC3B_7P5MS)
+            active = (c.fs == 32000 && p.nbytes >= 61 && p.nbytes < 150) || (c.fs >= 44100 && p.nbytes >= 75 && p.nbytes < 150);
+        else
+            active = (c.fs == 32000 && p.nbytes > 80) || (c.fs >= 41000 && p.nbytes >= 100);
+        if (!active) {
+            if (lane == 0) {
+                es[ES_ATT_ENERGY_LAST] = (int32_t)__float_as_uint(0.0f);
+                es[ES_ATT_MAX_ENERGY_LAST] = (int32_t)__float_as_uint(0.0f);
+                es[ES_ATT_POS_LAST] = -1;
+            }
+        } else {
+            int32_t* ds = (int32_t*)wk;             // num_downsampled ints, then hp floats behind them
+            float* hp = wk + 160;
+            const int nds = c.att_num_ds, block_len = nf / nds;
+            const int tm1 = es[ES_ATT_TM1], tm2 = es[ES_ATT_TM2];
+            __syncwarp();
+            for (int n = lane; n < nds; n += 32) {
+                int32_t s = 0;
+                for (int j = 0; j < block_len; j++) s += (int32_t)x[block_len * n + j];
+                ds[n] = s;
+            }
+            __syncwarp();
+            for (int n = lane; n < nds; n += 32) {
+                const float d0 = (float)ds[n];
+                const float d1 = n >= 1 ? (float)ds[n - 1] : (float)tm1;
+                const float d2 = n >= 2 ? (float)ds[n - 2] : (n == 1 ? (float)tm1 : (float)tm2);
+                hp[n] = 0.375f * d0 - 0.5f * d1 + 0.125f * d2;
+            }
+            __syncwarp();
+            float energy = 0.0f;
+            if (lane < c.att_num_blocks)
+                for (int j = 40 * lane; j < 40 * lane + 40; j++) energy += hp[j] * hp[j];
+            // gather the block energies on lane 0 and run the envelope recurrence there
+            float en_blk[4];
+#pragma unroll
+            for (int n = 0; n < 4; n++) en_blk[n] = __shfl_sync(0xffffffffu, energy, n);
+            if (lane == 0) {
+                float energy_last = __uint_as_float((uint32_t)es[ES_ATT_ENERGY_LAST]);
+                float max_energy_last = __uint_as_float((uint32_t)es[ES_ATT_MAX_ENERGY_LAST]);
+                int attack_position = -1;
+                for (int n = 0; n < c.att_num_blocks; n++) {
+                    const float en = en_blk[n];
+                    const float a = 0.25f * max_energy_last;
+                    const float max_energy = maxf_rs(a, energy_last);
+                    if (en > 8.5f * max_energy) attack_position = n;
+                    energy_last = en;
+                    max_energy_last = max_energy;
+                }
+                const int pos_last = es[ES_ATT_POS_LAST];
+                attack_detected = attack_position >= 0 || pos_last >= c.att_pos_limit;
+                es[ES_ATT_POS_LAST] = attack_position;
+                es[ES_ATT_ENERGY_LAST] = (int32_t)__float_as_uint(energy_last);
+                es[ES_ATT_MAX_ENERGY_LAST] = (int32_t)__float_as_uint(max_energy_last);
+                es[ES_ATT_TM1] = ds[nds - 1];
+                es[ES_ATT_TM2] = ds[nds - 2];
+            }
+            attack_detected = __shfl_sync(0xffffffffu, attack_detected, 0);
+        }
+    }
+    __syncwarp();
+
+    // ---- LTPF analysis (long_term_post_filter.rs:139-215)
+    constexpr int NMEM = 232, K_MIN = 17, K_MAX = 114;
+    const int len12 = c.len12p8, len6 = c.len6p4, up = c.up;
+    const int t_nbits = c.n_ms == LC3B_7P5MS ? (int)round((double)(p.nbytes * 8) * 10.0 / 7.5) : p.nbytes * 8;
+    const bool gain_ltpf_on = t_nbits < 560 + c.fs_ind * 80;
+    {   // shift_out_old_samples (:217-230)
+        const int ns_keep = 240 / up;
+        int16_t* xh = p.xs_hist + (size_t)stream * 64;
+        float* g12 = p.x12 + (size_t)stream * c.x12_len;
+        float* g6 = p.x6 + (size_t)stream * 178;
+        for (int n = lane; n < ns_keep; n += 32) xs[n] = xh[n];
+        for (int n = lane; n < nf; n += 32) xs[ns_keep + n] = x[n];
+        for (int n = lane; n < c.x12_len - len12; n += 32) x12[n] = g12[n + len12];
+        for (int n = lane; n < 178 - len6; n += 32) x6[n] = g6[n + len6];
+        for (int n = 178 - len6 + lane; n < 178; n += 32) x6[n] = 0.0f;   // overwritten below where it matters
+        __syncwarp();
+        for (int n = lane; n < ns_keep; n += 32) xh[n] = xs[nf + n];       // last 240/up samples of this frame
+    }
+    float* x12n = x12 + c.delay + NMEM;             // where this frame's resampled samples go
+    for (int n = lane; n < len12; n += 32) {        // resampling (:152-166)
+        float acc = 0.0f;
+        const int q15 = (15 * n) / up, r15 = (15 * n) % up;
+        for (int k = -120 / up; k <= 120 / up; k++) {
+            const int index_x_s = q15 + k - 120 / up;
+            const int index_h = up * k - r15;
+            if (index_h > -120 && index_h < 120) acc += (float)xs[240 / up + index_x_s] * LC3T_TAB_RESAMP_FILTER[119 + index_h];
+        }
+        x12n[n] = acc * ((float)up * c.resamp_fac);
+    }
+    __syncwarp();
+    if (lane == 0) {                                 // 50 Hz high-pass biquad (:169-177), serial
+        float m1 = __uint_as_float((uint32_t)es[ES_H50_M1]), m2 = __uint_as_float((uint32_t)es[ES_H50_M2]);
+        for (int n = 0; n < len12; n++) {
+            const float h50 = x12n[n] - -1.9652933726226904f * m1 - 0.9658854605688177f * m2;
+            x12n[n] = 0.9827947082978771f * h50 + -1.965589416595754f * m1 + 0.9827947082978771f * m2;
+            m2 = m1;
+            m1 = h50;
+        }
+        es[ES_H50_M1] = (int32_t)__float_as_uint(m1);
+        es[ES_H50_M2] = (int32_t)__float_as_uint(m2);
+    }
+    __syncwarp();
+    {   // write the shifted + new 12.8 kHz samples back (state for the next frame)
+        float* g12 = p.x12 + (size_t)stream * c.x12_len;
+        for (int n = lane; n < c.x12_len; n += 32) g12[n] = x12[n];
+    }
+    // pitch_detection (:232-290)
+    for (int i = lane; i < len6; i += 32) {
+        const float* s = x12 + NMEM - 3 + 2 * i;
+        x6[K_MAX + i] = 0.1236796411180537f * s[0] + 0.2353512128364889f * s[1] + 0.2819382920909148f * s[2] +
+                        0.2353512128364889f * s[3] + 0.1236796411180537f * s[4];
+    }
+    __syncwarp();
+    {
+        float* g6 = p.x6 + (size_t)stream * 178;
+        for (int n = lane; n < 178; n += 32) g6[n] = x6[n];
+    }
+    float* r6 = (float*)cx;                          // 98 lags
+    float* rw6 = r6 + 98;
+    float* r12 = rw6 + 98;                           // up to 233 values (needs 196 + 233 <= 2N: checked at init)
+    constexpr int NR = K_MAX + 1 - K_MIN;
+    for (int k = lane; k < NR; k += 32) {
+        const int from_k = K_MAX - K_MIN - k;
+        float s = 0.0f;
+        for (int n = 0; n < len6; n++) s += x6[K_MAX + n] * x6[from_k + n];
+        r6[k] = s;
+        const float weight = 1.0f - 0.5f * (float)k / (float)(K_MAX - K_MIN);
+        rw6[k] = weight * s;
+    }
+    __syncwarp();
+    int t_current = 0, pitch_present = 0;
+    if (lane == 0) {
+        auto index_of_max = [](const float* s, int n) {
+            if (n == 0) return 0;
+            float mx = s[0];
+            int idx = 0;
+            for (int i = 0; i < n; i++) if (s[i] > mx) { idx = i; mx = s[i]; }
+            return idx;
+        };
+        const int t_prev = es[ES_T_PREV];
+        const int lag_t1 = index_of_max(rw6, NR) + K_MIN;
+        const int k_from = (K_MIN > t_prev - 4 ? K_MIN : t_prev - 4) - K_MIN;
+        const int k_to = (K_MAX < t_prev + 4 ? K_MAX : t_prev + 4) - K_MIN + 1;
+        const int lag_t2 = index_of_max(r6 + k_from, k_to - k_from) + k_from + K_MIN;
+        auto normvalue = [&](int lag) {
+            float v = 0.0f;
+            const int from = K_MAX - lag;
+            for (int n = from; n < from + len6; n++) v += x6[n] * x6[n];
+            return v;
+        };
+        const float nv0 = normvalue(0), nv1 = normvalue(lag_t1);
+        const float normvalue1 = sqrtf(nv0 * nv1);
+        const float normcorr1 = maxf_rs(0.0f, r6[lag_t1 - K_MIN] / normvalue1);
+        float normcorr2;
+        if (lag_t1 == lag_t2) normcorr2 = normcorr1;
+        else {
+            const float nv2 = normvalue(lag_t2);
+            const float normvalue2 = sqrtf(nv0 * nv2);
+            normcorr2 = maxf_rs(0.0f, r6[lag_t2 - K_MIN] / normvalue2);
+        }
+        if (normcorr2 > 0.85f * normcorr1) { t_current = lag_t2; pitch_present = normcorr2 > 0.6f; }
+        else { t_current = lag_t1; pitch_present = normcorr1 > 0.6f; }
+    }
+    t_current = __shfl_sync(0xffffffffu, t_current, 0);
+    pitch_present = __shfl_sync(0xffffffffu, pitch_present, 0);
+    // pitch_lag_parameter (:292-363)
+    const int k_min = 32 > 2 * t_current - 4 ? 32 : 2 * t_current - 4;
+    const int k_max = 228 < 2 * t_current + 4 ? 228 : 2 * t_current + 4;
+    const float* cur = x12 + NMEM;
+    for (int i = lane; i < 233; i += 32) r12[i] = 0.0f;
+    __syncwarp();
+    for (int k = k_min - 4 + lane; k <= k_max + 4; k += 32) {
+        float cv = 0.0f;
+        for (int n = 0; n < len12; n++) cv += cur[n] * cur[n - k];
+        r12[k - (k_min - 4)] = cv;
+    }
+    __syncwarp();
+    int pitch_int = k_min, pitch_fr = 0, pitch_index = 0;
+    if (lane == 0) {
+        float max_corr = 0.0f;
+        for (int k = k_min - 4; k <= k_max + 4; k++) {
+            const float cv = r12[k - (k_min - 4)];
+            if (cv > max_corr && k >= k_min && k <= k_max) { max_corr = cv; pitch_int = k; }
+        }
+        const int rel = pitch_int - (k_min - 4);
+        auto interpolate = [&](int d) {
+            float v = 0.0f;
+            for (int m = -4; m <= 4; m++) {
+                const int n = 4 * m - d;
+                if (n > -16 && n < 16) v += r12[rel + m] * LC3T_TAB_LTPF_INTERP_R[n + 15];
+            }
+            return v;
+        };
+        if (pitch_int == 32) {
+            float mx = 0.0f;
+            for (int d = 0; d <= 3; d++) { const float v = interpolate(d); if (v > mx) { mx = v; pitch_fr = d; } }
+        } else if (pitch_int < 127 && pitch_int > 32) {
+            float mx = 0.0f;
+            for (int d = -3; d <= 3; d++) { const float v = interpolate(d); if (v > mx) { mx = v; pitch_fr = d; } }
+        } else if (pitch_int >= 127 && pitch_int < 157) {
+            float mx = 0.0f;
+            for (int d = -2; d <= 2; d += 2) { const float v = interpolate(d); if (v > mx) { mx = v; pitch_fr = d; } }
+        }
+        if (pitch_fr < 0) { pitch_int -= 1; pitch_fr += 4; }
+        if (pitch_int < 127) pitch_index = 4 * pitch_int + pitch_fr - 128;
+        else if (pitch_int < 157) pitch_index = 2 * pitch_int + pitch_fr / 2 - 126;
+        else pitch_index = pitch_int + 283;
+    }
+    pitch_int = __shfl_sync(0xffffffffu, pitch_int, 0);
+    pitch_fr = __shfl_sync(0xffffffffu, pitch_fr, 0);
+    pitch_index = __shfl_sync(0xffffffffu, pitch_index, 0);
+    // activation_bit (:365-409): per-sample interpolated values in parallel, the three running sums serially
+    float* nd_a = wk;                                // len12 floats each (2 * 128 <= nf for every config? no: checked below)
+    float* sh_a = wk + 128;
+    auto dot = [&](int n, int d) {
+        float v = 0.0f;
+        for (int k = -2; k <= 2; k++) {
+            const int hi = 4 * k - d;
+            if (hi > -8 && hi < 8) v += x12[NMEM + n - k] * LC3T_TAB_LTPF_INTERP_X12K8[hi + 7];
+        }
+        return v;
+    };
+    __syncwarp();
+    for (int n = lane; n < len12; n += 32) {
+        nd_a[n] = dot(n, 0);
+        sh_a[n] = dot(n - pitch_int, pitch_fr);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float nc_num = 0.0f, nd_tot = 0.0f, sh_tot = 0.0f;
+        for (int n = 0; n < len12; n++) {
+            const float nd = nd_a[n], sh = sh_a[n];
+            nc_num += nd * sh;
+            nd_tot += nd * nd;
+            sh_tot += sh * sh;
+        }
+        const float nc_den = sqrtf(nd_tot * sh_tot);
+        float nc = nc_den > 0.0f ? nc_num / nc_den : 0.0f;
+        const float pitch = (float)pitch_int + (float)pitch_fr / 4.0f;
+        const bool mem_active = es[ES_MEM_LTPF_ACTIVE] != 0;
+        const float mem_nc = __uint_as_float((uint32_t)es[ES_MEM_NC]);
+        const float mem_mem_nc = __uint_as_float((uint32_t)es[ES_MEM_MEM_NC]);
+        const float mem_pitch = __uint_as_float((uint32_t)es[ES_MEM_PITCH]);
+        bool ltpf_active = false;
+        if (gain_ltpf_on && !near_nyquist) {
+            ltpf_active = (!mem_active && (c.n_ms == LC3B_10MS || mem_mem_nc > 0.94f) && mem_nc > 0.94f && nc > 0.94f) ||
+                          (mem_active && nc > 0.9f) ||
+                          (mem_active && fabsf(pitch - mem_pitch) < 2.0f && (nc - mem_nc) > -0.1f && nc > 0.84f);
+        }
+        if (!pitch_present) { pitch_index = 0; nc = 0.0f; }
+        es[ES_T_PREV] = t_current;
+        es[ES_MEM_MEM_NC] = (int32_t)__float_as_uint(mem_nc);
+        if (pitch_present) {
+            es[ES_MEM_PITCH] = (int32_t)__float_as_uint(pitch);
+            es[ES_MEM_LTPF_ACTIVE] = ltpf_active;
+            es[ES_MEM_NC] = (int32_t)__float_as_uint(nc);
+        } else {
+            es[ES_MEM_PITCH] = (int32_t)__float_as_uint(0.0f);
+            es[ES_MEM_LTPF_ACTIVE] = 0;
+            es[ES_MEM_NC] = (int32_t)__float_as_uint(0.0f);
+        }
+        int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
+        eh[EH_NEAR_NYQUIST] = near_nyquist;
+        eh[EH_ATTACK] = attack_detected;
+        eh[EH_PITCH_INDEX] = pitch_index;
+        eh[EH_PITCH_PRESENT] = pitch_present;
+        eh[EH_LTPF_ACTIVE] = ltpf_active;
+        eh[EH_NBITS_LTPF] = pitch_present ? 11 : 1;
+    }
+}
+
+cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, cudaStream_t stream) {
+    AnalysisParams p;
+    p.cfg = st.ecfg;
+    p.win = st.win;
+    p.dtw = st.dtw;
+    p.ftw = st.ftw;
+    p.perm = st.perm;
+    p.pcm = pcm;
+    p.pcm_stride = pcm_stride;
+    p.nbytes = nbytes;
+    p.n_streams = st.n_streams;
+    p.thist = st.thist;
+    p.xs_hist = st.xs_hist;
+    p.x12 = st.x12;
+    p.x6 = st.x6;
+    p.estate = st.estate;
+    p.xf = st.xf;
+    p.e_b = st.e_b;
+    p.ehand = st.ehand;
+    const int nf = st.cfg.nf, N = nf / 2;
+    const int x12_len = (st.cfg.n_ms == LC3B_10MS ? 128 + 24 : 96 + 44) + 232;
+    // wk must hold max(nf, 160 + 160 attack scratch, 256 activation scratch) floats; cx must hold 196 + 233 floats
+    const int wk_floats = nf > 320 ? nf : 320;
+    const int cx_c2 = N > 215 ? N : 215;
+    size_t per_warp = (size_t)wk_floats * 4 + (size_t)cx_c2 * 8 + (size_t)x12_len * 4 + 178 * 4 + (size_t)2 * nf * 2 + 544 * 2;
+    per_warp = (per_warp + 15) & ~(size_t)15;
+    p.smem_per_warp = (int)per_warp;
+    p.wk_floats = wk_floats;
+    p.cx_c2 = cx_c2;
+    const size_t smem = per_warp * ANA_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(enc_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    enc_analysis_kernel<<<(st.n_streams + ANA_WARPS - 1) / ANA_WARPS, ANA_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace lc3b

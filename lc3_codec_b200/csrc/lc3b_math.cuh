@@ -31,6 +31,7 @@ LC3B_HD double ds(double a, double b) { return __dsub_rn(a, b); }
 LC3B_HD uint32_t f2u(float f) { return __float_as_uint(f); }
 LC3B_HD float u2f(uint32_t u) { return __uint_as_float(u); }
 LC3B_HD double u2d(uint64_t u) { return __longlong_as_double((long long)u); }
+LC3B_HD float d2f(double d) { return __double2float_rn(d); }
 #else
 LC3B_HD float xm(float a, float b) { return a * b; }
 LC3B_HD float xa(float a, float b) { return a + b; }
@@ -42,6 +43,7 @@ LC3B_HD double ds(double a, double b) { return a - b; }
 LC3B_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 LC3B_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 LC3B_HD double u2d(uint64_t u) { double f; memcpy(&f, &u, 8); return f; }
+LC3B_HD float d2f(double d) { return (float)d; }
 #endif
 
 LC3B_HD float trunc12(float v) { return u2f(f2u(v) & 0xfffff000u); }
@@ -193,12 +195,21 @@ LC3B_HD float log10f_msun(float x) {
 }
 
 // ---------------------------------------------------------------- exp2f for |x| < 126 (s_exp2f.c)
+#define LC3B_EXP2FT_INIT {                                                                          \
+        0x3fe6a09e667f3bcdull, 0x3fe7a11473eb0187ull, 0x3fe8ace5422aa0dbull, 0x3fe9c49182a3f090ull,     \
+        0x3feae89f995ad3adull, 0x3fec199bdd85529cull, 0x3fed5818dcfba487ull, 0x3feea4afa2a490daull,     \
+        0x3ff0000000000000ull, 0x3ff0b5586cf9890full, 0x3ff172b83c7d517bull, 0x3ff2387a6e756238ull,     \
+        0x3ff306fe0a31b715ull, 0x3ff3dea64c123422ull, 0x3ff4bfdad5362a27ull, 0x3ff5ab07dd485429ull}
+static const uint64_t EXP2FT_HOST[16] = LC3B_EXP2FT_INIT;
+#if defined(__CUDACC__)
+static __device__ const uint64_t EXP2FT_DEV[16] = LC3B_EXP2FT_INIT;
+#endif
 LC3B_HD float exp2f_msun(float x) {
-    const uint64_t T[16] = {
-        0x3fe6a09e667f3bcdull, 0x3fe7a11473eb0187ull, 0x3fe8ace5422aa0dbull, 0x3fe9c49182a3f090ull,
-        0x3feae89f995ad3adull, 0x3fec199bdd85529cull, 0x3fed5818dcfba487ull, 0x3feea4afa2a490daull,
-        0x3ff0000000000000ull, 0x3ff0b5586cf9890full, 0x3ff172b83c7d517bull, 0x3ff2387a6e756238ull,
-        0x3ff306fe0a31b715ull, 0x3ff3dea64c123422ull, 0x3ff4bfdad5362a27ull, 0x3ff5ab07dd485429ull};
+#if defined(__CUDA_ARCH__)
+    const uint64_t* T = EXP2FT_DEV;
+#else
+    const uint64_t* T = EXP2FT_HOST;
+#endif
     const float redux = 786432.0f;
     const double P1 = (double)0x1.62e430p-1f, P2 = (double)0x1.ebfbe0p-3f, P3 = (double)0x1.c6b348p-5f,
                  P4 = (double)0x1.3b2c9cp-7f;
@@ -214,7 +225,7 @@ LC3B_HD float exp2f_msun(float x) {
     double r = u2d(T[i0]);
     double t = dm(r, z);
     r = da(da(r, dm(t, da(P1, dm(z, P2)))), dm(dm(t, dm(z, z)), da(P3, dm(z, P4))));
-    return (float)dm(r, uk);
+    return d2f(dm(r, uk));
 }
 
 // ---------------------------------------------------------------- asinf for |x| <= 1 (e_asinf.c)

