@@ -84,6 +84,13 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
                             int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
                             void* cuda_stream);
 
+/* Optional pipelining of lc3b_decode_frames_host.  Off (default): every copy and kernel rides `cuda_stream`, PCM is
+ * valid once that stream has drained.  On: the device->host PCM copy of call i runs on an internal stream from a
+ * double-buffered staging area and overlaps the kernels of call i+1; PCM of a call is valid after
+ * lc3b_decoder_host_fence(h, s) followed by draining stream s (the fence makes s wait for all outstanding copies). */
+int lc3b_decoder_set_host_pipelining(lc3b_decoder* h, int on);
+int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream);
+
 /* Inspection (parity gate i): when set, every decode also writes, per stream, a record of
  * LC3B_TRACE_WORDS int32 (layout below) and the entropy-decoded integer spectrum x[0..ne).  Device pointers,
  * NULL to disable.  trace: [n_streams][LC3B_TRACE_WORDS], x: [n_streams][ne]. */

@@ -79,7 +79,7 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
     L.side = cv.take(sizeof(int32_t) * ns * SIDE_WORDS);
     L.sstate = cv.take(sizeof(int32_t) * ns * SS_WORDS);
     L.stage_in = cv.take(ns * (size_t)max_nbytes);
-    L.stage_out = cv.take(sizeof(int16_t) * ns * c.nf);
+    L.stage_out = cv.take(sizeof(int16_t) * ns * c.nf * 2);   // double-buffered for the pipelined host path
     L.stage_len = cv.take(sizeof(int32_t) * ns);
     L.stage_status = cv.take(sizeof(int32_t) * ns);
     L.total = cv.off;
@@ -228,6 +228,13 @@ using namespace lc3b;
 struct lc3b_decoder {
     DecoderState st;
     int stage_mask;
+    // optional pipelining of the host entry point: PCM leaves on an internal copy stream from a double-buffered
+    // staging area, so the device->host copy of call i overlaps the kernels of call i+1
+    int pipelined;
+    int buf;
+    cudaStream_t copy_stream;
+    cudaEvent_t compute_done[2], d2h_done[2];
+    bool d2h_pending[2];
 };
 
 extern "C" {
@@ -304,7 +311,36 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
         return cuda_fail(e);
     }
     h->stage_mask = 3;
+    h->pipelined = 0;
+    h->buf = 0;
+    h->copy_stream = nullptr;
+    h->d2h_pending[0] = h->d2h_pending[1] = false;
     *out = h;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_set_host_pipelining(lc3b_decoder* h, int on) {
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    if (on && !h->copy_stream) {
+        CU(cudaSetDevice(h->st.device));
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&h->compute_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->d2h_done[i], cudaEventDisableTiming));
+        }
+    }
+    h->pipelined = on ? 1 : 0;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream) {
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    for (int i = 0; i < 2; i++) {
+        if (h->d2h_pending[i]) {
+            CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->d2h_done[i], 0));
+            h->d2h_pending[i] = false;
+        }
+    }
     return LC3B_OK;
 }
 
@@ -352,12 +388,29 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
     if (frame_nbytes) CU(cudaMemcpyAsync(st.stage_len, frame_nbytes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, stream));
     CU(launch_entropy(st, st.stage_in, frame_nbytes ? st.stage_len : nullptr, nbytes, (size_t)nbytes,
                       status_out ? st.stage_status : nullptr, stream));
-    CU(launch_synth(st, st.stage_out, (size_t)st.cfg.nf, stream));
+    const size_t out_elems = ns * (size_t)st.cfg.nf;
+    int16_t* stage = st.stage_out + (h->pipelined ? (size_t)h->buf * out_elems : 0);
+    cudaStream_t out_stream = stream;
+    if (h->pipelined) {
+        // the staging half about to be overwritten must have left the device (copy issued two calls ago)
+        if (h->d2h_pending[h->buf]) CU(cudaStreamWaitEvent(stream, h->d2h_done[h->buf], 0));
+        out_stream = h->copy_stream;
+    }
+    CU(launch_synth(st, stage, (size_t)st.cfg.nf, stream));
+    if (h->pipelined) {
+        CU(cudaEventRecord(h->compute_done[h->buf], stream));
+        CU(cudaStreamWaitEvent(out_stream, h->compute_done[h->buf], 0));
+    }
     if (pcm_stride == (size_t)st.cfg.nf)
-        CU(cudaMemcpyAsync(pcm_out, st.stage_out, ns * (size_t)st.cfg.nf * sizeof(int16_t), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(pcm_out, stage, out_elems * sizeof(int16_t), cudaMemcpyDeviceToHost, out_stream));
     else
-        CU(cudaMemcpy2DAsync(pcm_out, pcm_stride * sizeof(int16_t), st.stage_out, (size_t)st.cfg.nf * sizeof(int16_t),
-                             (size_t)st.cfg.nf * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpy2DAsync(pcm_out, pcm_stride * sizeof(int16_t), stage, (size_t)st.cfg.nf * sizeof(int16_t),
+                             (size_t)st.cfg.nf * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, out_stream));
+    if (h->pipelined) {
+        CU(cudaEventRecord(h->d2h_done[h->buf], out_stream));
+        h->d2h_pending[h->buf] = true;
+        h->buf ^= 1;
+    }
     if (status_out) CU(cudaMemcpyAsync(status_out, st.stage_status, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, stream));
     return LC3B_OK;
 }
@@ -371,7 +424,15 @@ int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream) {
     return LC3B_OK;
 }
 
-void lc3b_decoder_destroy(lc3b_decoder* h) { free(h); }
+void lc3b_decoder_destroy(lc3b_decoder* h) {
+    if (!h) return;
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(h->compute_done[i]); cudaEventDestroy(h->d2h_done[i]); }
+        cudaStreamDestroy(h->copy_stream);
+    }
+    free(h);
+}
 
 int lc3b_selftest_math_host(int which, const float* x, const float* y, float* out, int n) {
     if (!x || !out || n < 0 || which < 0 || which > 6) return LC3B_ERR_INVALID_ARG;

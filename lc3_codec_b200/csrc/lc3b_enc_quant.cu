@@ -41,15 +41,23 @@ struct SnsRes { int ind_lf, ind_hf, shape_j, gind, ls_inda, ls_indb; uint64_t jo
 struct TnsRes { int nbits_tns, lpc_weighting, num_filters; int rc_order[2]; int rc_i[16]; float rc_q[16]; };
 struct QRes { int gg_ind, nbits_spec, nbits_lsb, nbits_trunc, lsb_mode, rate_flag, lastnz_trunc; float gg; };
 
+// Constant tables live at namespace scope: a function-local 64-bit table (msun's exp2f) was observed to be laid
+// over live stack data by nvcc 12.9 at -O3, so nothing table-like is left on the stack in this file.
+__device__ const int START10[4][4] = {{53, 0, 0, 0}, {47, 59, 0, 0}, {44, 54, 60, 0}, {41, 51, 57, 61}};   // bandwidth_detector.rs:5-18
+__device__ const int STOP10[4][4] = {{63, 0, 0, 0}, {56, 63, 0, 0}, {52, 59, 63, 0}, {49, 55, 60, 63}};
+__device__ const int START75[4][4] = {{51, 0, 0, 0}, {45, 58, 0, 0}, {42, 53, 60, 0}, {40, 51, 57, 61}};
+__device__ const int STOP75[4][4] = {{63, 0, 0, 0}, {55, 63, 0, 0}, {51, 58, 63, 0}, {48, 55, 60, 63}};
+__device__ const int NBITS_BW[5] = {0, 1, 2, 2, 3};
+__device__ const int QUIET[4] = {20, 10, 10, 10}, CUTOFF[4] = {15, 23, 20, 20};
+__device__ const int L10[4] = {4, 4, 3, 1}, L75[4] = {4, 4, 3, 2};
+__device__ const float SNS_W[6] = {1.0f / 12.0f, 2.0f / 12.0f, 3.0f / 12.0f, 3.0f / 12.0f, 2.0f / 12.0f, 1.0f / 12.0f};   // spectral_noise_shaping.rs:59
+__device__ const float TNS_LAG[9] = {1.0f, 0.9980280260203829f, 0.9921354055113971f, 0.9823915844707989f, 0.9689107911912967f,
+                                     0.9518498073692735f, 0.9314049334023056f, 0.9078082299969592f, 0.8813231366694713f};   // temporal_noise_shaping.rs:81-84
+__device__ const int GGA_T1[5] = {80, 230, 380, 530, 680}, GGA_T2[5] = {500, 1025, 1550, 2075, 2600},
+                     GGA_T3[5] = {850, 1700, 2550, 3400, 4250};   // spectral_quantization.rs:351-353
+
 // ---------------------------------------------------------------- bandwidth_detector.rs:64-127
 __device__ BwRes bandwidth_detect(const EncConfig& c, const float* e_b) {
-    const int START10[4][4] = {{53, 0, 0, 0}, {47, 59, 0, 0}, {44, 54, 60, 0}, {41, 51, 57, 61}};
-    const int STOP10[4][4] = {{63, 0, 0, 0}, {56, 63, 0, 0}, {52, 59, 63, 0}, {49, 55, 60, 63}};
-    const int START75[4][4] = {{51, 0, 0, 0}, {45, 58, 0, 0}, {42, 53, 60, 0}, {40, 51, 57, 61}};
-    const int STOP75[4][4] = {{63, 0, 0, 0}, {55, 63, 0, 0}, {51, 58, 63, 0}, {48, 55, 60, 63}};
-    const int NBITS_BW[5] = {0, 1, 2, 2, 3};
-    const int QUIET[4] = {20, 10, 10, 10}, CUTOFF[4] = {15, 23, 20, 20};
-    const int L10[4] = {4, 4, 3, 1}, L75[4] = {4, 4, 3, 2};
     const int n_bw = c.fs_ind, nbits = NBITS_BW[n_bw];
     if (n_bw == 0) return {0, nbits};
     const bool d10 = c.n_ms == LC3B_10MS;
@@ -248,7 +256,7 @@ __device__ void sns_run_quant(const float* scf, float* scfq, SnsRes* res) {   //
 }
 
 __device__ SnsRes sns_encode(const EncConfig& c, float* x, const float* e_b, bool attack) {   // :203-282
-    const float W[6] = {1.0f / 12.0f, 2.0f / 12.0f, 3.0f / 12.0f, 3.0f / 12.0f, 2.0f / 12.0f, 1.0f / 12.0f};
+    const float* W = SNS_W;
     float padded[64], e[64];
     const int nb = c.nb, diff = 64 - nb;
     if (diff > 0) {
@@ -369,8 +377,7 @@ __device__ void tns_encode(const EncConfig& c, float* x, int p_bw, int nbits, bo
     r.num_filters = tp.nf;
     r.lpc_weighting = (c.n_ms == LC3B_10MS ? nbits < 480 : nbits < 360) ? 1 : 0;
     const int ne = c.ne;
-    const float LAG[9] = {1.0f, 0.9980280260203829f, 0.9921354055113971f, 0.9823915844707989f, 0.9689107911912967f,
-                          0.9518498073692735f, 0.9314049334023056f, 0.9078082299969592f, 0.8813231366694713f};
+    const float* LAG = TNS_LAG;
     for (int f = 0; f < tp.nf; f++) {
         float rr[9];
         for (int k = 0; k < 9; k++) {
@@ -605,8 +612,7 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
     es[ES_Q_NBITS_OFFSET_OLD] = (int32_t)__float_as_uint(nbits_offset);   // state saved BEFORE the adjustment (:96-100)
     es[ES_Q_NBITS_EST_OLD] = bc.nbits_est;
     es[ES_Q_RESET_OFFSET_OLD] = reset_offset;
-    const int T1[5] = {80, 230, 380, 530, 680}, T2[5] = {500, 1025, 1550, 2075, 2600}, T3[5] = {850, 1700, 2550, 3400, 4250};
-    const int t1 = T1[fs_ind], t2 = T2[fs_ind], t3 = T3[fs_ind];
+    const int t1 = GGA_T1[fs_ind], t2 = GGA_T2[fs_ind], t3 = GGA_T3[fs_ind];
     const int nbits_est = bc.nbits_est;
     float delta;
     if (nbits_est < t1) delta = ((float)nbits_est + 48.0f) / 16.0f;

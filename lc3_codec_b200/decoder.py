@@ -112,6 +112,19 @@ class Lc3BatchDecoder:
         self._trace = (tr, x)
         return tr, x
 
+    def set_host_pipelining(self, on: bool) -> None:
+        """Overlap the PCM device->host copy of call i with the kernels of call i+1 (see include/lc3b.h)."""
+        rc = native.lib().lc3b_decoder_set_host_pipelining(self._h, int(bool(on)))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_set_host_pipelining")
+
+    def host_fence(self) -> None:
+        """Make the current CUDA stream wait for every outstanding pipelined PCM copy."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = native.lib().lc3b_decoder_host_fence(self._h, C.c_void_p(stream))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_host_fence")
+
     def set_stage_mask(self, mask: int) -> None:
         """Profiling hook: 1 = entropy kernel only, 2 = synthesis kernel only, 3 = both (default)."""
         rc = native.lib().lc3b_decoder_set_stage_mask(self._h, mask)

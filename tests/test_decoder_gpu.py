@@ -121,6 +121,29 @@ def test_host_buffer_entry_point():
     assert_parity(24000, 10, frames, host=True)
 
 
+def test_pipelined_host_entry_point():
+    """lc3b_decoder_set_host_pipelining: PCM copies overlap the next call's kernels; results are unchanged."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from oracle import pyoracle as O
+    _, frames = corpus(48000, 10, 100, 70, 12)
+    S, F, nb = frames.shape
+    sf, fd = L.SamplingFrequency.Hz48000, L.FrameDuration.TenMs
+    ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(S, fd, sf, nb), dtype=torch.uint8, device="cuda:0")
+    dec = L.Lc3BatchDecoder(S, fd, sf, ws, nb)
+    dec.set_host_pipelining(True)
+    host_in = torch.from_numpy(np.ascontiguousarray(frames.transpose(1, 0, 2))).pin_memory()      # [F,S,nb]
+    host_out = torch.zeros((F, S, 480), dtype=torch.int16).pin_memory()
+    for f in range(F):
+        dec.decode_frames_host(16, host_in[f], host_out[f])
+    dec.host_fence()
+    torch.cuda.synchronize()
+    o_pcm = O.decode_streams(frames, 48000, 10)
+    d = np.abs(host_out.numpy().transpose(1, 0, 2).astype(np.int32) - o_pcm.astype(np.int32))
+    assert d.max() <= PCM_TOL
+
+
 def test_ragged_stream_counts():
     """Stream counts that are not multiples of the warp / CTA sizes."""
     for n in (1, 31, 33, 129):
