@@ -1,18 +1,23 @@
 #!/usr/bin/env python3
 """bench.py - decoded frames/s (48 kHz, 10 ms, mono, 150 B) per GPU, with HBM-roofline fraction and CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
   (N > 1: launched by torchrun, one rank per GPU; streams are sharded, no collective on the data path)
 
-A "step" is one Lc3Decoder::decode_frame for EVERY stream of the batch (one frame per stream): the batched hot path.
-Workload: BASELINE.json config 5's per-GPU shard - 32,768 concurrent 48 kHz / 10 ms / 150 B mono streams per GPU
-(weak scaling: every rank owns 32,768 streams).  Bitstreams: tests/golden/bench_c1_frames.npy (1,024 distinct synthetic
-streams x 8 frames, oracle-encoded once by tools/make_bench_corpus.py), tiled over the batch.
+A "step" is one Lc3Decoder::decode_frame (or Lc3Encoder::encode_frame) for EVERY stream of the batch: the batched hot
+path, one frame per stream.  Default workload `decode48`: BASELINE.json config 5's 262,144 concurrent 48 kHz / 10 ms /
+150 B mono streams, all of them on one GPU at N = 1 (they fit: 2.9 GB of codec state) and the same count on every
+GPU at N > 1 (weak scaling).  Bitstreams: tests/golden/bench_c1_frames.npy (1,024 distinct synthetic streams x 8
+frames, oracle-encoded once by tools/make_bench_corpus.py), tiled over the batch.
+Other workloads (extra measurements for BASELINE.md, same JSON shape): `encode48` (config 2: 48 kHz stereo, 120 B per
+channel, 4,096 stereo streams = 8,192 channels), `decode16` (config 3: 16 kHz / 7.5 ms / 30 B, 16,384 streams, LTPF
+active), `roundtrip48` (config 5: encode + decode of 262,144 streams at 150 B).  Their inputs are synthetic PCM
+(tools/corpus.py) and, for decode16, bitstreams produced by the GPU encoder itself.
 
 Printed JSON (one line, rank 0):
-  value        frames/s with inputs resident in HBM (CUDA events, max over ranks, whole job)
-  e2e          same metric through the host-buffer entry point: pinned host frames in, pinned host PCM out, every step
-  roofline     dominant kernel vs the measured HBM copy bandwidth; achieved = 1110 B x frames per launch / kernel time
+  value        units/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks, whole job)
+  e2e          same metric through the host-buffer entry points: pinned host buffers in and out, every step
+  roofline     dominant kernel vs the measured HBM copy bandwidth; achieved = algorithmic bytes per launch / kernel time
   cpu_baseline the oracle (C++ restatement of the reference) on the host cores, bounded sample, reported not targeted
 """
 from __future__ import annotations
@@ -31,11 +36,27 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-FS, MS, NBYTES, NF = 48000, 10, 150, 480
-STREAMS_PER_GPU = 32768
-ALGO_BYTES_PER_FRAME = NBYTES + 2 * NF          # 150 B in + 960 B PCM out = 1110 B
-METRIC = "decoded frames/sec (48kHz 10ms mono) per GPU"
-WORKLOAD = "decode 48 kHz mono 10 ms, 150 B/frame, 32768 concurrent streams per GPU, 1 frame per stream per step"
+WORKLOADS = {
+    "decode48": dict(fs=48000, ms=10, nbytes=150, nf=480, streams=262144, mode="decode",
+                     metric="decoded frames/sec (48kHz 10ms mono) per GPU",
+                     desc="decode 48 kHz mono 10 ms, 150 B/frame, 262144 concurrent streams per GPU (BASELINE config 5's "
+                          "stream count on every GPU, weak scaling), 1 frame per stream per step"),
+    "encode48": dict(fs=48000, ms=10, nbytes=120, nf=480, streams=8192, mode="encode",
+                     metric="encoded channel-frames/sec (48kHz 10ms, 120 B/channel) per GPU",
+                     desc="encode 48 kHz stereo 10 ms at 120 B/frame/channel, 4096 stereo streams = 8192 channels per GPU "
+                          "(BASELINE config 2), 1 frame per channel per step"),
+    "decode16": dict(fs=16000, ms=7.5, nbytes=30, nf=120, streams=16384, mode="decode",
+                     metric="decoded frames/sec (16kHz 7.5ms mono, 30 B) per GPU",
+                     desc="decode 16 kHz mono 7.5 ms at 30 B/frame (LTPF and TNS active), 16384 concurrent streams per GPU "
+                          "(BASELINE config 3)"),
+    "roundtrip48": dict(fs=48000, ms=10, nbytes=150, nf=480, streams=262144, mode="roundtrip",
+                        metric="encode+decode round trips/sec (48kHz 10ms mono, 150 B) per GPU",
+                        desc="encode then decode 48 kHz mono 10 ms at 150 B/frame, 262144 streams per GPU (BASELINE config 5)"),
+}
+
+
+def algo_bytes(w):
+    return w["nbytes"] + 2 * w["nf"]                  # bitstream bytes + 2 bytes per PCM sample, one direction
 
 
 def load_frames() -> np.ndarray:
@@ -97,51 +118,68 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(frames: np.ndarray, target_s: float = 8.0):
-    """Oracle decoder on all host cores over a bounded sample of the same bitstreams."""
+def cpu_sample(w, cores):
+    """Bounded sample of the workload for the oracle: (frames or None, pcm or None)."""
+    from tools.corpus import make_pcm
+    if w["mode"] == "decode" and w["fs"] == 48000:
+        frames = load_frames()
+        return np.ascontiguousarray(frames[:min(frames.shape[0], max(cores * 8, 64))]), None
+    from oracle import pyoracle as O
+    pcm = make_pcm(max(cores * 8, 64), 8, w["fs"], w["nf"])
+    frames = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"]) if w["mode"] == "decode" else None
+    return frames, pcm
+
+
+def cpu_run(w, frames, pcm, cores):
+    from oracle import pyoracle as O
+    if w["mode"] == "decode":
+        O.decode_streams(frames, w["fs"], w["ms"], nthreads=cores)
+        return frames.shape[0] * frames.shape[1]
+    enc = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"], nthreads=cores)
+    if w["mode"] == "roundtrip":
+        O.decode_streams(enc, w["fs"], w["ms"], nthreads=cores)
+    return pcm.shape[0] * pcm.shape[1]
+
+
+def cpu_baseline(w, target_s: float = 8.0):
+    """Oracle on all host cores over a bounded sample of the same workload."""
     from oracle import pyoracle as O
     cores = O.ncores()
-    n = min(frames.shape[0], max(cores * 8, 64))
-    sample = np.ascontiguousarray(frames[:n])
-    O.decode_streams(sample[:cores], FS, MS)                       # warm (page-in, table init)
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        O.decode_streams(sample, FS, MS, nthreads=cores)
+    frames, pcm = cpu_sample(w, cores)
+    cpu_run(w, frames, pcm, cores)                                  # warm
+    t0, units, reps = time.perf_counter(), 0, 0
+    while time.perf_counter() - t0 < target_s:
+        units += cpu_run(w, frames, pcm, cores)
         reps += 1
-        if time.perf_counter() - t0 > target_s:
-            break
     dt = time.perf_counter() - t0
-    fps = reps * sample.shape[0] * sample.shape[1] / dt
-    return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} x ({sample.shape[0]} streams x {sample.shape[1]} frames), {dt:.1f} s, one thread per core, "
+    shape = frames.shape if frames is not None else pcm.shape
+    return {"value": units / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x ({shape[0]} streams x {shape[1]} frames), {dt:.1f} s, one thread per core, "
                       "C++ restatement of lc3-codec (the Rust reference cannot be built here)"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, w, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     if rank != 0:
         return
     from oracle import pyoracle as O
-    frames = load_frames()
     cores = O.ncores()
-    n = min(frames.shape[0], max(cores * 4, 32))
-    sample = np.ascontiguousarray(frames[:n])
-    per_step = sample.shape[0] * sample.shape[1]
+    frames, pcm = cpu_sample(w, cores)
     for _ in range(args.warmup):
-        O.decode_streams(sample, FS, MS, nthreads=cores)
-    t0 = time.perf_counter()
+        cpu_run(w, frames, pcm, cores)
+    t0, units = time.perf_counter(), 0
     for _ in range(args.steps):
-        O.decode_streams(sample, FS, MS, nthreads=cores)
+        units += cpu_run(w, frames, pcm, cores)
     dt = time.perf_counter() - t0
-    fps = args.steps * per_step / dt
+    fps = units / dt
+    shape = frames.shape if frames is not None else pcm.shape
     cb = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-          "sample": f"each step decodes {sample.shape[0]} streams x {sample.shape[1]} frames of the bench bitstreams on {cores} threads"}
+          "sample": f"each step processes {shape[0]} streams x {shape[1]} frames of the workload on {cores} threads"}
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": w["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU path; a step here is a bounded sample, see cpu_baseline.sample"},
+        "config": {"workload": w["desc"], "note": "CPU path; a step here is a bounded sample, see cpu_baseline.sample"},
         "cpu_baseline": cb,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -150,25 +188,30 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: the named workload)")
+    ap.add_argument("--workload", default="decode48", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the named workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="device-resident loop only (for ncu captures; not a bench value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    w = dict(WORKLOADS[args.workload])
+    if args.streams:
+        w["streams"] = args.streams
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, w, rank)
         return
 
     import torch
 
     import lc3_codec_b200 as L
+    from tools.corpus import make_pcm
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: lc3_codec_b200 has no CPU fallback")
@@ -179,18 +222,46 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    S = args.streams
-    frames_np = load_frames()
-    U, F, _ = frames_np.shape
-    # rank r owns streams [r*S, (r+1)*S) of the job; stream s replays corpus stream s mod U
-    idx = (np.arange(S) + rank * S) % U
-    dev_frames = torch.from_numpy(frames_np).to(dev)[torch.from_numpy(idx).to(dev)].permute(1, 0, 2).contiguous()  # [F,S,150]
-    sf, fd = L.SamplingFrequency.Hz48000, L.FrameDuration.TenMs
-    ws_bytes = L.Lc3BatchDecoder.calc_working_buffer_lengths(S, fd, sf, NBYTES)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    dec = L.Lc3BatchDecoder(S, fd, sf, ws, NBYTES)
-    pcm = torch.empty((S, NF), dtype=torch.int16, device=dev)
+    S, NB, NF, mode = w["streams"], w["nbytes"], w["nf"], w["mode"]
+    sf, fd = L.SamplingFrequency.from_hz(w["fs"]), L.FrameDuration.from_ms(w["ms"])
     stream = torch.cuda.current_stream(dev)
+    U, F, WARM = 1024, 8, 4
+    # rank r owns streams [r*S, (r+1)*S) of the job; stream s replays corpus stream s mod U
+    idx = torch.from_numpy((np.arange(S) + rank * S) % U).to(dev)
+
+    dec = enc = None
+    ws_bytes = 0
+    if mode in ("decode", "roundtrip"):
+        n = L.Lc3BatchDecoder.calc_working_buffer_lengths(S, fd, sf, NB)
+        ws_bytes += n
+        dec_ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        dec = L.Lc3BatchDecoder(S, fd, sf, dec_ws, NB)
+    if mode in ("encode", "roundtrip"):
+        n = L.Lc3BatchEncoder.calc_working_buffer_lengths(S, fd, sf, NB)
+        ws_bytes += n
+        enc_ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        enc = L.Lc3BatchEncoder(S, fd, sf, enc_ws, NB)
+
+    # ---- inputs, resident in HBM: [F][S][...] so that step i reads one contiguous frame set
+    dev_pcm_in = dev_frames = None
+    if args.workload == "decode48":
+        dev_frames = torch.from_numpy(load_frames()).to(dev)[idx].permute(1, 0, 2).contiguous()        # [F,S,150]
+    else:
+        pcm_u = torch.from_numpy(make_pcm(U, WARM + F, w["fs"], NF)).to(dev)                             # [U,WARM+F,nf]
+        if mode == "decode":                                   # bitstreams from the GPU encoder itself
+            n = L.Lc3BatchEncoder.calc_working_buffer_lengths(U, fd, sf, NB)
+            tmp_ws = torch.empty(n, dtype=torch.uint8, device=dev)
+            tmp_enc = L.Lc3BatchEncoder(U, fd, sf, tmp_ws, NB)
+            fr_u = torch.empty((WARM + F, U, NB), dtype=torch.uint8, device=dev)
+            for f in range(WARM + F):
+                tmp_enc.encode_frames(pcm_u[:, f].contiguous(), fr_u[f])
+            dev_frames = fr_u[WARM:][:, idx].contiguous()                                                # [F,S,NB]
+            torch.cuda.synchronize(dev)
+            del tmp_enc, tmp_ws
+        else:
+            dev_pcm_in = pcm_u[:, WARM:][idx].permute(1, 0, 2).contiguous()                              # [F,S,nf]
+    pcm_out = torch.empty((S, NF), dtype=torch.int16, device=dev) if dec else None
+    frames_out = torch.empty((S, NB), dtype=torch.uint8, device=dev) if enc else None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -220,71 +291,106 @@ def main():
         return ms
 
     def step_dev(i):
-        dec.decode_frames(16, dev_frames[i % F], pcm)
+        if mode == "decode":
+            dec.decode_frames(16, dev_frames[i % F], pcm_out)
+        elif mode == "encode":
+            enc.encode_frames(dev_pcm_in[i % F], frames_out)
+        else:
+            enc.encode_frames(dev_pcm_in[i % F], frames_out)
+            dec.decode_frames(16, frames_out, pcm_out)
+
+    launches_per_step = {"decode": 2, "encode": 2, "roundtrip": 4}[mode]
 
     # ---- device-resident throughput (value) with clocks sampled during the timed region
     with ClockSampler(local_rank) as clk:
         ms_total = timed(step_dev, args.steps, args.warmup)
     clocks = clk.summary()
-    fps = world * S * args.steps / (ms_total * 1e-3)
-
+    ups = world * S * args.steps / (ms_total * 1e-3)
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "value": fps, "unit": "frames/s", "ms_per_step": ms_total / args.steps}))
+            print(json.dumps({"quick": True, "value": ups, "unit": "frames/s", "ms_per_step": ms_total / args.steps}))
         return
 
-    # ---- per-kernel time, each kernel alone (profiling hook), same inputs
+    # ---- per-kernel time, each kernel alone (profiling hooks), same inputs
     k_steps = max(20, min(args.steps, 100))
-    dec.set_stage_mask(1)
-    ms_entropy = timed(step_dev, k_steps, 3) / k_steps
-    dec.set_stage_mask(2)
-    ms_synth = timed(step_dev, k_steps, 3) / k_steps
-    dec.set_stage_mask(3)
-    dom_name, dom_ms = ("lc3b::entropy_kernel", ms_entropy) if ms_entropy >= ms_synth else ("lc3b::synth_kernel", ms_synth)
+    kernels_ms = {}
+
+    def time_masks(obj, names, fn):
+        for mask, name in zip((1, 2), names):
+            obj.set_stage_mask(mask)
+            kernels_ms[name] = timed(fn, k_steps, 3) / k_steps
+        obj.set_stage_mask(3)
+
+    if enc:
+        time_masks(enc, ("lc3b::enc_analysis_kernel", "lc3b::enc_quant_kernel"),
+                   lambda i: enc.encode_frames(dev_pcm_in[i % F], frames_out))
+    if dec:
+        if mode == "roundtrip":
+            enc.encode_frames(dev_pcm_in[0], frames_out)           # valid bitstreams for the decoder-only timing
+        time_masks(dec, ("lc3b::entropy_kernel", "lc3b::synth_kernel"),
+                   lambda i: dec.decode_frames(16, dev_frames[i % F] if dev_frames is not None else frames_out, pcm_out))
+    dom_name = max(kernels_ms, key=kernels_ms.get)
+    dom_ms = kernels_ms[dom_name]
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES_PER_FRAME * S / (dom_ms * 1e-3) / 1e9
+    achieved = algo_bytes(w) * S / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
-                "kernels_ms": {"entropy_kernel": ms_entropy, "synth_kernel": ms_synth},
-                "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
-                "note": "codec stages are issue/latency bound, not HBM bound (DESIGN.md); traffic: see profiles/"}
+                "kernels_ms": kernels_ms, "algorithmic_bytes_per_frame": algo_bytes(w),
+                "note": "codec stages are issue/latency bound, not HBM bound (DESIGN.md section 5); traffic from profiles/traffic.json"}
     traffic_file = ROOT / "profiles" / "traffic.json"
     if traffic_file.exists():
         try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name)
+            t = json.loads(traffic_file.read_text())
+            roofline["traffic"] = t.get(args.workload, {}).get(dom_name)
         except Exception:
             pass
 
-    # ---- end to end through the host-buffer entry point: pinned host frames in, pinned host PCM out, every step
-    host_frames = dev_frames.cpu().pin_memory()                         # [F,S,150]
-    host_pcm = [torch.empty((S, NF), dtype=torch.int16).pin_memory() for _ in range(2)]
-    dec.set_host_pipelining(True)       # PCM copy of step i overlaps the kernels of step i+1 (include/lc3b.h)
+    # ---- end to end through the host-buffer entry points: pinned host in, pinned host out, every step
+    e2e_steps = max(10, min(args.steps, 100))
+    if mode == "decode":
+        host_in = dev_frames.cpu().pin_memory()
+        host_out = [torch.empty((S, NF), dtype=torch.int16).pin_memory() for _ in range(2)]
+        dec.set_host_pipelining(True)       # PCM copy of step i overlaps the kernels of step i+1 (include/lc3b.h)
+        ms_e2e = timed(lambda i: dec.decode_frames_host(16, host_in[i % F], host_out[i & 1]), e2e_steps, 3, finish=dec.host_fence)
+        dec.set_host_pipelining(False)
+        h2d, d2h = S * NB, S * NF * 2
+        api = "lc3b_decode_frames_host (Lc3BatchDecoder.decode_frames_host), host pipelining on, host_fence before the end event"
+    elif mode == "encode":
+        host_in = dev_pcm_in.cpu().pin_memory()
+        host_out = torch.empty((S, NB), dtype=torch.uint8).pin_memory()
+        ms_e2e = timed(lambda i: enc.encode_frames_host(host_in[i % F], host_out), e2e_steps, 3)
+        h2d, d2h = S * NF * 2, S * NB
+        api = "lc3b_encode_frames_host (Lc3BatchEncoder.encode_frames_host)"
+    else:
+        host_in = dev_pcm_in.cpu().pin_memory()
+        host_bits = torch.empty((S, NB), dtype=torch.uint8).pin_memory()
+        host_out = [torch.empty((S, NF), dtype=torch.int16).pin_memory() for _ in range(2)]
+        dec.set_host_pipelining(True)
 
-    def step_host(i):
-        dec.decode_frames_host(16, host_frames[i % F], host_pcm[i & 1])
-
-    e2e_steps = max(10, min(args.steps, 200))
-    ms_e2e = timed(step_host, e2e_steps, 3, finish=dec.host_fence)
-    dec.set_host_pipelining(False)
-    e2e = {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * NBYTES,
-           "d2h_bytes_per_step": S * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
-           "api": "lc3b_decode_frames_host (Lc3BatchDecoder.decode_frames_host), host pipelining on, "
-                  "host_fence before the end event"}
+        def rt(i):                          # PCM host -> bitstream host -> PCM host, as two callers of the reference would
+            enc.encode_frames_host(host_in[i % F], host_bits)
+            dec.decode_frames_host(16, host_bits, host_out[i & 1])
+        ms_e2e = timed(rt, e2e_steps, 3, finish=dec.host_fence)
+        dec.set_host_pipelining(False)
+        h2d, d2h = S * (NF * 2 + NB), S * (NB + NF * 2)
+        api = "lc3b_encode_frames_host then lc3b_decode_frames_host (bitstream crosses the host)"
+    e2e = {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "api": api}
 
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(frames_np)
-        state_mb = ws_bytes / 1e6
+            cb = cpu_baseline(w)
         out = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "frame_bytes": NBYTES, "nf": NF,
+            "config": {"workload": w["desc"], "name": args.workload, "streams_per_gpu": S, "frame_bytes": NB, "nf": NF,
                        "l2": f"no explicit flush: each step streams the per-stream codec state + I/O "
-                             f"({state_mb:.0f} MB workspace per GPU) which exceeds the 126 MB L2",
+                             f"({ws_bytes / 1e6:.0f} MB workspace per GPU), far more than the 126 MB L2",
                        "parallelism": f"{world} x independent stream shards, no collective on the data path"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "cpu_baseline": cb,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
+            "cpu_baseline": cb,
         }
         print(json.dumps(out))
     if dist is not None:

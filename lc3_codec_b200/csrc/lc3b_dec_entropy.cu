@@ -280,17 +280,19 @@ constexpr int ENT_THREADS = 128;
 //   tns_cf  (2*8 + 8*17)*4  order tables then coef tables
 //   lev     7*T*4           lsb-mode save_lev flags, one bit per tuple
 //   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
-//   tile    (T/32)*32*33*4  per-warp transpose tile for the spectrum write-out
-//   ring    16*T*4          per-thread prefetch ring for pass 2 (cp.async from the xq scratch)
+//   tile    (T/32)*16*33*4  per-warp transpose tile for the spectrum write-out (16 lines at a time)
+//   ring    8*T*4           per-thread prefetch ring for pass 2 (cp.async from the xq scratch)
 //   band    68*4            I_fs band edges
+//   sort    2*T*4           work-sorting keys and the resulting frame assignment
 //   rows    T*row_pitch     staged frame bytes
 __host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
     return 4096 + 64 * 17 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 16 * ENT_THREADS * 4 +
-           (ENT_THREADS / 32) * 32 * 33 * 4 + 16 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
+           (ENT_THREADS / 32) * 16 * 33 * 4 + 8 * ENT_THREADS * 4 + 68 * 4 + 2 * ENT_THREADS * 4 +
+           (size_t)ENT_THREADS * row_pitch;
 }
 
 template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
-__global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
+__global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* s_lookup = smem;
     uint32_t* s_spec_cf = (uint32_t*)(smem + 4096);
@@ -298,15 +300,15 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     uint32_t* s_lev = s_tns_cf + (2 * 8 + 8 * 17);
     float* s_scf = (float*)(s_lev + 7 * ENT_THREADS);
     float* s_tile = s_scf + 16 * ENT_THREADS;
-    int32_t* s_ring = (int32_t*)(s_tile + (ENT_THREADS / 32) * 32 * 33);
-    int32_t* s_band = s_ring + 16 * ENT_THREADS;
-    uint8_t* s_rows = (uint8_t*)(s_band + 68);
+    int32_t* s_ring = (int32_t*)(s_tile + (ENT_THREADS / 32) * 16 * 33);
+    int32_t* s_band = s_ring + 8 * ENT_THREADS;
+    int32_t* s_key = s_band + 68;
+    int32_t* s_owner = s_key + ENT_THREADS;
+    uint8_t* s_rows = (uint8_t*)(s_owner + ENT_THREADS);
 
     const DevConfig& c = *p.cfg;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int stream0 = blockIdx.x * ENT_THREADS;
-    const int stream = stream0 + tid;
-    const bool live = stream < p.n_streams;
     const int ne = c.ne;
 
     // ---- stage tables and frame bytes
@@ -329,9 +331,41 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     }
     __syncthreads();
 
+    // ---- work sorting: the spectral loop runs lastnz/2 tuples, which varies widely between streams.  Frames of the
+    // CTA are handed to threads in order of decreasing lastnz so that the 32 lanes of a warp finish together
+    // (frames live in shared rows, so any thread can take any frame; per-thread scratch stays indexed by tid).
+    {
+        int key = -1;
+        const int s_me = stream0 + tid;
+        if (s_me < p.n_streams) {
+            int len = p.frame_nbytes ? p.frame_nbytes[s_me] : p.nbytes;
+            len = min(max(len, 0), p.nbytes);
+            Reader pr;
+            pr.buf = s_rows + tid * p.row_pitch;
+            pr.len = len; pr.head = 0; pr.tail = 0; pr.tw = 0; pr.tw_n = 0;
+            uint32_t v = 0;
+            key = 0;
+            bool good = true;
+            if (c.nbits_bw > 0) good = pr.tail_uint(c.nbits_bw, v);
+            if (good && pr.tail_uint(c.lastnz_bits, v)) key = (int)((v + 1) << 1);
+        }
+        s_key[tid] = key;
+        __syncthreads();
+        int rank = 0;
+        for (int u = 0; u < ENT_THREADS; u++) {
+            const int ku = s_key[u];
+            rank += (ku > key) || (ku == key && u < tid);
+        }
+        s_owner[rank] = tid;
+        __syncthreads();
+    }
+    const int fid = s_owner[tid];                                      // frame (row) of this CTA handled by this thread
+    const int stream = stream0 + fid;
+    const bool live = stream < p.n_streams;
+
     // ---- per-frame serial decode (pass 1)
     Reader rd;
-    rd.buf = s_rows + tid * p.row_pitch;
+    rd.buf = s_rows + fid * p.row_pitch;
     rd.len = live ? (p.frame_nbytes ? p.frame_nbytes[stream] : p.nbytes) : 0;
     if (rd.len > p.nbytes) rd.len = p.nbytes;
     if (rd.len < 0) rd.len = 0;
@@ -340,7 +374,7 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
     rd.tw = 0;
     rd.tw_n = 0;
     const int nbits = rd.len * 8;
-    int32_t* xq = p.xq + ((size_t)(stream >> 5) * ne) * 32 + lane;   // element k at xq[k * 32]
+    int32_t* xq = p.xq + ((size_t)((stream0 + tid) >> 5) * ne) * 32 + lane;   // thread-private column, element k at xq[k * 32]
 
     SideInfoD si;
     bool ok = live && read_side_info(rd, c, si);
@@ -556,11 +590,11 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
         return exp2_raw_fm(s);
     };
 
-    float* tile = s_tile + wid * 32 * 33;
-    // streams of one warp may sit in different slots (a slot only flips on a good frame): address rows per stream
-    float* out_base = p.spec + (size_t)(stream0 + wid * 32) * ne;
+    float* tile = s_tile + wid * 16 * 33;
+    // rows of one warp belong to arbitrary streams of the CTA (work sorting) and may sit in different slots
+    // (a slot only flips on a good frame): every row is addressed through its own stream id and slot
     const size_t slot_stride = (size_t)p.n_streams * ne;
-    const int rows_valid = min(32, p.n_streams - (stream0 + wid * 32));
+    const long long my_row_off_ll = (long long)((size_t)new_slot * slot_stride + (size_t)stream * ne);
 
     const bool any_ok = __any_sync(0xffffffffu, ok);
     if (any_ok) {
@@ -573,12 +607,12 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
         float gband = ok ? band_gain(0) : 0.0f;
         // The integers come back from the lane-interleaved scratch through a 16-slot per-thread ring filled by
         // cp.async PF lines ahead, so the L2 round trip never sits on the serial per-line chain.
-        constexpr int PF = 12;
-        int32_t* ring = s_ring + tid;                                  // slot e at ring[(e & 15) * ENT_THREADS]
+        constexpr int PF = 6;
+        int32_t* ring = s_ring + tid;                                  // slot e at ring[(e & 7) * ENT_THREADS]
         const int n_valid = ok ? lastnz : 0;                           // lines >= lastnz are zero and never fetched
         auto issue = [&](int e) {
             if (e < n_valid) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (e & 15) * ENT_THREADS);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (e & 7) * ENT_THREADS);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(xq + e * 32));
             }
             asm volatile("cp.async.commit_group;\n" ::);
@@ -599,7 +633,7 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
                 const int j = k + W;
                 issue(j + PF);
                 asm volatile("cp.async.wait_group %0;\n" ::"n"(PF));
-                win[W] = j < n_valid ? ring[(j & 15) * ENT_THREADS] : 0;
+                win[W] = j < n_valid ? ring[(j & 7) * ENT_THREADS] : 0;
                 if (win[W] != 0 && j < bw_stop) last_nz = j;
             }
             const int32_t xi = win[0];
@@ -625,14 +659,17 @@ __global__ void __launch_bounds__(ENT_THREADS) entropy_kernel(EntropyParams p) {
                 v = xm(v, gband);
             }
             // transpose through the warp tile, flush every 32 lines
-            tile[(k & 31) * 33 + lane] = v;
-            if ((k & 31) == 31 || k == ne - 1) {
+            tile[(k & 15) * 33 + lane] = v;
+            if ((k & 15) == 15 || k == ne - 1) {
                 __syncwarp();
-                const int k0 = k & ~31, cnt = (k & 31) + 1;
-                for (int r = 0; r < rows_valid; r++) {
+                // 16 lines x 32 rows: two rows per pass, each half-warp writes one row's 64-byte segment
+                const int k0 = k & ~15, cnt = (k & 15) + 1;
+                const int hl = lane & 15, hw = lane >> 4;
+                for (int r2 = 0; r2 < 32; r2 += 2) {
+                    const int r = r2 + hw;
                     const bool row_ok = __shfl_sync(0xffffffffu, (int)ok, r);
-                    const int row_slot = __shfl_sync(0xffffffffu, new_slot, r);
-                    if (row_ok && lane < cnt) out_base[row_slot * slot_stride + (size_t)r * ne + k0 + lane] = tile[lane * 33 + r];
+                    const long long row_off = __shfl_sync(0xffffffffu, my_row_off_ll, r);
+                    if (row_ok && hl < cnt) p.spec[row_off + k0 + hl] = tile[hl * 33 + r];
                 }
                 __syncwarp();
             }

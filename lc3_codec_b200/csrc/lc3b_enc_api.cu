@@ -156,6 +156,7 @@ using namespace lc3b;
 
 struct lc3b_encoder {
     EncoderState st;
+    int stage_mask;
 };
 
 extern bool lc3b_make_config(int sf, int fd, lc3b_config* c);
@@ -234,7 +235,14 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
         g_enc_last_cuda_error = (int)e;
         return LC3B_ERR_CUDA;
     }
+    h->stage_mask = 3;
     *out = h;
+    return LC3B_OK;
+}
+
+int lc3b_encoder_set_stage_mask(lc3b_encoder* h, int mask) {
+    if (!h || mask < 1 || mask > 3) return LC3B_ERR_INVALID_ARG;
+    h->stage_mask = mask;
     return LC3B_OK;
 }
 
@@ -247,8 +255,8 @@ int lc3b_encode_frames(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride
     if (nbytes < 20 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    CU(launch_enc_analysis(st, pcm_in, pcm_stride, nbytes, stream));
-    CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, stream));
+    if (h->stage_mask & 1) CU(launch_enc_analysis(st, pcm_in, pcm_stride, nbytes, stream));
+    if (h->stage_mask & 2) CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, stream));
     return LC3B_OK;
 }
 

@@ -77,6 +77,12 @@ class Lc3BatchEncoder:
         if rc:
             raise Lc3bError(rc, fn.__name__)
 
+    def set_stage_mask(self, mask: int) -> None:
+        """Profiling hook: 1 = analysis kernel only, 2 = quantisation kernel only, 3 = both (default)."""
+        rc = native.lib().lc3b_encoder_set_stage_mask(self._h, mask)
+        if rc:
+            raise Lc3bError(rc, "lc3b_encoder_set_stage_mask")
+
     def debug_read(self):
         """(xf, e_b, hand, xq) device tensors of the last encode's intermediates (test hook)."""
         S, ne = self.num_streams, self.ne
