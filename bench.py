@@ -49,6 +49,10 @@ WORKLOADS = {
                      metric="decoded frames/sec (16kHz 7.5ms mono, 30 B) per GPU",
                      desc="decode 16 kHz mono 7.5 ms at 30 B/frame (LTPF and TNS active), 16384 concurrent streams per GPU "
                           "(BASELINE config 3)"),
+    "mixed": dict(fs=0, ms=0, nbytes=0, nf=0, streams=65536, mode="mixed",
+                  metric="decoded frames/sec (mixed 8/16/24/32/44.1/48 kHz, 7.5 and 10 ms) per GPU",
+                  desc="mixed-rate batch decode: 65536 streams, stream s uses (fs_list[s mod 6], duration[(s/6) mod 2]) at "
+                       "20..120 B/frame (BASELINE config 4), one Lc3MixedBatchDecoder call per step"),
     "roundtrip48": dict(fs=48000, ms=10, nbytes=150, nf=480, streams=262144, mode="roundtrip",
                         metric="encode+decode round trips/sec (48kHz 10ms mono, 150 B) per GPU",
                         desc="encode then decode 48 kHz mono 10 ms at 150 B/frame, 262144 streams per GPU (BASELINE config 5)"),
@@ -185,6 +189,107 @@ def run_reference(args, w, rank):
     }))
 
 
+def run_mixed(args, w, rank, local_rank, world, dev, dist):
+    """BASELINE config 4: twelve configurations in one batch through Lc3MixedBatchDecoder."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from tools.corpus import MIXED_NBYTES, make_pcm
+
+    S = w["streams"]
+    fs_list, dur_list = [8000, 16000, 24000, 32000, 44100, 48000], [7.5, 10]
+    stream_cfg = [(fs_list[s % 6], dur_list[(s // 6) % 2]) for s in range(S)]
+    dec = L.Lc3MixedBatchDecoder([(L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)) for fs, ms in stream_cfg],
+                                 max_nbytes=120, device=dev)
+    U, F, WARM, STRIDE = 512, 8, 4, 120
+    frames = torch.zeros((F, S, STRIDE), dtype=torch.uint8, device=dev)
+    lens = torch.zeros(S, dtype=torch.int32, device=dev)
+    algo = 0
+    for ((sf, fd), first, count), nf in zip(dec.buckets, dec.nf):
+        fs = [8000, 16000, 24000, 32000, 44100, 48000][sf]
+        ms = 10 if fd == 1 else 7.5
+        nb = MIXED_NBYTES[(fs, ms)]
+        if fs == 8000:            # committed oracle-encoded fixture (no 8 kHz encoder exists in the reference)
+            fr_u = torch.from_numpy(np.load(ROOT / "tests" / "golden" / f"bench_mixed_8k_{str(ms).replace('.', 'p')}ms.npy")).to(dev)
+            fr_u = fr_u.permute(1, 0, 2).contiguous()                                    # [F,U,nb]
+        else:                     # bitstreams from the GPU encoder itself
+            pcm_u = torch.from_numpy(make_pcm(U, WARM + F, fs, nf)).to(dev)
+            n = L.Lc3BatchEncoder.calc_working_buffer_lengths(U, L.FrameDuration(fd), L.SamplingFrequency(sf), nb)
+            ews = torch.empty(n, dtype=torch.uint8, device=dev)
+            enc = L.Lc3BatchEncoder(U, L.FrameDuration(fd), L.SamplingFrequency(sf), ews, nb)
+            fr_all = torch.empty((WARM + F, U, nb), dtype=torch.uint8, device=dev)
+            for f in range(WARM + F):
+                enc.encode_frames(pcm_u[:, f].contiguous(), fr_all[f])
+            torch.cuda.synchronize(dev)
+            fr_u = fr_all[WARM:]
+            del enc, ews
+        idx = torch.arange(count, device=dev) % fr_u.shape[1]
+        frames[:, first:first + count, :nb] = fr_u[:, idx]
+        lens[first:first + count] = nb
+        algo += count * (nb + 2 * nf)
+    pcm = torch.empty((S, 480), dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_
+
+    with ClockSampler(local_rank) as clk:
+        ms_total = timed(lambda i: dec.decode_frames(16, frames[i % F], lens, pcm), args.steps, args.warmup)
+    ups = world * S * args.steps / (ms_total * 1e-3)
+    host_in = frames.cpu().pin_memory()
+    host_out = torch.empty((S, 480), dtype=torch.int16).pin_memory()
+    dev_in = torch.empty((S, STRIDE), dtype=torch.uint8, device=dev)
+
+    def e2e_step(i):
+        dev_in.copy_(host_in[i % F], non_blocking=True)
+        dec.decode_frames(16, dev_in, lens, pcm)
+        host_out.copy_(pcm, non_blocking=True)
+    e2e_steps = max(10, min(args.steps, 100))
+    ms_e2e = timed(e2e_step, e2e_steps, 3)
+    peak, peak_src = measured_peak()
+    step_ms = ms_total / args.steps
+    achieved = algo / (step_ms * 1e-3) / 1e9
+    if rank == 0:
+        cb = None
+        print(json.dumps({
+            "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": w["desc"], "name": "mixed", "streams_per_gpu": S,
+                       "parallelism": f"{world} x independent stream shards; 12 per-configuration decoders on 12 CUDA streams"},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * STRIDE,
+                    "d2h_bytes_per_step": S * 480 * 2, "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "pinned-host rows copied in, Lc3MixedBatchDecoder.decode_frames, padded PCM rows copied out, every step"},
+            "gpu_launches": 24 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "whole step (12 configurations x 2 kernels on concurrent streams)", "kernel_ms": step_ms,
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": algo},
+            "cpu_baseline": cb}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -222,6 +327,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if w["mode"] == "mixed":
+        run_mixed(args, w, rank, local_rank, world, dev, dist)
+        return
     S, NB, NF, mode = w["streams"], w["nbytes"], w["nf"], w["mode"]
     sf, fd = L.SamplingFrequency.from_hz(w["fs"]), L.FrameDuration.from_ms(w["ms"])
     stream = torch.cuda.current_stream(dev)

@@ -7,3 +7,4 @@ streams.  There is no CPU fallback: importing the native module without the buil
 from .native import FrameDuration, Lc3bError, SamplingFrequency, lib, lib_path  # noqa: F401
 from .decoder import Lc3BatchDecoder, Lc3DecoderError  # noqa: F401
 from .encoder import Lc3BatchEncoder  # noqa: F401
+from .mixed import Lc3MixedBatchDecoder  # noqa: F401

@@ -165,3 +165,40 @@ def test_only_16_bits_per_sample():
         dec.decode_frames(24, fr, out)
     with pytest.raises(L.Lc3bError):
         dec.decode_frames(16, fr, out[:, :100])          # short output slice: the reference would truncate/panic
+
+
+def test_mixed_rate_batch():
+    """BASELINE config 4 at test size: all twelve (fs, duration) configurations decoded by one mixed-rate call per frame."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from oracle import pyoracle as O
+    per, F = 24, 10
+    cfgs, frames_by, pcm_by = [], {}, {}
+    for (fs, ms) in ALL_CONFIGS:
+        _, fr = corpus(fs, ms, MIXED_NBYTES[(fs, ms)], per, F)
+        frames_by[(fs, ms)] = fr
+        pcm_by[(fs, ms)] = O.decode_streams(fr, fs, ms)
+    # interleave the configurations over stream ids like SURVEY.md 8d: stream s -> config s mod 12
+    stream_cfg = [ALL_CONFIGS[s % 12] for s in range(12 * per)]
+    dec = L.Lc3MixedBatchDecoder([(L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)) for fs, ms in stream_cfg],
+                                 max_nbytes=120, device="cuda:0")
+    S = len(stream_cfg)
+    got = np.zeros((S, F, 480), np.int16)
+    for f in range(F):
+        rows = np.zeros((S, 120), np.uint8)
+        lens = np.zeros(S, np.int32)
+        for pos, s in enumerate(dec.order):
+            fs, ms = stream_cfg[s]
+            fr = frames_by[(fs, ms)][s // 12, f]
+            rows[pos, :len(fr)] = fr
+            lens[pos] = len(fr)
+        out = torch.zeros((S, 480), dtype=torch.int16, device="cuda:0")
+        dec.decode_frames(16, torch.from_numpy(rows).cuda(), torch.from_numpy(lens).cuda(), out)
+        torch.cuda.synchronize()
+        got[:, f] = out.cpu().numpy()
+    for pos, s in enumerate(dec.order):
+        fs, ms = stream_cfg[s]
+        exp = pcm_by[(fs, ms)][s // 12]
+        nf = exp.shape[-1]
+        assert np.abs(got[pos, :, :nf].astype(np.int32) - exp.astype(np.int32)).max() <= PCM_TOL, (fs, ms, s)

@@ -22,3 +22,12 @@ frames = O.encode_streams(pcm, 48000, 10, 150)[:, WARM_FRAMES:]   # skip the enc
 out = ROOT / "tests" / "golden" / "bench_c1_frames.npy"
 np.save(out, np.ascontiguousarray(frames))
 print(out, frames.shape, frames.dtype, out.stat().st_size)
+
+# 8 kHz bitstreams for the mixed-rate bench (BASELINE config 4): the reference encoder (and therefore the GPU
+# encoder) cannot be constructed at 8 kHz, so these come from the oracle encoder's spec-following 8 kHz path.
+for ms, nb, nf in ((7.5, 20, 60), (10, 26, 80)):
+    pcm8 = make_pcm(512, WARM_FRAMES + N_FRAMES, 8000, nf)
+    fr8 = O.encode_streams(pcm8, 8000, ms, nb)[:, WARM_FRAMES:]
+    out8 = ROOT / "tests" / "golden" / f"bench_mixed_8k_{str(ms).replace('.', 'p')}ms.npy"
+    np.save(out8, np.ascontiguousarray(fr8))
+    print(out8, fr8.shape, out8.stat().st_size)
