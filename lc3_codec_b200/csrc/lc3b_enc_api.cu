@@ -282,6 +282,7 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
 // xf [S][ne] f32 is the spectrum AFTER SNS/TNS (the quantiser's input), e_b [S][64], hand [S][8] i32, xq [S][ne] i16.
 int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* hand, int16_t* xq, void* cuda_stream) {
     if (!h) return LC3B_ERR_INVALID_ARG;
+    h->st.debug = 1;       // from the next encode on, the quantisation kernel writes xf / xq back to global memory
     const EncoderState& st = h->st;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const size_t ns = (size_t)st.n_streams;

@@ -41,6 +41,7 @@ enum {
 struct EncoderState {
     lc3b_config cfg;
     int n_streams, max_nbytes, device;
+    int debug;             // quantisation kernel writes its shared-memory intermediates back (lc3b_encoder_debug_read)
     EncConfig* ecfg;
     float* win;            // [2*nf]  w_N (unmodified)
     float2* dtw;           // [n_fft] DCT-IV twiddles

@@ -32,9 +32,14 @@ struct QuantParams {
     uint8_t* lsbs;
     uint8_t* frames_out;
     int row_pitch;
+    int debug;
 };
 
-constexpr int QNT_THREADS = 64;
+constexpr int QNT_THREADS = 32;
+// The frame's spectrum (f32), quantised spectrum (i16) and 4-line energies live in shared memory as per-thread
+// columns: element k of lane l at [k * XS + l].  XS = 33 keeps both the thread-private walks (fixed lane, any k) and
+// the transposed load of stream-major rows (fixed row, consecutive k) free of bank conflicts.
+constexpr int XS = 33;
 
 struct BwRes { int bw, nbits; };
 struct SnsRes { int ind_lf, ind_hf, shape_j, gind, ls_inda, ls_indb; uint64_t joint; };
@@ -338,7 +343,7 @@ __device__ SnsRes sns_encode(const EncConfig& c, float* x, const float* e_b, boo
     }
     for (int b = 0; b < nb; b++) {
         const float g = exp2f_msun(-it[b]);
-        for (int k = c.band_idx[b]; k < c.band_idx[b + 1]; k++) x[k] *= g;
+        for (int k = c.band_idx[b]; k < c.band_idx[b + 1]; k++) x[k * XS] *= g;
     }
     return res;
 }
@@ -379,20 +384,39 @@ __device__ void tns_encode(const EncConfig& c, float* x, int p_bw, int nbits, bo
     const int ne = c.ne;
     const float* LAG = TNS_LAG;
     for (int f = 0; f < tp.nf; f++) {
+        // compute_normalized_autocorrelation :80-115.  The reference recomputes the sub-block energy for every lag and
+        // walks the sub-block once per lag; the sums below are the same sums (same operands, same order), gathered in
+        // ONE walk per sub-block with the last eight lines held in registers.
+        float es_s[3], ac_s[3][9];
+        for (int sb = 0; sb < 3; sb++) {
+            const int start = tp.ss[f][sb], stop = tp.se[f][sb];
+            float acc[9], w8[8];
+#pragma unroll
+            for (int k = 0; k < 9; k++) acc[k] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) w8[k] = 0.0f;
+            int cnt = 0;
+            for (int n = start; n < stop; n++) {
+                const float xn = x[n * XS];
+                acc[0] += xn * xn;
+#pragma unroll
+                for (int k = 1; k < 9; k++) if (cnt >= k) acc[k] += w8[k - 1] * xn;
+#pragma unroll
+                for (int k = 7; k > 0; k--) w8[k] = w8[k - 1];
+                w8[0] = xn;
+                cnt++;
+            }
+            es_s[sb] = acc[0];
+#pragma unroll
+            for (int k = 0; k < 9; k++) ac_s[sb][k] = acc[k];
+        }
         float rr[9];
         for (int k = 0; k < 9; k++) {
             const float r0 = k == 0 ? 3.0f : 0.0f;
             float rk = 0.0f, e_prod = 1.0f;
-            for (int s = 0; s < 3; s++) {
-                const int start = tp.ss[f][s], stop = tp.se[f][s];
-                float es = 0.0f;
-                for (int n = start; n < stop; n++) es += x[n] * x[n];
-                float ac = 0.0f;
-                const int k_from = start + k;
-                if (k_from < ne && k_from < stop)
-                    for (int n = 0; k_from + n < stop; n++) ac += x[start + n] * x[k_from + n];
-                e_prod *= es;
-                rk += ac / es;
+            for (int sb = 0; sb < 3; sb++) {
+                e_prod *= es_s[sb];
+                rk += ac_s[sb][k] / es_s[sb];
             }
             rr[k] = (e_prod == 0.0f ? r0 : rk) * LAG[k];
         }
@@ -460,7 +484,7 @@ __device__ void tns_encode(const EncConfig& c, float* x, int p_bw, int nbits, bo
     for (int f = 0; f < tp.nf; f++) {
         if (r.rc_order[f] == 0) continue;
         for (int n = tp.start[f]; n < tp.stop[f]; n++) {
-            float t = x[n], st_save = t;
+            float t = x[n * XS], st_save = t;
             const int po = r.rc_order[f] - 1;
             for (int k = 0; k < po; k++) {
                 const float rq = r.rc_q[f * 8 + k];
@@ -471,7 +495,7 @@ __device__ void tns_encode(const EncConfig& c, float* x, int p_bw, int nbits, bo
             }
             t += r.rc_q[f * 8 + po] * st[po];
             st[po] = st_save;
-            x[n] = t;
+            x[n * XS] = t;
         }
     }
 }
@@ -484,13 +508,13 @@ __device__ BitCons compute_bit_consumption(int ne, int fs_ind, const int16_t* xq
     bc.rate_flag = nbits > (160 + fs_ind * 160) ? 512 : 0;
     bc.mode_flag = nbits >= (480 + fs_ind * 160);
     int lastnz = ne;
-    while (lastnz > 2 && xq[lastnz - 1] == 0 && xq[lastnz - 2] == 0) lastnz -= 2;
+    while (lastnz > 2 && xq[(lastnz - 1) * XS] == 0 && xq[(lastnz - 2) * XS] == 0) lastnz -= 2;
     uint32_t est = 0, trunc = 0;
     int nbits_lsb = 0, lastnz_trunc = 2, c = 0;
     for (int n = 0; n < lastnz; n += 2) {
         int t = c + bc.rate_flag;
         if (n > ne / 2) t += 256;
-        const int q0 = xq[n], q1 = xq[n + 1];
+        const int q0 = xq[n * XS], q1 = xq[(n + 1) * XS];
         uint32_t a = (uint32_t)(q0 < 0 ? -q0 : q0) & 0xffffu, a_lsb = a;
         uint32_t b = (uint32_t)(q1 < 0 ? -q1 : q1) & 0xffffu, b_lsb = b;
         int lev = 0;
@@ -539,11 +563,11 @@ __device__ BitCons quantize_spectrum(const EncConfig& c, const float* xf, int16_
     const int ne = c.ne;
     const float gg = gain_of(c, gg_ind, gg_off);
     for (int k = 0; k < ne; k++) {
-        const float v = xf[k];
-        xq[k] = v >= 0.0f ? cast_i16(v / gg + 0.375f) : cast_i16(v / gg - 0.375f);
+        const float v = xf[k * XS];
+        xq[k * XS] = v >= 0.0f ? cast_i16(v / gg + 0.375f) : cast_i16(v / gg - 0.375f);
     }
     BitCons bc = compute_bit_consumption(ne, c.fs_ind, xq, nbits, nbits_spec);
-    for (int k = bc.lastnz_trunc; k < bc.lastnz; k++) xq[k] = 0;
+    for (int k = bc.lastnz_trunc; k < bc.lastnz; k++) xq[k * XS] = 0;
     *gg_out = gg;
     *lsb_mode = bc.mode_flag && bc.nbits_est > nbits_spec;
     return bc;
@@ -574,9 +598,9 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
     const int gg_off = -(115 < q ? 115 : q) - 105 - 5 * (fs_ind + 1);
     const int ne4 = ne / 4;
     for (int i = 0; i < ne4; i++) {                                    // compute_spectral_energy :390-395
-        const float* pp = xf + 4 * i;
-        const float total = pp[0] * pp[0] + pp[1] * pp[1] + pp[2] * pp[2] + pp[3] * pp[3];
-        e[i] = 10.0f * log10f_msun(1.1920929e-07f + total);
+        const float* pp = xf + 4 * i * XS;
+        const float total = pp[0] * pp[0] + pp[XS] * pp[XS] + pp[2 * XS] * pp[2 * XS] + pp[3 * XS] * pp[3 * XS];
+        e[i * XS] = 10.0f * log10f_msun(1.1920929e-07f + total);
     }
     int fac = 256, gg_ind = 255;                                       // global_gain_estimation :174-210
     for (int it = 0; it < 8; it++) {
@@ -586,7 +610,7 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
         bool is_zero = true;
         const float g = (float)gg_ind + (float)gg_off;
         for (int i = ne4 - 1; i >= 0; i--) {
-            const float ei = e[i];
+            const float ei = e[i * XS];
             if (ei * 28.0f / 20.0f < g) {
                 if (!is_zero) tmp += 2.7f * 28.0f / 20.0f;
             } else {
@@ -600,7 +624,7 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
         if ((tmp > (float)nbits_spec_adj * 1.4f * 28.0f / 20.0f) && !is_zero) gg_ind += fac;
     }
     float xmax = 0.0f;                                                 // global_gain_limitation :212-228
-    for (int k = 0; k < ne; k++) xmax = maxf_rs(xmax, fabsf(xf[k]));
+    for (int k = 0; k < ne; k++) xmax = maxf_rs(xmax, fabsf(xf[k * XS]));
     int gg_min = 0;
     if (xmax > 0.0f) gg_min = (int)(int16_t)(cast_i16(ceilf(28.0f * log10f_msun(xmax / (32768.0f - 0.375f)))) - (int16_t)gg_off);
     bool reset_offset;
@@ -645,11 +669,13 @@ __device__ int noise_factor(const EncConfig& c, const float* xf, const int16_t* 
     float sum = 0.0f;
     int count = 0;
     const int nf_stop = c.ne < bw_stop ? c.ne : bw_stop;
+    // a line is relevant when xq is zero on [k - w, min(bw_stop - 1, k + w)]; track the last non-zero index seen by
+    // a scan pointer that runs w lines ahead instead of re-reading the window for every line
+    int last_nz = -1000, scan = nf_start - nf_width;
     for (int k = nf_start; k < nf_stop; k++) {
-        const int from = k - nf_width, to = bw_stop < k + nf_width + 1 ? bw_stop : k + nf_width + 1;
-        bool rel = true;
-        for (int j = from; j < to; j++) if (xq[j] != 0) { rel = false; break; }
-        if (rel) { sum += fabsf(xf[k]) / gg; count++; }
+        const int hi = bw_stop - 1 < k + nf_width ? bw_stop - 1 : k + nf_width;
+        while (scan <= hi) { if (xq[scan * XS] != 0) last_nz = scan; scan++; }
+        if (last_nz < k - nf_width) { sum += fabsf(xf[k * XS]) / gg; count++; }
     }
     const float level = count > 0 ? sum / (float)count : 0.0f;
     const float diff = 8.0f - 16.0f * level;
@@ -767,7 +793,7 @@ __device__ void bitstream_encode(const EncConfig& c, const BwRes& bw, const SnsR
     int cctx = 0;
     for (int k = 0; k < q.lastnz_trunc; k += 2) {
         int t = cctx + q.rate_flag + (k > ne / 2 ? 256 : 0);
-        const int q0 = xq[k], q1 = xq[k + 1];
+        const int q0 = xq[k * XS], q1 = xq[(k + 1) * XS];
         uint32_t a = (uint32_t)(q0 < 0 ? -q0 : q0) & 0xffffu, a_lsb = a;
         uint32_t b = (uint32_t)(q1 < 0 ? -q1 : q1) & 0xffffu, b_lsb = b;
         int lev = 0;
@@ -847,15 +873,27 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quant_kernel(QuantParams p) {
     const int tid = threadIdx.x;
     const int stream0 = blockIdx.x * QNT_THREADS;
     const int stream = stream0 + tid;
-    uint8_t* row = smem + (size_t)tid * p.row_pitch;
+    const int ne = c.ne;
+    float* s_xf = (float*)smem;                                   // [ne][XS]
+    float* s_e = s_xf + ne * XS;                                  // [100][XS]
+    int16_t* s_xq = (int16_t*)(s_e + 100 * XS);                   // [ne][XS]
+    uint8_t* s_rows = (uint8_t*)(s_xq + ne * XS + (ne & 1));      // [QNT_THREADS][row_pitch], 4-byte aligned
+    uint8_t* row = s_rows + (size_t)tid * p.row_pitch;
+    const int n_rows = min(QNT_THREADS, p.n_streams - stream0);
+    // transposed load of the CTA's stream-major spectra: row r is read coalesced, lane = k
+    for (int r = 0; r < n_rows; r++) {
+        const float* src = p.xf + (size_t)(stream0 + r) * ne;
+        for (int k = tid; k < ne; k += QNT_THREADS) s_xf[k * XS + r] = src[k];
+    }
+    __syncthreads();
     if (stream < p.n_streams) {
-        const int ne = c.ne, nbytes = p.nbytes, nbits = nbytes * 8;
-        float* xf = p.xf + (size_t)stream * ne;
+        const int nbytes = p.nbytes, nbits = nbytes * 8;
+        float* xf = s_xf + tid;
         const float* e_b = p.e_b + (size_t)stream * 64;
         const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
         int32_t* es = p.estate + (size_t)stream * ES_WORDS;
-        int16_t* xq = p.xq + (size_t)stream * ne;
-        float* e4 = p.scratch_e + (size_t)stream * 100;
+        int16_t* xq = s_xq + tid;
+        float* e4 = s_e + tid;
         uint8_t* lsbs = p.lsbs + (size_t)stream * 2 * ne;
 
         const BwRes bw = bandwidth_detect(c, e_b);
@@ -873,10 +911,10 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quant_kernel(QuantParams p) {
             if (mx > 0) {
                 for (int k = 0; k < ne; k++) {
                     if (n_res >= mx) break;
-                    const int v = xq[k];
+                    const int v = xq[k * XS];
                     if (v != 0) {
                         if (n_res >= 400) break;
-                        if (xf[k] >= (float)v * q.gg) res_bits[n_res >> 5] |= 1u << (n_res & 31);
+                        if (xf[k * XS] >= (float)v * q.gg) res_bits[n_res >> 5] |= 1u << (n_res & 31);
                         n_res++;
                     }
                 }
@@ -887,14 +925,22 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quant_kernel(QuantParams p) {
                          nff, xq, lsbs, row, nbytes);
     }
     __syncthreads();
-    const int n_rows = min(QNT_THREADS, p.n_streams - stream0);
     for (int i = tid; i < n_rows * p.nbytes; i += QNT_THREADS) {
         const int r = i / p.nbytes, b = i - r * p.nbytes;
-        p.frames_out[(size_t)(stream0 + r) * p.frame_stride + b] = smem[(size_t)r * p.row_pitch + b];
+        p.frames_out[(size_t)(stream0 + r) * p.frame_stride + b] = s_rows[(size_t)r * p.row_pitch + b];
+    }
+    if (p.debug) {                                                // test hook: make the intermediates readable
+        for (int r = 0; r < n_rows; r++) {
+            for (int k = tid; k < ne; k += QNT_THREADS) {
+                p.xf[(size_t)(stream0 + r) * ne + k] = s_xf[k * XS + r];
+                p.xq[(size_t)(stream0 + r) * ne + k] = s_xq[k * XS + r];
+            }
+        }
     }
 }
 
 cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, cudaStream_t stream) {
+    const int ne = st.cfg.ne;
     QuantParams p;
     p.cfg = st.ecfg;
     p.n_streams = st.n_streams;
@@ -911,7 +957,8 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     int words = (nbytes + 3) / 4;
     if ((words & 1) == 0) words++;
     p.row_pitch = words * 4;
-    const size_t smem = (size_t)QNT_THREADS * p.row_pitch;
+    p.debug = st.debug;
+    const size_t smem = (size_t)ne * XS * 4 + 100 * XS * 4 + ((size_t)ne * XS + (ne & 1)) * 2 + (size_t)QNT_THREADS * p.row_pitch;
     cudaError_t e = cudaFuncSetAttribute(enc_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     enc_quant_kernel<<<(st.n_streams + QNT_THREADS - 1) / QNT_THREADS, QNT_THREADS, smem, stream>>>(p);
