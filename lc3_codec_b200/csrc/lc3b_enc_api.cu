@@ -17,7 +17,7 @@ static thread_local int g_enc_last_cuda_error = 0;
     } while (0)
 
 struct EncLayout {
-    size_t ecfg, win, dtw, ftw, perm, thist, xs_hist, x12, x6, estate, xf, e_b, ehand, xq, scratch_e, lsbs, stage_in,
+    size_t ecfg, win, dtw, ftw, perm, thist, xs_hist, x12, x6, estate, xf, e_b, ehand, xq, qhand, lsbs, stage_in,
         stage_out, total;
 };
 
@@ -47,7 +47,7 @@ static EncLayout make_enc_layout(const lc3b_config& c, int n_streams, int max_nb
     L.e_b = take(off, sizeof(float) * ns * 64);
     L.ehand = take(off, sizeof(int32_t) * ns * EH_WORDS);
     L.xq = take(off, sizeof(int16_t) * ns * c.ne);
-    L.scratch_e = take(off, sizeof(float) * ns * 100);
+    L.qhand = take(off, sizeof(int32_t) * ns * QH_WORDS);
     L.lsbs = take(off, ns * 2 * c.ne);
     L.stage_in = take(off, sizeof(int16_t) * ns * c.nf);
     L.stage_out = take(off, ns * (size_t)max_nbytes);
@@ -78,6 +78,11 @@ __global__ void enc_init_band_kernel(EncConfig* cfg) {
              : cfg->fs_ind == 2 ? LC3T_I_24000_10MS : cfg->fs_ind == 3 ? LC3T_I_32000_10MS : LC3T_I_48000_10MS;
     }
     for (int b = threadIdx.x; b < 65; b += blockDim.x) cfg->band_idx[b] = b <= cfg->nb ? bi[b] : cfg->ne;
+    for (int k = threadIdx.x; k < 400; k += blockDim.x) {
+        int band = 255;
+        for (int b = 0; b < cfg->nb; b++) if (k >= bi[b] && k < bi[b + 1]) band = b;
+        cfg->band_of[k] = (uint8_t)band;
+    }
 }
 
 __global__ void enc_init_streams_kernel(int32_t* estate, int n_streams) {
@@ -206,7 +211,7 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
     st.e_b = (float*)(base + L.e_b);
     st.ehand = (int32_t*)(base + L.ehand);
     st.xq = (int16_t*)(base + L.xq);
-    st.scratch_e = (float*)(base + L.scratch_e);
+    st.qhand = (int32_t*)(base + L.qhand);
     st.lsbs = base + L.lsbs;
     st.stage_in = (int16_t*)(base + L.stage_in);
     st.stage_out = base + L.stage_out;
@@ -282,7 +287,6 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
 // xf [S][ne] f32 is the spectrum AFTER SNS/TNS (the quantiser's input), e_b [S][64], hand [S][8] i32, xq [S][ne] i16.
 int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* hand, int16_t* xq, void* cuda_stream) {
     if (!h) return LC3B_ERR_INVALID_ARG;
-    h->st.debug = 1;       // from the next encode on, the quantisation kernel writes xf / xq back to global memory
     const EncoderState& st = h->st;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const size_t ns = (size_t)st.n_streams;

@@ -15,6 +15,7 @@ struct EncConfig {
     int32_t n_levels;                 // kissfft factor levels
     int32_t fac_p[8], fac_m[8], fac_stride[8];   // kf_factor (kissfft.rs:47): radix, sub-length, fstride per level
     int32_t band_idx[65];
+    uint8_t band_of[400];             // line -> band (255: beyond the last band)
     // LTPF analysis (encoder/long_term_post_filter.rs:91-124)
     int32_t len12p8, len6p4, delay, up, x_s_ext_len, x12_len;
     float resamp_fac;
@@ -29,6 +30,7 @@ struct EncConfig {
 enum {
     EH_NEAR_NYQUIST = 0, EH_ATTACK, EH_PITCH_INDEX, EH_PITCH_PRESENT, EH_LTPF_ACTIVE, EH_NBITS_LTPF, EH_WORDS = 8
 };
+constexpr int QH_WORDS = 40;
 
 // per-stream persistent scalars of the encoder (int32 words; floats as bits)
 enum {
@@ -41,7 +43,6 @@ enum {
 struct EncoderState {
     lc3b_config cfg;
     int n_streams, max_nbytes, device;
-    int debug;             // quantisation kernel writes its shared-memory intermediates back (lc3b_encoder_debug_read)
     EncConfig* ecfg;
     float* win;            // [2*nf]  w_N (unmodified)
     float2* dtw;           // [n_fft] DCT-IV twiddles
@@ -56,7 +57,7 @@ struct EncoderState {
     float* e_b;            // [S][64]
     int32_t* ehand;        // [S][EH_WORDS]
     int16_t* xq;           // [S][ne]       quantised spectrum
-    float* scratch_e;      // [S][100]      4-line energies for the gain bisection
+    int32_t* qhand;        // [S][QH_WORDS] decisions handed from kernel to kernel (lc3b_enc_quant.cu)
     uint8_t* lsbs;         // [S][ne]       deferred LSBs / sign bits in lsb_mode (bitstream_encoding.rs:22)
     int16_t* stage_in;     // [S][nf]       staging for the host entry point
     uint8_t* stage_out;    // [S][max_nbytes]

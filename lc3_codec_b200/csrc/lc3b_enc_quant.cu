@@ -1,4 +1,7 @@
-// lc3b engine, encoder kernel 2 of 2: spectrum + analysis results -> bitstream, one THREAD per frame.
+// lc3b engine, encoder kernels 2-4 of 4: spectrum + analysis results -> bitstream, one WARP per frame.
+// Three kernels (shape: BW/SNS/TNS, quantise: gain search + rate loop, bitstream) so that each one's code stays near
+// the SM's 32 KB L1.5 instruction cache: as ONE kernel the 14k-instruction body made instruction fetch the top stall
+// (49 % of samples), every resident warp being in a different phase.
 // Compiled with -fmad=false: every expression below rounds exactly like the reference's f32 code.
 //
 // Replaces, per stream, the second half of EncoderChannel::encode (src/encoder/lc3_encoder.rs:74-110):
@@ -9,10 +12,19 @@
 //   ResidualBitsEncoder::encode     src/encoder/residual_spectrum.rs:33
 //   NoiseLevelEstimation            src/encoder/noise_level_estimation.rs:21
 //   BitstreamEncoding::encode       src/encoder/bitstream_encoding.rs:77 with BufferWriter (buffer_writer.rs:5)
-// Everything here is decision logic and serial recurrences (codebook argmins, Levinson, the rate loop's context walk,
-// the range coder), so the parallel axis is frames.  The frame's bytes are assembled in a shared-memory row and
-// copied out coalesced.
-#include <stdio.h>
+//
+// The frame lives in the warp's slice of shared memory.  The byte-identity bar fixes the ORDER of every f32 sum,
+// so the work is split along the axes that leave each sum intact:
+//   * independent results go to different lanes (64 band energies, 32 codebook rows, 27 autocorrelation sums,
+//     100 four-line energies, 400 quantised lines, 200 two-tuples of the context walk);
+//   * a long ordered sum keeps its order: its terms are produced in parallel and one chain adds them;
+//   * the TNS lattice runs as a systolic pipeline, lane k holding stage k (same operations per sample);
+//   * integer accumulations (bit estimates, ranks, offsets) are exact in any order and use warp scans;
+//   * the range coder consumes a queue of (cumulative, frequency) pairs the lanes prepared, and the backward
+//     side-bit stream is assembled by the lanes at prefix-summed offsets.
+// The reference writes both ends of the frame interleaved; when they never meet the result is the OR of the two
+// streams, which is what the fast path builds.  A frame whose two ends collide (the encoder overspent its budget)
+// is re-encoded by one lane with the reference's interleaved write order (bitstream_encode_serial).
 #include "lc3b_enc_common.cuh"
 #include "lc3b_math.cuh"
 #include "lc3_tables.h"
@@ -28,22 +40,22 @@ struct QuantParams {
     const int32_t* ehand;
     int32_t* estate;
     int16_t* xq;
-    float* scratch_e;
+    int32_t* qhand;
     uint8_t* lsbs;
     uint8_t* frames_out;
-    int row_pitch;
-    int debug;
+    int w_bytes, side_words, sym_cap, out_words;     // per-warp shared-memory slice
 };
 
-constexpr int QNT_THREADS = 32;
-// The frame's spectrum (f32), quantised spectrum (i16) and 4-line energies live in shared memory as per-thread
-// columns: element k of lane l at [k * XS + l].  XS = 33 keeps both the thread-private walks (fixed lane, any k) and
-// the transposed load of stream-major rows (fixed row, consecutive k) free of bank conflicts.
-constexpr int XS = 33;
+constexpr int QW = 4;                       // frames (warps) per CTA
+constexpr int QNT_THREADS = QW * 32;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NE_MAX = 400;
+constexpr int S_FLOATS = 384;               // per-warp scratch
+constexpr int TAIL_WORDS = 26;              // 800 deferred LSB / 400 residual bits
 
 struct BwRes { int bw, nbits; };
 struct SnsRes { int ind_lf, ind_hf, shape_j, gind, ls_inda, ls_indb; uint64_t joint; };
-struct TnsRes { int nbits_tns, lpc_weighting, num_filters; int rc_order[2]; int rc_i[16]; float rc_q[16]; };
+struct TnsRes { int nbits_tns, lpc_weighting, num_filters; int rc_order[2]; const int* rc_i; };
 struct QRes { int gg_ind, nbits_spec, nbits_lsb, nbits_trunc, lsb_mode, rate_flag, lastnz_trunc; float gg; };
 
 // Constant tables live at namespace scope: a function-local 64-bit table (msun's exp2f) was observed to be laid
@@ -61,7 +73,40 @@ __device__ const float TNS_LAG[9] = {1.0f, 0.9980280260203829f, 0.99213540551139
 __device__ const int GGA_T1[5] = {80, 230, 380, 530, 680}, GGA_T2[5] = {500, 1025, 1550, 2075, 2600},
                      GGA_T3[5] = {850, 1700, 2550, 3400, 4250};   // spectral_quantization.rs:351-353
 
-// ---------------------------------------------------------------- bandwidth_detector.rs:64-127
+__device__ __forceinline__ float shf(float v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ int shi(int v, int src) { return __shfl_sync(FULL, v, src); }
+
+// Lexicographic (value, index) minimum over the warp: the result of the reference's `if d < d_min` scan over
+// ascending indices.  NaN and +inf never win; *idx comes back as the smallest contributed index when nothing does.
+__device__ __forceinline__ void warp_argmin(float& v, int& idx) {
+    if (!(v < INFINITY)) v = INFINITY;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, v, off);
+        const int oi = __shfl_xor_sync(FULL, idx, off);
+        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, v, off);
+        if (lane >= off) v += o;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------- bandwidth_detector.rs:64-127 (every lane, same values)
 __device__ BwRes bandwidth_detect(const EncConfig& c, const float* e_b) {
     const int n_bw = c.fs_ind, nbits = NBITS_BW[n_bw];
     if (n_bw == 0) return {0, nbits};
@@ -89,45 +134,52 @@ __device__ BwRes bandwidth_detect(const EncConfig& c, const float* e_b) {
 }
 
 // ---------------------------------------------------------------- spectral_noise_shaping.rs
-__device__ void add_unit_pulse(const float* abs_x, int n_max, int k, int k_max, int* cand, float* corr_xy, float* energy_y) {   // :285-316
-    float corr_last = *corr_xy, en_last = *energy_y;
+// add_unit_pulse :285-316.  Lane n < n_max owns abs_x[n] and cand[n]; the best-candidate scan keeps the reference's
+// order (and its habit of leaving the LAST candidate's correlation/energy in the in-out arguments).
+__device__ __forceinline__ void add_unit_pulse_w(float ax, int n_max, int k, int k_max, int& cand, float& corr_xy, float& energy_y,
+                                                 int lane) {
+    float corr_last = corr_xy, en_last = energy_y;
+#pragma unroll 1
     for (int it = k; it < k_max; it++) {
+        const float my_corr = corr_last + ax;
+        const float my_en = en_last + 2.0f * (float)cand + 1.0f;
         int n_best = 0;
-        *corr_xy = corr_last + abs_x[0];
-        float best_corr_sq = *corr_xy * *corr_xy;
-        float best_en = en_last + 2.0f * (float)cand[0] + 1.0f;
+        corr_xy = shf(my_corr, 0);
+        float best_corr_sq = corr_xy * corr_xy;
+        float best_en = shf(my_en, 0);
+#pragma unroll 1
         for (int n_c = 1; n_c < n_max; n_c++) {
-            *corr_xy = corr_last + abs_x[n_c];
-            *energy_y = en_last + 2.0f * (float)cand[n_c] + 1.0f;
-            if (*corr_xy * *corr_xy * best_en > best_corr_sq * *energy_y) {
+            corr_xy = shf(my_corr, n_c);
+            energy_y = shf(my_en, n_c);
+            if (corr_xy * corr_xy * best_en > best_corr_sq * energy_y) {
                 n_best = n_c;
-                best_corr_sq = *corr_xy * *corr_xy;
-                best_en = *energy_y;
+                best_corr_sq = corr_xy * corr_xy;
+                best_en = energy_y;
             }
         }
-        corr_last += abs_x[n_best];
-        en_last += 2.0f * (float)cand[n_best] + 1.0f;
-        cand[n_best] += 1;
+        corr_last += shf(ax, n_best);
+        en_last += 2.0f * (float)shi(cand, n_best) + 1.0f;
+        if (lane == n_best) cand += 1;
     }
 }
 
-__device__ void normalize_candidate(const int* y, float* xq, int n_max) {   // :629-648
-    float norm = 0.0f;
-    for (int n = 0; n < n_max; n++) if (y[n] != 0) norm += (float)y[n] * (float)y[n];
-    norm = sqrtf(norm);
-    for (int n = 0; n < n_max; n++) {
-        xq[n] = (float)y[n];
-        if (y[n] != 0) xq[n] /= norm;
-    }
-    for (int n = n_max; n < 16; n++) xq[n] = 0.0f;
+// normalize_candidate :629-648 (the squared norm is a sum of small integers: exact in any order)
+__device__ __forceinline__ float normalize_w(int y, bool in_range) {
+    const int yy = in_range ? y : 0;
+    const int sq = warp_sum_i(yy * yy);
+    const float norm = sqrtf((float)sq);
+    float v = (float)yy;
+    if (yy != 0) v /= norm;
+    return v;
 }
 
-__device__ void mvpq_enum(uint64_t* index, int* lead_sign_ind, int dim_in, const int* vec_in) {   // :585-627
+__device__ __noinline__ void mvpq_enum(uint64_t* index, int* lead_sign_ind, int dim_in, const int* vec_in) {   // :585-627
     int next_sign_ind = INT32_MIN;
     int8_t k_val_acc = 0;
     *index = 0;
     int n = 0;
     uint64_t tmp_h_row = LC3T_MPVQ_OFFSETS[n][0];
+#pragma unroll 1
     for (int pos = dim_in - 1; pos >= 0; pos--) {
         const int8_t tmp_val = (int8_t)vec_in[pos];
         if (((uint32_t)next_sign_ind & 0x80000000u) == 0 && tmp_val != 0) *index = 2 * *index + (uint64_t)next_sign_ind;
@@ -141,210 +193,226 @@ __device__ void mvpq_enum(uint64_t* index, int* lead_sign_ind, int dim_in, const
     *lead_sign_ind = next_sign_ind;
 }
 
-__device__ void sns_run_quant(const float* scf, float* scfq, SnsRes* res) {   // :318-582
-    float st1[16], r1[16];
-    float dlf_min = INFINITY, dhf_min = INFINITY;
-    int ind_lf = 0, ind_hf = 0;
-    for (int i = 0; i < 32; i++) {
-        float dlf = 0.0f, dhf = 0.0f;
-        for (int n = 0; n < 8; n++) {
-            dlf += (scf[n] - LC3T_LFCB[i][n]) * (scf[n] - LC3T_LFCB[i][n]);
-            dhf += (scf[8 + n] - LC3T_HFCB[i][n]) * (scf[8 + n] - LC3T_HFCB[i][n]);
-        }
-        if (dlf < dlf_min) { ind_lf = i; dlf_min = dlf; }
-        if (dhf < dhf_min) { ind_hf = i; dhf_min = dhf; }
+// sns_run_quant :318-582.  In: lane n < 16 holds scf[n].  Out: lane n < 16 holds scfq[n].
+__device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane) {
+    float* xqs = S + 208;                 // [4][16] normalised shapes
+    float* t2s = S + 192;                 // [16] rotated residual
+    int* ys = (int*)(S + 320);            // [4][16] pulse vectors
+    const int n16 = lane & 15;
+    // stage 1: lane i evaluates codebook row i of both halves
+    float dlf = 0.0f, dhf = 0.0f;
+    for (int n = 0; n < 8; n++) {
+        const float a = shf(scf_v, n), b = shf(scf_v, 8 + n);
+        dlf += (a - LC3T_LFCB[lane][n]) * (a - LC3T_LFCB[lane][n]);
+        dhf += (b - LC3T_HFCB[lane][n]) * (b - LC3T_HFCB[lane][n]);
     }
-    for (int n = 0; n < 8; n++) { st1[n] = LC3T_LFCB[ind_lf][n]; st1[8 + n] = LC3T_HFCB[ind_hf][n]; }
-    for (int n = 0; n < 16; n++) r1[n] = scf[n] - st1[n];
-
-    float t2rot[16];
-    int y0[16], y1[16], y2[16], y3[16];
-    float xq0[16], xq1[16], xq2[16], xq3[16];
-    for (int n = 0; n < 16; n++) { t2rot[n] = 0.0f; y0[n] = y1[n] = y2[n] = y3[n] = 0; }
-    for (int row = 0; row < 16; row++)
-        for (int n = 0; n < 16; n++) t2rot[n] += r1[row] * LC3T_D[row][n];
-    int k = 0;
-    float abs_sum = 0.0f, abs_x[16];
-    for (int n = 0; n < 16; n++) { abs_x[n] = fabsf(t2rot[n]); abs_sum += abs_x[n]; }
+    int ind_lf = lane, ind_hf = lane;
+    warp_argmin(dlf, ind_lf);
+    if (!(dlf < INFINITY)) ind_lf = 0;
+    warp_argmin(dhf, ind_hf);
+    if (!(dhf < INFINITY)) ind_hf = 0;
+    const float st1 = n16 < 8 ? LC3T_LFCB[ind_lf][n16] : LC3T_HFCB[ind_hf][n16 - 8];
+    const float r1 = scf_v - st1;
+    // stage 2 target: t2rot = r1 * D
+    float t2rot = 0.0f;
+    for (int row = 0; row < 16; row++) t2rot += shf(r1, row) * LC3T_D[row][n16];
+    const float ax = fabsf(t2rot);
+    float abs_sum = 0.0f;
+    for (int n = 0; n < 16; n++) abs_sum += shf(ax, n);
     const float proj = (6.0f - 1.0f) / abs_sum;
+    int y3 = cast_i32(floorf(ax * proj));
     float corr_xy = 0.0f, energy_y = 0.0f;
+    int k = 0;
     for (int n = 0; n < 16; n++) {
-        y3[n] = cast_i32(floorf(abs_x[n] * proj));
-        if (y3[n] != 0) {
-            k += y3[n];
-            corr_xy += (float)y3[n] * abs_x[n];
-            energy_y += (float)y3[n] * (float)y3[n];
+        const int yn = shi(y3, n);
+        const float an = shf(ax, n);
+        if (yn != 0) {
+            k += yn;
+            corr_xy += (float)yn * an;
+            energy_y += (float)yn * (float)yn;
         }
     }
-    add_unit_pulse(abs_x, 16, k, 6, y3, &corr_xy, &energy_y);
-    for (int n = 0; n < 16; n++) y2[n] = y3[n];
-    add_unit_pulse(abs_x, 16, 6, 8, y2, &corr_xy, &energy_y);
-    for (int n = 0; n < 10; n++) y1[n] = y2[n];
+    add_unit_pulse_w(ax, 16, k, 6, y3, corr_xy, energy_y, lane);
+    int y2 = y3;
+    add_unit_pulse_w(ax, 16, 6, 8, y2, corr_xy, energy_y, lane);
+    int y1 = lane < 10 ? y2 : 0;
     int k1 = 8;
     for (int n = 10; n < 16; n++) {
-        if (y2[n] != 0) {
-            k1 -= y2[n];
-            corr_xy -= (float)y2[n] * abs_x[n];
-            energy_y -= (float)y2[n] * (float)y2[n];
+        const int yn = shi(y2, n);
+        const float an = shf(ax, n);
+        if (yn != 0) {
+            k1 -= yn;
+            corr_xy -= (float)yn * an;
+            energy_y -= (float)yn * (float)yn;
         }
     }
-    add_unit_pulse(abs_x, 10, k1, 10, y1, &corr_xy, &energy_y);
-    for (int n = 0; n < 10; n++) y0[n] = y1[n];
-    float max_abs_x = 0.0f;
-    int n_best = 0;
-    for (int n_c = 10; n_c < 16; n_c++) {
-        y0[n_c] = 0;
-        if (abs_x[n_c] > max_abs_x) { max_abs_x = abs_x[n_c]; n_best = n_c; }
+    add_unit_pulse_w(ax, 10, k1, 10, y1, corr_xy, energy_y, lane);
+    int y0 = lane < 10 ? y1 : 0;
+    {
+        float max_abs_x = 0.0f;
+        int n_best = 0;
+        for (int n_c = 10; n_c < 16; n_c++) {
+            const float an = shf(ax, n_c);
+            if (an > max_abs_x) { max_abs_x = an; n_best = n_c; }
+        }
+        if (lane == n_best) y0 = 1;
     }
-    y0[n_best] = 1;
-    for (int n = 0; n < 10; n++)
-        if (t2rot[n] < 0.0f) { y0[n] *= -1; y1[n] *= -1; y2[n] *= -1; y3[n] *= -1; }
-    for (int n = 10; n < 16; n++)
-        if (t2rot[n] < 0.0f) { y0[n] *= -1; y2[n] *= -1; y3[n] *= -1; }
-    normalize_candidate(y0, xq0, 16);
-    normalize_candidate(y1, xq1, 10);
-    normalize_candidate(y2, xq2, 16);
-    normalize_candidate(y3, xq3, 16);
-
+    if (t2rot < 0.0f) { y0 = -y0; y1 = -y1; y2 = -y2; y3 = -y3; }      // y1 is zero beyond n = 9 either way
+    const bool lo16 = lane < 16;
+    const float xq0 = normalize_w(y0, lo16), xq1 = normalize_w(y1, lane < 10), xq2 = normalize_w(y2, lo16),
+                xq3 = normalize_w(y3, lo16);
+    if (lo16) {
+        xqs[lane] = xq0; xqs[16 + lane] = xq1; xqs[32 + lane] = xq2; xqs[48 + lane] = xq3;
+        ys[lane] = y0; ys[16 + lane] = y1; ys[32 + lane] = y2; ys[48 + lane] = y3;
+        t2s[lane] = t2rot;
+    }
+    __syncwarp();
+    // shape / gain search: candidate c = lane, in the reference's (j, i) order
+    int cj = 0, ci = 0;
+    const float* gains = LC3T_SNS_VQ_REG_ADJ_GAINS;
+    if (lane >= 7) { cj = 3; ci = lane - 7; gains = LC3T_SNS_VQ_FAR_ADJ_GAINS; }
+    else if (lane >= 4) { cj = 2; ci = lane - 4; gains = LC3T_SNS_VQ_NEAR_ADJ_GAINS; }
+    else if (lane >= 1) { cj = 1; ci = lane - 1; gains = LC3T_SNS_VQ_REG_LF_ADJ_GAINS; }
+    float d = INFINITY, g_c = 0.0f;
+    if (lane < 14) {
+        g_c = gains[ci];
+        d = 0.0f;
+        for (int n = 0; n < 16; n++) {
+            const float diff = t2s[n] - g_c * xqs[cj * 16 + n];
+            d += diff * diff;
+        }
+    }
+    int best = lane;
+    warp_argmin(d, best);
     int shape_j = 0, gind = 0;
     float g_sel = 0.0f;
-    const float* xq_sel = xq0;
-    float d_min = INFINITY;
-    for (int j = 0; j < 4; j++) {
-        int g_max;
-        const float *gains, *xq;
-        switch (j) {
-            case 0: g_max = 1; gains = LC3T_SNS_VQ_REG_ADJ_GAINS; xq = xq0; break;
-            case 1: g_max = 3; gains = LC3T_SNS_VQ_REG_LF_ADJ_GAINS; xq = xq1; break;
-            case 2: g_max = 3; gains = LC3T_SNS_VQ_NEAR_ADJ_GAINS; xq = xq2; break;
-            default: g_max = 7; gains = LC3T_SNS_VQ_FAR_ADJ_GAINS; xq = xq3; break;
-        }
-        for (int i = 0; i < g_max; i++) {
-            float d = 0.0f;
-            for (int n = 0; n < 16; n++) {
-                const float diff = t2rot[n] - gains[i] * xq[n];
-                d += diff * diff;
-            }
-            if (d < d_min) { shape_j = j; gind = i; d_min = d; g_sel = gains[i]; xq_sel = xq; }
-        }
+    if (d < INFINITY) {
+        shape_j = best >= 7 ? 3 : best >= 4 ? 2 : best >= 1 ? 1 : 0;
+        gind = best - (best >= 7 ? 7 : best >= 4 ? 4 : best >= 1 ? 1 : 0);
     }
+    g_sel = d < INFINITY ? shf(g_c, best) : 0.0f;
     const int lsb_gain = gind & 1;
     uint64_t idxa = 0, idxb = 0;
     int ls_inda = 0, ls_indb = 0;
     uint64_t joint;
     switch (shape_j) {
         case 0:
-            mvpq_enum(&idxa, &ls_inda, 10, y0);
-            mvpq_enum(&idxb, &ls_indb, 6, y0 + 10);
+            mvpq_enum(&idxa, &ls_inda, 10, ys);
+            mvpq_enum(&idxb, &ls_indb, 6, ys + 10);
             joint = (2 * idxb + (uint64_t)(int64_t)ls_indb + 2) * 2390004ull + idxa;
             break;
         case 1:
-            mvpq_enum(&idxa, &ls_inda, 10, y1);
+            mvpq_enum(&idxa, &ls_inda, 10, ys + 16);
             joint = (uint64_t)lsb_gain * 2390004ull + idxa;
             break;
         case 2:
-            mvpq_enum(&idxa, &ls_inda, 16, y2);
+            mvpq_enum(&idxa, &ls_inda, 16, ys + 32);
             joint = idxa;
             break;
         default:
-            mvpq_enum(&idxa, &ls_inda, 16, y3);
+            mvpq_enum(&idxa, &ls_inda, 16, ys + 48);
             joint = 15158272ull + (uint64_t)lsb_gain + 2 * idxa;
             break;
     }
-    for (int n = 0; n < 16; n++) {
-        float factor = 0.0f;
-        for (int col = 0; col < 16; col++) factor += xq_sel[col] * LC3T_D[n][col];
-        scfq[n] = st1[n] + g_sel * factor;
-    }
+    float factor = 0.0f;
+    for (int col = 0; col < 16; col++) factor += xqs[shape_j * 16 + col] * LC3T_D[n16][col];
+    const float scfq = st1 + g_sel * factor;
     res->ind_lf = ind_lf; res->ind_hf = ind_hf; res->shape_j = shape_j; res->gind = gind;
     res->ls_inda = ls_inda; res->ls_indb = ls_indb; res->joint = joint;
+    __syncwarp();
+    return scfq;
 }
 
-__device__ SnsRes sns_encode(const EncConfig& c, float* x, const float* e_b, bool attack) {   // :203-282
+// SpectralNoiseShaping::run :203-282.  S[0..64) holds the band energies on entry.
+__device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool attack, int lane) {
     const float* W = SNS_W;
-    float padded[64], e[64];
+    float* eb = S;
+    float* e = S + 64;
     const int nb = c.nb, diff = 64 - nb;
-    if (diff > 0) {
-        for (int i = 0; i < 64; i++) padded[i] = 0.0f;
-        for (int i = 0; i < diff; i++) { padded[2 * i] = e_b[i]; padded[2 * i + 1] = e_b[i]; }
-        for (int i = 0; i < nb - diff; i++) padded[2 * diff + i] = e_b[diff + i];
-    } else {
-        for (int i = 0; i < 64; i++) padded[i] = e_b[i];
+    for (int b = lane; b < 64; b += 32) {
+        auto pad = [&](int j) -> float { return diff > 0 ? (j < 2 * diff ? eb[j >> 1] : eb[j - diff]) : eb[j]; };
+        float v;
+        if (b == 0) v = 0.75f * pad(0) + 0.25f * pad(1);
+        else if (b == 63) v = 0.25f * pad(62) + 0.75f * pad(63);
+        else v = 0.25f * pad(b - 1) + 0.5f * pad(b) + 0.25f * pad(b + 1);
+        e[b] = v * c.pre_emph[b];
     }
-    e[0] = 0.75f * padded[0] + 0.25f * padded[1];
-    for (int b = 1; b < 63; b++) e[b] = 0.25f * padded[b - 1] + 0.5f * padded[b] + 0.25f * padded[b + 1];
-    e[63] = 0.25f * padded[62] + 0.75f * padded[63];
-    for (int b = 0; b < 64; b++) e[b] *= c.pre_emph[b];
+    __syncwarp();
     float total = 0.0f;
     for (int b = 0; b < 64; b++) total += e[b];
     total = (total / 64.0f) * powi_nt(10.0f, -4);
     const float floor_ = maxf_rs(powi_nt(2.0f, -32), total);
-    for (int b = 0; b < 64; b++) e[b] = maxf_rs(e[b], floor_);
-    for (int b = 0; b < 64; b++) e[b] = log2f_msun(1.1920929e-07f + e[b]) / 2.0f;
-    float ds[16];
-    ds[0] = W[0] * e[0];
-    for (int k = 1; k < 6; k++) ds[0] += W[k] * e[k - 1];
-    for (int b2 = 1; b2 < 15; b2++) {
-        float v = 0.0f;
-        const int from = 4 * b2 - 1;
-        for (int k = 0; k < 6; k++) v += W[k] * e[from + k];
-        ds[b2] = v;
+    __syncwarp();
+    for (int b = lane; b < 64; b += 32) e[b] = log2f_msun(1.1920929e-07f + maxf_rs(e[b], floor_)) / 2.0f;
+    __syncwarp();
+    const int n16 = lane & 15;
+    float ds;
+    if (n16 == 0) {
+        ds = W[0] * e[0];
+        for (int k = 1; k < 6; k++) ds += W[k] * e[k - 1];
+    } else if (n16 == 15) {
+        ds = W[5] * e[63];
+        for (int k = 0; k < 5; k++) ds += W[k] * e[60 + k - 1];
+    } else {
+        ds = 0.0f;
+        const int from = 4 * n16 - 1;
+        for (int k = 0; k < 6; k++) ds += W[k] * e[from + k];
     }
-    ds[15] = W[5] * e[63];
-    for (int k = 0; k < 5; k++) ds[15] += W[k] * e[60 + k - 1];
     float tot = 0.0f;
-    for (int n = 0; n < 16; n++) tot += ds[n];
+    for (int n = 0; n < 16; n++) tot += shf(ds, n);
     const float avg = tot / 16.0f;
-    for (int n = 0; n < 16; n++) ds[n] = 0.85f * (ds[n] - avg);
-    float scf[16];
+    ds = 0.85f * (ds - avg);
+    float scf = ds;
     if (attack) {
-        scf[0] = (ds[0] + ds[1] + ds[2]) / 3.0f;
-        scf[1] = (ds[0] + ds[1] + ds[2] + ds[3]) / 4.0f;
-        for (int n = 2; n < 14; n++) {
-            float s = 0.0f;
-            for (int j = n - 2; j < n + 3; j++) s += ds[j];
-            scf[n] = s / 5.0f;
+        const int lo = n16 - 2 < 0 ? 0 : n16 - 2, hi = n16 + 2 > 15 ? 15 : n16 + 2;
+        float s = shf(ds, lo);
+        for (int j = 1; j < 5; j++) {
+            const float v = shf(ds, lo + j > 15 ? 15 : lo + j);
+            if (lo + j <= hi) s += v;
         }
-        scf[14] = (ds[12] + ds[13] + ds[14] + ds[15]) / 4.0f;
-        scf[15] = (ds[13] + ds[14] + ds[15]) / 3.0f;
+        scf = s / (float)(hi - lo + 1);
         float st = 0.0f;
-        for (int n = 0; n < 16; n++) st += scf[n];
+        for (int n = 0; n < 16; n++) st += shf(scf, n);
         const float sa = st / 16.0f;
         const float att = c.n_ms == LC3B_10MS ? 0.5f : 0.3f;
-        for (int n = 0; n < 16; n++) scf[n] = att * (scf[n] - sa);
-    } else {
-        for (int n = 0; n < 16; n++) scf[n] = ds[n];
+        scf = att * (scf - sa);
     }
-    float scfq[16];
     SnsRes res;
-    sns_run_quant(scf, scfq, &res);
-#ifdef LC3B_DEBUG_PRINT
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        printf("e_b0..3 %g %g %g %g  e[0..3] %g %g %g %g pre %g %g\n", e_b[0], e_b[1], e_b[2], e_b[3], e[0], e[1], e[2], e[3], c.pre_emph[0], c.pre_emph[1]);
-        printf("scf "); for (int n = 0; n < 16; n++) printf("%g ", scf[n]); printf("\nscfq "); for (int n = 0; n < 16; n++) printf("%g ", scfq[n]);
-        printf("\nres %d %d %d %d\n", res.ind_lf, res.ind_hf, res.shape_j, res.gind);
+    const float scfq = sns_run_quant_w(scf, S, &res, lane);
+    // 16 -> 64 interpolation :85-98 of the decoder's twin, then the nb < 64 folding and g = 2^-scf
+    float* it = S + 64;
+    float* gs = S;
+    const float s00 = shf(scfq, 0);
+    for (int j = 0; j < 2; j++) {
+        const int b = lane + 32 * j;
+        const int bb = b < 2 ? 2 : b;
+        const int n = (bb - 2) >> 2, r = (bb - 2) & 3;
+        const float cf = 0.125f + 0.25f * (float)r;
+        const int i0 = n < 15 ? n : 15, i1 = n < 15 ? n + 1 : 14;
+        const float s0 = shf(scfq, i0), s1 = shf(scfq, i1);
+        float v = n < 15 ? s0 + (cf * (s1 - s0)) : s0 + (cf * (s0 - s1));
+        if (b < 2) v = s00;
+        it[b] = v;
     }
-#endif
-    float it[64];
-    it[0] = scfq[0];
-    it[1] = scfq[0];
-    for (int n = 0; n < 15; n++) {
-        const float d = scfq[n + 1] - scfq[n];
-        it[4 * n + 2] = scfq[n] + (0.125f * d);
-        it[4 * n + 3] = scfq[n] + (0.375f * d);
-        it[4 * n + 4] = scfq[n] + (0.625f * d);
-        it[4 * n + 5] = scfq[n] + (0.875f * d);
+    __syncwarp();
+    float itv[2];
+    for (int j = 0; j < 2; j++) {
+        const int b = lane + 32 * j;
+        float v = it[b];
+        if (diff > 0) {
+            if (b < diff) v = (it[2 * b] + it[2 * b + 1]) / 2.0f;
+            else if (b < nb) v = it[diff + 1];
+        }
+        itv[j] = v;
     }
-    it[62] = scfq[15] + (0.125f * (scfq[15] - scfq[14]));
-    it[63] = scfq[15] + (0.375f * (scfq[15] - scfq[14]));
-    if (diff > 0) {
-        for (int i = 0; i < diff; i++) it[i] = (it[2 * i] + it[2 * i + 1]) / 2.0f;
-        for (int i = diff; i < nb; i++) it[i] = it[diff + 1];
+    __syncwarp();
+    for (int j = 0; j < 2; j++) gs[lane + 32 * j] = exp2f_msun(-itv[j]);
+    __syncwarp();
+    for (int k = lane; k < c.ne; k += 32) {
+        const int b = c.band_of[k];
+        if (b < nb) x[k] *= gs[b];
     }
-    for (int b = 0; b < nb; b++) {
-        const float g = exp2f_msun(-it[b]);
-        for (int k = c.band_idx[b]; k < c.band_idx[b + 1]; k++) x[k * XS] *= g;
-    }
+    __syncwarp();
     return res;
 }
 
@@ -376,178 +444,238 @@ __device__ const TnsP TNS_T75[5] = {
     {2, {9, 150}, {150, 300}, {{9, 56, 103}, {150, 200, 250}}, {{56, 103, 150}, {200, 250, 300}}},
 };
 
-__device__ void tns_encode(const EncConfig& c, float* x, int p_bw, int nbits, bool near_nyquist, TnsRes& r) {   // :40-78
+// TemporalNoiseShaping::run :40-78.  Scratch: ac[2][27] at S, raw reflection coefficients at S+64,
+// results rc_i (int[16]) at S+256 and rc_q (float[16]) at S+272 (kept until the bitstream is written).
+__device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, int nbits, bool near_nyquist, TnsRes& r, int lane) {
     const TnsP& tp = (c.n_ms == LC3B_10MS ? TNS_T10 : TNS_T75)[p_bw];
-    for (int i = 0; i < 16; i++) { r.rc_i[i] = 0; r.rc_q[i] = 0.0f; }
+    float* ac = S;
+    float* rc_raw = S + 64;
+    int* rc_i = (int*)(S + 256);
+    float* rc_q = S + 272;
+    r.rc_i = rc_i;
     r.num_filters = tp.nf;
     r.lpc_weighting = (c.n_ms == LC3B_10MS ? nbits < 480 : nbits < 360) ? 1 : 0;
-    const int ne = c.ne;
     const float* LAG = TNS_LAG;
+    // compute_normalized_autocorrelation :80-115: 3 sub-blocks x 9 lags = 27 ordered sums per filter, one per lane
     for (int f = 0; f < tp.nf; f++) {
-        // compute_normalized_autocorrelation :80-115.  The reference recomputes the sub-block energy for every lag and
-        // walks the sub-block once per lag; the sums below are the same sums (same operands, same order), gathered in
-        // ONE walk per sub-block with the last eight lines held in registers.
-        float es_s[3], ac_s[3][9];
-        for (int sb = 0; sb < 3; sb++) {
+        if (lane < 27) {
+            const int sb = lane / 9, lag = lane - 9 * sb;
             const int start = tp.ss[f][sb], stop = tp.se[f][sb];
-            float acc[9], w8[8];
-#pragma unroll
-            for (int k = 0; k < 9; k++) acc[k] = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 8; k++) w8[k] = 0.0f;
-            int cnt = 0;
-            for (int n = start; n < stop; n++) {
-                const float xn = x[n * XS];
-                acc[0] += xn * xn;
-#pragma unroll
-                for (int k = 1; k < 9; k++) if (cnt >= k) acc[k] += w8[k - 1] * xn;
-#pragma unroll
-                for (int k = 7; k > 0; k--) w8[k] = w8[k - 1];
-                w8[0] = xn;
-                cnt++;
-            }
-            es_s[sb] = acc[0];
-#pragma unroll
-            for (int k = 0; k < 9; k++) ac_s[sb][k] = acc[k];
+            float acc = 0.0f;
+            for (int n = start + lag; n < stop; n++) acc += x[n - lag] * x[n];
+            ac[f * 27 + lane] = acc;
         }
+    }
+    __syncwarp();
+    {   // Levinson-Durbin :204-232 and LPC weighting / LPC -> RC :234-257: lane f works on filter f
+        const int f = (lane & 1) < tp.nf ? (lane & 1) : 0;
+        const float* acf = ac + f * 27;
         float rr[9];
+#pragma unroll
         for (int k = 0; k < 9; k++) {
             const float r0 = k == 0 ? 3.0f : 0.0f;
             float rk = 0.0f, e_prod = 1.0f;
+#pragma unroll
             for (int sb = 0; sb < 3; sb++) {
-                e_prod *= es_s[sb];
-                rk += ac_s[sb][k] / es_s[sb];
+                e_prod *= acf[sb * 9];
+                rk += acf[sb * 9 + k] / acf[sb * 9];
             }
             rr[k] = (e_prod == 0.0f ? r0 : rk) * LAG[k];
         }
-        float mem[2][9];
-        for (int i = 0; i < 9; i++) mem[0][i] = mem[1][i] = 0.0f;
-        float* a = mem[0];
-        float* a_last = mem[1];
+        float a[9], al[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) a[i] = al[i] = 0.0f;
         float e = rr[0];
         a[0] = 1.0f;
+#pragma unroll
         for (int k = 1; k < 9; k++) {
-            float* tmp = a_last; a_last = a; a = tmp;
+#pragma unroll
+            for (int i = 0; i < 9; i++) al[i] = a[i];
             float rc = 0.0f;
-            for (int n = 0; n < k; n++) rc -= a_last[n] * rr[k - n];
+#pragma unroll
+            for (int n = 0; n < k; n++) rc -= al[n] * rr[k - n];
             if (e != 0.0f) rc /= e;
             a[0] = 1.0f;
-            for (int n = 1; n < k; n++) a[n] = a_last[n] + rc * a_last[k - n];
+#pragma unroll
+            for (int n = 1; n < k; n++) a[n] = al[n] + rc * al[k - n];
             a[k] = rc;
             e *= 1.0f - rc * rc;
         }
         const float pred_gain = e == 0.0f ? rr[0] : rr[0] / e;
-        float* rcq = r.rc_q + f * 8;
+        float rcq[8];
         if (pred_gain > 1.5f && !near_nyquist) {
             float gamma = 1.0f;
             if (r.lpc_weighting > 0 && pred_gain < 2.0f) gamma -= (1.0f - 0.85f) * (2.0f - pred_gain) / (2.0f - 1.5f);
+#pragma unroll
             for (int k = 0; k < 9; k++) a[k] *= powi_nt(gamma, k);
-            float* a_k = a;
-            float* a_km1 = a_last;
+#pragma unroll
             for (int k = 8; k >= 1; k--) {
-                rcq[k - 1] = a_k[k];
+                rcq[k - 1] = a[k];
                 const float ee = 1.0f - rcq[k - 1] * rcq[k - 1];
+#pragma unroll
                 for (int n = 1; n < k; n++) {
-                    a_km1[n] = a_k[n] - rcq[k - 1] * a_k[k - n];
-                    a_km1[n] /= ee;
+                    float v = a[n] - rcq[k - 1] * a[k - n];
+                    v /= ee;
+                    al[n] = v;
                 }
-                float* tmp = a_k; a_k = a_km1; a_km1 = tmp;
+#pragma unroll
+                for (int n = 1; n < k; n++) a[n] = al[n];
             }
         } else {
+#pragma unroll
             for (int k = 0; k < 8; k++) rcq[k] = 0.0f;
         }
-    }
-    const float step = (float)M_PI / 17.0f;
-    for (int f = 0; f < tp.nf; f++) {
-        for (int k = 0; k < 8; k++) {
-            const int idx = f * 8 + k;
-            r.rc_i[idx] = (int)(tns_to_int(asinf_msun(r.rc_q[idx]) / step) + 8);
-            r.rc_q[idx] = c.tns_sin[r.rc_i[idx]];        // sin(step * (rc_i - 8)), tabulated (17 arguments)
+        if (lane < tp.nf) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) rc_raw[lane * 8 + k] = rcq[k];
         }
-        int k = 7;
-        while (k >= 0 && r.rc_i[f * 8 + k] == 8) k--;
-        r.rc_order[f] = k + 1;
     }
-    for (int f = tp.nf; f < 2; f++) {
-        for (int k = 0; k < 8; k++) { r.rc_i[f * 8 + k] = 8; r.rc_q[f * 8 + k] = 0.0f; }
-        r.rc_order[f] = 0;
+    __syncwarp();
+    if (lane < 16) {                                         // quantisation :259-283: one coefficient per lane
+        const float step = (float)M_PI / 17.0f;
+        int qi = 8;
+        float qv = 0.0f;
+        if (lane < 8 * tp.nf) {
+            qi = (int)(tns_to_int(asinf_msun(rc_raw[lane]) / step) + 8);
+            qv = c.tns_sin[qi];                              // sin(step * (rc_i - 8)), tabulated (17 arguments)
+        }
+        rc_i[lane] = qi;
+        rc_q[lane] = qv;
     }
+    __syncwarp();
     int nbits_tns = 0;
+    for (int f = 0; f < 2; f++) {
+        int k = 7;
+        while (k >= 0 && rc_i[f * 8 + k] == 8) k--;
+        r.rc_order[f] = f < tp.nf ? k + 1 : 0;
+    }
     for (int f = 0; f < tp.nf; f++) {
         const int ob = r.rc_order[f] != 0 ? LC3T_AC_TNS_ORDER_BITS[r.lpc_weighting][r.rc_order[f] - 1] : 0;
         int cb = 0;
-        for (int k = 0; k < r.rc_order[f]; k++) cb += LC3T_AC_TNS_COEF_BITS[k][r.rc_i[f * 8 + k]];
+        for (int k = 0; k < r.rc_order[f]; k++) cb += LC3T_AC_TNS_COEF_BITS[k][rc_i[f * 8 + k]];
         nbits_tns += (int)ceilf((2048.0f + (float)ob + (float)cb) / 2048.0f);
     }
     r.nbits_tns = nbits_tns;
-    float st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // forward lattice :285-310 as a systolic pipeline: lane k is stage k and keeps st[k]; sample n enters lane 0 at
+    // step n and leaves the last stage (lane order-1) at step n + order - 1.  The state survives from filter 0 to 1.
+    float st = 0.0f;
     for (int f = 0; f < tp.nf; f++) {
-        if (r.rc_order[f] == 0) continue;
-        for (int n = tp.start[f]; n < tp.stop[f]; n++) {
-            float t = x[n * XS], st_save = t;
-            const int po = r.rc_order[f] - 1;
-            for (int k = 0; k < po; k++) {
-                const float rq = r.rc_q[f * 8 + k];
-                const float st_tmp = rq * t + st[k];
-                t += rq * st[k];
-                st[k] = st_save;
-                st_save = st_tmp;
+        const int order = r.rc_order[f];
+        if (order == 0) continue;
+        const int po = order - 1;
+        const float rq = lane <= po ? rc_q[f * 8 + lane] : 0.0f;
+        const int start = tp.start[f], N = tp.stop[f] - start;
+        float t_out = 0.0f, s_out = 0.0f;
+        for (int step = 0; step < N + po; step++) {
+            float t_in = __shfl_up_sync(FULL, t_out, 1), s_in = __shfl_up_sync(FULL, s_out, 1);
+            if (lane == 0) { t_in = step < N ? x[start + step] : 0.0f; s_in = t_in; }
+            const int n = step - lane;
+            if (lane <= po && n >= 0 && n < N) {
+                if (lane < po) {
+                    const float st_tmp = rq * t_in + st;
+                    t_out = t_in + rq * st;
+                    st = s_in;
+                    s_out = st_tmp;
+                } else {
+                    t_out = t_in + rq * st;
+                    st = s_in;
+                    x[start + n] = t_out;
+                }
             }
-            t += r.rc_q[f * 8 + po] * st[po];
-            st[po] = st_save;
-            x[n * XS] = t;
         }
+        __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------- spectral_quantization.rs
 struct BitCons { int rate_flag, lastnz, nbits_lsb, lastnz_trunc, nbits_est, nbits_trunc; bool mode_flag; };
 
-__device__ BitCons compute_bit_consumption(int ne, int fs_ind, const int16_t* xq, int nbits, int nbits_spec) {   // :265-348
+// magnitude pair of a two-tuple after its escape levels, and the context digit it leaves behind (:333-346)
+struct Tup { int q0, q1; uint32_t a0, b0, a, b; int L; };
+__device__ __forceinline__ Tup tup_of(uint32_t w) {
+    Tup t;
+    t.q0 = (int)(int16_t)(w & 0xffffu);
+    t.q1 = (int)(int16_t)(w >> 16);
+    t.a0 = (uint32_t)(t.q0 < 0 ? -t.q0 : t.q0) & 0xffffu;
+    t.b0 = (uint32_t)(t.q1 < 0 ? -t.q1 : t.q1) & 0xffffu;
+    const uint32_t m = t.a0 > t.b0 ? t.a0 : t.b0;
+    t.L = m < 4 ? 0 : 30 - __clz(m);                     // escapes: while max(a, b) >= 4 { a >>= 1; b >>= 1 }
+    t.a = t.a0 >> t.L;
+    t.b = t.b0 >> t.L;
+    return t;
+}
+__device__ __forceinline__ int tup_digit(const Tup& t) {
+    const int l = t.L < 3 ? t.L : 3;
+    return l <= 1 ? 1 + (int)(t.a + t.b) * (l + 1) : 12 + l;
+}
+
+// compute_bit_consumption :265-348.  The context of tuple n is 16 * digit(n-2) + digit(n-1), so every tuple's cost
+// is known from its own and its two predecessors' magnitudes: lane l walks tuples [l*CH, (l+1)*CH), the running
+// totals the truncation test needs are integer prefix sums.
+__device__ BitCons compute_bit_consumption_w(int ne, int fs_ind, const int16_t* xq, uint32_t* pre, int nbits, int nbits_spec, int lane) {
     BitCons bc;
     bc.rate_flag = nbits > (160 + fs_ind * 160) ? 512 : 0;
     bc.mode_flag = nbits >= (480 + fs_ind * 160);
-    int lastnz = ne;
-    while (lastnz > 2 && xq[(lastnz - 1) * XS] == 0 && xq[(lastnz - 2) * XS] == 0) lastnz -= 2;
-    uint32_t est = 0, trunc = 0;
-    int nbits_lsb = 0, lastnz_trunc = 2, c = 0;
-    for (int n = 0; n < lastnz; n += 2) {
-        int t = c + bc.rate_flag;
-        if (n > ne / 2) t += 256;
-        const int q0 = xq[n * XS], q1 = xq[(n + 1) * XS];
-        uint32_t a = (uint32_t)(q0 < 0 ? -q0 : q0) & 0xffffu, a_lsb = a;
-        uint32_t b = (uint32_t)(q1 < 0 ? -q1 : q1) & 0xffffu, b_lsb = b;
-        int lev = 0;
-        while ((a > b ? a : b) >= 4) {
-            const int pki = LC3T_AC_SPEC_LOOKUP[t + lev * 1024];
+    const uint32_t* xw = (const uint32_t*)xq;
+    const int nt = ne >> 1;
+    const int CH = (nt + 31) >> 5;
+    const int n0 = lane * CH;
+    int last = -1;
+#pragma unroll 1
+    for (int n = n0; n < n0 + CH && n < nt; n++) if (xw[n] != 0) last = n;
+    last = warp_max_i(last);
+    const int lastnz = last < 0 ? 2 : 2 * last + 2;
+    const int ntz = lastnz >> 1;
+    int d2 = 0, d1 = 0;                                   // digits of tuples n-2, n-1
+    if (n0 >= 1 && n0 - 1 < ntz) d1 = tup_digit(tup_of(xw[n0 - 1]));
+    if (n0 >= 2 && n0 - 2 < ntz) d2 = tup_digit(tup_of(xw[n0 - 2]));
+    uint32_t est = 0;
+    int lsb = 0;
+    const int n1 = n0 + CH < ntz ? n0 + CH : ntz;
+#pragma unroll 1
+    for (int n = n0; n < n1; n++) {
+        const Tup t = tup_of(xw[n]);
+        const int tc = d2 * 16 + d1 + bc.rate_flag + (2 * n > ne / 2 ? 256 : 0);
+#pragma unroll 1
+        for (int lev = 0; lev < t.L; lev++) {
+            const int pki = LC3T_AC_SPEC_LOOKUP[tc + (lev < 3 ? lev : 3) * 1024];
             est += LC3T_AC_SPEC_BITS[pki][16];
-            if (lev == 0 && bc.mode_flag) nbits_lsb += 2; else est += 2 * 2048;
-            a >>= 1;
-            b >>= 1;
-            lev = lev + 1 < 3 ? lev + 1 : 3;
+            if (lev == 0 && bc.mode_flag) lsb += 2; else est += 2 * 2048;
         }
-        const int pki = LC3T_AC_SPEC_LOOKUP[t + lev * 1024];
-        const int sym = (int)(a + 4 * b);
-        est += LC3T_AC_SPEC_BITS[pki][sym];
-        if (a_lsb > 0) est += 2048;
-        if (b_lsb > 0) est += 2048;
-        if (lev > 0 && bc.mode_flag) {
-            a_lsb >>= 1;
-            b_lsb >>= 1;
-            if (a_lsb == 0 && q0 != 0) nbits_lsb += 1;
-            if (b_lsb == 0 && q1 != 0) nbits_lsb += 1;
+        const int pki = LC3T_AC_SPEC_LOOKUP[tc + (t.L < 3 ? t.L : 3) * 1024];
+        est += LC3T_AC_SPEC_BITS[pki][t.a + 4 * t.b];
+        if (t.a0 > 0) est += 2048;
+        if (t.b0 > 0) est += 2048;
+        if (t.L > 0 && bc.mode_flag) {
+            if ((t.a0 >> 1) == 0 && t.q0 != 0) lsb += 1;
+            if ((t.b0 >> 1) == 0 && t.q1 != 0) lsb += 1;
         }
-        if ((q0 != 0 || q1 != 0) && (int)ceilf((float)est / 2048.0f) <= nbits_spec) {
-            lastnz_trunc = n + 2;
-            trunc = est;
-        }
-        t = lev <= 1 ? 1 + (int)(a + b) * (lev + 1) : 12 + lev;
-        c = (c & 15) * 16 + t;
+        pre[n] = est | ((t.q0 != 0 || t.q1 != 0) ? 0x80000000u : 0u);     // est < 2^31
+        d2 = d1;
+        d1 = tup_digit(t);
     }
+    const uint32_t incl = warp_incl_scan(est, lane);
+    const uint32_t base = incl - est;
+    const uint32_t est_total = __shfl_sync(FULL, incl, 31);
+    int qual = -1;                                        // last tuple of this lane that is non-zero and still fits
+    uint32_t qual_est = 0;
+#pragma unroll 1
+    for (int n = n0; n < n1; n++) {
+        const uint32_t pv = pre[n];
+        const uint32_t e_n = base + (pv & 0x7fffffffu);
+        if ((pv >> 31) != 0 && (int)ceilf((float)e_n / 2048.0f) <= nbits_spec) { qual = n; qual_est = e_n; }
+    }
+    const int qmax = warp_max_i(qual);
+    uint32_t trunc = 0;
+    int lastnz_trunc = 2;
+    if (qmax >= 0) {
+        lastnz_trunc = 2 * qmax + 2;
+        trunc = __shfl_sync(FULL, qual_est, qmax / CH);
+    }
+    bc.nbits_lsb = warp_sum_i(lsb);
     bc.lastnz = lastnz;
     bc.lastnz_trunc = lastnz_trunc;
-    bc.nbits_lsb = nbits_lsb;
-    bc.nbits_est = (int)ceilf((float)est / 2048.0f) + nbits_lsb;
+    bc.nbits_est = (int)ceilf((float)est_total / 2048.0f) + bc.nbits_lsb;
     bc.nbits_trunc = (int)ceilf((float)trunc / 2048.0f);
     return bc;
 }
@@ -558,23 +686,26 @@ __device__ float gain_of(const EncConfig& c, int gg_ind, int gg_off) {   // 10^(
     return powf_msun(10.0f, ((float)gg_ind + (float)gg_off) / 28.0f);
 }
 
-__device__ BitCons quantize_spectrum(const EncConfig& c, const float* xf, int16_t* xq, int nbits, int gg_off, int gg_ind,
-                                     int nbits_spec, float* gg_out, bool* lsb_mode) {   // :230-263
+__device__ __noinline__ BitCons quantize_spectrum_w(const EncConfig& c, const float* xf, int16_t* xq, uint32_t* pre, int nbits, int gg_off, int gg_ind,
+                                       int nbits_spec, float* gg_out, bool* lsb_mode, int lane) {   // :230-263
     const int ne = c.ne;
     const float gg = gain_of(c, gg_ind, gg_off);
-    for (int k = 0; k < ne; k++) {
-        const float v = xf[k * XS];
-        xq[k * XS] = v >= 0.0f ? cast_i16(v / gg + 0.375f) : cast_i16(v / gg - 0.375f);
+    for (int k = lane; k < ne; k += 32) {
+        const float v = xf[k];
+        xq[k] = v >= 0.0f ? cast_i16(v / gg + 0.375f) : cast_i16(v / gg - 0.375f);
     }
-    BitCons bc = compute_bit_consumption(ne, c.fs_ind, xq, nbits, nbits_spec);
-    for (int k = bc.lastnz_trunc; k < bc.lastnz; k++) xq[k * XS] = 0;
+    __syncwarp();
+    BitCons bc = compute_bit_consumption_w(ne, c.fs_ind, xq, pre, nbits, nbits_spec, lane);
+    for (int k = bc.lastnz_trunc + lane; k < bc.lastnz; k += 32) xq[k] = 0;
+    __syncwarp();
     *gg_out = gg;
     *lsb_mode = bc.mode_flag && bc.nbits_est > nbits_spec;
     return bc;
 }
 
-__device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const float* xf, int16_t* xq, float* e, int nbits,
-                                      int nbits_bw, int nbits_tns, int nbits_ltpf) {   // :75-120
+// SpectralQuantization::run :75-120.  e4: [ne/4] energies, T: [224] scratch (bisection terms, then per-tuple bit prefixes).
+__device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const float* xf, int16_t* xq, float* e4, float* T,
+                                        int nbits, int nbits_bw, int nbits_tns, int nbits_ltpf, int lane) {
     const int ne = c.ne, fs_ind = c.fs_ind;
     int lg = 0;
     while ((1 << lg) < ne / 2) lg++;
@@ -583,6 +714,7 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
     const bool reset_offset_old = es[ES_Q_RESET_OFFSET_OLD] != 0;
     const float nbits_offset_old = __uint_as_float((uint32_t)es[ES_Q_NBITS_OFFSET_OLD]);
     const int nbits_est_old = es[ES_Q_NBITS_EST_OLD];
+    __syncwarp();                                                      // every lane has read the state before lane 0 updates it
     float nbits_offset;
     if (reset_offset_old) nbits_offset = 0.0f;
     else {
@@ -597,34 +729,58 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
     const int q = (int16_t)nbits / (int16_t)(10 * (fs_ind + 1));
     const int gg_off = -(115 < q ? 115 : q) - 105 - 5 * (fs_ind + 1);
     const int ne4 = ne / 4;
-    for (int i = 0; i < ne4; i++) {                                    // compute_spectral_energy :390-395
-        const float* pp = xf + 4 * i * XS;
-        const float total = pp[0] * pp[0] + pp[XS] * pp[XS] + pp[2 * XS] * pp[2 * XS] + pp[3 * XS] * pp[3 * XS];
-        e[i * XS] = 10.0f * log10f_msun(1.1920929e-07f + total);
+    float xmax = 0.0f;                                                 // global_gain_limitation :212-228 (max is order-free)
+    for (int i = lane; i < ne4; i += 32) {                             // compute_spectral_energy :390-395
+        const float4 p4 = ((const float4*)xf)[i];
+        const float total = p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
+        e4[i] = 10.0f * log10f_msun(1.1920929e-07f + total);
+        xmax = maxf_rs(xmax, fabsf(p4.x));
+        xmax = maxf_rs(xmax, fabsf(p4.y));
+        xmax = maxf_rs(xmax, fabsf(p4.z));
+        xmax = maxf_rs(xmax, fabsf(p4.w));
     }
-    int fac = 256, gg_ind = 255;                                       // global_gain_estimation :174-210
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) xmax = maxf_rs(xmax, __shfl_xor_sync(FULL, xmax, off));
+    __syncwarp();
+    // global_gain_estimation :174-210.  Per step: the 100 terms of the ordered sum are produced by the lanes (the
+    // only coupling is "has a louder block been seen above me", a ballot), then added from the top down by one chain.
+    int fac = 256, gg_ind = 255;
+    const int rounds = (ne4 + 31) >> 5;
     for (int it = 0; it < 8; it++) {
         fac >>= 1;
         gg_ind -= fac;
-        float tmp = 0.0f;
-        bool is_zero = true;
         const float g = (float)gg_ind + (float)gg_off;
-        for (int i = ne4 - 1; i >= 0; i--) {
-            const float ei = e[i * XS];
-            if (ei * 28.0f / 20.0f < g) {
-                if (!is_zero) tmp += 2.7f * 28.0f / 20.0f;
-            } else {
-                if (g < (ei * 28.0f / 20.0f - 43.0f * 28.0f / 20.0f))
-                    tmp += 2.0f * ei * 28.0f / 20.0f - 2.0f * g - 36.0f * 28.0f / 20.0f;
-                else
-                    tmp += ei * 28.0f / 20.0f - g + 7.0f * 28.0f / 20.0f;
-                is_zero = false;
-            }
+        uint32_t ball[4];
+        float ev[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = r * 32 + lane;
+            ev[r] = (r < rounds && i < ne4) ? e4[i] : -INFINITY;
+            const bool loud = (r < rounds && i < ne4) && !(ev[r] * 28.0f / 20.0f < g);
+            ball[r] = __ballot_sync(FULL, loud);
         }
+        bool any_loud = false;
+#pragma unroll
+        for (int r = 3; r >= 0; r--) {
+            const int i = r * 32 + lane;
+            if (r < rounds && i < ne4) {
+                const float ei = ev[r];
+                const bool above = any_loud || (lane < 31 && (ball[r] >> (lane + 1)) != 0);
+                float term;
+                if (ei * 28.0f / 20.0f < g) term = above ? 2.7f * 28.0f / 20.0f : 0.0f;
+                else if (g < (ei * 28.0f / 20.0f - 43.0f * 28.0f / 20.0f)) term = 2.0f * ei * 28.0f / 20.0f - 2.0f * g - 36.0f * 28.0f / 20.0f;
+                else term = ei * 28.0f / 20.0f - g + 7.0f * 28.0f / 20.0f;
+                T[i] = term;
+            }
+            any_loud = any_loud || ball[r] != 0;
+        }
+        const bool is_zero = !any_loud;
+        __syncwarp();
+        float tmp = 0.0f;
+        for (int i = ne4 - 1; i >= 0; i--) tmp += T[i];
+        __syncwarp();
         if ((tmp > (float)nbits_spec_adj * 1.4f * 28.0f / 20.0f) && !is_zero) gg_ind += fac;
     }
-    float xmax = 0.0f;                                                 // global_gain_limitation :212-228
-    for (int k = 0; k < ne; k++) xmax = maxf_rs(xmax, fabsf(xf[k * XS]));
     int gg_min = 0;
     if (xmax > 0.0f) gg_min = (int)(int16_t)(cast_i16(ceilf(28.0f * log10f_msun(xmax / (32768.0f - 0.375f)))) - (int16_t)gg_off);
     bool reset_offset;
@@ -632,10 +788,12 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
 
     float gg;
     bool lsb_mode;
-    BitCons bc = quantize_spectrum(c, xf, xq, nbits, gg_off, gg_ind, nbits_spec, &gg, &lsb_mode);
-    es[ES_Q_NBITS_OFFSET_OLD] = (int32_t)__float_as_uint(nbits_offset);   // state saved BEFORE the adjustment (:96-100)
-    es[ES_Q_NBITS_EST_OLD] = bc.nbits_est;
-    es[ES_Q_RESET_OFFSET_OLD] = reset_offset;
+    BitCons bc = quantize_spectrum_w(c, xf, xq, (uint32_t*)T, nbits, gg_off, gg_ind, nbits_spec, &gg, &lsb_mode, lane);
+    if (lane == 0) {
+        es[ES_Q_NBITS_OFFSET_OLD] = (int32_t)__float_as_uint(nbits_offset);   // state saved BEFORE the adjustment (:96-100)
+        es[ES_Q_NBITS_EST_OLD] = bc.nbits_est;
+        es[ES_Q_RESET_OFFSET_OLD] = reset_offset;
+    }
     const int t1 = GGA_T1[fs_ind], t2 = GGA_T2[fs_ind], t3 = GGA_T3[fs_ind];
     const int nbits_est = bc.nbits_est;
     float delta;
@@ -654,29 +812,49 @@ __device__ QRes spectral_quantization(const EncConfig& c, int32_t* es, const flo
         else gg_ind += 2;
         gg_ind = gg_ind > gg_min ? gg_ind : gg_min;
     }
-    if (origin != gg_ind) bc = quantize_spectrum(c, xf, xq, nbits, gg_off, gg_ind, nbits_spec, &gg, &lsb_mode);
+    if (origin != gg_ind) bc = quantize_spectrum_w(c, xf, xq, (uint32_t*)T, nbits, gg_off, gg_ind, nbits_spec, &gg, &lsb_mode, lane);
     QRes r;
     r.gg_ind = gg_ind; r.nbits_spec = nbits_spec; r.nbits_lsb = bc.nbits_lsb; r.lsb_mode = lsb_mode;
     r.nbits_trunc = bc.nbits_trunc; r.rate_flag = bc.rate_flag; r.lastnz_trunc = bc.lastnz_trunc; r.gg = gg;
     return r;
 }
 
+// ---------------------------------------------------------------- residual_spectrum.rs:33-62
+// One bit per non-zero line in line order, at most mx (and 400): ranks come from ballots.  Bits land in tail[].
+__device__ int residual_bits_w(int ne, const float* xf, const int16_t* xq, float gg, int mx, uint32_t* tail, int lane) {
+    if (mx <= 0) return 0;
+    const int lim = mx < 400 ? mx : 400;
+    int base = 0;
+    for (int k0 = 0; k0 < ne && base < lim; k0 += 32) {
+        const int k = k0 + lane;
+        const int v = k < ne ? xq[k] : 0;
+        const uint32_t nz = __ballot_sync(FULL, v != 0);
+        const int rank = base + __popc(nz & ((1u << lane) - 1u));
+        if (v != 0 && rank < lim && xf[k] >= (float)v * gg) atomicOr(&tail[rank >> 5], 1u << (rank & 31));
+        base += __popc(nz);
+    }
+    return base < lim ? base : lim;
+}
+
 // ---------------------------------------------------------------- noise_level_estimation.rs:21-55
-__device__ int noise_factor(const EncConfig& c, const float* xf, const int16_t* xq, int bw_ind, float gg) {
+// The qualifying lines' |x|/gg replace the spectrum in place (0 elsewhere), then one chain adds them in line order.
+__device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, int bw_ind, float gg, int lane) {
     const bool d10 = c.n_ms == LC3B_10MS;
     const int bw_stop = d10 ? 80 * (bw_ind + 1) : 60 * (bw_ind + 1);
     const int nf_start = d10 ? 24 : 18, nf_width = d10 ? 3 : 2;
-    float sum = 0.0f;
-    int count = 0;
     const int nf_stop = c.ne < bw_stop ? c.ne : bw_stop;
-    // a line is relevant when xq is zero on [k - w, min(bw_stop - 1, k + w)]; track the last non-zero index seen by
-    // a scan pointer that runs w lines ahead instead of re-reading the window for every line
-    int last_nz = -1000, scan = nf_start - nf_width;
-    for (int k = nf_start; k < nf_stop; k++) {
+    int count = 0;
+    for (int k = nf_start + lane; k < nf_stop; k += 32) {
         const int hi = bw_stop - 1 < k + nf_width ? bw_stop - 1 : k + nf_width;
-        while (scan <= hi) { if (xq[scan * XS] != 0) last_nz = scan; scan++; }
-        if (last_nz < k - nf_width) { sum += fabsf(xf[k * XS]) / gg; count++; }
+        bool quiet = true;
+        for (int j = k - nf_width; j <= hi; j++) quiet = quiet && xq[j] == 0;
+        xf[k] = quiet ? fabsf(xf[k]) / gg : 0.0f;
+        count += quiet ? 1 : 0;
     }
+    count = warp_sum_i(count);
+    __syncwarp();
+    float sum = 0.0f;
+    for (int k = nf_start; k < nf_stop; k++) sum += xf[k];
     const float level = count > 0 ? sum / (float)count : 0.0f;
     const float diff = 8.0f - 16.0f * level;
     if (diff >= 0.0f) {
@@ -687,31 +865,39 @@ __device__ int noise_factor(const EncConfig& c, const float* xf, const int16_t* 
 }
 
 // ---------------------------------------------------------------- bitstream_encoding.rs + buffer_writer.rs
+// Reference-order writer, used by one lane when the frame's two ends collide.
 struct Writer {
     uint8_t* buf;
+    int nbytes;
     int bp;
     int bp_side;
     uint32_t mask_side;
-    __device__ __forceinline__ void bool_backward(bool bit) {                 // buffer_writer.rs:27-40
-        if (!bit) buf[bp_side] &= (uint8_t)~mask_side; else buf[bp_side] |= (uint8_t)mask_side;
+    __device__ __noinline__ void bool_backward(bool bit) {                 // buffer_writer.rs:27-40
+        if (bp_side >= 0) {
+            if (!bit) buf[bp_side] &= (uint8_t)~mask_side; else buf[bp_side] |= (uint8_t)mask_side;
+        }
         if (mask_side == 0x80) { mask_side = 1; bp_side -= 1; } else mask_side <<= 1;
     }
-    __device__ __forceinline__ void uint_backward(uint64_t val, int nbits) {   // :19-25
+    __device__ __noinline__ void uint_backward(uint64_t val, int nbits) {   // :19-25
+#pragma unroll 1
         for (int i = 0; i < nbits; i++) { bool_backward((val & 1) != 0); val >>= 1; }
     }
-    __device__ __forceinline__ void uint_forward(uint32_t val, int nbits) {    // :42-53 (QUIRK: bp is not advanced)
+    __device__ __noinline__ void uint_forward(uint32_t val, int nbits) {    // :42-53 (QUIRK: bp is not advanced)
         uint32_t mask = 0x80;
+        if (bp >= nbytes) return;
+#pragma unroll 1
         for (int i = 0; i < nbits; i++) {
             if (((val & 0xff) & mask) == 0) buf[bp] &= (uint8_t)~mask; else buf[bp] |= (uint8_t)mask;
             mask >>= 1;
         }
     }
-    __device__ __forceinline__ void byte_forward(uint32_t v) { buf[bp++] = (uint8_t)v; }
+    __device__ __forceinline__ void byte_forward(uint32_t v) { if (bp < nbytes) buf[bp] = (uint8_t)v; bp++; }
     __device__ __forceinline__ int nbits_side_written(int nbits) const { return nbits - (8 * bp_side + 8 - (31 - __clz(mask_side))); }
 };
 struct AcEnc { uint32_t low, range; int cache, carry, carry_count; };
 
-__device__ __forceinline__ void ac_shift(AcEnc& st, Writer& w) {              // bitstream_encoding.rs:397-415
+template <class W>
+__device__ __forceinline__ void ac_shift(AcEnc& st, W& w) {              // bitstream_encoding.rs:397-415
     if (st.low < 0x00ff0000u || st.carry == 1) {
         if (st.cache >= 0) w.byte_forward((uint32_t)((st.cache + st.carry) & 0xff));
         while (st.carry_count > 0) {
@@ -726,7 +912,8 @@ __device__ __forceinline__ void ac_shift(AcEnc& st, Writer& w) {              //
     st.low <<= 8;
     st.low &= 0x00ffffffu;
 }
-__device__ __forceinline__ void ac_encode(AcEnc& st, Writer& w, int cum, int freq) {   // :417-429
+template <class W>
+__device__ __forceinline__ void ac_encode(AcEnc& st, W& w, int cum, int freq) {   // :417-429
     const uint32_t r = st.range >> 10;
     st.low += r * (uint32_t)cum;
     if (st.low >> 24 != 0) st.carry = 1;
@@ -737,55 +924,88 @@ __device__ __forceinline__ void ac_encode(AcEnc& st, Writer& w, int cum, int fre
         ac_shift(st, w);
     }
 }
+__device__ __noinline__ void ac_encode_serial(AcEnc& st, Writer& w, int cum, int freq) { ac_encode(st, w, cum, freq); }
+// ac_enc_finish :354-395 up to (not including) the final partial byte; returns the bit count of that byte
+template <class W>
+__device__ __forceinline__ int ac_finish(AcEnc& st, W& w) {
+    int bits = 1;
+    while ((st.range >> (24 - bits)) == 0) bits++;
+    uint32_t mask = 0x00ffffffu >> bits;
+    uint32_t val = st.low + mask;
+    const uint32_t over1 = val >> 24;
+    const uint32_t high = st.low + st.range;
+    const uint32_t over2 = high >> 24;
+    val &= 0x00ffffffu & ~mask;
+    if (over1 == over2) {
+        if ((val + mask) >= high) {
+            bits += 1;
+            mask >>= 1;
+            val = ((st.low + mask) & 0x00ffffffu) & ~mask;
+        }
+        if (val < st.low) st.carry = 1;
+    }
+    st.low = val;
+    while (bits > 0) { ac_shift(st, w); bits -= 8; }
+    bits += 8;
+    return bits;
+}
 
-__device__ void bitstream_encode(const EncConfig& c, const BwRes& bw, const SnsRes& sns, const TnsRes& tns, int pitch_present,
-                                 int ltpf_active, int pitch_index, const QRes& q, const uint32_t* res_bits, int n_res,
-                                 int nf_factor, const int16_t* xq, uint8_t* lsbs, uint8_t* out, int nbytes) {   // :77-136
+struct SideHdr {
+    const BwRes* bw; const SnsRes* sns; const TnsRes* tns; const QRes* q;
+    int pitch_present, ltpf_active, pitch_index, nf_factor, lg;
+};
+
+// side information in the reference's order (bitstream_encoding.rs:138-232) through any `put(value, nbits)`
+template <class P>
+__device__ __forceinline__ void write_side_info(const SideHdr& h, P& put) {
+    if (h.bw->nbits > 0) put((uint64_t)h.bw->bw, h.bw->nbits);
+    put((uint64_t)((h.q->lastnz_trunc >> 1) - 1), h.lg);
+    put((uint64_t)(h.q->lsb_mode != 0), 1);
+    put((uint64_t)(int64_t)h.q->gg_ind, 8);
+    for (int f = 0; f < h.tns->num_filters; f++) put((uint64_t)(h.tns->rc_order[f] != 0), 1);
+    put((uint64_t)(h.pitch_present != 0), 1);
+    put((uint64_t)h.sns->ind_lf, 5);
+    put((uint64_t)h.sns->ind_hf, 5);
+    const bool submode_msb = (h.sns->shape_j >> 1) != 0;
+    put((uint64_t)submode_msb, 1);
+    put((uint64_t)(h.sns->gind >> LC3T_SNS_GAIN_LSB_BITS[h.sns->shape_j]), LC3T_SNS_GAIN_MSB_BITS[h.sns->shape_j]);
+    put((uint64_t)(h.sns->ls_inda != 0), 1);
+    if (!submode_msb) {
+        put(h.sns->joint, 13);
+        put(h.sns->joint >> 13, 12);
+    } else {
+        put(h.sns->joint, 12);
+        put(h.sns->joint >> 12, 12);
+    }
+    if (h.pitch_present) {
+        put((uint64_t)(h.ltpf_active != 0), 1);
+        put((uint64_t)h.pitch_index, 9);
+    }
+    put((uint64_t)h.nf_factor, 3);
+}
+
+// BitstreamEncoding::encode :77-136 exactly as written (interleaved writes), one thread
+__device__ __noinline__ void bitstream_encode_serial(const EncConfig& c, const SideHdr& h, const uint32_t* res_bits, int n_res,
+                                                     const int16_t* xq, uint8_t* lsbs, uint8_t* out, int nbytes) {
+    const QRes& q = *h.q;
+    const TnsRes& tns = *h.tns;
     const int ne = c.ne, nbits = nbytes * 8;
     for (int i = 0; i < nbytes; i++) out[i] = 0;
     Writer w;
     w.buf = out;
+    w.nbytes = nbytes;
     w.bp = 0;
     w.bp_side = nbytes - 1;
     w.mask_side = 1;
-    if (bw.nbits > 0) w.uint_backward((uint64_t)bw.bw, bw.nbits);
-    {
-        int lg = 0;
-        while ((1 << lg) < ne / 2) lg++;
-        w.uint_backward((uint64_t)((q.lastnz_trunc >> 1) - 1), lg);
-    }
-    w.bool_backward(q.lsb_mode != 0);
-    w.uint_backward((uint64_t)(int64_t)q.gg_ind, 8);
-    for (int f = 0; f < tns.num_filters; f++) w.bool_backward(tns.rc_order[f] != 0);
-    w.bool_backward(pitch_present != 0);
-    w.uint_backward((uint64_t)sns.ind_lf, 5);
-    w.uint_backward((uint64_t)sns.ind_hf, 5);
-    {
-        const bool submode_msb = (sns.shape_j >> 1) != 0;
-        w.bool_backward(submode_msb);
-        const int gain_msbs = sns.gind >> LC3T_SNS_GAIN_LSB_BITS[sns.shape_j];
-        w.uint_backward((uint64_t)gain_msbs, LC3T_SNS_GAIN_MSB_BITS[sns.shape_j]);
-        w.bool_backward(sns.ls_inda != 0);
-        if (!submode_msb) {
-            w.uint_backward(sns.joint, 13);
-            w.uint_backward(sns.joint >> 13, 12);
-        } else {
-            w.uint_backward(sns.joint, 12);
-            w.uint_backward(sns.joint >> 12, 12);
-        }
-    }
-    if (pitch_present) {
-        w.bool_backward(ltpf_active != 0);
-        w.uint_backward((uint64_t)pitch_index, 9);
-    }
-    w.uint_backward((uint64_t)nf_factor, 3);
+    auto put = [&](uint64_t v, int n) { w.uint_backward(v, n); };
+    write_side_info(h, put);
     AcEnc st{0, 0x00ffffffu, -1, 0, 0};
     for (int f = 0; f < tns.num_filters; f++) {
         if (tns.rc_order[f] > 0) {
-            ac_encode(st, w, LC3T_AC_TNS_ORDER_CUMFREQ[tns.lpc_weighting][tns.rc_order[f] - 1],
+            ac_encode_serial(st, w, LC3T_AC_TNS_ORDER_CUMFREQ[tns.lpc_weighting][tns.rc_order[f] - 1],
                       LC3T_AC_TNS_ORDER_FREQ[tns.lpc_weighting][tns.rc_order[f] - 1]);
             for (int k = 0; k < tns.rc_order[f]; k++)
-                ac_encode(st, w, LC3T_AC_TNS_COEF_CUMFREQ[k][tns.rc_i[k + 8 * f]], LC3T_AC_TNS_COEF_FREQ[k][tns.rc_i[k + 8 * f]]);
+                ac_encode_serial(st, w, LC3T_AC_TNS_COEF_CUMFREQ[k][tns.rc_i[k + 8 * f]], LC3T_AC_TNS_COEF_FREQ[k][tns.rc_i[k + 8 * f]]);
         }
     }
     int nlsbs = 0;
@@ -793,14 +1013,14 @@ __device__ void bitstream_encode(const EncConfig& c, const BwRes& bw, const SnsR
     int cctx = 0;
     for (int k = 0; k < q.lastnz_trunc; k += 2) {
         int t = cctx + q.rate_flag + (k > ne / 2 ? 256 : 0);
-        const int q0 = xq[k * XS], q1 = xq[(k + 1) * XS];
+        const int q0 = xq[k], q1 = xq[k + 1];
         uint32_t a = (uint32_t)(q0 < 0 ? -q0 : q0) & 0xffffu, a_lsb = a;
         uint32_t b = (uint32_t)(q1 < 0 ? -q1 : q1) & 0xffffu, b_lsb = b;
         int lev = 0;
         uint32_t lsb0 = 0, lsb1 = 0;
         while ((a > b ? a : b) >= 4) {
             const int pki = LC3T_AC_SPEC_LOOKUP[t + (lev < 3 ? lev : 3) * 1024];
-            ac_encode(st, w, LC3T_AC_SPEC_CUMFREQ[pki][16], LC3T_AC_SPEC_FREQ[pki][16]);
+            ac_encode_serial(st, w, LC3T_AC_SPEC_CUMFREQ[pki][16], LC3T_AC_SPEC_FREQ[pki][16]);
             if (q.lsb_mode && lev == 0) { lsb0 = a & 1; lsb1 = b & 1; }
             else { w.bool_backward((a & 1) == 1); w.bool_backward((b & 1) == 1); }
             a >>= 1;
@@ -809,7 +1029,7 @@ __device__ void bitstream_encode(const EncConfig& c, const BwRes& bw, const SnsR
         }
         const int pki = LC3T_AC_SPEC_LOOKUP[t + (lev < 3 ? lev : 3) * 1024];
         const int sym = (int)(a + 4 * b);
-        ac_encode(st, w, LC3T_AC_SPEC_CUMFREQ[pki][sym], LC3T_AC_SPEC_FREQ[pki][sym]);
+        ac_encode_serial(st, w, LC3T_AC_SPEC_CUMFREQ[pki][sym], LC3T_AC_SPEC_FREQ[pki][sym]);
         if (q.lsb_mode && lev > 0) {
             a_lsb >>= 1;
             b_lsb >>= 1;
@@ -839,25 +1059,7 @@ __device__ void bitstream_encode(const EncConfig& c, const BwRes& bw, const SnsR
         const int m = nres_enc < nlsbs ? nres_enc : nlsbs;
         for (int i = 0; i < m; i++) w.bool_backward(lsbs[i] == 1);
     }
-    int bits = 1;                                     // ac_enc_finish :354-395
-    while ((st.range >> (24 - bits)) == 0) bits++;
-    uint32_t mask = 0x00ffffffu >> bits;
-    uint32_t val = st.low + mask;
-    const uint32_t over1 = val >> 24;
-    const uint32_t high = st.low + st.range;
-    const uint32_t over2 = high >> 24;
-    val &= 0x00ffffffu & ~mask;
-    if (over1 == over2) {
-        if ((val + mask) >= high) {
-            bits += 1;
-            mask >>= 1;
-            val = ((st.low + mask) & 0x00ffffffu) & ~mask;
-        }
-        if (val < st.low) st.carry = 1;
-    }
-    st.low = val;
-    while (bits > 0) { ac_shift(st, w); bits -= 8; }
-    bits += 8;
+    const int bits = ac_finish(st, w);
     if (st.carry_count > 0) {
         w.byte_forward((uint32_t)st.cache & 0xff);
         while (st.carry_count > 1) { w.byte_forward(0xff); st.carry_count -= 1; }
@@ -867,80 +1069,314 @@ __device__ void bitstream_encode(const EncConfig& c, const BwRes& bw, const SnsR
     }
 }
 
-__global__ void __launch_bounds__(QNT_THREADS) enc_quant_kernel(QuantParams p) {
+// forward byte sink of the fast path: every lane tracks bp, lane 0 stores
+struct FwdSink {
+    uint8_t* buf;
+    int nbytes, bp, lane;
+    __device__ __forceinline__ void byte_forward(uint32_t v) {
+        if (lane == 0 && bp < nbytes) buf[bp] = (uint8_t)v;
+        bp++;
+    }
+};
+
+// append `n` bits (LSB first) to a little-endian bit array at position pos
+__device__ __forceinline__ void bits_or(uint32_t* arr, int n_words, int pos, uint64_t val, int n) {
+    if (n <= 0) return;
+    const int w = pos >> 5, sh = pos & 31;
+    const uint64_t v = (n < 64 ? (val & ((1ull << n) - 1ull)) : val) << sh;       // n <= 32 here
+    if (w < n_words && (uint32_t)v != 0) atomicOr(&arr[w], (uint32_t)v);
+    if (w + 1 < n_words && (uint32_t)(v >> 32) != 0) atomicOr(&arr[w + 1], (uint32_t)(v >> 32));
+}
+
+// Fast path of BitstreamEncoding::encode.  Returns false when the two ends of the frame meet (caller falls back).
+__device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_res, const int16_t* xq, uint32_t* side, int side_words,
+                                   uint32_t* tail, uint32_t* symq, int sym_cap, uint8_t* out, int out_words, int nbytes, int lane) {
+    const QRes& q = *h.q;
+    const TnsRes& tns = *h.tns;
+    const int ne = c.ne, nbits = nbytes * 8;
+    for (int i = lane; i < side_words; i += 32) side[i] = 0;
+    for (int i = lane; i < out_words; i += 32) ((uint32_t*)out)[i] = 0;
+    if (q.lsb_mode) for (int i = lane; i < TAIL_WORDS; i += 32) tail[i] = 0;
+    __syncwarp();
+    int spos = 0;
+    {
+        auto put = [&](uint64_t v, int n) {
+            if (lane == 0) {
+                const int w = spos >> 5, sh = spos & 31;
+                const uint64_t vv = (v & ((1ull << n) - 1ull)) << sh;
+                if (w < side_words) side[w] |= (uint32_t)vv;
+                if (w + 1 < side_words) side[w + 1] |= (uint32_t)(vv >> 32);
+            }
+            spos += n;
+        };
+        write_side_info(h, put);
+    }
+    __syncwarp();
+    // ---- per-tuple preparation: symbols -> queue, side bits and deferred LSBs -> bit arrays
+    const uint32_t* xw = (const uint32_t*)xq;
+    const int ntt = q.lastnz_trunc >> 1;
+    const int CH = ((ne >> 1) + 31) >> 5;
+    const int n0 = lane * CH;
+    uint32_t cnt_a = 0, cnt_l = 0;                       // (symbols | side bits << 16), deferred LSB entries
+    const int n1 = n0 + CH < ntt ? n0 + CH : ntt;
+#pragma unroll 1
+    for (int n = n0; n < n1; n++) {
+        const Tup t = tup_of(xw[n]);
+        const bool defer = q.lsb_mode && t.L > 0;
+        const uint32_t al = defer ? t.a0 >> 1 : t.a0, bl = defer ? t.b0 >> 1 : t.b0;
+        const int sb = (defer ? 2 * (t.L - 1) : 2 * t.L) + (al > 0) + (bl > 0);
+        cnt_a += (uint32_t)(t.L + 1) | ((uint32_t)sb << 16);
+        if (defer) cnt_l += 2 + (al == 0 && t.q0 != 0) + (bl == 0 && t.q1 != 0);
+    }
+    const uint32_t inc_a = warp_incl_scan(cnt_a, lane), inc_l = warp_incl_scan(cnt_l, lane);
+    const uint32_t tot_a = __shfl_sync(FULL, inc_a, 31);
+    const int nlsbs = (int)__shfl_sync(FULL, inc_l, 31);
+    const int nsym = (int)(tot_a & 0xffffu), nside_tup = (int)(tot_a >> 16);
+    if (nsym > sym_cap) return false;
+    {
+        int so = (int)((inc_a - cnt_a) & 0xffffu), bo = spos + (int)((inc_a - cnt_a) >> 16), lo = (int)(inc_l - cnt_l);
+        int d2 = 0, d1 = 0;
+        if (n0 >= 1 && n0 - 1 < ntt) d1 = tup_digit(tup_of(xw[n0 - 1]));
+        if (n0 >= 2 && n0 - 2 < ntt) d2 = tup_digit(tup_of(xw[n0 - 2]));
+#pragma unroll 1
+        for (int n = n0; n < n1; n++) {
+            {
+                const Tup t = tup_of(xw[n]);
+                const int tc = d2 * 16 + d1 + q.rate_flag + (2 * n > ne / 2 ? 256 : 0);
+                uint64_t sbits = 0;
+                int ns = 0;
+                uint32_t a = t.a0, b = t.b0, lsb0 = 0, lsb1 = 0;
+#pragma unroll 1
+                for (int lev = 0; lev < t.L; lev++) {
+                    const int pki = LC3T_AC_SPEC_LOOKUP[tc + (lev < 3 ? lev : 3) * 1024];
+                    symq[so++] = (uint32_t)LC3T_AC_SPEC_CUMFREQ[pki][16] | ((uint32_t)LC3T_AC_SPEC_FREQ[pki][16] << 16);
+                    if (q.lsb_mode && lev == 0) { lsb0 = a & 1; lsb1 = b & 1; }
+                    else { sbits |= (uint64_t)(a & 1) << ns; sbits |= (uint64_t)(b & 1) << (ns + 1); ns += 2; }
+                    a >>= 1;
+                    b >>= 1;
+                }
+                const int pki = LC3T_AC_SPEC_LOOKUP[tc + (t.L < 3 ? t.L : 3) * 1024];
+                const int sym = (int)(a + 4 * b);
+                symq[so++] = (uint32_t)LC3T_AC_SPEC_CUMFREQ[pki][sym] | ((uint32_t)LC3T_AC_SPEC_FREQ[pki][sym] << 16);
+                uint32_t al = t.a0, bl = t.b0;
+                if (q.lsb_mode && t.L > 0) {
+                    al >>= 1;
+                    bl >>= 1;
+                    uint32_t lb = lsb0;
+                    int nl = 1;
+                    if (al == 0 && t.q0 != 0) { lb |= (uint32_t)(t.q0 > 0 ? 0 : 1) << nl; nl++; }
+                    lb |= lsb1 << nl;
+                    nl++;
+                    if (bl == 0 && t.q1 != 0) { lb |= (uint32_t)(t.q1 > 0 ? 0 : 1) << nl; nl++; }
+                    bits_or(tail, TAIL_WORDS, lo, lb, nl);
+                    lo += nl;
+                }
+                if (al > 0) { sbits |= (uint64_t)(t.q0 <= 0) << ns; ns++; }
+                if (bl > 0) { sbits |= (uint64_t)(t.q1 <= 0) << ns; ns++; }
+                bits_or(side, side_words, bo, sbits, ns);
+                bo += ns;
+                d2 = d1;
+                d1 = tup_digit(t);
+            }
+        }
+    }
+    spos += nside_tup;
+    __syncwarp();
+    // ---- the range coder proper: every lane runs the same chain, lane 0 stores the bytes
+    FwdSink w{out, nbytes, 0, lane};
+    AcEnc st{0, 0x00ffffffu, -1, 0, 0};
+    for (int f = 0; f < tns.num_filters; f++) {
+        if (tns.rc_order[f] > 0) {
+            ac_encode(st, w, LC3T_AC_TNS_ORDER_CUMFREQ[tns.lpc_weighting][tns.rc_order[f] - 1],
+                      LC3T_AC_TNS_ORDER_FREQ[tns.lpc_weighting][tns.rc_order[f] - 1]);
+            for (int k = 0; k < tns.rc_order[f]; k++)
+                ac_encode(st, w, LC3T_AC_TNS_COEF_CUMFREQ[k][tns.rc_i[k + 8 * f]], LC3T_AC_TNS_COEF_FREQ[k][tns.rc_i[k + 8 * f]]);
+        }
+    }
+    for (int i = 0; i < nsym; i++) {
+        const uint32_t cf = symq[i];
+        ac_encode(st, w, (int)(cf & 0xffffu), (int)(cf >> 16));
+    }
+    const int nbits_side = spos;
+    int nbits_ari = w.bp * 8;
+    nbits_ari += 25 - (31 - __clz(st.range));
+    nbits_ari += 8;                                   // QUIRK: `carry >= 0` is always true (:67)
+    if (st.carry_count > 0) nbits_ari += st.carry_count * 8;
+    int nres_enc = nbits - (nbits_side + nbits_ari);
+    if (nres_enc < 0) nres_enc = 0;
+    const int m = q.lsb_mode ? (nres_enc < nlsbs ? nres_enc : nlsbs) : (n_res < nres_enc ? n_res : nres_enc);
+    if (lane < TAIL_WORDS) {                          // tail bits [0, m) -> side stream at spos
+        const int lo = lane * 32;
+        if (lo < m) {
+            const int n = m - lo < 32 ? m - lo : 32;
+            bits_or(side, side_words, spos + lo, tail[lane], n);
+        }
+    }
+    spos += m;
+    const int bits = ac_finish(st, w);
+    uint32_t last;
+    if (st.carry_count > 0) {
+        w.byte_forward((uint32_t)st.cache & 0xff);
+        while (st.carry_count > 1) { w.byte_forward(0xff); st.carry_count -= 1; }
+        last = 0xffu >> (8 - bits);
+    } else {
+        last = (uint32_t)st.cache;
+    }
+    if (w.bp >= nbytes || 8 * w.bp + bits + spos > nbits) return false;
+    if (lane == 0) out[w.bp] |= (uint8_t)(last & (0xff00u >> bits) & 0xffu);
+    __syncwarp();
+    return true;
+}
+
+// hand-off record between the three kernels of this file (int32 words per stream)
+enum {
+    QH_BW = 0, QH_NBITS_BW, QH_IND_LF, QH_IND_HF, QH_SHAPE_J, QH_GIND, QH_LS_INDA, QH_LS_INDB, QH_JOINT_LO, QH_JOINT_HI,
+    QH_NBITS_TNS, QH_LPC_WEIGHTING, QH_NUM_FILTERS, QH_ORDER0, QH_ORDER1, QH_PAD0,
+    QH_RC_I = 16,
+    QH_GG_IND = 32, QH_NBITS_SPEC, QH_NBITS_LSB, QH_NBITS_TRUNC, QH_LSB_MODE, QH_RATE_FLAG, QH_LASTNZ_TRUNC, QH_GG,
+};
+static_assert(QH_GG < QH_WORDS, "hand-off record too small");
+
+// Kernel A: bandwidth detector, SNS, TNS.  Spectrum in place in global memory, decisions into the hand-off record.
+__global__ void __launch_bounds__(QNT_THREADS) enc_shape_kernel(QuantParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
-    const int tid = threadIdx.x;
-    const int stream0 = blockIdx.x * QNT_THREADS;
-    const int stream = stream0 + tid;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int stream = blockIdx.x * QW + wib;
+    if (stream >= p.n_streams) return;                            // warps are independent: no CTA-wide barrier below
     const int ne = c.ne;
-    float* s_xf = (float*)smem;                                   // [ne][XS]
-    float* s_e = s_xf + ne * XS;                                  // [100][XS]
-    int16_t* s_xq = (int16_t*)(s_e + 100 * XS);                   // [ne][XS]
-    uint8_t* s_rows = (uint8_t*)(s_xq + ne * XS + (ne & 1));      // [QNT_THREADS][row_pitch], 4-byte aligned
-    uint8_t* row = s_rows + (size_t)tid * p.row_pitch;
-    const int n_rows = min(QNT_THREADS, p.n_streams - stream0);
-    // transposed load of the CTA's stream-major spectra: row r is read coalesced, lane = k
-    for (int r = 0; r < n_rows; r++) {
-        const float* src = p.xf + (size_t)(stream0 + r) * ne;
-        for (int k = tid; k < ne; k += QNT_THREADS) s_xf[k * XS + r] = src[k];
+    float* xf = (float*)(smem + (size_t)wib * (sizeof(float) * (NE_MAX + S_FLOATS)));   // [NE_MAX]
+    float* S = xf + NE_MAX;                                                             // [S_FLOATS]
+    float4* gx = (float4*)(p.xf + (size_t)stream * ne);
+    for (int i = lane; i < ne / 4; i += 32) ((float4*)xf)[i] = gx[i];
+    const float* eb = p.e_b + (size_t)stream * 64;
+    S[lane] = eb[lane];
+    S[lane + 32] = eb[lane + 32];
+    __syncwarp();
+    const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
+    const BwRes bw = bandwidth_detect(c, S);
+    const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane);
+    TnsRes tns;
+    tns_encode_w(c, xf, S, bw.bw, p.nbytes * 8, eh[EH_NEAR_NYQUIST] != 0, tns, lane);
+    for (int i = lane; i < ne / 4; i += 32) gx[i] = ((const float4*)xf)[i];
+    int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
+    if (lane == 0) {
+        qh[QH_BW] = bw.bw; qh[QH_NBITS_BW] = bw.nbits;
+        qh[QH_IND_LF] = sns.ind_lf; qh[QH_IND_HF] = sns.ind_hf; qh[QH_SHAPE_J] = sns.shape_j; qh[QH_GIND] = sns.gind;
+        qh[QH_LS_INDA] = sns.ls_inda; qh[QH_LS_INDB] = sns.ls_indb;
+        qh[QH_JOINT_LO] = (int32_t)(uint32_t)sns.joint; qh[QH_JOINT_HI] = (int32_t)(uint32_t)(sns.joint >> 32);
+        qh[QH_NBITS_TNS] = tns.nbits_tns; qh[QH_LPC_WEIGHTING] = tns.lpc_weighting; qh[QH_NUM_FILTERS] = tns.num_filters;
+        qh[QH_ORDER0] = tns.rc_order[0]; qh[QH_ORDER1] = tns.rc_order[1];
     }
-    __syncthreads();
-    if (stream < p.n_streams) {
-        const int nbytes = p.nbytes, nbits = nbytes * 8;
-        float* xf = s_xf + tid;
-        const float* e_b = p.e_b + (size_t)stream * 64;
-        const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
-        int32_t* es = p.estate + (size_t)stream * ES_WORDS;
-        int16_t* xq = s_xq + tid;
-        float* e4 = s_e + tid;
-        uint8_t* lsbs = p.lsbs + (size_t)stream * 2 * ne;
+    if (lane < 16) qh[QH_RC_I + lane] = tns.rc_i[lane];
+}
 
-        const BwRes bw = bandwidth_detect(c, e_b);
-        const SnsRes sns = sns_encode(c, xf, e_b, eh[EH_ATTACK] != 0);
-        TnsRes tns;
-        tns_encode(c, xf, bw.bw, nbits, eh[EH_NEAR_NYQUIST] != 0, tns);
-        const QRes q = spectral_quantization(c, es, xf, xq, e4, nbits, bw.nbits, tns.nbits_tns, eh[EH_NBITS_LTPF]);
-        // residual_spectrum.rs:33-62
-        uint32_t res_bits[13];
-        for (int i = 0; i < 13; i++) res_bits[i] = 0;
-        int n_res = 0;
-        {
-            int mx = q.nbits_spec - q.nbits_trunc + 4;
-            if (mx < 0) mx = 0;
-            if (mx > 0) {
-                for (int k = 0; k < ne; k++) {
-                    if (n_res >= mx) break;
-                    const int v = xq[k * XS];
-                    if (v != 0) {
-                        if (n_res >= 400) break;
-                        if (xf[k * XS] >= (float)v * q.gg) res_bits[n_res >> 5] |= 1u << (n_res & 31);
-                        n_res++;
-                    }
-                }
-            }
-        }
-        const int nff = noise_factor(c, xf, xq, bw.bw, q.gg);
-        bitstream_encode(c, bw, sns, tns, eh[EH_PITCH_PRESENT], eh[EH_LTPF_ACTIVE], eh[EH_PITCH_INDEX], q, res_bits, n_res,
-                         nff, xq, lsbs, row, nbytes);
-    }
-    __syncthreads();
-    for (int i = tid; i < n_rows * p.nbytes; i += QNT_THREADS) {
-        const int r = i / p.nbytes, b = i - r * p.nbytes;
-        p.frames_out[(size_t)(stream0 + r) * p.frame_stride + b] = s_rows[(size_t)r * p.row_pitch + b];
-    }
-    if (p.debug) {                                                // test hook: make the intermediates readable
-        for (int r = 0; r < n_rows; r++) {
-            for (int k = tid; k < ne; k += QNT_THREADS) {
-                p.xf[(size_t)(stream0 + r) * ne + k] = s_xf[k * XS + r];
-                p.xq[(size_t)(stream0 + r) * ne + k] = s_xq[k * XS + r];
-            }
-        }
+// Kernel B: SpectralQuantization::run.  Shaped spectrum -> quantised spectrum + gain decisions.
+__global__ void __launch_bounds__(QNT_THREADS) enc_quantize_kernel(QuantParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int stream = blockIdx.x * QW + wib;
+    if (stream >= p.n_streams) return;
+    const int ne = c.ne;
+    uint8_t* wb = smem + (size_t)wib * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX);
+    float* xf = (float*)wb;                                       // [NE_MAX]
+    float* e4 = xf + NE_MAX;                                      // [100]
+    float* T = e4 + 100;                                          // [224]
+    int16_t* xq = (int16_t*)(T + 224);                            // [NE_MAX]
+    const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
+    for (int i = lane; i < ne / 4; i += 32) ((float4*)xf)[i] = gx[i];
+    __syncwarp();
+    const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
+    int32_t* es = p.estate + (size_t)stream * ES_WORDS;
+    int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
+    const QRes q = spectral_quantization_w(c, es, xf, xq, e4, T, p.nbytes * 8, qh[QH_NBITS_BW], qh[QH_NBITS_TNS], eh[EH_NBITS_LTPF], lane);
+    uint32_t* gq = (uint32_t*)(p.xq + (size_t)stream * ne);
+    for (int i = lane; i < ne / 2; i += 32) gq[i] = ((const uint32_t*)xq)[i];
+    if (lane == 0) {
+        qh[QH_GG_IND] = q.gg_ind; qh[QH_NBITS_SPEC] = q.nbits_spec; qh[QH_NBITS_LSB] = q.nbits_lsb; qh[QH_NBITS_TRUNC] = q.nbits_trunc;
+        qh[QH_LSB_MODE] = q.lsb_mode; qh[QH_RATE_FLAG] = q.rate_flag; qh[QH_LASTNZ_TRUNC] = q.lastnz_trunc;
+        qh[QH_GG] = (int32_t)__float_as_uint(q.gg);
     }
 }
 
+// Kernel C: residual bits, noise factor, bitstream.
+__global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int stream = blockIdx.x * QW + wib;
+    if (stream >= p.n_streams) return;
+    const int ne = c.ne;
+    uint8_t* wb = smem + (size_t)wib * p.w_bytes;
+    float* xf = (float*)wb;                                       // [NE_MAX]
+    int16_t* xq = (int16_t*)(xf + NE_MAX);                        // [NE_MAX]
+    int* rc_i = (int*)(xq + NE_MAX);                              // [16]
+    uint32_t* tail = (uint32_t*)(rc_i + 16);                      // [TAIL_WORDS]
+    uint32_t* side = tail + TAIL_WORDS;                           // [side_words]
+    uint32_t* symq = side + p.side_words;                         // [sym_cap]
+    uint8_t* out = (uint8_t*)(symq + p.sym_cap);                  // [out_words * 4]
+    const int nbytes = p.nbytes;
+    const int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
+    {
+        const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
+        for (int i = lane; i < ne / 4; i += 32) ((float4*)xf)[i] = gx[i];
+        const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
+        for (int i = lane; i < ne / 2; i += 32) ((uint32_t*)xq)[i] = gq[i];
+        if (lane < 16) rc_i[lane] = qh[QH_RC_I + lane];
+        if (lane < TAIL_WORDS) tail[lane] = 0;
+    }
+    __syncwarp();
+    const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
+    BwRes bw{qh[QH_BW], qh[QH_NBITS_BW]};
+    SnsRes sns;
+    sns.ind_lf = qh[QH_IND_LF]; sns.ind_hf = qh[QH_IND_HF]; sns.shape_j = qh[QH_SHAPE_J]; sns.gind = qh[QH_GIND];
+    sns.ls_inda = qh[QH_LS_INDA]; sns.ls_indb = qh[QH_LS_INDB];
+    sns.joint = (uint64_t)(uint32_t)qh[QH_JOINT_LO] | ((uint64_t)(uint32_t)qh[QH_JOINT_HI] << 32);
+    TnsRes tns;
+    tns.nbits_tns = qh[QH_NBITS_TNS]; tns.lpc_weighting = qh[QH_LPC_WEIGHTING]; tns.num_filters = qh[QH_NUM_FILTERS];
+    tns.rc_order[0] = qh[QH_ORDER0]; tns.rc_order[1] = qh[QH_ORDER1];
+    tns.rc_i = rc_i;
+    QRes q;
+    q.gg_ind = qh[QH_GG_IND]; q.nbits_spec = qh[QH_NBITS_SPEC]; q.nbits_lsb = qh[QH_NBITS_LSB]; q.nbits_trunc = qh[QH_NBITS_TRUNC];
+    q.lsb_mode = qh[QH_LSB_MODE]; q.rate_flag = qh[QH_RATE_FLAG]; q.lastnz_trunc = qh[QH_LASTNZ_TRUNC];
+    q.gg = __uint_as_float((uint32_t)qh[QH_GG]);
+
+    int n_res = 0;
+    if (!q.lsb_mode) n_res = residual_bits_w(ne, xf, xq, q.gg, q.nbits_spec - q.nbits_trunc + 4, tail, lane);
+    __syncwarp();
+    const int nff = noise_factor_w(c, xf, xq, bw.bw, q.gg, lane);
+
+    SideHdr h;
+    h.bw = &bw; h.sns = &sns; h.tns = &tns; h.q = &q;
+    h.pitch_present = eh[EH_PITCH_PRESENT]; h.ltpf_active = eh[EH_LTPF_ACTIVE]; h.pitch_index = eh[EH_PITCH_INDEX];
+    h.nf_factor = nff;
+    h.lg = 0;
+    while ((1 << h.lg) < ne / 2) h.lg++;
+    const bool ok = bitstream_encode_w(c, h, n_res, xq, side, p.side_words, tail, symq, p.sym_cap, out, p.out_words, nbytes, lane);
+    uint8_t* dst = p.frames_out + (size_t)stream * p.frame_stride;
+    if (ok) {
+        for (int b = lane; b < nbytes; b += 32) {
+            const int i = nbytes - 1 - b;
+            dst[b] = out[b] | (uint8_t)(side[i >> 2] >> (8 * (i & 3)));
+        }
+    } else {
+        __syncwarp();
+        if (lane == 0) bitstream_encode_serial(c, h, tail, n_res, xq, p.lsbs + (size_t)stream * 2 * ne, out, nbytes);
+        __syncwarp();
+        for (int b = lane; b < nbytes; b += 32) dst[b] = out[b];
+    }
+}
+
+template <class K>
+static cudaError_t launch_one(K kernel, const QuantParams& p, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<(p.n_streams + QW - 1) / QW, QNT_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, cudaStream_t stream) {
-    const int ne = st.cfg.ne;
     QuantParams p;
     p.cfg = st.ecfg;
     p.n_streams = st.n_streams;
@@ -951,18 +1387,22 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     p.ehand = st.ehand;
     p.estate = st.estate;
     p.xq = st.xq;
-    p.scratch_e = st.scratch_e;
+    p.qhand = st.qhand;
     p.lsbs = st.lsbs;
     p.frames_out = frames_out;
-    int words = (nbytes + 3) / 4;
-    if ((words & 1) == 0) words++;
-    p.row_pitch = words * 4;
-    p.debug = st.debug;
-    const size_t smem = (size_t)ne * XS * 4 + 100 * XS * 4 + ((size_t)ne * XS + (ne & 1)) * 2 + (size_t)QNT_THREADS * p.row_pitch;
-    cudaError_t e = cudaFuncSetAttribute(enc_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nbits = nbytes * 8;
+    p.side_words = (nbits + 31) / 32 + 2;
+    p.sym_cap = st.cfg.ne / 2 + nbits / 2 + 32;       // tuples + escapes the truncation rule can admit (2 bits each at least)
+    p.out_words = (nbytes + 3) / 4 + 1;
+    size_t wbytes = sizeof(float) * NE_MAX + sizeof(int16_t) * NE_MAX + sizeof(int) * 16 +
+                    sizeof(uint32_t) * (size_t)(TAIL_WORDS + p.side_words + p.sym_cap + p.out_words);
+    wbytes = (wbytes + 15) & ~(size_t)15;
+    p.w_bytes = (int)wbytes;
+    cudaError_t e = launch_one(enc_shape_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
     if (e != cudaSuccess) return e;
-    enc_quant_kernel<<<(st.n_streams + QNT_THREADS - 1) / QNT_THREADS, QNT_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
+    e = launch_one(enc_quantize_kernel, p, QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX), stream);
+    if (e != cudaSuccess) return e;
+    return launch_one(enc_bitstream_kernel, p, QW * wbytes, stream);
 }
 
 }  // namespace lc3b
