@@ -240,13 +240,13 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
         g_enc_last_cuda_error = (int)e;
         return LC3B_ERR_CUDA;
     }
-    h->stage_mask = 3;
+    h->stage_mask = 15;
     *out = h;
     return LC3B_OK;
 }
 
 int lc3b_encoder_set_stage_mask(lc3b_encoder* h, int mask) {
-    if (!h || mask < 1 || mask > 3) return LC3B_ERR_INVALID_ARG;
+    if (!h || mask < 1 || mask > 15) return LC3B_ERR_INVALID_ARG;
     h->stage_mask = mask;
     return LC3B_OK;
 }
@@ -261,7 +261,7 @@ int lc3b_encode_frames(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride
         return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     if (h->stage_mask & 1) CU(launch_enc_analysis(st, pcm_in, pcm_stride, nbytes, stream));
-    if (h->stage_mask & 2) CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, stream));
+    if (h->stage_mask & 14) CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, h->stage_mask >> 1, stream));
     return LC3B_OK;
 }
 
@@ -277,7 +277,7 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
     else CU(cudaMemcpy2DAsync(st.stage_in, nf * sizeof(int16_t), pcm_in, pcm_stride * sizeof(int16_t), nf * sizeof(int16_t), ns,
                               cudaMemcpyHostToDevice, stream));
     CU(launch_enc_analysis(st, st.stage_in, nf, nbytes, stream));
-    CU(launch_enc_quant(st, st.stage_out, nbytes, (size_t)nbytes, stream));
+    CU(launch_enc_quant(st, st.stage_out, nbytes, (size_t)nbytes, 7, stream));
     if (frame_stride == (size_t)nbytes) CU(cudaMemcpyAsync(frames_out, st.stage_out, ns * (size_t)nbytes, cudaMemcpyDeviceToHost, stream));
     else CU(cudaMemcpy2DAsync(frames_out, frame_stride, st.stage_out, (size_t)nbytes, (size_t)nbytes, ns, cudaMemcpyDeviceToHost, stream));
     return LC3B_OK;

@@ -64,6 +64,7 @@ struct EncoderState {
 };
 
 cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, cudaStream_t stream);
-cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, cudaStream_t stream);
+// stages: bit 0 shape kernel (BW/SNS/TNS), bit 1 quantise kernel, bit 2 bitstream kernel
+cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream);
 
 }  // namespace lc3b

@@ -568,20 +568,14 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         float t_out = 0.0f, s_out = 0.0f;
         for (int step = 0; step < N + po; step++) {
             float t_in = __shfl_up_sync(FULL, t_out, 1), s_in = __shfl_up_sync(FULL, s_out, 1);
-            if (lane == 0) { t_in = step < N ? x[start + step] : 0.0f; s_in = t_in; }
+            const float xin = x[start + (step < N ? step : N - 1)];
+            if (lane == 0) { t_in = xin; s_in = xin; }
             const int n = step - lane;
-            if (lane <= po && n >= 0 && n < N) {
-                if (lane < po) {
-                    const float st_tmp = rq * t_in + st;
-                    t_out = t_in + rq * st;
-                    st = s_in;
-                    s_out = st_tmp;
-                } else {
-                    t_out = t_in + rq * st;
-                    st = s_in;
-                    x[start + n] = t_out;
-                }
-            }
+            const bool act = lane <= po && n >= 0 && n < N;
+            const float tn = t_in + rq * st;              // every stage
+            const float st_tmp = rq * t_in + st;          // handed on by the inner stages
+            if (act) { t_out = tn; s_out = st_tmp; st = s_in; }
+            if (act && lane == po) x[start + n] = tn;
         }
         __syncwarp();
     }
@@ -777,7 +771,11 @@ __device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const f
         const bool is_zero = !any_loud;
         __syncwarp();
         float tmp = 0.0f;
-        for (int i = ne4 - 1; i >= 0; i--) tmp += T[i];
+        for (int i = ne4 - 1; i >= (ne4 & ~3); i--) tmp += T[i];
+        for (int i4 = ne4 / 4 - 1; i4 >= 0; i4--) {
+            const float4 t4 = ((const float4*)T)[i4];
+            tmp += t4.w; tmp += t4.z; tmp += t4.y; tmp += t4.x;
+        }
         __syncwarp();
         if ((tmp > (float)nbits_spec_adj * 1.4f * 28.0f / 20.0f) && !is_zero) gg_ind += fac;
     }
@@ -844,12 +842,29 @@ __device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, 
     const int nf_start = d10 ? 24 : 18, nf_width = d10 ? 3 : 2;
     const int nf_stop = c.ne < bw_stop ? c.ne : bw_stop;
     int count = 0;
-    for (int k = nf_start + lane; k < nf_stop; k += 32) {
-        const int hi = bw_stop - 1 < k + nf_width ? bw_stop - 1 : k + nf_width;
-        bool quiet = true;
-        for (int j = k - nf_width; j <= hi; j++) quiet = quiet && xq[j] == 0;
-        xf[k] = quiet ? fabsf(xf[k]) / gg : 0.0f;
-        count += quiet ? 1 : 0;
+    // nzm[r] = ballot of "xq[32 r + lane] != 0"; a line's window [k - w, hi] is then a bit range of at most 7 bits
+    uint32_t nzm[13];
+#pragma unroll
+    for (int r = 0; r < 13; r++) {
+        const int k = 32 * r + lane;
+        nzm[r] = __ballot_sync(FULL, k < c.ne && xq[k] != 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 13; r++) {
+        const int k = 32 * r + lane;
+        if (k >= nf_start && k < nf_stop) {
+            const int hi = bw_stop - 1 < k + nf_width ? bw_stop - 1 : k + nf_width;
+            const int lo = k - nf_width;
+            // 64-bit view of words r-1, r, r+1 around the lane: bits [lo, hi] relative to 32 (r - 1)
+            const uint32_t wm = r > 0 ? nzm[r - 1] : 0u, w0 = nzm[r], wp = r < 12 ? nzm[r + 1] : 0u;
+            const int rel = lo - 32 * (r - 1);                     // 32 - w + lane >= 29
+            const uint64_t lo64 = (uint64_t)wm | ((uint64_t)w0 << 32);
+            const uint64_t hi64 = (uint64_t)w0 | ((uint64_t)wp << 32);
+            const uint32_t win = rel < 32 ? (uint32_t)(lo64 >> rel) : (uint32_t)(hi64 >> (rel - 32));
+            const bool quiet = (win & ((1u << (hi - lo + 1)) - 1u)) == 0;
+            xf[k] = quiet ? fabsf(xf[k]) / gg : 0.0f;
+            count += quiet ? 1 : 0;
+        }
     }
     count = warp_sum_i(count);
     __syncwarp();
@@ -1069,12 +1084,13 @@ __device__ __noinline__ void bitstream_encode_serial(const EncConfig& c, const S
     }
 }
 
-// forward byte sink of the fast path: every lane tracks bp, lane 0 stores
+// forward byte sink of the fast path: every lane runs the same chain and stores the same byte (a lane-0-only store
+// would split the warp and the rest of the symbol loop would issue twice)
 struct FwdSink {
     uint8_t* buf;
     int nbytes, bp, lane;
     __device__ __forceinline__ void byte_forward(uint32_t v) {
-        if (lane == 0 && bp < nbytes) buf[bp] = (uint8_t)v;
+        if (bp < nbytes) buf[bp] = (uint8_t)v;
         bp++;
     }
 };
@@ -1193,9 +1209,11 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
                 ac_encode(st, w, LC3T_AC_TNS_COEF_CUMFREQ[k][tns.rc_i[k + 8 * f]], LC3T_AC_TNS_COEF_FREQ[k][tns.rc_i[k + 8 * f]]);
         }
     }
+    uint32_t cf = symq[0];
     for (int i = 0; i < nsym; i++) {
-        const uint32_t cf = symq[i];
+        const uint32_t nxt = symq[i + 1 < nsym ? i + 1 : i];
         ac_encode(st, w, (int)(cf & 0xffffu), (int)(cf >> 16));
+        cf = nxt;
     }
     const int nbits_side = spos;
     int nbits_ari = w.bp * 8;
@@ -1223,7 +1241,7 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
         last = (uint32_t)st.cache;
     }
     if (w.bp >= nbytes || 8 * w.bp + bits + spos > nbits) return false;
-    if (lane == 0) out[w.bp] |= (uint8_t)(last & (0xff00u >> bits) & 0xffu);
+    out[w.bp] |= (uint8_t)(last & (0xff00u >> bits) & 0xffu);
     __syncwarp();
     return true;
 }
@@ -1376,7 +1394,7 @@ static cudaError_t launch_one(K kernel, const QuantParams& p, size_t smem, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, cudaStream_t stream) {
+cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream) {
     QuantParams p;
     p.cfg = st.ecfg;
     p.n_streams = st.n_streams;
@@ -1398,11 +1416,13 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
                     sizeof(uint32_t) * (size_t)(TAIL_WORDS + p.side_words + p.sym_cap + p.out_words);
     wbytes = (wbytes + 15) & ~(size_t)15;
     p.w_bytes = (int)wbytes;
-    cudaError_t e = launch_one(enc_shape_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
+    cudaError_t e = cudaSuccess;
+    if (stages & 1) e = launch_one(enc_shape_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
     if (e != cudaSuccess) return e;
-    e = launch_one(enc_quantize_kernel, p, QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX), stream);
+    if (stages & 2) e = launch_one(enc_quantize_kernel, p, QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX), stream);
     if (e != cudaSuccess) return e;
-    return launch_one(enc_bitstream_kernel, p, QW * wbytes, stream);
+    if (stages & 4) e = launch_one(enc_bitstream_kernel, p, QW * wbytes, stream);
+    return e;
 }
 
 }  // namespace lc3b
