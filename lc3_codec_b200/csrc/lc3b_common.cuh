@@ -11,6 +11,12 @@
 #define LC3_TABLE(T) static const T
 #endif
 
+// Lane-strided loops with a warp-uniform trip count.  `for (i = lane; i < n; i += 32)` gives the lanes different trip
+// counts; the warp then splits and was observed to stay split through the following uniform code (every later
+// instruction issued twice, ncu thr/inst = 16).  Here every lane runs ceil(n/32) iterations with a predicated body.
+#define WARP_STRIDE(v, n) for (int v##_b = 0, v = lane; v##_b < (n); v##_b += 32, v += 32) if (v < (n))
+#define WARP_STRIDE_FROM(v, start, n) for (int v##_b = (start), v = (start) + lane; v##_b < (n); v##_b += 32, v += 32) if (v < (n))
+
 namespace lc3b {
 
 constexpr int MAX_NE = 400;

@@ -127,15 +127,15 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     int32_t* es = p.estate + (size_t)stream * ES_WORDS;
 
     // ---- update_time_buffer (modified_dct.rs:126-138)
-    for (int n = lane; n < nf - z; n += 32) tb[n] = thist[n];
-    for (int n = lane; n < nf; n += 32) tb[nf - z + n] = in[n];
-    for (int n = lane; n < z; n += 32) tb[2 * nf - z + n] = 0;
+    WARP_STRIDE(n, nf - z) tb[n] = thist[n];
+    WARP_STRIDE(n, nf) tb[nf - z + n] = in[n];
+    WARP_STRIDE(n, z) tb[2 * nf - z + n] = 0;
     __syncwarp();
-    for (int n = lane; n < nf - z; n += 32) thist[n] = tb[nf + n];
+    WARP_STRIDE(n, nf - z) thist[n] = tb[nf + n];
     // ---- window + fold (:73-97)
     {
         const int mid = 3 * half;
-        for (int i = lane; i < half; i += 32) {
+        WARP_STRIDE(i, half) {
             const int a = mid - 1 - i, b = mid + i;
             wk[i] = -((float)tb[a] * p.win[a]) - ((float)tb[b] * p.win[b]);
             const int a2 = i, b2 = nf - 1 - i;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     }
     __syncwarp();
     // ---- DCT-IV (dct_iv.rs:49-67): pre-twiddle straight into kissfft's leaf order, levels innermost first
-    for (int o = lane; o < N; o += 32) {
+    WARP_STRIDE(o, N) {
         const int n = p.perm[o];
         cx[o] = cmul(ld(p.dtw, n), C2{wk[2 * n], wk[nf - 2 * n - 1]});
     }
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     for (int lv = c.n_levels - 1; lv >= 0; lv--) {
         const int pp = c.fac_p[lv], m = c.fac_m[lv], fs = c.fac_stride[lv];
         const int nbf = N / pp;
-        for (int b = lane; b < nbf; b += 32) {
+        WARP_STRIDE(b, nbf) {
             const int blk = b / m, u = b - blk * m;
             C2* f = cx + blk * (pp * m);
             switch (pp) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     }
     {
         const float gain = 1.0f / sqrtf(2.0f * (float)nf);
-        for (int n = lane; n < N; n += 32) {
+        WARP_STRIDE(n, N) {
             const C2 v = cmul(ld(p.dtw, n), cx[n]);
             const float a = v.r * 2.0f, b = -v.i * 2.0f;
             wk[2 * n] = a * gain;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     // ---- band energies (:140-152, divide inside the sum) and near-Nyquist flag (:154-178)
     float* e_b = p.e_b + (size_t)stream * 64;
     float* ebs = (float*)cx;                        // staging of the energies for the serial sums below
-    for (int b = lane; b < c.nb; b += 32) {
+    WARP_STRIDE(b, c.nb) {
         const int from = c.band_idx[b], to = c.band_idx[b + 1];
         const float width = (float)(to - from);
         float e = 0.0f;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
         e_b[b] = e;
         ebs[b] = e;
     }
-    for (int k = lane; k < ne; k += 32) p.xf[(size_t)stream * ne + k] = wk[k];
+    WARP_STRIDE(k, ne) p.xf[(size_t)stream * ne + k] = wk[k];
     __syncwarp();
     int near_nyquist = 0;
     if (c.fs <= 32000 && lane == 0) {
@@ -220,13 +220,13 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
             const int nds = c.att_num_ds, block_len = nf / nds;
             const int tm1 = es[ES_ATT_TM1], tm2 = es[ES_ATT_TM2];
             __syncwarp();
-            for (int n = lane; n < nds; n += 32) {
+            WARP_STRIDE(n, nds) {
                 int32_t s = 0;
                 for (int j = 0; j < block_len; j++) s += (int32_t)x[block_len * n + j];
                 ds[n] = s;
             }
             __syncwarp();
-            for (int n = lane; n < nds; n += 32) {
+            WARP_STRIDE(n, nds) {
                 const float d0 = (float)ds[n];
                 const float d1 = n >= 1 ? (float)ds[n - 1] : (float)tm1;
                 const float d2 = n >= 2 ? (float)ds[n - 2] : (n == 1 ? (float)tm1 : (float)tm2);
@@ -275,16 +275,16 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
         int16_t* xh = p.xs_hist + (size_t)stream * 64;
         float* g12 = p.x12 + (size_t)stream * c.x12_len;
         float* g6 = p.x6 + (size_t)stream * 178;
-        for (int n = lane; n < ns_keep; n += 32) xs[n] = xh[n];
-        for (int n = lane; n < nf; n += 32) xs[ns_keep + n] = x[n];
-        for (int n = lane; n < c.x12_len - len12; n += 32) x12[n] = g12[n + len12];
-        for (int n = lane; n < 178 - len6; n += 32) x6[n] = g6[n + len6];
-        for (int n = 178 - len6 + lane; n < 178; n += 32) x6[n] = 0.0f;   // overwritten below where it matters
+        WARP_STRIDE(n, ns_keep) xs[n] = xh[n];
+        WARP_STRIDE(n, nf) xs[ns_keep + n] = x[n];
+        WARP_STRIDE(n, c.x12_len - len12) x12[n] = g12[n + len12];
+        WARP_STRIDE(n, 178 - len6) x6[n] = g6[n + len6];
+        WARP_STRIDE_FROM(n, 178 - len6, 178) x6[n] = 0.0f;   // overwritten below where it matters
         __syncwarp();
-        for (int n = lane; n < ns_keep; n += 32) xh[n] = xs[nf + n];       // last 240/up samples of this frame
+        WARP_STRIDE(n, ns_keep) xh[n] = xs[nf + n];       // last 240/up samples of this frame
     }
     float* x12n = x12 + c.delay + NMEM;             // where this frame's resampled samples go
-    for (int n = lane; n < len12; n += 32) {        // resampling (:152-166)
+    WARP_STRIDE(n, len12) {        // resampling (:152-166)
         float acc = 0.0f;
         const int q15 = (15 * n) / up, r15 = (15 * n) % up;
         for (int k = -120 / up; k <= 120 / up; k++) {
@@ -309,10 +309,10 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     __syncwarp();
     {   // write the shifted + new 12.8 kHz samples back (state for the next frame)
         float* g12 = p.x12 + (size_t)stream * c.x12_len;
-        for (int n = lane; n < c.x12_len; n += 32) g12[n] = x12[n];
+        WARP_STRIDE(n, c.x12_len) g12[n] = x12[n];
     }
     // pitch_detection (:232-290)
-    for (int i = lane; i < len6; i += 32) {
+    WARP_STRIDE(i, len6) {
         const float* s = x12 + NMEM - 3 + 2 * i;
         x6[K_MAX + i] = 0.1236796411180537f * s[0] + 0.2353512128364889f * s[1] + 0.2819382920909148f * s[2] +
                         0.2353512128364889f * s[3] + 0.1236796411180537f * s[4];
@@ -320,13 +320,13 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     __syncwarp();
     {
         float* g6 = p.x6 + (size_t)stream * 178;
-        for (int n = lane; n < 178; n += 32) g6[n] = x6[n];
+        WARP_STRIDE(n, 178) g6[n] = x6[n];
     }
     float* r6 = (float*)cx;                          // 98 lags
     float* rw6 = r6 + 98;
     float* r12 = rw6 + 98;                           // up to 233 values (needs 196 + 233 <= 2N: checked at init)
     constexpr int NR = K_MAX + 1 - K_MIN;
-    for (int k = lane; k < NR; k += 32) {
+    WARP_STRIDE(k, NR) {
         const int from_k = K_MAX - K_MIN - k;
         float s = 0.0f;
         for (int n = 0; n < len6; n++) s += x6[K_MAX + n] * x6[from_k + n];
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     const int k_min = 32 > 2 * t_current - 4 ? 32 : 2 * t_current - 4;
     const int k_max = 228 < 2 * t_current + 4 ? 228 : 2 * t_current + 4;
     const float* cur = x12 + NMEM;
-    for (int i = lane; i < 233; i += 32) r12[i] = 0.0f;
+    WARP_STRIDE(i, 233) r12[i] = 0.0f;
     __syncwarp();
     for (int k = k_min - 4 + lane; k <= k_max + 4; k += 32) {
         float cv = 0.0f;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
         return v;
     };
     __syncwarp();
-    for (int n = lane; n < len12; n += 32) {
+    WARP_STRIDE(n, len12) {
         nd_a[n] = dot(n, 0);
         sh_a[n] = dot(n - pitch_int, pitch_fr);
     }

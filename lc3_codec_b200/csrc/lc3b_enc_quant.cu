@@ -329,7 +329,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     float* eb = S;
     float* e = S + 64;
     const int nb = c.nb, diff = 64 - nb;
-    for (int b = lane; b < 64; b += 32) {
+    WARP_STRIDE(b, 64) {
         auto pad = [&](int j) -> float { return diff > 0 ? (j < 2 * diff ? eb[j >> 1] : eb[j - diff]) : eb[j]; };
         float v;
         if (b == 0) v = 0.75f * pad(0) + 0.25f * pad(1);
@@ -343,7 +343,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     total = (total / 64.0f) * powi_nt(10.0f, -4);
     const float floor_ = maxf_rs(powi_nt(2.0f, -32), total);
     __syncwarp();
-    for (int b = lane; b < 64; b += 32) e[b] = log2f_msun(1.1920929e-07f + maxf_rs(e[b], floor_)) / 2.0f;
+    WARP_STRIDE(b, 64) e[b] = log2f_msun(1.1920929e-07f + maxf_rs(e[b], floor_)) / 2.0f;
     __syncwarp();
     const int n16 = lane & 15;
     float ds;
@@ -408,7 +408,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     __syncwarp();
     for (int j = 0; j < 2; j++) gs[lane + 32 * j] = exp2f_msun(-itv[j]);
     __syncwarp();
-    for (int k = lane; k < c.ne; k += 32) {
+    WARP_STRIDE(k, c.ne) {
         const int b = c.band_of[k];
         if (b < nb) x[k] *= gs[b];
     }
@@ -616,7 +616,7 @@ __device__ BitCons compute_bit_consumption_w(int ne, int fs_ind, const int16_t* 
     const int n0 = lane * CH;
     int last = -1;
 #pragma unroll 1
-    for (int n = n0; n < n0 + CH && n < nt; n++) if (xw[n] != 0) last = n;
+    for (int n = n0; n < n0 + CH; n++) if (n < nt && xw[n] != 0) last = n;
     last = warp_max_i(last);
     const int lastnz = last < 0 ? 2 : 2 * last + 2;
     const int ntz = lastnz >> 1;
@@ -627,7 +627,7 @@ __device__ BitCons compute_bit_consumption_w(int ne, int fs_ind, const int16_t* 
     int lsb = 0;
     const int n1 = n0 + CH < ntz ? n0 + CH : ntz;
 #pragma unroll 1
-    for (int n = n0; n < n1; n++) {
+    for (int n = n0; n < n0 + CH; n++) if (n < n1) {
         const Tup t = tup_of(xw[n]);
         const int tc = d2 * 16 + d1 + bc.rate_flag + (2 * n > ne / 2 ? 256 : 0);
 #pragma unroll 1
@@ -654,7 +654,7 @@ __device__ BitCons compute_bit_consumption_w(int ne, int fs_ind, const int16_t* 
     int qual = -1;                                        // last tuple of this lane that is non-zero and still fits
     uint32_t qual_est = 0;
 #pragma unroll 1
-    for (int n = n0; n < n1; n++) {
+    for (int n = n0; n < n0 + CH; n++) if (n < n1) {
         const uint32_t pv = pre[n];
         const uint32_t e_n = base + (pv & 0x7fffffffu);
         if ((pv >> 31) != 0 && (int)ceilf((float)e_n / 2048.0f) <= nbits_spec) { qual = n; qual_est = e_n; }
@@ -684,13 +684,13 @@ __device__ __noinline__ BitCons quantize_spectrum_w(const EncConfig& c, const fl
                                        int nbits_spec, float* gg_out, bool* lsb_mode, int lane) {   // :230-263
     const int ne = c.ne;
     const float gg = gain_of(c, gg_ind, gg_off);
-    for (int k = lane; k < ne; k += 32) {
+    WARP_STRIDE(k, ne) {
         const float v = xf[k];
         xq[k] = v >= 0.0f ? cast_i16(v / gg + 0.375f) : cast_i16(v / gg - 0.375f);
     }
     __syncwarp();
     BitCons bc = compute_bit_consumption_w(ne, c.fs_ind, xq, pre, nbits, nbits_spec, lane);
-    for (int k = bc.lastnz_trunc + lane; k < bc.lastnz; k += 32) xq[k] = 0;
+    WARP_STRIDE_FROM(k, bc.lastnz_trunc, bc.lastnz) xq[k] = 0;
     __syncwarp();
     *gg_out = gg;
     *lsb_mode = bc.mode_flag && bc.nbits_est > nbits_spec;
@@ -724,7 +724,7 @@ __device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const f
     const int gg_off = -(115 < q ? 115 : q) - 105 - 5 * (fs_ind + 1);
     const int ne4 = ne / 4;
     float xmax = 0.0f;                                                 // global_gain_limitation :212-228 (max is order-free)
-    for (int i = lane; i < ne4; i += 32) {                             // compute_spectral_energy :390-395
+    WARP_STRIDE(i, ne4) {                             // compute_spectral_energy :390-395
         const float4 p4 = ((const float4*)xf)[i];
         const float total = p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
         e4[i] = 10.0f * log10f_msun(1.1920929e-07f + total);
@@ -1110,9 +1110,9 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
     const QRes& q = *h.q;
     const TnsRes& tns = *h.tns;
     const int ne = c.ne, nbits = nbytes * 8;
-    for (int i = lane; i < side_words; i += 32) side[i] = 0;
-    for (int i = lane; i < out_words; i += 32) ((uint32_t*)out)[i] = 0;
-    if (q.lsb_mode) for (int i = lane; i < TAIL_WORDS; i += 32) tail[i] = 0;
+    WARP_STRIDE(i, side_words) side[i] = 0;
+    WARP_STRIDE(i, out_words) ((uint32_t*)out)[i] = 0;
+    if (q.lsb_mode) WARP_STRIDE(i, TAIL_WORDS) tail[i] = 0;
     __syncwarp();
     int spos = 0;
     {
@@ -1136,7 +1136,7 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
     uint32_t cnt_a = 0, cnt_l = 0;                       // (symbols | side bits << 16), deferred LSB entries
     const int n1 = n0 + CH < ntt ? n0 + CH : ntt;
 #pragma unroll 1
-    for (int n = n0; n < n1; n++) {
+    for (int n = n0; n < n0 + CH; n++) if (n < n1) {
         const Tup t = tup_of(xw[n]);
         const bool defer = q.lsb_mode && t.L > 0;
         const uint32_t al = defer ? t.a0 >> 1 : t.a0, bl = defer ? t.b0 >> 1 : t.b0;
@@ -1155,7 +1155,7 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
         if (n0 >= 1 && n0 - 1 < ntt) d1 = tup_digit(tup_of(xw[n0 - 1]));
         if (n0 >= 2 && n0 - 2 < ntt) d2 = tup_digit(tup_of(xw[n0 - 2]));
 #pragma unroll 1
-        for (int n = n0; n < n1; n++) {
+        for (int n = n0; n < n0 + CH; n++) if (n < n1) {
             {
                 const Tup t = tup_of(xw[n]);
                 const int tc = d2 * 16 + d1 + q.rate_flag + (2 * n > ne / 2 ? 256 : 0);
@@ -1266,7 +1266,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_shape_kernel(QuantParams p) {
     float* xf = (float*)(smem + (size_t)wib * (sizeof(float) * (NE_MAX + S_FLOATS)));   // [NE_MAX]
     float* S = xf + NE_MAX;                                                             // [S_FLOATS]
     float4* gx = (float4*)(p.xf + (size_t)stream * ne);
-    for (int i = lane; i < ne / 4; i += 32) ((float4*)xf)[i] = gx[i];
+    WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
     const float* eb = p.e_b + (size_t)stream * 64;
     S[lane] = eb[lane];
     S[lane + 32] = eb[lane + 32];
@@ -1276,7 +1276,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_shape_kernel(QuantParams p) {
     const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane);
     TnsRes tns;
     tns_encode_w(c, xf, S, bw.bw, p.nbytes * 8, eh[EH_NEAR_NYQUIST] != 0, tns, lane);
-    for (int i = lane; i < ne / 4; i += 32) gx[i] = ((const float4*)xf)[i];
+    WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     if (lane == 0) {
         qh[QH_BW] = bw.bw; qh[QH_NBITS_BW] = bw.nbits;
@@ -1303,14 +1303,14 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quantize_kernel(QuantParams p
     float* T = e4 + 100;                                          // [224]
     int16_t* xq = (int16_t*)(T + 224);                            // [NE_MAX]
     const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
-    for (int i = lane; i < ne / 4; i += 32) ((float4*)xf)[i] = gx[i];
+    WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
     __syncwarp();
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     int32_t* es = p.estate + (size_t)stream * ES_WORDS;
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     const QRes q = spectral_quantization_w(c, es, xf, xq, e4, T, p.nbytes * 8, qh[QH_NBITS_BW], qh[QH_NBITS_TNS], eh[EH_NBITS_LTPF], lane);
     uint32_t* gq = (uint32_t*)(p.xq + (size_t)stream * ne);
-    for (int i = lane; i < ne / 2; i += 32) gq[i] = ((const uint32_t*)xq)[i];
+    WARP_STRIDE(i, ne / 2) gq[i] = ((const uint32_t*)xq)[i];
     if (lane == 0) {
         qh[QH_GG_IND] = q.gg_ind; qh[QH_NBITS_SPEC] = q.nbits_spec; qh[QH_NBITS_LSB] = q.nbits_lsb; qh[QH_NBITS_TRUNC] = q.nbits_trunc;
         qh[QH_LSB_MODE] = q.lsb_mode; qh[QH_RATE_FLAG] = q.rate_flag; qh[QH_LASTNZ_TRUNC] = q.lastnz_trunc;
@@ -1338,9 +1338,9 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams 
     const int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     {
         const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
-        for (int i = lane; i < ne / 4; i += 32) ((float4*)xf)[i] = gx[i];
+        WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
         const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
-        for (int i = lane; i < ne / 2; i += 32) ((uint32_t*)xq)[i] = gq[i];
+        WARP_STRIDE(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
         if (lane < 16) rc_i[lane] = qh[QH_RC_I + lane];
         if (lane < TAIL_WORDS) tail[lane] = 0;
     }
@@ -1374,7 +1374,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams 
     const bool ok = bitstream_encode_w(c, h, n_res, xq, side, p.side_words, tail, symq, p.sym_cap, out, p.out_words, nbytes, lane);
     uint8_t* dst = p.frames_out + (size_t)stream * p.frame_stride;
     if (ok) {
-        for (int b = lane; b < nbytes; b += 32) {
+        WARP_STRIDE(b, nbytes) {
             const int i = nbytes - 1 - b;
             dst[b] = out[b] | (uint8_t)(side[i >> 2] >> (8 * (i & 3)));
         }
@@ -1382,7 +1382,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams 
         __syncwarp();
         if (lane == 0) bitstream_encode_serial(c, h, tail, n_res, xq, p.lsbs + (size_t)stream * 2 * ne, out, nbytes);
         __syncwarp();
-        for (int b = lane; b < nbytes; b += 32) dst[b] = out[b];
+        WARP_STRIDE(b, nbytes) dst[b] = out[b];
     }
 }
 
