@@ -407,7 +407,7 @@ def main():
             enc.encode_frames(dev_pcm_in[i % F], frames_out)
             dec.decode_frames(16, frames_out, pcm_out)
 
-    launches_per_step = {"decode": 2, "encode": 4, "roundtrip": 6}[mode]
+    launches_per_step = {"decode": 2, "encode": 6, "roundtrip": 8}[mode]
 
     # ---- device-resident throughput (value) with clocks sampled during the timed region
     with ClockSampler(local_rank) as clk:
@@ -431,15 +431,15 @@ def main():
 
     if enc:
         # the encoder's later kernels consume what the earlier ones leave in the workspace, so they are timed as
-        # growing prefixes of the chain (masks 1, 3, 7, 15) and reported as differences
+        # growing prefixes of the chain (masks 1, 3, 7, 15, 31, 63) and reported as differences
         prev = 0.0
-        for mask, name in ((1, "lc3b::enc_analysis_kernel"), (3, "lc3b::enc_shape_kernel"), (7, "lc3b::enc_quantize_kernel"),
-                           (15, "lc3b::enc_bitstream_kernel")):
+        for mask, name in ((1, "lc3b::enc_mdct_kernel"), (3, "lc3b::enc_ltpf_kernel"), (7, "lc3b::enc_sns_kernel"),
+                           (15, "lc3b::enc_tns_kernel"), (31, "lc3b::enc_quantize_kernel"), (63, "lc3b::enc_bitstream_kernel")):
             enc.set_stage_mask(mask)
             t = timed(lambda i: enc.encode_frames(dev_pcm_in[i % F], frames_out), k_steps, 3) / k_steps
             kernels_ms[name] = max(t - prev, 0.0)
             prev = t
-        enc.set_stage_mask(15)
+        enc.set_stage_mask(63)
     if dec:
         if mode == "roundtrip":
             enc.encode_frames(dev_pcm_in[0], frames_out)           # valid bitstreams for the decoder-only timing

@@ -133,8 +133,9 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
  * input, after SNS and TNS), e_b [S][64] f32, hand [S][8] i32 (near_nyquist, attack, pitch_index, pitch_present,
  * ltpf_active, nbits_ltpf), xq [S][ne] i16. */
 int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* hand, int16_t* xq, void* cuda_stream);
-/* Profiling hook, like lc3b_decoder_set_stage_mask: bit 0 = analysis kernel, bit 1 = shape kernel (BW/SNS/TNS),
- * bit 2 = quantise kernel, bit 3 = bitstream kernel.  Default 15 (all). */
+/* Profiling hook, like lc3b_decoder_set_stage_mask: bit 0 = MDCT kernel, bit 1 = attack/LTPF analysis kernel,
+ * bit 2 = SNS kernel (with the bandwidth detector), bit 3 = TNS kernel, bit 4 = quantise kernel, bit 5 = bitstream
+ * kernel.  Default 63 (all). */
 int lc3b_encoder_set_stage_mask(lc3b_encoder* h, int mask);
 void lc3b_encoder_destroy(lc3b_encoder* h);
 

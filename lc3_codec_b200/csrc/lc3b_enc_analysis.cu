@@ -1,5 +1,5 @@
-// lc3b engine, encoder kernel 1 of 2: PCM -> MDCT spectrum, band energies, attack flag, LTPF parameters.
-// One WARP per frame.  Compiled with -fmad=false: every expression below rounds exactly like the reference's f32 code.
+// lc3b engine, encoder kernels 1-2 of 6: PCM -> MDCT spectrum + band energies (enc_mdct_kernel), attack flag + LTPF
+// parameters (enc_ltpf_kernel).  One WARP per frame.  Two kernels so each one's code stays near the SM's instruction cache.  Compiled with -fmad=false: every expression below rounds exactly like the reference's f32 code.
 //
 // Replaces, per stream, the first half of EncoderChannel::encode (src/encoder/lc3_encoder.rs:63-90):
 //   ModDiscreteCosTrans::run     src/encoder/modified_dct.rs:108 (time buffer :126, window+fold :73, DCT-IV
@@ -36,7 +36,7 @@ struct AnalysisParams {
     float* xf;
     float* e_b;
     int32_t* ehand;
-    int smem_per_warp, wk_floats, cx_c2;
+    int smem_per_warp;
 };
 
 constexpr int ANA_WARPS = 4;
@@ -106,7 +106,7 @@ __device__ __forceinline__ void bfly5(C2* f, const float2* tw, int fs, int m, in
     f[u + m3] = csub(s11, s12);
 }
 
-__global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisParams p) {
+__global__ void __launch_bounds__(ANA_WARPS * 32) enc_mdct_kernel(AnalysisParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -115,16 +115,12 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     const int nf = c.nf, ne = c.ne, z = c.z, N = c.n_fft, half = nf / 2;
 
     uint8_t* base = smem + (size_t)wid * p.smem_per_warp;
-    float* wk = (float*)base;                       // max(nf, 320) floats
-    C2* cx = (C2*)(wk + p.wk_floats);               // max(N, 215) complex; later r6[98] + rw6[98] + r12[233]
-    float* x12 = (float*)(cx + p.cx_c2);            // x12_len floats
-    float* x6 = x12 + c.x12_len;                    // 178 floats
-    int16_t* tb = (int16_t*)(x6 + 178);             // 2*nf
-    int16_t* xs = tb + 2 * nf;                      // x_s_ext_len (<= 540)
+    float* wk = (float*)base;                       // nf floats
+    C2* cx = (C2*)(wk + nf);                        // N complex
+    int16_t* tb = (int16_t*)(cx + N);               // 2*nf
 
     const int16_t* in = p.pcm + (size_t)stream * p.pcm_stride;
     int16_t* thist = p.thist + (size_t)stream * (nf - z);
-    int32_t* es = p.estate + (size_t)stream * ES_WORDS;
 
     // ---- update_time_buffer (modified_dct.rs:126-138)
     WARP_STRIDE(n, nf - z) tb[n] = thist[n];
@@ -194,10 +190,30 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
         for (int n = 0; n < c.nb; n++) { if (n < nn_idx) lo += ebs[n]; else hi += ebs[n]; }
         near_nyquist = hi > 30.0f * lo;
     }
-    near_nyquist = __shfl_sync(0xffffffffu, near_nyquist, 0);
-    __syncwarp();
+    if (lane == 0) p.ehand[(size_t)stream * EH_WORDS + EH_NEAR_NYQUIST] = near_nyquist;
+}
 
-    const int16_t* x = tb + (nf - z);               // this frame's input samples
+// Kernel 2: attack detector and LTPF analysis (runs after enc_mdct_kernel, whose near-Nyquist flag it reads).
+__global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int stream = blockIdx.x * ANA_WARPS + wid;
+    if (stream >= p.n_streams) return;
+    const int nf = c.nf;
+
+    uint8_t* base = smem + (size_t)wid * p.smem_per_warp;
+    float* wk = (float*)base;                       // 320 floats: attack scratch, later the activation sums' inputs
+    float* r6 = wk + 320;                           // 98 lags
+    float* rw6 = r6 + 98;                           // 98 weighted lags
+    float* r12 = rw6 + 98;                          // up to 233 values
+    float* x12 = r12 + 236;                         // x12_len floats
+    float* x6 = x12 + c.x12_len;                    // 178 floats
+    int16_t* xs = (int16_t*)(x6 + 178);             // x_s_ext_len (<= 540)
+
+    const int16_t* x = p.pcm + (size_t)stream * p.pcm_stride;     // this frame's input samples
+    int32_t* es = p.estate + (size_t)stream * ES_WORDS;
+    const int near_nyquist = p.ehand[(size_t)stream * EH_WORDS + EH_NEAR_NYQUIST];
 
     // ---- attack detector (attack_detector.rs:45-105)
     int attack_detected = 0;
@@ -287,11 +303,13 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     WARP_STRIDE(n, len12) {        // resampling (:152-166)
         float acc = 0.0f;
         const int q15 = (15 * n) / up, r15 = (15 * n) % up;
-        for (int k = -120 / up; k <= 120 / up; k++) {
-            const int index_x_s = q15 + k - 120 / up;
-            const int index_h = up * k - r15;
-            if (index_h > -120 && index_h < 120) acc += (float)xs[240 / up + index_x_s] * LC3T_TAB_RESAMP_FILTER[119 + index_h];
-        }
+        // the reference walks k = -120/up ..= 120/up and skips taps with |up k - r15| >= 120: exactly the first one,
+        // and the last one when r15 == 0 (up divides 120)
+        const int kq = 120 / up;
+        const int16_t* xp = xs + 240 / up + q15 - kq;
+        const float* hp = LC3T_TAB_RESAMP_FILTER + 119 - r15;
+        for (int k = -kq + 1; k < kq; k++) acc += (float)xp[k] * hp[up * k];
+        if (r15 != 0) acc += (float)xp[kq] * hp[up * kq];
         x12n[n] = acc * ((float)up * c.resamp_fac);
     }
     __syncwarp();
@@ -322,9 +340,6 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
         float* g6 = p.x6 + (size_t)stream * 178;
         WARP_STRIDE(n, 178) g6[n] = x6[n];
     }
-    float* r6 = (float*)cx;                          // 98 lags
-    float* rw6 = r6 + 98;
-    float* r12 = rw6 + 98;                           // up to 233 values (needs 196 + 233 <= 2N: checked at init)
     constexpr int NR = K_MAX + 1 - K_MIN;
     WARP_STRIDE(k, NR) {
         const int from_k = K_MAX - K_MIN - k;
@@ -336,50 +351,59 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     }
     __syncwarp();
     int t_current = 0, pitch_present = 0;
-    if (lane == 0) {
-        auto index_of_max = [](const float* s, int n) {
-            if (n == 0) return 0;
-            float mx = s[0];
-            int idx = 0;
-            for (int i = 0; i < n; i++) if (s[i] > mx) { idx = i; mx = s[i]; }
-            return idx;
+    {
+        // index_of_max (:411-423): first maximum wins; per-lane scan in ascending order, then a (value, index) reduction
+        auto index_of_max_w = [&](const float* s, int n) {
+            float mx = -INFINITY;
+            int idx = 0x7fffffff;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < n && s[i] > mx) { mx = s[i]; idx = i; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, mx, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+                if (ov > mx || (ov == mx && oi < idx)) { mx = ov; idx = oi; }
+            }
+            return idx == 0x7fffffff ? 0 : idx;
         };
         const int t_prev = es[ES_T_PREV];
-        const int lag_t1 = index_of_max(rw6, NR) + K_MIN;
+        const int lag_t1 = index_of_max_w(rw6, NR) + K_MIN;
         const int k_from = (K_MIN > t_prev - 4 ? K_MIN : t_prev - 4) - K_MIN;
         const int k_to = (K_MAX < t_prev + 4 ? K_MAX : t_prev + 4) - K_MIN + 1;
-        const int lag_t2 = index_of_max(r6 + k_from, k_to - k_from) + k_from + K_MIN;
-        auto normvalue = [&](int lag) {
-            float v = 0.0f;
-            const int from = K_MAX - lag;
-            for (int n = from; n < from + len6; n++) v += x6[n] * x6[n];
-            return v;
-        };
-        const float nv0 = normvalue(0), nv1 = normvalue(lag_t1);
+        const int lag_t2 = index_of_max_w(r6 + k_from, k_to - k_from) + k_from + K_MIN;
+        // the three norm values are independent ordered sums: lanes 0, 1, 2 take one each
+        const int my_lag = lane == 1 ? lag_t1 : lane == 2 ? lag_t2 : 0;
+        float nv = 0.0f;
+        {
+            const int from = K_MAX - my_lag;
+            for (int n = from; n < from + len6; n++) nv += x6[n] * x6[n];
+        }
+        const float nv0 = __shfl_sync(0xffffffffu, nv, 0), nv1 = __shfl_sync(0xffffffffu, nv, 1), nv2 = __shfl_sync(0xffffffffu, nv, 2);
         const float normvalue1 = sqrtf(nv0 * nv1);
         const float normcorr1 = maxf_rs(0.0f, r6[lag_t1 - K_MIN] / normvalue1);
         float normcorr2;
         if (lag_t1 == lag_t2) normcorr2 = normcorr1;
         else {
-            const float nv2 = normvalue(lag_t2);
             const float normvalue2 = sqrtf(nv0 * nv2);
             normcorr2 = maxf_rs(0.0f, r6[lag_t2 - K_MIN] / normvalue2);
         }
         if (normcorr2 > 0.85f * normcorr1) { t_current = lag_t2; pitch_present = normcorr2 > 0.6f; }
         else { t_current = lag_t1; pitch_present = normcorr1 > 0.6f; }
     }
-    t_current = __shfl_sync(0xffffffffu, t_current, 0);
-    pitch_present = __shfl_sync(0xffffffffu, pitch_present, 0);
     // pitch_lag_parameter (:292-363)
     const int k_min = 32 > 2 * t_current - 4 ? 32 : 2 * t_current - 4;
     const int k_max = 228 < 2 * t_current + 4 ? 228 : 2 * t_current + 4;
     const float* cur = x12 + NMEM;
     WARP_STRIDE(i, 233) r12[i] = 0.0f;
     __syncwarp();
-    for (int k = k_min - 4 + lane; k <= k_max + 4; k += 32) {
+    {                                                // at most 17 lags: one per lane
+        const int k = k_min - 4 + lane;
+        const int kk = k <= k_max + 4 ? k : k_max + 4;
         float cv = 0.0f;
-        for (int n = 0; n < len12; n++) cv += cur[n] * cur[n - k];
-        r12[k - (k_min - 4)] = cv;
+        for (int n = 0; n < len12; n++) cv += cur[n] * cur[n - kk];
+        if (k <= k_max + 4) r12[k - (k_min - 4)] = cv;
     }
     __syncwarp();
     int pitch_int = k_min, pitch_fr = 0, pitch_index = 0;
@@ -433,14 +457,15 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
         sh_a[n] = dot(n - pitch_int, pitch_fr);
     }
     __syncwarp();
+    float acc3 = 0.0f;
+    {   // the three running sums are independent ordered sums: lane 0 nd*sh, lane 1 nd*nd, lane 2 sh*sh
+        const float* pa = lane == 2 ? sh_a : nd_a;
+        const float* pb = lane == 1 ? nd_a : sh_a;
+        for (int n = 0; n < len12; n++) acc3 += pa[n] * pb[n];
+    }
+    const float nd_tot = __shfl_sync(0xffffffffu, acc3, 1), sh_tot = __shfl_sync(0xffffffffu, acc3, 2);
     if (lane == 0) {
-        float nc_num = 0.0f, nd_tot = 0.0f, sh_tot = 0.0f;
-        for (int n = 0; n < len12; n++) {
-            const float nd = nd_a[n], sh = sh_a[n];
-            nc_num += nd * sh;
-            nd_tot += nd * nd;
-            sh_tot += sh * sh;
-        }
+        const float nc_num = acc3;
         const float nc_den = sqrtf(nd_tot * sh_tot);
         float nc = nc_den > 0.0f ? nc_num / nc_den : 0.0f;
         const float pitch = (float)pitch_int + (float)pitch_fr / 4.0f;
@@ -467,7 +492,6 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
             es[ES_MEM_NC] = (int32_t)__float_as_uint(0.0f);
         }
         int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
-        eh[EH_NEAR_NYQUIST] = near_nyquist;
         eh[EH_ATTACK] = attack_detected;
         eh[EH_PITCH_INDEX] = pitch_index;
         eh[EH_PITCH_PRESENT] = pitch_present;
@@ -476,7 +500,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_analysis_kernel(AnalysisPa
     }
 }
 
-cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, cudaStream_t stream) {
+cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream) {
     AnalysisParams p;
     p.cfg = st.ecfg;
     p.win = st.win;
@@ -497,19 +521,31 @@ cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size
     p.ehand = st.ehand;
     const int nf = st.cfg.nf, N = nf / 2;
     const int x12_len = (st.cfg.n_ms == LC3B_10MS ? 128 + 24 : 96 + 44) + 232;
-    // wk must hold max(nf, 160 + 160 attack scratch, 256 activation scratch) floats; cx must hold 196 + 233 floats
-    const int wk_floats = nf > 320 ? nf : 320;
-    const int cx_c2 = N > 215 ? N : 215;
-    size_t per_warp = (size_t)wk_floats * 4 + (size_t)cx_c2 * 8 + (size_t)x12_len * 4 + 178 * 4 + (size_t)2 * nf * 2 + 544 * 2;
-    per_warp = (per_warp + 15) & ~(size_t)15;
-    p.smem_per_warp = (int)per_warp;
-    p.wk_floats = wk_floats;
-    p.cx_c2 = cx_c2;
-    const size_t smem = per_warp * ANA_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(enc_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    enc_analysis_kernel<<<(st.n_streams + ANA_WARPS - 1) / ANA_WARPS, ANA_WARPS * 32, smem, stream>>>(p);
-    return cudaGetLastError();
+    const int grid = (st.n_streams + ANA_WARPS - 1) / ANA_WARPS;
+    cudaError_t e = cudaSuccess;
+    if (stages & 1) {
+        size_t per_warp = (size_t)nf * 4 + (size_t)N * 8 + (size_t)2 * nf * 2;
+        per_warp = (per_warp + 15) & ~(size_t)15;
+        p.smem_per_warp = (int)per_warp;
+        const size_t smem = per_warp * ANA_WARPS;
+        e = cudaFuncSetAttribute(enc_mdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        enc_mdct_kernel<<<grid, ANA_WARPS * 32, smem, stream>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (stages & 2) {
+        // 320 scratch floats (160 + 160 attack scratch, 2 x 128 activation scratch), 98 + 98 + 236 correlation values
+        size_t per_warp = (size_t)(320 + 98 + 98 + 236 + x12_len + 178) * 4 + 544 * 2;
+        per_warp = (per_warp + 15) & ~(size_t)15;
+        p.smem_per_warp = (int)per_warp;
+        const size_t smem = per_warp * ANA_WARPS;
+        e = cudaFuncSetAttribute(enc_ltpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        enc_ltpf_kernel<<<grid, ANA_WARPS * 32, smem, stream>>>(p);
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 }  // namespace lc3b

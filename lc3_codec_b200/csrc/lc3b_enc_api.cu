@@ -240,13 +240,13 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
         g_enc_last_cuda_error = (int)e;
         return LC3B_ERR_CUDA;
     }
-    h->stage_mask = 15;
+    h->stage_mask = 63;
     *out = h;
     return LC3B_OK;
 }
 
 int lc3b_encoder_set_stage_mask(lc3b_encoder* h, int mask) {
-    if (!h || mask < 1 || mask > 15) return LC3B_ERR_INVALID_ARG;
+    if (!h || mask < 1 || mask > 63) return LC3B_ERR_INVALID_ARG;
     h->stage_mask = mask;
     return LC3B_OK;
 }
@@ -260,8 +260,8 @@ int lc3b_encode_frames(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride
     if (nbytes < 20 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (h->stage_mask & 1) CU(launch_enc_analysis(st, pcm_in, pcm_stride, nbytes, stream));
-    if (h->stage_mask & 14) CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, h->stage_mask >> 1, stream));
+    if (h->stage_mask & 3) CU(launch_enc_analysis(st, pcm_in, pcm_stride, nbytes, h->stage_mask & 3, stream));
+    if (h->stage_mask & 60) CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, h->stage_mask >> 2, stream));
     return LC3B_OK;
 }
 
@@ -276,8 +276,8 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
     if (pcm_stride == nf) CU(cudaMemcpyAsync(st.stage_in, pcm_in, ns * nf * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
     else CU(cudaMemcpy2DAsync(st.stage_in, nf * sizeof(int16_t), pcm_in, pcm_stride * sizeof(int16_t), nf * sizeof(int16_t), ns,
                               cudaMemcpyHostToDevice, stream));
-    CU(launch_enc_analysis(st, st.stage_in, nf, nbytes, stream));
-    CU(launch_enc_quant(st, st.stage_out, nbytes, (size_t)nbytes, 7, stream));
+    CU(launch_enc_analysis(st, st.stage_in, nf, nbytes, 3, stream));
+    CU(launch_enc_quant(st, st.stage_out, nbytes, (size_t)nbytes, 15, stream));
     if (frame_stride == (size_t)nbytes) CU(cudaMemcpyAsync(frames_out, st.stage_out, ns * (size_t)nbytes, cudaMemcpyDeviceToHost, stream));
     else CU(cudaMemcpy2DAsync(frames_out, frame_stride, st.stage_out, (size_t)nbytes, (size_t)nbytes, ns, cudaMemcpyDeviceToHost, stream));
     return LC3B_OK;

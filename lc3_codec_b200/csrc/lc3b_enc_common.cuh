@@ -63,8 +63,9 @@ struct EncoderState {
     uint8_t* stage_out;    // [S][max_nbytes]
 };
 
-cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, cudaStream_t stream);
-// stages: bit 0 shape kernel (BW/SNS/TNS), bit 1 quantise kernel, bit 2 bitstream kernel
+// stages: bit 0 MDCT kernel, bit 1 attack detector + LTPF analysis kernel
+cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream);
+// stages: bit 0 SNS kernel (with the bandwidth detector), bit 1 TNS kernel, bit 2 quantise kernel, bit 3 bitstream kernel
 cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream);
 
 }  // namespace lc3b

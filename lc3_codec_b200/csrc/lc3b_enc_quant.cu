@@ -1,5 +1,5 @@
-// lc3b engine, encoder kernels 2-4 of 4: spectrum + analysis results -> bitstream, one WARP per frame.
-// Three kernels (shape: BW/SNS/TNS, quantise: gain search + rate loop, bitstream) so that each one's code stays near
+// lc3b engine, encoder kernels 2-5 of 5: spectrum + analysis results -> bitstream, one WARP per frame.
+// Four kernels (BW/SNS, TNS, quantise: gain search + rate loop, bitstream) so that each one's code stays near
 // the SM's 32 KB L1.5 instruction cache: as ONE kernel the 14k-instruction body made instruction fetch the top stall
 // (49 % of samples), every resident warp being in a different phase.
 // Compiled with -fmad=false: every expression below rounds exactly like the reference's f32 code.
@@ -1255,8 +1255,8 @@ enum {
 };
 static_assert(QH_GG < QH_WORDS, "hand-off record too small");
 
-// Kernel A: bandwidth detector, SNS, TNS.  Spectrum in place in global memory, decisions into the hand-off record.
-__global__ void __launch_bounds__(QNT_THREADS) enc_shape_kernel(QuantParams p) {
+// Kernel A1: bandwidth detector and SNS.  Spectrum in place in global memory, decisions into the hand-off record.
+__global__ void __launch_bounds__(QNT_THREADS) enc_sns_kernel(QuantParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1274,8 +1274,6 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_shape_kernel(QuantParams p) {
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     const BwRes bw = bandwidth_detect(c, S);
     const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane);
-    TnsRes tns;
-    tns_encode_w(c, xf, S, bw.bw, p.nbytes * 8, eh[EH_NEAR_NYQUIST] != 0, tns, lane);
     WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     if (lane == 0) {
@@ -1283,6 +1281,30 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_shape_kernel(QuantParams p) {
         qh[QH_IND_LF] = sns.ind_lf; qh[QH_IND_HF] = sns.ind_hf; qh[QH_SHAPE_J] = sns.shape_j; qh[QH_GIND] = sns.gind;
         qh[QH_LS_INDA] = sns.ls_inda; qh[QH_LS_INDB] = sns.ls_indb;
         qh[QH_JOINT_LO] = (int32_t)(uint32_t)sns.joint; qh[QH_JOINT_HI] = (int32_t)(uint32_t)(sns.joint >> 32);
+    }
+}
+
+// Kernel A2: TNS analysis and filtering.
+__global__ void __launch_bounds__(QNT_THREADS) enc_tns_kernel(QuantParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int stream = blockIdx.x * QW + wib;
+    if (stream >= p.n_streams) return;
+    const int ne = c.ne;
+    float* xf = (float*)(smem + (size_t)wib * (sizeof(float) * (NE_MAX + S_FLOATS)));   // [NE_MAX]
+    float* S = xf + NE_MAX;                                                             // [S_FLOATS]
+    float4* gx = (float4*)(p.xf + (size_t)stream * ne);
+    WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
+    __syncwarp();
+    const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
+    int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
+    TnsRes tns;
+    tns_encode_w(c, xf, S, qh[QH_BW], p.nbytes * 8, eh[EH_NEAR_NYQUIST] != 0, tns, lane);
+    if (tns.rc_order[0] != 0 || tns.rc_order[1] != 0) {           // the spectrum only changes when a filter is active
+        WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
+    }
+    if (lane == 0) {
         qh[QH_NBITS_TNS] = tns.nbits_tns; qh[QH_LPC_WEIGHTING] = tns.lpc_weighting; qh[QH_NUM_FILTERS] = tns.num_filters;
         qh[QH_ORDER0] = tns.rc_order[0]; qh[QH_ORDER1] = tns.rc_order[1];
     }
@@ -1417,11 +1439,13 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     wbytes = (wbytes + 15) & ~(size_t)15;
     p.w_bytes = (int)wbytes;
     cudaError_t e = cudaSuccess;
-    if (stages & 1) e = launch_one(enc_shape_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
+    if (stages & 1) e = launch_one(enc_sns_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
     if (e != cudaSuccess) return e;
-    if (stages & 2) e = launch_one(enc_quantize_kernel, p, QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX), stream);
+    if (stages & 2) e = launch_one(enc_tns_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
     if (e != cudaSuccess) return e;
-    if (stages & 4) e = launch_one(enc_bitstream_kernel, p, QW * wbytes, stream);
+    if (stages & 4) e = launch_one(enc_quantize_kernel, p, QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX), stream);
+    if (e != cudaSuccess) return e;
+    if (stages & 8) e = launch_one(enc_bitstream_kernel, p, QW * wbytes, stream);
     return e;
 }
 
