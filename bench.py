@@ -457,7 +457,10 @@ def main():
     if traffic_file.exists():
         try:
             t = json.loads(traffic_file.read_text())
-            roofline["traffic"] = t.get(args.workload, {}).get(dom_name)
+            per_frame = t.get("dram_bytes_per_stream_frame", {}).get(args.workload, {}).get(dom_name)
+            if per_frame is not None:                  # ncu figure is per stream-frame; one launch covers S of them
+                roofline["traffic"] = per_frame * S
+                roofline["traffic_source"] = t.get("source")
         except Exception:
             pass
 
