@@ -209,11 +209,20 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
     float* r12 = rw6 + 98;                          // up to 233 values
     float* x12 = r12 + 236;                         // x12_len floats
     float* x6 = x12 + c.x12_len;                    // 178 floats
-    int16_t* xs = (int16_t*)(x6 + 178);             // x_s_ext_len (<= 540)
+    float* xs = x6 + 178;                           // x_s_ext_len (<= 540) input samples as f32 (exact)
 
     const int16_t* x = p.pcm + (size_t)stream * p.pcm_stride;     // this frame's input samples
     int32_t* es = p.estate + (size_t)stream * ES_WORDS;
     const int near_nyquist = p.ehand[(size_t)stream * EH_WORDS + EH_NEAR_NYQUIST];
+    const int up = c.up, ns_keep = 240 / up;
+    {   // x_s_extended (long_term_post_filter.rs:217-224): last 240/up samples of the previous frame, then this frame
+        int16_t* xh = p.xs_hist + (size_t)stream * 64;
+        WARP_STRIDE(n, ns_keep) xs[n] = (float)xh[n];
+        WARP_STRIDE(n, nf) xs[ns_keep + n] = (float)x[n];
+        WARP_STRIDE(n, ns_keep) xh[n] = x[nf - ns_keep + n];
+    }
+    __syncwarp();
+    const float* xcur = xs + ns_keep;                // this frame's samples in shared memory
 
     // ---- attack detector (attack_detector.rs:45-105)
     int attack_detected = 0;
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
             __syncwarp();
             WARP_STRIDE(n, nds) {
                 int32_t s = 0;
-                for (int j = 0; j < block_len; j++) s += (int32_t)x[block_len * n + j];
+                for (int j = 0; j < block_len; j++) s += (int32_t)xcur[block_len * n + j];
                 ds[n] = s;
             }
             __syncwarp();
@@ -283,21 +292,16 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
 
     // ---- LTPF analysis (long_term_post_filter.rs:139-215)
     constexpr int NMEM = 232, K_MIN = 17, K_MAX = 114;
-    const int len12 = c.len12p8, len6 = c.len6p4, up = c.up;
+    const int len12 = c.len12p8, len6 = c.len6p4;
     const int t_nbits = c.n_ms == LC3B_7P5MS ? (int)round((double)(p.nbytes * 8) * 10.0 / 7.5) : p.nbytes * 8;
     const bool gain_ltpf_on = t_nbits < 560 + c.fs_ind * 80;
     {   // shift_out_old_samples (:217-230)
-        const int ns_keep = 240 / up;
-        int16_t* xh = p.xs_hist + (size_t)stream * 64;
         float* g12 = p.x12 + (size_t)stream * c.x12_len;
         float* g6 = p.x6 + (size_t)stream * 178;
-        WARP_STRIDE(n, ns_keep) xs[n] = xh[n];
-        WARP_STRIDE(n, nf) xs[ns_keep + n] = x[n];
         WARP_STRIDE(n, c.x12_len - len12) x12[n] = g12[n + len12];
         WARP_STRIDE(n, 178 - len6) x6[n] = g6[n + len6];
         WARP_STRIDE_FROM(n, 178 - len6, 178) x6[n] = 0.0f;   // overwritten below where it matters
         __syncwarp();
-        WARP_STRIDE(n, ns_keep) xh[n] = xs[nf + n];       // last 240/up samples of this frame
     }
     float* x12n = x12 + c.delay + NMEM;             // where this frame's resampled samples go
     WARP_STRIDE(n, len12) {        // resampling (:152-166)
@@ -305,24 +309,39 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
         const int q15 = (15 * n) / up, r15 = (15 * n) % up;
         // the reference walks k = -120/up ..= 120/up and skips taps with |up k - r15| >= 120: exactly the first one,
         // and the last one when r15 == 0 (up divides 120)
+        // (up divides 120).  resamp_ph is the filter in phase-major order: ph[j] = h[up (j - kq + 1) - r15].
         const int kq = 120 / up;
-        const int16_t* xp = xs + 240 / up + q15 - kq;
-        const float* hp = LC3T_TAB_RESAMP_FILTER + 119 - r15;
-        for (int k = -kq + 1; k < kq; k++) acc += (float)xp[k] * hp[up * k];
-        if (r15 != 0) acc += (float)xp[kq] * hp[up * kq];
+        const float* xp = xs + q15 + 1;
+        const float* ph = c.resamp_ph + r15 * (2 * kq);
+#pragma unroll 4
+        for (int j = 0; j < 2 * kq - 1; j++) acc += xp[j] * ph[j];
+        if (r15 != 0) acc += xp[2 * kq - 1] * ph[2 * kq - 1];
         x12n[n] = acc * ((float)up * c.resamp_fac);
     }
     __syncwarp();
-    if (lane == 0) {                                 // 50 Hz high-pass biquad (:169-177), serial
-        float m1 = __uint_as_float((uint32_t)es[ES_H50_M1]), m2 = __uint_as_float((uint32_t)es[ES_H50_M2]);
-        for (int n = 0; n < len12; n++) {
-            const float h50 = x12n[n] - -1.9652933726226904f * m1 - 0.9658854605688177f * m2;
-            x12n[n] = 0.9827947082978771f * h50 + -1.965589416595754f * m1 + 0.9827947082978771f * m2;
-            m2 = m1;
-            m1 = h50;
+    {   // 50 Hz high-pass biquad (:169-177): the recursive half (h50) is a serial chain on lane 0, the feed-forward
+        // half only needs h50[n], h50[n-1], h50[n-2] and runs on all lanes
+        const float m1_0 = __uint_as_float((uint32_t)es[ES_H50_M1]), m2_0 = __uint_as_float((uint32_t)es[ES_H50_M2]);
+        float* h50s = wk;                            // len12 <= 128 floats (attack scratch is dead by now)
+        __syncwarp();
+        if (lane == 0) {
+            float m1 = m1_0, m2 = m2_0;
+            for (int n = 0; n < len12; n++) {
+                const float h50 = x12n[n] - -1.9652933726226904f * m1 - 0.9658854605688177f * m2;
+                h50s[n] = h50;
+                m2 = m1;
+                m1 = h50;
+            }
+            es[ES_H50_M1] = (int32_t)__float_as_uint(m1);
+            es[ES_H50_M2] = (int32_t)__float_as_uint(m2);
         }
-        es[ES_H50_M1] = (int32_t)__float_as_uint(m1);
-        es[ES_H50_M2] = (int32_t)__float_as_uint(m2);
+        __syncwarp();
+        WARP_STRIDE(n, len12) {
+            const float h50 = h50s[n];
+            const float m1 = n >= 1 ? h50s[n - 1] : m1_0;
+            const float m2 = n >= 2 ? h50s[n - 2] : (n == 1 ? m1_0 : m2_0);
+            x12n[n] = 0.9827947082978771f * h50 + -1.965589416595754f * m1 + 0.9827947082978771f * m2;
+        }
     }
     __syncwarp();
     {   // write the shifted + new 12.8 kHz samples back (state for the next frame)
@@ -341,13 +360,31 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
         WARP_STRIDE(n, 178) g6[n] = x6[n];
     }
     constexpr int NR = K_MAX + 1 - K_MIN;
-    WARP_STRIDE(k, NR) {
-        const int from_k = K_MAX - K_MIN - k;
-        float s = 0.0f;
-        for (int n = 0; n < len6; n++) s += x6[K_MAX + n] * x6[from_k + n];
-        r6[k] = s;
-        const float weight = 1.0f - 0.5f * (float)k / (float)(K_MAX - K_MIN);
-        rw6[k] = weight * s;
+    {   // 98 lags: lane l owns lags l, l+32, l+64 (and l+96 for l < 2), accumulated side by side so that the
+        // x6[K_MAX + n] load and the loop are shared; each sum keeps its own order
+        const int k0 = lane, k1 = lane + 32, k2 = lane + 64, k3 = lane + 96 < NR ? lane + 96 : NR - 1;
+        const float* a = x6 + K_MAX;
+        const float* b0 = x6 + (K_MAX - K_MIN - k0);
+        const float* b1 = x6 + (K_MAX - K_MIN - k1);
+        const float* b2 = x6 + (K_MAX - K_MIN - k2);
+        const float* b3 = x6 + (K_MAX - K_MIN - k3);
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        for (int n = 0; n < len6; n++) {
+            const float an = a[n];
+            s0 += an * b0[n];
+            s1 += an * b1[n];
+            s2 += an * b2[n];
+            s3 += an * b3[n];
+        }
+        auto put = [&](int k, float sv) {
+            r6[k] = sv;
+            const float weight = 1.0f - 0.5f * (float)k / (float)(K_MAX - K_MIN);
+            rw6[k] = weight * sv;
+        };
+        put(k0, s0);
+        put(k1, s1);
+        put(k2, s2);
+        if (lane + 96 < NR) put(k3, s3);
     }
     __syncwarp();
     int t_current = 0, pitch_present = 0;
@@ -536,7 +573,7 @@ cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size
     }
     if (stages & 2) {
         // 320 scratch floats (160 + 160 attack scratch, 2 x 128 activation scratch), 98 + 98 + 236 correlation values
-        size_t per_warp = (size_t)(320 + 98 + 98 + 236 + x12_len + 178) * 4 + 544 * 2;
+        size_t per_warp = (size_t)(320 + 98 + 98 + 236 + x12_len + 178 + 544) * 4;
         per_warp = (per_warp + 15) & ~(size_t)15;
         p.smem_per_warp = (int)per_warp;
         const size_t smem = per_warp * ANA_WARPS;

@@ -78,6 +78,14 @@ __global__ void enc_init_band_kernel(EncConfig* cfg) {
              : cfg->fs_ind == 2 ? LC3T_I_24000_10MS : cfg->fs_ind == 3 ? LC3T_I_32000_10MS : LC3T_I_48000_10MS;
     }
     for (int b = threadIdx.x; b < 65; b += blockDim.x) cfg->band_idx[b] = b <= cfg->nb ? bi[b] : cfg->ne;
+    {
+        const int up = cfg->up, kq = 120 / up;
+        for (int i = threadIdx.x; i < 240; i += blockDim.x) {
+            const int r = i / (2 * kq), j = i - r * (2 * kq);
+            const int index_h = up * (j - kq + 1) - r;
+            cfg->resamp_ph[i] = (index_h > -120 && index_h < 120) ? LC3T_TAB_RESAMP_FILTER[119 + index_h] : 0.0f;
+        }
+    }
     for (int k = threadIdx.x; k < 400; k += blockDim.x) {
         int band = 255;
         for (int b = 0; b < cfg->nb; b++) if (k >= bi[b] && k < bi[b + 1]) band = b;

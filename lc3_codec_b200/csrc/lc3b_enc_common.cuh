@@ -19,6 +19,7 @@ struct EncConfig {
     // LTPF analysis (encoder/long_term_post_filter.rs:91-124)
     int32_t len12p8, len6p4, delay, up, x_s_ext_len, x12_len;
     float resamp_fac;
+    float resamp_ph[240];             // TAB_RESAMP_FILTER in phase-major order: [r][j] = h[up (j - 120/up + 1) - r], 0 outside (-120, 120)
     // attack detector (attack_detector.rs:24-43)
     int32_t att_num_ds, att_num_blocks, att_pos_limit;
     float tns_sin[17];
