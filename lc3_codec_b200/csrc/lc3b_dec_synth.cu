@@ -31,6 +31,7 @@ struct SynthParams {
     size_t pcm_stride;
     int n_streams;
     int hist_len;        // ltpf_blocks * nf
+    int y_floats;        // max(hist_len, 2 * nf): the FFT ping-pong buffers and the LTPF history share this space
     int smem_per_warp;   // bytes
 };
 
@@ -119,8 +120,9 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
     uint8_t* base = smem + (size_t)wid * p.smem_per_warp;
     float2* bufA = (float2*)base;                 // N complex
     float2* bufB = bufA + N;                      // N complex
-    float* X = (float*)(bufB + N);                // nf floats: spectrum in, then DCT-IV output, then time samples
-    float* Y = X + nf;                            // hist_len floats: LTPF circular history (only touched when filtering)
+    float* Y = (float*)base;                      // hist_len floats: LTPF circular history, over the (then dead) FFT buffers
+    float* X = (float*)base + p.y_floats;         // nf floats: spectrum in, then DCT-IV output, then time samples
+    float* scratch = X + nf;                      // l_num + norm floats: frozen history for transition case 5
 
     const int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
     int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
@@ -130,8 +132,14 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
     const float* sp = p.spec + ((size_t)slot * p.n_streams + stream) * ne;
 
     // ---- spectrum load, with concealment (packet_loss_concealment.rs:63-85) when the frame was bad
+    // overlap memory: requested now, consumed after the FFT (ceil(300 / 32) = 10 values per lane at most)
+    float* ola = p.ola + (size_t)stream * (nf - z);
+    float ola_r[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) { const int n = lane + 32 * j; ola_r[j] = n < nf - z ? ola[n] : 0.0f; }
     if (ok) {
-        for (int k = lane; k < nf; k += 32) X[k] = k < ne ? sp[k] : 0.0f;
+        for (int k4 = lane; k4 < nf / 4; k4 += 32)
+            ((float4*)X)[k4] = 4 * k4 < ne ? ((const float4*)sp)[k4] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (lane == 0) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
     } else {
         int lost = ss[SS_PLC_LOST];
@@ -191,18 +199,22 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
         if (m < nf + h) return -X[h - 1 - (m - nf)];
         return -X[m - 3 * h];
     };
-    float* ola = p.ola + (size_t)stream * (nf - z);
-    float* T = (float*)bufA;                       // reuse: nf output samples + (nf - z) new overlap memory fit in 2N complex
-    for (int n = lane; n < nf; n += 32) {
-        float o;
-        if (n < nf - z) o = ola[n] + t_at(z + n) * p.win[z + n];
-        else o = t_at(nf + (n - (nf - z))) * p.win[nf + (n - (nf - z))];
-        T[n] = o;
+    float* T = (float*)bufA;                       // reuse: nf output samples fit in N complex
+#pragma unroll
+    for (int j = 0; j < 15; j++) {
+        const int n = lane + 32 * j;
+        if (n < nf) {
+            float o;
+            if (n < nf - z) o = (j < 10 ? ola_r[j < 10 ? j : 0] : 0.0f) + t_at(z + n) * p.win[z + n];
+            else o = t_at(nf + (n - (nf - z))) * p.win[nf + (n - (nf - z))];
+            T[n] = o;
+        }
     }
     __syncwarp();                                  // all reads of the old X-derived values for the first half are done
     for (int n = lane; n < nf - z; n += 32) ola[n] = t_at(nf + z + n) * p.win[nf + z + n];
     __syncwarp();
     for (int n = lane; n < nf; n += 32) X[n] = T[n];   // X = x_hat (input of the post filter)
+    const float xtail_next = T[nf - 16 + (lane & 15)]; // last 16 samples of the filter INPUT, kept before Y reuses the buffer
     __syncwarp();
 
     // ---- long term post filter (long_term_post_filter.rs:252-343)
@@ -292,7 +304,6 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
         } else {                                     // case 5
             deactivate_first();
             // activate_first_2p5ms_from_mem :345-378: numerator taps read a frozen copy of y[blk-l_num .. blk+norm)
-            float* scratch = (float*)bufB;
             for (int i = lane; i < l_num + norm; i += 32) {
                 int src;
                 if (blk < l_num) src = i < l_num ? blocks * nf - l_num + i : i - l_num;
@@ -314,9 +325,8 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
         for (int n = lane; n < nf; n += 32) { const float v = Y[blk + n]; yhist[blk + n] = v; X[n] = v; }
     }
     __syncwarp();
-    // x tail for the next frame: last 16 samples of this frame's x_hat (the filter INPUT).  X may hold the
-    // filter output by now; T (bufA) still holds the input (case 5's scratch lives in bufB).
-    if (lane < 16) xtail[lane] = T[nf - 16 + lane];
+    // x tail for the next frame: last 16 samples of this frame's x_hat (the filter INPUT; X may hold the output by now)
+    if (lane < 16) xtail[lane] = xtail_next;
     if (lane == 0) {
         ss[SS_LTPF_PREV] = (active ? 1 : 0) | ((active ? code : 4) << 8);
         ss[SS_LTPF_PINT] = p_int;
@@ -354,7 +364,9 @@ cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_st
     const int nf = st.cfg.nf, N = nf / 2;
     const int blocks = st.cfg.n_ms == LC3B_10MS ? 2 : 3;
     p.hist_len = blocks * nf;
-    size_t per_warp = (size_t)2 * N * sizeof(float2) + (size_t)nf * 4 + (size_t)p.hist_len * 4;
+    // [FFT ping-pong buffers | LTPF history] + spectrum/time samples + case-5 scratch
+    p.y_floats = p.hist_len > 4 * N ? p.hist_len : 4 * N;
+    size_t per_warp = (size_t)p.y_floats * 4 + (size_t)nf * 4 + (size_t)(16 + nf / 3 + 16) * 4;
     per_warp = (per_warp + 15) & ~(size_t)15;
     p.smem_per_warp = (int)per_warp;
     const size_t smem = per_warp * SYN_WARPS;
