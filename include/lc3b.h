@@ -129,6 +129,11 @@ int lc3b_encode_frames(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride
 /* Same with HOST buffers (pinned => asynchronous). */
 int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride, uint8_t* frames_out, int nbytes,
                             size_t frame_stride, void* cuda_stream);
+/* Optional pipelining of lc3b_encode_frames_host.  Off (default): copies and kernels ride `cuda_stream`.  On: the
+ * host->device PCM copy runs on an internal stream into a double-buffered staging area, so the upload of call i+1
+ * overlaps the kernels of call i.  Results are ordered on `cuda_stream` as before (the bitstream copy stays on it);
+ * the caller's PCM buffer must stay valid until the call's work has drained, as with any asynchronous copy. */
+int lc3b_encoder_set_host_pipelining(lc3b_encoder* h, int on);
 /* Test hook: device copies of the last encode's intermediates (any pointer may be NULL): xf [S][ne] f32 (quantiser
  * input, after SNS and TNS), e_b [S][64] f32, hand [S][8] i32 (near_nyquist, attack, pitch_index, pitch_present,
  * ltpf_active, nbits_ltpf), xq [S][ne] i16. */

@@ -300,6 +300,8 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     cudaError_t e = cudaMemsetAsync(dev_workspace, 0, L.total, stream);   // the reference is handed zeroed buffers
     if (e == cudaSuccess) e = cudaMemcpyAsync(st.dcfg, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);               // hc is a stack object
+    if (e == cudaSuccess) e = prepare_entropy(st);
+    if (e == cudaSuccess) e = prepare_synth(st);
     if (e == cudaSuccess) {
         init_tables_kernel<<<1, 256, 0, stream>>>(st.dcfg, st.win, st.dtw, st.ftw);
         init_sym_lut_kernel<<<64, 256, 0, stream>>>(st.sym_lut);

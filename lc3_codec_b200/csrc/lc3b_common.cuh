@@ -92,6 +92,8 @@ enum {
     SS_WORDS = 8
 };
 
+cudaError_t prepare_entropy(const DecoderState& st);   // shared-memory limits of the kernels, once per handle
+cudaError_t prepare_synth(const DecoderState& st);
 cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
                            size_t frame_stride, int32_t* status_out, cudaStream_t stream);
 cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream);

@@ -720,6 +720,19 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
     }
 }
 
+static int entropy_row_pitch(int nbytes) {
+    int words = (nbytes + 3) / 4 + 1;
+    if ((words & 1) == 0) words++;                 // odd word pitch: lanes land on distinct banks
+    return words * 4;
+}
+
+// dynamic shared memory limit, once per handle (lc3b_decoder_init) for the largest frame the handle accepts
+cudaError_t prepare_entropy(const DecoderState& st) {
+    const int smem = (int)entropy_smem_bytes(entropy_row_pitch(st.max_nbytes));
+    if (st.cfg.n_ms == LC3B_10MS) return cudaFuncSetAttribute(entropy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return cudaFuncSetAttribute(entropy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
                            size_t frame_stride, int32_t* status_out, cudaStream_t stream) {
     EntropyParams p;
@@ -737,21 +750,11 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
     p.trace = st.trace;
     p.trace_x = st.trace_x;
     p.sym_lut = st.sym_lut;
-    int words = (nbytes + 3) / 4 + 1;
-    if ((words & 1) == 0) words++;                 // odd word pitch: lanes land on distinct banks
-    p.row_pitch = words * 4;
+    p.row_pitch = entropy_row_pitch(nbytes);
     const size_t smem = entropy_smem_bytes(p.row_pitch);
     const int grid = (st.n_streams + ENT_THREADS - 1) / ENT_THREADS;
-    cudaError_t e;
-    if (st.cfg.n_ms == LC3B_10MS) {
-        e = cudaFuncSetAttribute(entropy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        entropy_kernel<3><<<grid, ENT_THREADS, smem, stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(entropy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        entropy_kernel<2><<<grid, ENT_THREADS, smem, stream>>>(p);
-    }
+    if (st.cfg.n_ms == LC3B_10MS) entropy_kernel<3><<<grid, ENT_THREADS, smem, stream>>>(p);
+    else entropy_kernel<2><<<grid, ENT_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -346,6 +346,24 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
     }
 }
 
+static size_t synth_warp_bytes(const lc3b_config& c, int* hist_len, int* y_floats) {
+    const int nf = c.nf, N = nf / 2;
+    const int blocks = c.n_ms == LC3B_10MS ? 2 : 3;
+    const int hl = blocks * nf;
+    // [FFT ping-pong buffers | LTPF history] + spectrum/time samples + case-5 scratch
+    const int yf = hl > 4 * N ? hl : 4 * N;
+    size_t per_warp = (size_t)yf * 4 + (size_t)nf * 4 + (size_t)(16 + nf / 3 + 16) * 4;
+    per_warp = (per_warp + 15) & ~(size_t)15;
+    if (hist_len) *hist_len = hl;
+    if (y_floats) *y_floats = yf;
+    return per_warp;
+}
+
+cudaError_t prepare_synth(const DecoderState& st) {
+    return cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(synth_warp_bytes(st.cfg, nullptr, nullptr) * SYN_WARPS));
+}
+
 cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream) {
     SynthParams p;
     p.cfg = st.dcfg;
@@ -361,19 +379,10 @@ cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_st
     p.pcm_out = pcm_out;
     p.pcm_stride = pcm_stride;
     p.n_streams = st.n_streams;
-    const int nf = st.cfg.nf, N = nf / 2;
-    const int blocks = st.cfg.n_ms == LC3B_10MS ? 2 : 3;
-    p.hist_len = blocks * nf;
-    // [FFT ping-pong buffers | LTPF history] + spectrum/time samples + case-5 scratch
-    p.y_floats = p.hist_len > 4 * N ? p.hist_len : 4 * N;
-    size_t per_warp = (size_t)p.y_floats * 4 + (size_t)nf * 4 + (size_t)(16 + nf / 3 + 16) * 4;
-    per_warp = (per_warp + 15) & ~(size_t)15;
+    const size_t per_warp = synth_warp_bytes(st.cfg, &p.hist_len, &p.y_floats);
     p.smem_per_warp = (int)per_warp;
-    const size_t smem = per_warp * SYN_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const int grid = (st.n_streams + SYN_WARPS - 1) / SYN_WARPS;
-    synth_kernel<<<grid, SYN_WARPS * 32, smem, stream>>>(p);
+    synth_kernel<<<grid, SYN_WARPS * 32, per_warp * SYN_WARPS, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -537,6 +537,27 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
     }
 }
 
+static size_t mdct_warp_bytes(int nf) {
+    size_t per_warp = (size_t)nf * 4 + (size_t)(nf / 2) * 8 + (size_t)2 * nf * 2;
+    return (per_warp + 15) & ~(size_t)15;
+}
+static size_t ltpf_warp_bytes(const lc3b_config& c) {
+    const int x12_len = (c.n_ms == LC3B_10MS ? 128 + 24 : 96 + 44) + 232;
+    // 320 scratch floats (160 + 160 attack scratch, 2 x 128 activation scratch), 98 + 98 + 236 correlation values,
+    // the 12.8 kHz and 6.4 kHz buffers, the input samples as f32
+    size_t per_warp = (size_t)(320 + 98 + 98 + 236 + x12_len + 178 + 544) * 4;
+    return (per_warp + 15) & ~(size_t)15;
+}
+
+// dynamic shared memory limits, once per handle (lc3b_encoder_init)
+cudaError_t prepare_enc_analysis(const EncoderState& st) {
+    cudaError_t e = cudaFuncSetAttribute(enc_mdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(mdct_warp_bytes(st.cfg.nf) * ANA_WARPS));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(enc_ltpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ltpf_warp_bytes(st.cfg) * ANA_WARPS));
+    return e;
+}
+
 cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream) {
     AnalysisParams p;
     p.cfg = st.ecfg;
@@ -556,33 +577,18 @@ cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size
     p.xf = st.xf;
     p.e_b = st.e_b;
     p.ehand = st.ehand;
-    const int nf = st.cfg.nf, N = nf / 2;
-    const int x12_len = (st.cfg.n_ms == LC3B_10MS ? 128 + 24 : 96 + 44) + 232;
     const int grid = (st.n_streams + ANA_WARPS - 1) / ANA_WARPS;
-    cudaError_t e = cudaSuccess;
     if (stages & 1) {
-        size_t per_warp = (size_t)nf * 4 + (size_t)N * 8 + (size_t)2 * nf * 2;
-        per_warp = (per_warp + 15) & ~(size_t)15;
+        const size_t per_warp = mdct_warp_bytes(st.cfg.nf);
         p.smem_per_warp = (int)per_warp;
-        const size_t smem = per_warp * ANA_WARPS;
-        e = cudaFuncSetAttribute(enc_mdct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        enc_mdct_kernel<<<grid, ANA_WARPS * 32, smem, stream>>>(p);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        enc_mdct_kernel<<<grid, ANA_WARPS * 32, per_warp * ANA_WARPS, stream>>>(p);
     }
     if (stages & 2) {
-        // 320 scratch floats (160 + 160 attack scratch, 2 x 128 activation scratch), 98 + 98 + 236 correlation values
-        size_t per_warp = (size_t)(320 + 98 + 98 + 236 + x12_len + 178 + 544) * 4;
-        per_warp = (per_warp + 15) & ~(size_t)15;
+        const size_t per_warp = ltpf_warp_bytes(st.cfg);
         p.smem_per_warp = (int)per_warp;
-        const size_t smem = per_warp * ANA_WARPS;
-        e = cudaFuncSetAttribute(enc_ltpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        enc_ltpf_kernel<<<grid, ANA_WARPS * 32, smem, stream>>>(p);
-        e = cudaGetLastError();
+        enc_ltpf_kernel<<<grid, ANA_WARPS * 32, per_warp * ANA_WARPS, stream>>>(p);
     }
-    return e;
+    return cudaGetLastError();
 }
 
 }  // namespace lc3b

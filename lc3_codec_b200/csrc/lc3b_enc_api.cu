@@ -49,7 +49,7 @@ static EncLayout make_enc_layout(const lc3b_config& c, int n_streams, int max_nb
     L.xq = take(off, sizeof(int16_t) * ns * c.ne);
     L.qhand = take(off, sizeof(int32_t) * ns * QH_WORDS);
     L.lsbs = take(off, ns * 2 * c.ne);
-    L.stage_in = take(off, sizeof(int16_t) * ns * c.nf);
+    L.stage_in = take(off, sizeof(int16_t) * ns * c.nf * 2);   // double-buffered for the pipelined host path
     L.stage_out = take(off, ns * (size_t)max_nbytes);
     L.total = off;
     return L;
@@ -170,6 +170,12 @@ using namespace lc3b;
 struct lc3b_encoder {
     EncoderState st;
     int stage_mask;
+    // optional pipelining of the host entry point: PCM arrives on an internal copy stream into a double-buffered
+    // staging area, so the upload of call i+1 overlaps the kernels of call i
+    int pipelined, buf;
+    cudaStream_t copy_stream;
+    cudaEvent_t h2d_done[2], consumed[2];
+    bool consumed_valid[2];
 };
 
 extern bool lc3b_make_config(int sf, int fd, lc3b_config* c);
@@ -237,6 +243,8 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
     if (e == cudaSuccess) e = cudaMemcpyAsync(st.perm, hp, sizeof(int32_t) * N, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     free(hc); free(hd); free(hf); free(hp);
+    if (e == cudaSuccess) e = prepare_enc_analysis(st);
+    if (e == cudaSuccess) e = prepare_enc_quant(st);
     if (e == cudaSuccess) {
         enc_init_band_kernel<<<1, 128, 0, stream>>>(st.ecfg);
         enc_init_tables_kernel<<<1, 256, 0, stream>>>(st.ecfg, st.win);
@@ -249,6 +257,10 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
         return LC3B_ERR_CUDA;
     }
     h->stage_mask = 63;
+    h->pipelined = 0;
+    h->buf = 0;
+    h->copy_stream = nullptr;
+    h->consumed_valid[0] = h->consumed_valid[1] = false;
     *out = h;
     return LC3B_OK;
 }
@@ -281,10 +293,26 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
         return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const size_t ns = (size_t)st.n_streams, nf = (size_t)st.cfg.nf;
-    if (pcm_stride == nf) CU(cudaMemcpyAsync(st.stage_in, pcm_in, ns * nf * sizeof(int16_t), cudaMemcpyHostToDevice, stream));
-    else CU(cudaMemcpy2DAsync(st.stage_in, nf * sizeof(int16_t), pcm_in, pcm_stride * sizeof(int16_t), nf * sizeof(int16_t), ns,
-                              cudaMemcpyHostToDevice, stream));
-    CU(launch_enc_analysis(st, st.stage_in, nf, nbytes, 3, stream));
+    int16_t* stage = st.stage_in + (h->pipelined ? (size_t)h->buf * ns * nf : 0);
+    cudaStream_t in_stream = stream;
+    if (h->pipelined) {
+        in_stream = h->copy_stream;
+        // the staging buffer is free again once the two analysis kernels of the call that used it have run
+        if (h->consumed_valid[h->buf]) CU(cudaStreamWaitEvent(in_stream, h->consumed[h->buf], 0));
+    }
+    if (pcm_stride == nf) CU(cudaMemcpyAsync(stage, pcm_in, ns * nf * sizeof(int16_t), cudaMemcpyHostToDevice, in_stream));
+    else CU(cudaMemcpy2DAsync(stage, nf * sizeof(int16_t), pcm_in, pcm_stride * sizeof(int16_t), nf * sizeof(int16_t), ns,
+                              cudaMemcpyHostToDevice, in_stream));
+    if (h->pipelined) {
+        CU(cudaEventRecord(h->h2d_done[h->buf], in_stream));
+        CU(cudaStreamWaitEvent(stream, h->h2d_done[h->buf], 0));
+    }
+    CU(launch_enc_analysis(st, stage, nf, nbytes, 3, stream));
+    if (h->pipelined) {
+        CU(cudaEventRecord(h->consumed[h->buf], stream));
+        h->consumed_valid[h->buf] = true;
+        h->buf ^= 1;
+    }
     CU(launch_enc_quant(st, st.stage_out, nbytes, (size_t)nbytes, 15, stream));
     if (frame_stride == (size_t)nbytes) CU(cudaMemcpyAsync(frames_out, st.stage_out, ns * (size_t)nbytes, cudaMemcpyDeviceToHost, stream));
     else CU(cudaMemcpy2DAsync(frames_out, frame_stride, st.stage_out, (size_t)nbytes, (size_t)nbytes, ns, cudaMemcpyDeviceToHost, stream));
@@ -305,6 +333,28 @@ int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* han
     return LC3B_OK;
 }
 
-void lc3b_encoder_destroy(lc3b_encoder* h) { free(h); }
+int lc3b_encoder_set_host_pipelining(lc3b_encoder* h, int on) {
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    if (on && !h->copy_stream) {
+        CU(cudaSetDevice(h->st.device));
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&h->h2d_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->consumed[i], cudaEventDisableTiming));
+        }
+    }
+    h->pipelined = on ? 1 : 0;
+    return LC3B_OK;
+}
+
+void lc3b_encoder_destroy(lc3b_encoder* h) {
+    if (!h) return;
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(h->h2d_done[i]); cudaEventDestroy(h->consumed[i]); }
+        cudaStreamDestroy(h->copy_stream);
+    }
+    free(h);
+}
 
 }  // extern "C"

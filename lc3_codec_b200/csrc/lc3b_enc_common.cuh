@@ -64,6 +64,8 @@ struct EncoderState {
     uint8_t* stage_out;    // [S][max_nbytes]
 };
 
+cudaError_t prepare_enc_analysis(const EncoderState& st);   // shared-memory limits of the kernels, once per handle
+cudaError_t prepare_enc_quant(const EncoderState& st);
 // stages: bit 0 MDCT kernel, bit 1 attack detector + LTPF analysis kernel
 cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream);
 // stages: bit 0 SNS kernel (with the bandwidth detector), bit 1 TNS kernel, bit 2 quantise kernel, bit 3 bitstream kernel

@@ -1408,12 +1408,29 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams 
     }
 }
 
-template <class K>
-static cudaError_t launch_one(K kernel, const QuantParams& p, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kernel<<<(p.n_streams + QW - 1) / QW, QNT_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
+static size_t bitstream_warp_bytes(int ne, int nbytes, QuantParams* p) {
+    const int nbits = nbytes * 8;
+    const int side_words = (nbits + 31) / 32 + 2;
+    const int sym_cap = ne / 2 + nbits / 2 + 32;      // tuples + escapes the truncation rule can admit (2 bits each at least)
+    const int out_words = (nbytes + 3) / 4 + 1;
+    size_t wbytes = sizeof(float) * NE_MAX + sizeof(int16_t) * NE_MAX + sizeof(int) * 16 +
+                    sizeof(uint32_t) * (size_t)(TAIL_WORDS + side_words + sym_cap + out_words);
+    wbytes = (wbytes + 15) & ~(size_t)15;
+    if (p) { p->side_words = side_words; p->sym_cap = sym_cap; p->out_words = out_words; p->w_bytes = (int)wbytes; }
+    return wbytes;
+}
+constexpr size_t SHAPE_SMEM = QW * sizeof(float) * (NE_MAX + S_FLOATS);
+constexpr size_t QUANTIZE_SMEM = QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX);
+
+// dynamic shared memory limits, once per handle (lc3b_encoder_init) for the largest frame the handle accepts
+cudaError_t prepare_enc_quant(const EncoderState& st) {
+    cudaError_t e = cudaFuncSetAttribute(enc_sns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHAPE_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_tns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHAPE_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QUANTIZE_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(enc_bitstream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(QW * bitstream_warp_bytes(st.cfg.ne, st.max_nbytes, nullptr)));
+    return e;
 }
 
 cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream) {
@@ -1430,23 +1447,13 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     p.qhand = st.qhand;
     p.lsbs = st.lsbs;
     p.frames_out = frames_out;
-    const int nbits = nbytes * 8;
-    p.side_words = (nbits + 31) / 32 + 2;
-    p.sym_cap = st.cfg.ne / 2 + nbits / 2 + 32;       // tuples + escapes the truncation rule can admit (2 bits each at least)
-    p.out_words = (nbytes + 3) / 4 + 1;
-    size_t wbytes = sizeof(float) * NE_MAX + sizeof(int16_t) * NE_MAX + sizeof(int) * 16 +
-                    sizeof(uint32_t) * (size_t)(TAIL_WORDS + p.side_words + p.sym_cap + p.out_words);
-    wbytes = (wbytes + 15) & ~(size_t)15;
-    p.w_bytes = (int)wbytes;
-    cudaError_t e = cudaSuccess;
-    if (stages & 1) e = launch_one(enc_sns_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
-    if (e != cudaSuccess) return e;
-    if (stages & 2) e = launch_one(enc_tns_kernel, p, QW * sizeof(float) * (NE_MAX + S_FLOATS), stream);
-    if (e != cudaSuccess) return e;
-    if (stages & 4) e = launch_one(enc_quantize_kernel, p, QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX), stream);
-    if (e != cudaSuccess) return e;
-    if (stages & 8) e = launch_one(enc_bitstream_kernel, p, QW * wbytes, stream);
-    return e;
+    const size_t wbytes = bitstream_warp_bytes(st.cfg.ne, nbytes, &p);
+    const int grid = (p.n_streams + QW - 1) / QW;
+    if (stages & 1) enc_sns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
+    if (stages & 2) enc_tns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
+    if (stages & 4) enc_quantize_kernel<<<grid, QNT_THREADS, QUANTIZE_SMEM, stream>>>(p);
+    if (stages & 8) enc_bitstream_kernel<<<grid, QNT_THREADS, QW * wbytes, stream>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace lc3b

@@ -77,6 +77,12 @@ class Lc3BatchEncoder:
         if rc:
             raise Lc3bError(rc, fn.__name__)
 
+    def set_host_pipelining(self, on: bool) -> None:
+        """Let the PCM upload of encode_frames_host call i+1 overlap the kernels of call i (include/lc3b.h)."""
+        rc = native.lib().lc3b_encoder_set_host_pipelining(self._h, 1 if on else 0)
+        if rc != 0:
+            raise Lc3bError(rc, "lc3b_encoder_set_host_pipelining")
+
     def set_stage_mask(self, mask: int) -> None:
         """Profiling hook: 1 = analysis kernel only, 2 = quantisation kernel only, 3 = both (default)."""
         rc = native.lib().lc3b_encoder_set_stage_mask(self._h, mask)

@@ -51,7 +51,8 @@ EXPORTS = ["lc3b_config_new", "lc3b_last_cuda_error", "lc3b_version", "lc3b_deco
            "lc3b_decoder_get_spectrum", "lc3b_decoder_set_stage_mask", "lc3b_decoder_set_host_pipelining",
            "lc3b_decoder_host_fence", "lc3b_decoder_destroy", "lc3b_selftest_math_host",
            "lc3b_selftest_math_device", "lc3b_encoder_workspace_bytes", "lc3b_encoder_init", "lc3b_encode_frames",
-           "lc3b_encode_frames_host", "lc3b_encoder_debug_read", "lc3b_encoder_set_stage_mask", "lc3b_encoder_destroy"]
+           "lc3b_encode_frames_host", "lc3b_encoder_set_host_pipelining", "lc3b_encoder_debug_read", "lc3b_encoder_set_stage_mask",
+           "lc3b_encoder_destroy"]
 
 _lib = None
 
@@ -87,6 +88,7 @@ def lib() -> C.CDLL:
         L.lc3b_encode_frames_host.argtypes = [vp, vp, sz, vp, i32, sz, vp]
         L.lc3b_encoder_debug_read.argtypes = [vp, vp, vp, vp, vp, vp]
         L.lc3b_encoder_set_stage_mask.argtypes = [vp, i32]
+        L.lc3b_encoder_set_host_pipelining.argtypes = [vp, i32]
         L.lc3b_encoder_destroy.argtypes = [vp]
         L.lc3b_encoder_destroy.restype = None
         L.lc3b_selftest_math_host.argtypes = [i32, vp, vp, vp, i32]

@@ -53,6 +53,26 @@ def test_host_entry_point_and_ragged_counts():
     assert assert_encoder_parity(24000, 7.5, 45, 1, 12) == 1.0
 
 
+def test_pipelined_host_entry_point():
+    """lc3b_encoder_set_host_pipelining: the upload of call i+1 overlaps the kernels of call i; bytes are unchanged."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from common import corpus
+    pcm, o_frames = corpus(48000, 10, 120, 70, 12)
+    S, F, nf = pcm.shape
+    sf, fd = L.SamplingFrequency.Hz48000, L.FrameDuration.TenMs
+    ws = torch.empty(L.Lc3BatchEncoder.calc_working_buffer_lengths(S, fd, sf, 120), dtype=torch.uint8, device="cuda:0")
+    enc = L.Lc3BatchEncoder(S, fd, sf, ws, 120)
+    enc.set_host_pipelining(True)
+    host_in = torch.from_numpy(np.ascontiguousarray(pcm.transpose(1, 0, 2))).pin_memory()          # [F,S,nf]
+    host_out = torch.zeros((F, S, 120), dtype=torch.uint8).pin_memory()
+    for f in range(F):
+        enc.encode_frames_host(host_in[f], host_out[f])      # no synchronisation between calls
+    torch.cuda.synchronize()
+    assert np.array_equal(host_out.numpy().transpose(1, 0, 2), o_frames)
+
+
 def test_8k_rejected_like_the_reference():
     """Lc3Encoder::new panics at 8 kHz (bandwidth_detector.rs:42-56) -> LC3B_ERR_INVALID_ARG."""
     import lc3_codec_b200 as L
