@@ -189,6 +189,25 @@ def run_reference(args, w, rank):
     }))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is allocated, so
+    the e2e leg's staging memory sits on the GPU's NUMA node.  One process per GPU makes this the natural placement;
+    without it the ranks of a multi-GPU run share one node's memory controllers.  Best effort: silently skipped."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w_ + b for w_, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_mixed(args, w, rank, local_rank, world, dev, dist):
     """BASELINE config 4: twelve configurations in one batch through Lc3MixedBatchDecoder."""
     import torch
@@ -322,6 +341,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: lc3_codec_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
