@@ -91,6 +91,20 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
 int lc3b_decoder_set_host_pipelining(lc3b_decoder* h, int on);
 int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream);
 
+/* Time-parallel decode: `n_frames` consecutive frames of EVERY stream in one call - the whole-file
+ * workflow of examples/decode.rs:85-123 without one launch per frame period.  Equivalent to n_frames calls of
+ * lc3b_decode_frames (same PCM, same per-stream state afterwards, so the two entry points can be mixed freely).
+ *   frames        device; frame f of stream s at frames + (s*n_frames + f)*frame_stride
+ *   frame_nbytes  device int32[n_streams*n_frames] or NULL (as in lc3b_decode_frames; 0 = lost frame)
+ *   pcm_out       device int16 [n_streams][n_frames*nf]: every stream's audio is contiguous in time
+ *   status_out    device int32[n_streams*n_frames] or NULL
+ *   scratch       device, at least lc3b_decoder_multi_scratch_bytes(h, n_frames) bytes, 256-byte aligned; caller-owned,
+ *                 only used during the call */
+int lc3b_decoder_multi_scratch_bytes(const lc3b_decoder* h, int n_frames, size_t* device_bytes);
+int lc3b_decode_stream_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                              int nbytes, size_t frame_stride, int n_frames, int16_t* pcm_out, int32_t* status_out,
+                              void* scratch, size_t scratch_bytes, void* cuda_stream);
+
 /* Inspection (parity gate i): when set, every decode also writes, per stream, a record of
  * LC3B_TRACE_WORDS int32 (layout below) and the entropy-decoded integer spectrum x[0..ne).  Device pointers,
  * NULL to disable.  trace: [n_streams][LC3B_TRACE_WORDS], x: [n_streams][ne]. */

@@ -294,6 +294,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     st.stage_status = (int32_t*)(base + L.stage_status);
     st.trace = nullptr;
     st.trace_x = nullptr;
+    st.fixed_slot = -1;
 
     DevConfig hc;
     fill_host_config(c, &hc);
@@ -302,6 +303,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);               // hc is a stack object
     if (e == cudaSuccess) e = prepare_entropy(st);
     if (e == cudaSuccess) e = prepare_synth(st);
+    if (e == cudaSuccess) e = prepare_multi(st);
     if (e == cudaSuccess) {
         init_tables_kernel<<<1, 256, 0, stream>>>(st.dcfg, st.win, st.dtw, st.ftw);
         init_sym_lut_kernel<<<64, 256, 0, stream>>>(st.sym_lut);
@@ -349,6 +351,27 @@ int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream) {
 int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask) {
     if (!h || mask < 1 || mask > 3) return LC3B_ERR_INVALID_ARG;
     h->stage_mask = mask;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_multi_scratch_bytes(const lc3b_decoder* h, int n_frames, size_t* device_bytes) {
+    if (!h || !device_bytes || n_frames <= 0) return LC3B_ERR_INVALID_ARG;
+    if ((long long)h->st.n_streams * n_frames > 0x7fffffffLL / 512) return LC3B_ERR_INVALID_ARG;   // 32-bit unit indices
+    *device_bytes = multi_scratch_bytes(h->st, n_frames);
+    return LC3B_OK;
+}
+
+int lc3b_decode_stream_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                              int nbytes, size_t frame_stride, int n_frames, int16_t* pcm_out, int32_t* status_out,
+                              void* scratch, size_t scratch_bytes, void* cuda_stream) {
+    if (!h || !frames || !pcm_out || !scratch) return LC3B_ERR_INVALID_ARG;
+    if (bits_per_sample != 16) return LC3B_ERR_BITS_PER_SAMPLE;             // lc3_decoder.rs:80
+    const DecoderState& st = h->st;
+    if (n_frames <= 0 || nbytes <= 0 || nbytes > st.max_nbytes || frame_stride < (size_t)nbytes) return LC3B_ERR_INVALID_ARG;
+    if ((long long)st.n_streams * n_frames > 0x7fffffffLL / 512) return LC3B_ERR_INVALID_ARG;
+    if (scratch_bytes < multi_scratch_bytes(st, n_frames) || ((uintptr_t)scratch & 255) != 0) return LC3B_ERR_WORKSPACE;
+    CU(launch_decode_multi(st, frames, frame_nbytes, nbytes, frame_stride, n_frames, pcm_out, status_out, scratch,
+                           (cudaStream_t)cuda_stream));
     return LC3B_OK;
 }
 

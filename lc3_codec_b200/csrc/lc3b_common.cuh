@@ -33,6 +33,7 @@ enum {
     SD_PLC_SEED,        // PLC LCG state BEFORE this frame's ne steps (concealed frames)
     SD_PLC_ALPHA,       // f32 bits: alpha to apply (concealed frames)
     SD_SLOT,            // which of the two spectrum slots holds the spectrum to transform
+    SD_SRC,             // time-parallel path: unit whose spectrum to transform (-2 own, -1 the handle's last good slot)
 };
 
 // Everything a kernel needs to know about the (fs, duration) configuration; lives in the workspace.
@@ -57,6 +58,7 @@ struct DecoderState {
     // configuration
     lc3b_config cfg;
     int n_streams, n_blocks32, max_nbytes, device;
+    int fixed_slot;      // -1: double-buffered spectrum slots tracked in sstate; >= 0: always write that slot (time-parallel path)
     // device pointers (carved from the caller's workspace)
     DevConfig* dcfg;
     float* win;          // [2*nf]
@@ -98,5 +100,12 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
                            size_t frame_stride, int32_t* status_out, cudaStream_t stream);
 cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream);
 cudaError_t launch_init_state(const DecoderState& st, cudaStream_t stream);
+
+// time-parallel decode, lc3b_dec_multi.cu
+size_t multi_scratch_bytes(const DecoderState& st, int n_frames);
+cudaError_t prepare_multi(const DecoderState& st);
+cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                                size_t frame_stride, int n_frames, int16_t* pcm_out, int32_t* status_out, void* scratch,
+                                cudaStream_t stream);
 
 }  // namespace lc3b

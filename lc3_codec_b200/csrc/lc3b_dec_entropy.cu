@@ -41,6 +41,7 @@ struct EntropyParams {
     int32_t* trace;       // nullable
     int32_t* trace_x;     // nullable
     const uint8_t* sym_lut;   // [64][1024] symbol for (pki, floor(low / (range >> 10)))
+    int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
     int row_pitch;        // bytes per staged frame row in shared memory
 };
 
@@ -503,8 +504,8 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
 
     // ---- pass 2: dequantise, noise fill, gain, TNS, SNS; spectrum -> inactive slot
     int slot = 0;
-    if (live) slot = p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
-    const int new_slot = slot ^ 1;
+    if (live && p.fixed_slot < 0) slot = p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
+    const int new_slot = p.fixed_slot >= 0 ? p.fixed_slot : slot ^ 1;
     float* s_y = s_scf + tid;                                          // PVQ vector / scale factors, stride T
     bool is_zero_frame = false;
     float gg = 0.0f, nf_level = 0.0f;
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
         sd[SD_PITCH_INDEX] = ok ? si.pitch_index : 0;
         sd[SD_NBITS] = nbits;
         sd[SD_SLOT] = ok ? new_slot : slot;
-        if (ok) p.sstate[(size_t)stream * SS_WORDS + SS_SLOT] = new_slot;
+        if (ok && p.fixed_slot < 0) p.sstate[(size_t)stream * SS_WORDS + SS_SLOT] = new_slot;
         if (p.status_out) p.status_out[stream] = ok ? 0 : 1;
         if (p.trace) {
             int32_t* tr = p.trace + (size_t)stream * LC3B_TRACE_WORDS;
@@ -750,6 +751,7 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
     p.trace = st.trace;
     p.trace_x = st.trace_x;
     p.sym_lut = st.sym_lut;
+    p.fixed_slot = st.fixed_slot;
     p.row_pitch = entropy_row_pitch(nbytes);
     const size_t smem = entropy_smem_bytes(p.row_pitch);
     const int grid = (st.n_streams + ENT_THREADS - 1) / ENT_THREADS;

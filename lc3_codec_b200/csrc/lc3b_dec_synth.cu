@@ -12,6 +12,7 @@
 // kissfft: the PCM contract is +-1 LSB, not bit equality).  The LTPF recursion only reaches back
 // p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are computed in parallel per step.
 #include "lc3b_common.cuh"
+#include "lc3b_fft.cuh"
 #include "lc3b_math.cuh"
 
 namespace lc3b {
@@ -36,78 +37,6 @@ struct SynthParams {
 };
 
 constexpr int SYN_WARPS = 4;
-
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-
-template <int R>
-__device__ __forceinline__ void dft(float2 (&v)[R]);
-template <>
-__device__ __forceinline__ void dft<2>(float2 (&v)[2]) {
-    float2 a = v[0], b = v[1];
-    v[0] = caddf(a, b);
-    v[1] = csubf(a, b);
-}
-template <>
-__device__ __forceinline__ void dft<3>(float2 (&v)[3]) {
-    const float S = -0.86602540378443864676f;          // -sin(2 pi / 3)
-    float2 t = caddf(v[1], v[2]);
-    float2 d = csubf(v[1], v[2]);
-    float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
-    float2 r = make_float2(-S * d.y, S * d.x);         // -i * sin * d  (forward transform)
-    v[0] = caddf(v[0], t);
-    v[1] = caddf(m, r);
-    v[2] = csubf(m, r);
-}
-template <>
-__device__ __forceinline__ void dft<4>(float2 (&v)[4]) {
-    float2 a = caddf(v[0], v[2]), b = csubf(v[0], v[2]);
-    float2 c = caddf(v[1], v[3]), d = csubf(v[1], v[3]);
-    float2 dj = make_float2(d.y, -d.x);                // -i * d
-    v[0] = caddf(a, c);
-    v[1] = caddf(b, dj);
-    v[2] = csubf(a, c);
-    v[3] = csubf(b, dj);
-}
-template <>
-__device__ __forceinline__ void dft<5>(float2 (&v)[5]) {
-    const float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
-    const float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
-    float2 a1 = caddf(v[1], v[4]), b1 = csubf(v[1], v[4]);
-    float2 a2 = caddf(v[2], v[3]), b2 = csubf(v[2], v[3]);
-    float2 m1 = make_float2(v[0].x + C1 * a1.x + C2 * a2.x, v[0].y + C1 * a1.y + C2 * a2.y);
-    float2 m2 = make_float2(v[0].x + C2 * a1.x + C1 * a2.x, v[0].y + C2 * a1.y + C1 * a2.y);
-    // forward transform: X[k] = m - i*(S..)*b ; -i*(x+iy) = (y, -x)
-    float2 n1 = make_float2(S1 * b1.y + S2 * b2.y, -(S1 * b1.x + S2 * b2.x));
-    float2 n2 = make_float2(S2 * b1.y - S1 * b2.y, -(S2 * b1.x - S1 * b2.x));
-    v[0] = make_float2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
-    v[1] = caddf(m1, n1);
-    v[4] = csubf(m1, n1);
-    v[2] = caddf(m2, n2);
-    v[3] = csubf(m2, n2);
-}
-
-// one Stockham stage: N/R butterflies spread over the warp
-template <int R>
-__device__ __forceinline__ void fft_stage(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ ftw,
-                                          int N, int Ns, int lane) {
-    const int nbf = N / R;
-    const int tw_step = N / (Ns * R);
-    for (int j = lane; j < nbf; j += 32) {
-        const int k = j % Ns;
-        float2 v[R];
-#pragma unroll
-        for (int t = 0; t < R; t++) {
-            v[t] = x[j + t * nbf];
-            if (t > 0) v[t] = cmulf(v[t], ftw[k * t * tw_step]);
-        }
-        dft<R>(v);
-        const int base = (j - k) * R + k;
-#pragma unroll
-        for (int t = 0; t < R; t++) y[base + t * Ns] = v[t];
-    }
-}
 
 __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -167,30 +96,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
     __syncwarp();
 
     // ---- DCT-IV: pre-twiddle, N-point FFT, post-twiddle (dct_iv.rs:49-67)
-    for (int n = lane; n < N; n += 32) bufA[n] = cmulf(p.dtw[n], make_float2(X[2 * n], X[nf - 1 - 2 * n]));
-    __syncwarp();
-    {
-        float2 *src = bufA, *dst = bufB;
-        int Ns = 1;
-        for (int sidx = 0; sidx < 8 && c.fft_radix[sidx] != 0; sidx++) {
-            const int R = c.fft_radix[sidx];
-            switch (R) {
-                case 2: fft_stage<2>(src, dst, p.ftw, N, Ns, lane); break;
-                case 3: fft_stage<3>(src, dst, p.ftw, N, Ns, lane); break;
-                case 4: fft_stage<4>(src, dst, p.ftw, N, Ns, lane); break;
-                default: fft_stage<5>(src, dst, p.ftw, N, Ns, lane); break;
-            }
-            Ns *= R;
-            float2* t = src; src = dst; dst = t;
-            __syncwarp();
-        }
-        for (int n = lane; n < N; n += 32) {
-            const float2 v = cmulf(p.dtw[n], src[n]);
-            X[2 * n] = v.x * 2.0f;
-            X[nf - 1 - 2 * n] = -v.y * 2.0f;
-        }
-    }
-    __syncwarp();
+    dct_iv_warp(X, bufA, bufB, p.dtw, p.ftw, c.fft_radix, nf, N, lane);
 
     // ---- unfold + window + overlap-add (modified_dct.rs:97-151); t[m] below is the reference's t_hat_mdct[m] / gain
     auto t_at = [&](int m) -> float {
@@ -205,7 +111,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
         const int n = lane + 32 * j;
         if (n < nf) {
             float o;
-            if (n < nf - z) o = (j < 10 ? ola_r[j < 10 ? j : 0] : 0.0f) + t_at(z + n) * p.win[z + n];
+            if (n < nf - z) o = xa(j < 10 ? ola_r[j < 10 ? j : 0] : 0.0f, xm(t_at(z + n), p.win[z + n]));   // two roundings, like the reference (and the time-parallel path)
             else o = t_at(nf + (n - (nf - z))) * p.win[nf + (n - (nf - z))];
             T[n] = o;
         }

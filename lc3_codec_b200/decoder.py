@@ -101,6 +101,39 @@ class Lc3BatchDecoder:
         if rc:
             raise Lc3bError(rc, fn.__name__)
 
+    # ------------------------------------------------------------------ time-parallel decode
+    def multi_scratch_bytes(self, n_frames: int) -> int:
+        n = C.c_size_t(0)
+        rc = native.lib().lc3b_decoder_multi_scratch_bytes(self._h, n_frames, C.byref(n))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_multi_scratch_bytes")
+        return int(n.value)
+
+    def decode_stream_frames(self, num_bits_per_audio_sample: int, frames: torch.Tensor, pcm_out: torch.Tensor,
+                             scratch: torch.Tensor, frame_nbytes: torch.Tensor | None = None,
+                             status_out: torch.Tensor | None = None) -> None:
+        """Many consecutive frames of every stream in one call (the file workflow of examples/decode.rs).
+        frames: CUDA uint8 [num_streams, n_frames, nbytes] contiguous; pcm_out: CUDA int16 [num_streams, n_frames * nf];
+        scratch: CUDA uint8, >= multi_scratch_bytes(n_frames); frame_nbytes / status_out: CUDA int32 [num_streams, n_frames]."""
+        if num_bits_per_audio_sample != 16:
+            raise Lc3DecoderError("Only16BitsPerAudioSampleSupported")
+        if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 3 and frames.shape[0] == self.num_streams
+                and frames.is_contiguous()):
+            raise Lc3bError(2, "frames: want contiguous CUDA uint8 [num_streams, n_frames, nbytes]")
+        F, nb = frames.shape[1], frames.shape[2]
+        if not (pcm_out.is_cuda and pcm_out.dtype == torch.int16 and pcm_out.is_contiguous()
+                and pcm_out.numel() == self.num_streams * F * self.nf):
+            raise Lc3bError(2, "pcm_out: want contiguous CUDA int16 [num_streams, n_frames * nf]")
+        for t, what in ((frame_nbytes, "frame_nbytes"), (status_out, "status_out")):
+            if t is not None and not (t.is_cuda and t.dtype == torch.int32 and t.numel() == self.num_streams * F and t.is_contiguous()):
+                raise Lc3bError(2, f"{what}: wrong device/dtype/shape")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = native.lib().lc3b_decode_stream_frames(self._h, 16, _ptr(frames), _ptr(frame_nbytes), nb, nb, F, _ptr(pcm_out),
+                                                        _ptr(status_out), _ptr(scratch), scratch.numel(), C.c_void_p(stream))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decode_stream_frames")
+
     # ------------------------------------------------------------------ inspection (parity gate i)
     def enable_trace(self):
         """Allocates and registers device buffers for the per-frame inspection record and integer spectrum."""

@@ -49,7 +49,8 @@ class Config(C.Structure):
 EXPORTS = ["lc3b_config_new", "lc3b_last_cuda_error", "lc3b_version", "lc3b_decoder_workspace_bytes",
            "lc3b_decoder_init", "lc3b_decode_frames", "lc3b_decode_frames_host", "lc3b_decoder_set_trace",
            "lc3b_decoder_get_spectrum", "lc3b_decoder_set_stage_mask", "lc3b_decoder_set_host_pipelining",
-           "lc3b_decoder_host_fence", "lc3b_decoder_destroy", "lc3b_selftest_math_host",
+           "lc3b_decoder_host_fence", "lc3b_decoder_multi_scratch_bytes", "lc3b_decode_stream_frames", "lc3b_decoder_destroy",
+           "lc3b_selftest_math_host",
            "lc3b_selftest_math_device", "lc3b_encoder_workspace_bytes", "lc3b_encoder_init", "lc3b_encode_frames",
            "lc3b_encode_frames_host", "lc3b_encoder_set_host_pipelining", "lc3b_encoder_debug_read", "lc3b_encoder_set_stage_mask",
            "lc3b_encoder_destroy"]
@@ -80,6 +81,8 @@ def lib() -> C.CDLL:
         L.lc3b_decoder_set_stage_mask.argtypes = [vp, i32]
         L.lc3b_decoder_set_host_pipelining.argtypes = [vp, i32]
         L.lc3b_decoder_host_fence.argtypes = [vp, vp]
+        L.lc3b_decoder_multi_scratch_bytes.argtypes = [vp, i32, C.POINTER(C.c_size_t)]
+        L.lc3b_decode_stream_frames.argtypes = [vp, i32, vp, vp, i32, sz, i32, vp, vp, vp, sz, vp]
         L.lc3b_decoder_destroy.argtypes = [vp]
         L.lc3b_decoder_destroy.restype = None
         L.lc3b_encoder_workspace_bytes.argtypes = [i32, i32, i32, i32, C.POINTER(sz)]
