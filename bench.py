@@ -53,6 +53,10 @@ WORKLOADS = {
                   metric="decoded frames/sec (mixed 8/16/24/32/44.1/48 kHz, 7.5 and 10 ms) per GPU",
                   desc="mixed-rate batch decode: 65536 streams, stream s uses (fs_list[s mod 6], duration[(s/6) mod 2]) at "
                        "20..120 B/frame (BASELINE config 4), one Lc3MixedBatchDecoder call per step"),
+    "file48": dict(fs=48000, ms=10, nbytes=150, nf=480, streams=64, frames=4096, mode="file",
+                   metric="decoded frames/sec (48kHz 10ms mono, whole files, time-parallel) per GPU",
+                   desc="time-parallel file decode (SURVEY 8f-1): 64 streams x 4096 consecutive frames (41 s of audio each) in "
+                        "ONE lc3b_decode_stream_frames call per step, 150 B/frame"),
     "roundtrip48": dict(fs=48000, ms=10, nbytes=150, nf=480, streams=262144, mode="roundtrip",
                         metric="encode+decode round trips/sec (48kHz 10ms mono, 150 B) per GPU",
                         desc="encode then decode 48 kHz mono 10 ms at 150 B/frame, 262144 streams per GPU (BASELINE config 5)"),
@@ -125,18 +129,18 @@ class ClockSampler:
 def cpu_sample(w, cores):
     """Bounded sample of the workload for the oracle: (frames or None, pcm or None)."""
     from tools.corpus import make_pcm
-    if w["mode"] == "decode" and w["fs"] == 48000:
+    if w["mode"] in ("decode", "file") and w["fs"] == 48000:
         frames = load_frames()
         return np.ascontiguousarray(frames[:min(frames.shape[0], max(cores * 8, 64))]), None
     from oracle import pyoracle as O
     pcm = make_pcm(max(cores * 8, 64), 8, w["fs"], w["nf"])
-    frames = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"]) if w["mode"] == "decode" else None
+    frames = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"]) if w["mode"] in ("decode", "file") else None
     return frames, pcm
 
 
 def cpu_run(w, frames, pcm, cores):
     from oracle import pyoracle as O
-    if w["mode"] == "decode":
+    if w["mode"] in ("decode", "file"):
         O.decode_streams(frames, w["fs"], w["ms"], nthreads=cores)
         return frames.shape[0] * frames.shape[1]
     enc = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"], nthreads=cores)
@@ -309,6 +313,99 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
         dist.destroy_process_group()
 
 
+def run_file(args, w, rank, local_rank, world, dev, dist):
+    """few streams, many frames - one time-parallel call per step, with the frame-by-frame path beside it."""
+    import torch
+
+    import lc3_codec_b200 as L
+
+    S, F, NB, NF = w["streams"], w["frames"], w["nbytes"], w["nf"]
+    sf, fd = L.SamplingFrequency.from_hz(w["fs"]), L.FrameDuration.from_ms(w["ms"])
+    ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(S, fd, sf, NB), dtype=torch.uint8, device=dev)
+    dec = L.Lc3BatchDecoder(S, fd, sf, ws, NB)
+    scratch = torch.empty(dec.multi_scratch_bytes(F), dtype=torch.uint8, device=dev)
+    corpus = torch.from_numpy(load_frames()).to(dev)                                  # [1024, 8, 150]
+    sidx = (torch.arange(S, device=dev) + rank * S) % corpus.shape[0]
+    fidx = torch.arange(F, device=dev) % corpus.shape[1]
+    frames = corpus[sidx][:, fidx].contiguous()                                       # [S, F, 150]: stream s replays its 8 frames
+    pcm = torch.empty((S, F * NF), dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms_], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_
+
+    with ClockSampler(local_rank) as clk:
+        ms_total = timed(lambda i: dec.decode_stream_frames(16, frames, pcm, scratch), args.steps, args.warmup)
+    ups = world * S * F * args.steps / (ms_total * 1e-3)
+    # the same files frame by frame (what the reference's loop shape gives a GPU): a 128-frame sample
+    out1 = torch.empty((S, NF), dtype=torch.int16, device=dev)
+    fb_frames = 128
+    per_frame = frames.permute(1, 0, 2).contiguous()                                  # [F, S, 150]
+
+    def fb(i):
+        for f in range(fb_frames):
+            dec.decode_frames(16, per_frame[f], out1)
+    ms_fb = timed(fb, 2, 1)
+    fb_ups = world * S * fb_frames * 2 / (ms_fb * 1e-3)
+    host_in = frames.cpu().pin_memory()
+    host_out = torch.empty((S, F * NF), dtype=torch.int16).pin_memory()
+    dev_in = torch.empty_like(frames)
+
+    def e2e_step(i):
+        dev_in.copy_(host_in, non_blocking=True)
+        dec.decode_stream_frames(16, dev_in, pcm, scratch)
+        host_out.copy_(pcm, non_blocking=True)
+    e2e_steps = max(5, min(args.steps, 50))
+    ms_e2e = timed(e2e_step, e2e_steps, 2)
+    peak, peak_src = measured_peak()
+    step_ms = ms_total / args.steps
+    achieved = algo_bytes(w) * S * F / (step_ms * 1e-3) / 1e9
+    if rank == 0:
+        cb = cpu_baseline(w) if (world == 1 and not args.no_cpu_baseline) else None
+        print(json.dumps({
+            "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": w["desc"], "name": "file48", "streams_per_gpu": S, "frames_per_call": F,
+                       "frame_by_frame_value": fb_ups,
+                       "frame_by_frame_note": f"same handle, {fb_frames} lc3b_decode_frames calls of {S} streams each",
+                       "l2": f"per-unit scratch {scratch.numel() / 1e6:.0f} MB per call, far more than the 126 MB L2",
+                       "parallelism": f"{world} x independent stream shards, no collective on the data path"},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * S * F * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * F * NB,
+                    "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames), device -> pinned host copy"},
+            "gpu_launches": 5 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "whole call (entropy, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
+                         "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes(w),
+                         "note": "issue/latency bound like the frame-by-frame kernels (DESIGN.md section 5)"},
+            "cpu_baseline": cb,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,6 +446,9 @@ def main():
 
     if w["mode"] == "mixed":
         run_mixed(args, w, rank, local_rank, world, dev, dist)
+        return
+    if w["mode"] == "file":
+        run_file(args, w, rank, local_rank, world, dev, dist)
         return
     S, NB, NF, mode = w["streams"], w["nbytes"], w["nf"], w["mode"]
     sf, fd = L.SamplingFrequency.from_hz(w["fs"]), L.FrameDuration.from_ms(w["ms"])

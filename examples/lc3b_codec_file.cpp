@@ -97,16 +97,33 @@ static int decode(const char* lc3_name, const char* wav_name, int hz, const std:
     const size_t nf = (size_t)dec.config.nf;
     const Lc3File lf{nch, nbytes};
     const size_t periods = lf.frame_periods(in.size());
-    int16_t* samples = nullptr;
-    uint8_t* bits = nullptr;
-    CUDA_OK(cudaMallocHost((void**)&samples, nf * nch * sizeof(int16_t)));
-    CUDA_OK(cudaMallocHost((void**)&bits, nch * nbytes));
+    // the whole file in ONE time-parallel call: channel-major staging [nch][periods][nbytes]
+    std::vector<uint8_t> staged(nch * periods * nbytes);
+    for (size_t p = 0; p < periods; p++)
+        for (size_t c = 0; c < nch; c++)
+            std::memcpy(staged.data() + (c * periods + p) * nbytes, lf.channel_frame(in.data(), p, c), nbytes);
+    uint8_t* d_frames = nullptr;
+    int16_t* d_pcm = nullptr;
+    void* d_scratch = nullptr;
+    const size_t scratch_bytes = periods ? dec.multi_scratch_bytes(periods) : 0;
+    std::vector<int16_t> by_channel(nch * periods * nf);
     std::vector<uint8_t> pcm(periods * nf * nch * 2);
-    for (size_t p = 0; p < periods; p++) {
-        for (size_t c = 0; c < nch; c++) std::memcpy(bits + c * nbytes, lf.channel_frame(in.data(), p, c), nbytes);
-        if (dec.decode_frames(16, Residency::Host, bits, nbytes, nbytes, samples)) { std::fprintf(stderr, "decoder error\n"); return 2; }
-        CUDA_OK(cudaStreamSynchronize(nullptr));
-        interleave(samples, nf, nch, pcm.data() + p * nf * nch * 2);
+    if (periods) {
+        CUDA_OK(cudaMalloc((void**)&d_frames, staged.size()));
+        CUDA_OK(cudaMalloc((void**)&d_pcm, by_channel.size() * sizeof(int16_t)));
+        CUDA_OK(cudaMalloc(&d_scratch, scratch_bytes));
+        CUDA_OK(cudaMemcpy(d_frames, staged.data(), staged.size(), cudaMemcpyHostToDevice));
+        if (dec.decode_stream_frames(16, d_frames, nbytes, periods, d_pcm, d_scratch, scratch_bytes)) {
+            std::fprintf(stderr, "decoder error\n");
+            return 2;
+        }
+        CUDA_OK(cudaMemcpy(by_channel.data(), d_pcm, by_channel.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        std::vector<int16_t> period(nch * nf);
+        for (size_t p = 0; p < periods; p++) {
+            for (size_t c = 0; c < nch; c++) std::memcpy(period.data() + c * nf, by_channel.data() + (c * periods + p) * nf, nf * sizeof(int16_t));
+            interleave(period.data(), nf, nch, pcm.data() + p * nf * nch * 2);
+        }
+        cudaFree(d_frames); cudaFree(d_pcm); cudaFree(d_scratch);
     }
     wav::WavHeader wh;
     wh.num_channels = nch;
@@ -122,8 +139,8 @@ static int decode(const char* lc3_name, const char* wav_name, int hz, const std:
     std::ofstream out(wav_name, std::ios::binary);
     out.write((const char*)hdr, sizeof(hdr));
     out.write((const char*)pcm.data(), (std::streamsize)pcm.size());
-    std::printf("decoded %zu frame periods x %zu channels\n", periods, nch);
-    cudaFreeHost(samples); cudaFreeHost(bits); cudaFree(ws);
+    std::printf("decoded %zu frame periods x %zu channels in one call\n", periods, nch);
+    cudaFree(ws);
     return 0;
 }
 

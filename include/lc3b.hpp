@@ -93,6 +93,23 @@ class Lc3BatchDecoder {
         detail::check(rc, "lc3b_decode_frames");
         return std::nullopt;
     }
+    // Time-parallel decode: n_frames consecutive frames of every stream in one call; equivalent to
+    // n_frames decode_frames calls (same PCM, same state afterwards).  Device buffers: frames [num_streams][n_frames][nbytes],
+    // samples_out [num_streams][n_frames * nf], scratch >= multi_scratch_bytes(n_frames) bytes (caller-owned).
+    size_t multi_scratch_bytes(size_t n_frames) const {
+        size_t n = 0;
+        detail::check(lc3b_decoder_multi_scratch_bytes(h_, (int)n_frames, &n), "lc3b_decoder_multi_scratch_bytes");
+        return n;
+    }
+    Result<Lc3DecoderError> decode_stream_frames(size_t num_bits_per_audio_sample, const uint8_t* frames, size_t nbytes,
+                                                 size_t n_frames, int16_t* samples_out, void* scratch, size_t scratch_bytes,
+                                                 const int32_t* frame_nbytes = nullptr, int32_t* status_out = nullptr) {
+        const int rc = lc3b_decode_stream_frames(h_, (int)num_bits_per_audio_sample, frames, frame_nbytes, (int)nbytes, nbytes,
+                                                 (int)n_frames, samples_out, status_out, scratch, scratch_bytes, stream_);
+        if (rc == LC3B_ERR_BITS_PER_SAMPLE) return Lc3DecoderError::Only16BitsPerAudioSampleSupported;
+        detail::check(rc, "lc3b_decode_stream_frames");
+        return std::nullopt;
+    }
     // extension: overlap the PCM read-back of call i with the kernels of call i+1 (host residency)
     void set_host_pipelining(bool on) { detail::check(lc3b_decoder_set_host_pipelining(h_, on ? 1 : 0), "lc3b_decoder_set_host_pipelining"); }
     void host_fence() { detail::check(lc3b_decoder_host_fence(h_, stream_), "lc3b_decoder_host_fence"); }

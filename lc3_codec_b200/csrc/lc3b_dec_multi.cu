@@ -70,38 +70,60 @@ struct MultiParams {
 constexpr int MW = 4;     // warps per CTA in the warp-per-unit kernels
 
 // ---------------------------------------------------------------- 2. concealment bookkeeping along time
-__global__ void plc_scan_kernel(MultiParams p) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per stream; the ok flags are fetched 32 frames at a time so that the walk along time is not one dependent
+// global load per frame.  Every lane tracks the same running state; lane j writes frame j's record.
+__global__ void __launch_bounds__(MW * 32) plc_scan_kernel(MultiParams p) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = blockIdx.x * MW + wid;
     if (s >= p.S) return;
     const int ne = p.cfg->ne;
     int32_t* ss = p.sstate + (size_t)s * SS_WORDS;
     int lost = ss[SS_PLC_LOST];
     float alpha = u2f((uint32_t)ss[SS_PLC_ALPHA]);
     uint32_t seed = (uint32_t)ss[SS_PLC_SEED];
+    __syncwarp();
     uint32_t A = 1, C = 0;                                        // ne steps of seed' = (16831 + seed * 12821) & 0xFFFF
     for (int i = 0; i < ne; i++) { C = (16831u + C * 12821u) & 0xFFFFu; A = (A * 12821u) & 0xFFFFu; }
     int last = -1;
-    for (int f = 0; f < p.F; f++) {
+    for (int f0 = 0; f0 < p.F; f0 += 32) {
+        const int f = f0 + lane;
         const int v = s * p.F + f;
         int32_t* sd = p.side_v + (size_t)v * SIDE_WORDS;
-        if (sd[SD_OK]) {
+        const bool in = f < p.F;
+        const bool ok = in && sd[SD_OK] != 0;
+        const uint32_t okm = __ballot_sync(0xffffffffu, ok), inm = __ballot_sync(0xffffffffu, in);
+        if (okm == inm) {                                          // the usual chunk: every frame decoded
+            if (in) sd[SD_SRC] = -2;
             lost = 0;
             alpha = 1.0f;
-            last = v;
-            sd[SD_SRC] = -2;
-        } else {
-            if (lost >= 4) alpha = xm(alpha, lost < 8 ? 0.9f : 0.85f);
-            sd[SD_SRC] = last;
-            sd[SD_PLC_ALPHA] = (int32_t)f2u(alpha);
-            sd[SD_PLC_SEED] = (int32_t)seed;
-            seed = (A * seed + C) & 0xFFFFu;
-            lost++;
+            last = s * p.F + f0 + (31 - __clz(inm));
+            continue;
+        }
+        const int cnt = __popc(inm);
+        for (int j = 0; j < cnt; j++) {
+            if ((okm >> j) & 1u) {
+                lost = 0;
+                alpha = 1.0f;
+                last = s * p.F + f0 + j;
+                if (lane == j) sd[SD_SRC] = -2;
+            } else {
+                if (lost >= 4) alpha = xm(alpha, lost < 8 ? 0.9f : 0.85f);
+                if (lane == j) {
+                    sd[SD_SRC] = last;
+                    sd[SD_PLC_ALPHA] = (int32_t)f2u(alpha);
+                    sd[SD_PLC_SEED] = (int32_t)seed;
+                }
+                seed = (A * seed + C) & 0xFFFFu;
+                lost++;
+            }
         }
     }
-    ss[SS_PLC_LOST] = lost;
-    ss[SS_PLC_ALPHA] = (int32_t)f2u(alpha);
-    ss[SS_PLC_SEED] = (int32_t)seed;
-    p.last_good[s] = last;
+    if (lane == 0) {
+        ss[SS_PLC_LOST] = lost;
+        ss[SS_PLC_ALPHA] = (int32_t)f2u(alpha);
+        ss[SS_PLC_SEED] = (int32_t)seed;
+        p.last_good[s] = last;
+    }
 }
 
 // ---------------------------------------------------------------- 3. spectrum -> windowed time signal, per unit
@@ -232,7 +254,18 @@ __global__ void __launch_bounds__(MW * 32) ltpf_multi_kernel(MultiParams p, int 
     __syncwarp();
     bool span1 = false, span2 = false, span3 = false;              // were frames f-1 / f-2 / f-3 filtered by this kernel
     const size_t v0 = (size_t)s * F;
+    uint32_t actm = 0;                                             // LTPF-active flags of the current 32-frame chunk
     for (int f = 0; f < F; f++) {
+        if ((f & 31) == 0) {                                       // fetch 32 frames' flags at once; skip idle chunks
+            const int fl = f + lane;
+            actm = __ballot_sync(0xffffffffu, fl < F && p.side_v[(v0 + fl) * SIDE_WORDS + SD_LTPF_ACTIVE] != 0);
+            if (actm == 0 && !prev_active) {
+                span1 = span2 = span3 = false;
+                prev_code = 4; p_int_mem = 0; p_fr_mem = 0;
+                f += 31;
+                continue;
+            }
+        }
         const size_t v = v0 + f;
         const LtpfPar cur = ltpf_params(c, p.side_v + v * SIDE_WORDS);
         const int active = cur.active, p_int = cur.p_int, p_fr = cur.p_fr, code = cur.code;
@@ -410,7 +443,7 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     p.spec = st.spec; p.ola = st.ola; p.ltpf_y = st.ltpf_y; p.ltpf_xtail = st.ltpf_xtail; p.sstate = st.sstate;
     p.pcm_out = pcm_out;
     p.hist_len = (st.cfg.n_ms == LC3B_10MS ? 2 : 3) * st.cfg.nf;
-    plc_scan_kernel<<<(S + 127) / 128, 128, 0, stream>>>(p);
+    plc_scan_kernel<<<(S + MW - 1) / MW, MW * 32, 0, stream>>>(p);
     const unsigned grid_v = (unsigned)((V + MW - 1) / MW);
     const size_t imdct_smem = MW * ((size_t)st.cfg.nf * 8 + (size_t)st.cfg.nf * 4);
     imdct_multi_kernel<<<grid_v, MW * 32, imdct_smem, stream>>>(p);
