@@ -55,6 +55,12 @@ extern "C" {
                                    pcm_stride: usize, status_out: *mut i32, cuda_stream: *mut c_void) -> c_int;
     pub fn lc3b_decoder_set_host_pipelining(h: *mut lc3b_decoder, on: c_int) -> c_int;
     pub fn lc3b_decoder_host_fence(h: *mut lc3b_decoder, cuda_stream: *mut c_void) -> c_int;
+    /// the frame loop of examples/decode.rs:85-123 as one call: `n_frames` frames of every stream (time-parallel)
+    pub fn lc3b_decoder_multi_scratch_bytes(h: *const lc3b_decoder, n_frames: c_int, device_bytes: *mut usize) -> c_int;
+    pub fn lc3b_decode_stream_frames(h: *mut lc3b_decoder, bits_per_sample: c_int, frames: *const u8, frame_nbytes: *const i32,
+                                     nbytes: c_int, frame_stride: usize, n_frames: c_int, pcm_out: *mut i16,
+                                     status_out: *mut i32, scratch: *mut c_void, scratch_bytes: usize,
+                                     cuda_stream: *mut c_void) -> c_int;
     pub fn lc3b_decoder_destroy(h: *mut lc3b_decoder);
 
     /// `Lc3Encoder::calc_working_buffer_lengths` (src/encoder/lc3_encoder.rs:194)
@@ -70,5 +76,6 @@ extern "C" {
     /// same, host buffers
     pub fn lc3b_encode_frames_host(h: *mut lc3b_encoder, pcm_in: *const i16, pcm_stride: usize, frames_out: *mut u8,
                                    nbytes: c_int, frame_stride: usize, cuda_stream: *mut c_void) -> c_int;
+    pub fn lc3b_encoder_set_host_pipelining(h: *mut lc3b_encoder, on: c_int) -> c_int;
     pub fn lc3b_encoder_destroy(h: *mut lc3b_encoder);
 }
