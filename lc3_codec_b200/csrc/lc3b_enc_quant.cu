@@ -568,7 +568,8 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         float t_out = 0.0f, s_out = 0.0f;
         for (int step = 0; step < N + po; step++) {
             float t_in = __shfl_up_sync(FULL, t_out, 1), s_in = __shfl_up_sync(FULL, s_out, 1);
-            const float xin = x[start + (step < N ? step : N - 1)];
+            // lane 0 fetches the next sample; the other lanes read line 0, which the lattice never writes (start >= 9)
+            const float xin = x[lane == 0 ? start + (step < N ? step : N - 1) : 0];
             if (lane == 0) { t_in = xin; s_in = xin; }
             const int n = step - lane;
             const bool act = lane <= po && n >= 0 && n < N;
@@ -576,6 +577,7 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
             const float st_tmp = rq * t_in + st;          // handed on by the inner stages
             if (act) { t_out = tn; s_out = st_tmp; st = s_in; }
             if (act && lane == po) x[start + n] = tn;
+            __syncwarp();                                  // orders lane 0's read of line `step` before its later overwrite
         }
         __syncwarp();
     }
@@ -690,6 +692,7 @@ __device__ __noinline__ BitCons quantize_spectrum_w(const EncConfig& c, const fl
     }
     __syncwarp();
     BitCons bc = compute_bit_consumption_w(ne, c.fs_ind, xq, pre, nbits, nbits_spec, lane);
+    __syncwarp();
     WARP_STRIDE_FROM(k, bc.lastnz_trunc, bc.lastnz) xq[k] = 0;
     __syncwarp();
     *gg_out = gg;
@@ -1241,7 +1244,8 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
         last = (uint32_t)st.cache;
     }
     if (w.bp >= nbytes || 8 * w.bp + bits + spos > nbits) return false;
-    out[w.bp] |= (uint8_t)(last & (0xff00u >> bits) & 0xffu);
+    __syncwarp();
+    if (lane == 0) out[w.bp] |= (uint8_t)(last & (0xff00u >> bits) & 0xffu);
     __syncwarp();
     return true;
 }
