@@ -395,9 +395,9 @@ def run_file(args, w, rank, local_rank, world, dev, dist):
             "e2e": {"value": world * S * F * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * F * NB,
                     "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames), device -> pinned host copy"},
-            "gpu_launches": 5 * args.steps,
+            "gpu_launches": 6 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "whole call (entropy, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
+                         "kernel": "whole call (entropy, dequant, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
                          "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes(w),
                          "note": "issue/latency bound like the frame-by-frame kernels (DESIGN.md section 5)"},
             "cpu_baseline": cb,
@@ -527,7 +527,7 @@ def main():
             enc.encode_frames(dev_pcm_in[i % F], frames_out)
             dec.decode_frames(16, frames_out, pcm_out)
 
-    launches_per_step = {"decode": 2, "encode": 6, "roundtrip": 8}[mode]
+    launches_per_step = {"decode": 3, "encode": 6, "roundtrip": 9}[mode]
 
     # ---- device-resident throughput (value) with clocks sampled during the timed region
     with ClockSampler(local_rank) as clk:
@@ -544,10 +544,10 @@ def main():
     kernels_ms = {}
 
     def time_masks(obj, names, fn):
-        for mask, name in zip((1, 2), names):
+        for mask, name in zip((1, 2, 4), names):
             obj.set_stage_mask(mask)
             kernels_ms[name] = timed(fn, k_steps, 3) / k_steps
-        obj.set_stage_mask(3)
+        obj.set_stage_mask(7)
 
     if enc:
         # the encoder's later kernels consume what the earlier ones leave in the workspace, so they are timed as
@@ -563,7 +563,7 @@ def main():
     if dec:
         if mode == "roundtrip":
             enc.encode_frames(dev_pcm_in[0], frames_out)           # valid bitstreams for the decoder-only timing
-        time_masks(dec, ("lc3b::entropy_kernel", "lc3b::synth_kernel"),
+        time_masks(dec, ("lc3b::entropy_kernel", "lc3b::dequant_kernel", "lc3b::synth_kernel"),
                    lambda i: dec.decode_frames(16, dev_frames[i % F] if dev_frames is not None else frames_out, pcm_out))
     dom_name = max(kernels_ms, key=kernels_ms.get)
     dom_ms = kernels_ms[dom_name]

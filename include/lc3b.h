@@ -114,8 +114,9 @@ int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x);
  * copied into `out` (device) on `cuda_stream`.  For stage-level parity tests. */
 int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream);
 
-/* Profiling hook: which kernels lc3b_decode_frames launches (bit 0 = entropy kernel, bit 1 = synthesis kernel;
- * default 3).  Lets bench.py time each kernel alone with CUDA events; results are only meaningful with mask 3. */
+/* Profiling hook: which kernels lc3b_decode_frames launches (bit 0 = entropy kernel, bit 1 = dequantisation kernel,
+ * bit 2 = synthesis kernel; default 7).  Lets bench.py time each kernel alone with CUDA events; results are only
+ * meaningful with mask 7. */
 int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask);
 
 void lc3b_decoder_destroy(lc3b_decoder* h);

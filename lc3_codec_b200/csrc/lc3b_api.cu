@@ -57,7 +57,7 @@ struct Carve {
 };
 
 struct Layout {
-    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, ola, ltpf_y, ltpf_xtail, side, sstate, stage_in, stage_out, stage_len,
+    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, ola, ltpf_y, ltpf_xtail, side, sstate, stage_in, stage_out, stage_len,
         stage_status, total;
 };
 
@@ -73,6 +73,7 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
     L.sym_lut = cv.take(64 * 1024);
     L.spec = cv.take(sizeof(float) * 2 * ns * c.ne);
     L.xq = cv.take(sizeof(int32_t) * nblk * c.ne * 32);
+    L.handoff = cv.take(sizeof(int32_t) * ((ns + 127) / 128) * 128 * HO_WORDS);   // every thread slot of whole entropy CTAs
     L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
     L.ltpf_y = cv.take(sizeof(float) * ns * blocks * c.nf);
     L.ltpf_xtail = cv.take(sizeof(float) * ns * 16);
@@ -283,6 +284,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     st.sym_lut = base + L.sym_lut;
     st.spec = (float*)(base + L.spec);
     st.xq = (int32_t*)(base + L.xq);
+    st.handoff = (int32_t*)(base + L.handoff);
     st.ola = (float*)(base + L.ola);
     st.ltpf_y = (float*)(base + L.ltpf_y);
     st.ltpf_xtail = (float*)(base + L.ltpf_xtail);
@@ -314,7 +316,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
         free(h);
         return cuda_fail(e);
     }
-    h->stage_mask = 3;
+    h->stage_mask = 7;
     h->pipelined = 0;
     h->buf = 0;
     h->copy_stream = nullptr;
@@ -349,7 +351,7 @@ int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream) {
 }
 
 int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask) {
-    if (!h || mask < 1 || mask > 3) return LC3B_ERR_INVALID_ARG;
+    if (!h || mask < 1 || mask > 7) return LC3B_ERR_INVALID_ARG;
     h->stage_mask = mask;
     return LC3B_OK;
 }
@@ -391,8 +393,8 @@ int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* fram
     if (nbytes < 0 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (h->stage_mask & 1) CU(launch_entropy(st, frames, frame_nbytes, nbytes, frame_stride, status_out, stream));
-    if (h->stage_mask & 2) CU(launch_synth(st, pcm_out, pcm_stride, stream));
+    if (h->stage_mask & 3) CU(launch_entropy(st, frames, frame_nbytes, nbytes, frame_stride, status_out, h->stage_mask & 3, stream));
+    if (h->stage_mask & 4) CU(launch_synth(st, pcm_out, pcm_stride, stream));
     return LC3B_OK;
 }
 
@@ -412,7 +414,7 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
     else CU(cudaMemcpy2DAsync(st.stage_in, (size_t)nbytes, frames, frame_stride, (size_t)nbytes, ns, cudaMemcpyHostToDevice, stream));
     if (frame_nbytes) CU(cudaMemcpyAsync(st.stage_len, frame_nbytes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, stream));
     CU(launch_entropy(st, st.stage_in, frame_nbytes ? st.stage_len : nullptr, nbytes, (size_t)nbytes,
-                      status_out ? st.stage_status : nullptr, stream));
+                      status_out ? st.stage_status : nullptr, 3, stream));
     const size_t out_elems = ns * (size_t)st.cfg.nf;
     int16_t* stage = st.stage_out + (h->pipelined ? (size_t)h->buf * out_elems : 0);
     cudaStream_t out_stream = stream;

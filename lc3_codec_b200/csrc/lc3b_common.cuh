@@ -22,7 +22,8 @@ namespace lc3b {
 constexpr int MAX_NE = 400;
 constexpr int MAX_NF = 480;
 constexpr int MAX_NBYTES = 400;      // LC3 frames are at most 400 bytes
-constexpr int SIDE_WORDS = 16;       // entropy -> synthesis hand-off record, int32 words per stream
+constexpr int SIDE_WORDS = 16;       // dequantisation -> synthesis hand-off record, int32 words per stream
+constexpr int HO_WORDS = 44;         // entropy -> dequantisation hand-off record, int32 words per thread slot
 
 // hand-off record written by the entropy kernel for the synthesis kernel
 enum {
@@ -66,7 +67,8 @@ struct DecoderState {
     float2* ftw;         // [n_fft]
     uint8_t* sym_lut;    // [64][1024] arithmetic-decoder symbol for (pki, quotient), built at init
     float* spec;         // [2][n_streams][ne]  double-buffered spectrum; the valid slot doubles as PLC "last good"
-    int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (private to the entropy kernel)
+    int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (entropy -> dequantisation kernel)
+    int32_t* handoff;    // [n_blocks32 * 32][HO_WORDS] decoded side information etc. (entropy -> dequantisation kernel)
     float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)
     float* ltpf_y;       // [n_streams][blocks*nf]  x_hat_ltpf_mem (long_term_post_filter.rs:30)
     float* ltpf_xtail;   // [n_streams][16]  last samples of x_hat_mem (only l_num <= 10 are ever read back)
@@ -97,7 +99,7 @@ enum {
 cudaError_t prepare_entropy(const DecoderState& st);   // shared-memory limits of the kernels, once per handle
 cudaError_t prepare_synth(const DecoderState& st);
 cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
-                           size_t frame_stride, int32_t* status_out, cudaStream_t stream);
+                           size_t frame_stride, int32_t* status_out, int stages, cudaStream_t stream);
 cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream);
 cudaError_t launch_init_state(const DecoderState& st, cudaStream_t stream);
 

@@ -35,6 +35,7 @@ struct EntropyParams {
     int n_streams;
     float* spec;          // [2][n_streams][ne]
     int32_t* xq;          // [n_blocks32][ne][32]
+    int32_t* handoff;     // [n_blocks32 * 32][HO_WORDS] entropy kernel -> dequantisation kernel
     int32_t* side;        // [n_streams][SIDE_WORDS]
     int32_t* sstate;      // [n_streams][SS_WORDS]
     int32_t* status_out;  // nullable
@@ -275,40 +276,49 @@ __device__ __forceinline__ float tns_lattice(float x, float (&st)[8], const floa
 
 constexpr int ENT_THREADS = 128;
 
-// shared-memory carve-up (bytes), T = ENT_THREADS
+// Hand-off record entropy_kernel -> dequant_kernel, one per THREAD SLOT (stream0 + tid) because the integer spectrum
+// sits in that thread's lane-interleaved scratch column; HO_FID names the frame (row of the CTA) the slot decoded.
+enum {
+    HO_OK = 0, HO_FID, HO_LASTNZ, HO_LSB_MODE, HO_GG_IND, HO_BW, HO_NUM_TNS, HO_NOISE_FACTOR, HO_RC_ORDER0, HO_RC_ORDER1,
+    HO_IND_LF, HO_IND_HF, HO_SUBMODE_MSB, HO_SUBMODE_LSB, HO_G_IND, HO_LS_INDA, HO_LS_INDB, HO_IDX_A, HO_IDX_B,
+    HO_NRES, HO_SEED, HO_TAIL, HO_HEAD, HO_LEN, HO_LTPF_ACTIVE, HO_PITCH_INDEX, HO_PAD0, HO_PAD1,
+    HO_RC_I = 28
+};
+static_assert(HO_RC_I + 16 == HO_WORDS, "hand-off record size");
+
+// shared-memory carve-ups (bytes), T = ENT_THREADS
+// entropy_kernel:
 //   lookup  4096            AC_SPEC_LOOKUP
 //   spec_cf 64*17*4         cum | freq << 16
 //   tns_cf  (2*8 + 8*17)*4  order tables then coef tables
 //   lev     7*T*4           lsb-mode save_lev flags, one bit per tuple
-//   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
-//   tile    (T/32)*16*33*4  per-warp transpose tile for the spectrum write-out (16 lines at a time)
-//   ring    8*T*4           per-thread prefetch ring for pass 2 (cp.async from the xq scratch)
-//   band    68*4            I_fs band edges
 //   sort    2*T*4           work-sorting keys and the resulting frame assignment
 //   rows    T*row_pitch     staged frame bytes
+// dequant_kernel:
+//   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
+//   tile    (T/32)*16*33*4  per-warp transpose tile for the spectrum write-out (16 lines at a time)
+//   ring    8*T*4           per-thread prefetch ring (cp.async from the xq scratch)
+//   band    68*4            I_fs band edges
+//   rows    T*row_pitch     staged frame bytes (residual bits)
 __host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
-    return 4096 + 64 * 17 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 16 * ENT_THREADS * 4 +
-           (ENT_THREADS / 32) * 16 * 33 * 4 + 8 * ENT_THREADS * 4 + 68 * 4 + 2 * ENT_THREADS * 4 +
-           (size_t)ENT_THREADS * row_pitch;
+    return 4096 + 64 * 17 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 2 * ENT_THREADS * 4 + (size_t)ENT_THREADS * row_pitch;
+}
+__host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
+    return 16 * ENT_THREADS * 4 + (ENT_THREADS / 32) * 16 * 33 * 4 + 8 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 
-template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
-__global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p) {
+__global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* s_lookup = smem;
     uint32_t* s_spec_cf = (uint32_t*)(smem + 4096);
     uint32_t* s_tns_cf = s_spec_cf + 64 * 17;
     uint32_t* s_lev = s_tns_cf + (2 * 8 + 8 * 17);
-    float* s_scf = (float*)(s_lev + 7 * ENT_THREADS);
-    float* s_tile = s_scf + 16 * ENT_THREADS;
-    int32_t* s_ring = (int32_t*)(s_tile + (ENT_THREADS / 32) * 16 * 33);
-    int32_t* s_band = s_ring + 8 * ENT_THREADS;
-    int32_t* s_key = s_band + 68;
+    int32_t* s_key = (int32_t*)(s_lev + 7 * ENT_THREADS);
     int32_t* s_owner = s_key + ENT_THREADS;
     uint8_t* s_rows = (uint8_t*)(s_owner + ENT_THREADS);
 
     const DevConfig& c = *p.cfg;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int stream0 = blockIdx.x * ENT_THREADS;
     const int ne = c.ne;
 
@@ -321,7 +331,6 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
     for (int i = tid; i < 8 * 17; i += ENT_THREADS)
         s_tns_cf[16 + i] = (uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_FREQ[0][0])[i] << 16);
     for (int i = tid; i < 7 * ENT_THREADS; i += ENT_THREADS) s_lev[i] = 0;
-    for (int i = tid; i < 65; i += ENT_THREADS) s_band[i] = p.cfg->band_idx[i];
     {
         const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
         const int nb = p.nbytes;
@@ -502,6 +511,120 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
         }
     }
 
+    // ---- hand-off to dequant_kernel, status, inspection
+    {
+        int32_t* ho = p.handoff + (size_t)(stream0 + tid) * HO_WORDS;
+        ho[HO_OK] = ok; ho[HO_FID] = fid;
+        ho[HO_LASTNZ] = si.lastnz; ho[HO_LSB_MODE] = si.lsb_mode; ho[HO_GG_IND] = si.gg_ind; ho[HO_BW] = si.bw;
+        ho[HO_NUM_TNS] = si.num_tns; ho[HO_NOISE_FACTOR] = si.noise_factor; ho[HO_RC_ORDER0] = rc_order0; ho[HO_RC_ORDER1] = rc_order1;
+        ho[HO_IND_LF] = si.ind_lf; ho[HO_IND_HF] = si.ind_hf; ho[HO_SUBMODE_MSB] = si.submode_msb; ho[HO_SUBMODE_LSB] = si.submode_lsb;
+        ho[HO_G_IND] = si.g_ind; ho[HO_LS_INDA] = si.ls_inda; ho[HO_LS_INDB] = si.ls_indb; ho[HO_IDX_A] = si.idx_a; ho[HO_IDX_B] = si.idx_b;
+        ho[HO_NRES] = nres; ho[HO_SEED] = (int32_t)seed_acc; ho[HO_TAIL] = rd.tail; ho[HO_HEAD] = rd.head; ho[HO_LEN] = rd.len;
+        ho[HO_LTPF_ACTIVE] = si.ltpf_active; ho[HO_PITCH_INDEX] = si.pitch_index;
+#pragma unroll
+        for (int i = 0; i < 16; i++) ho[HO_RC_I + i] = rc_i[i];
+    }
+    if (live) {
+        if (p.status_out) p.status_out[stream] = ok ? 0 : 1;
+        if (p.trace) {
+            const bool is_zero_frame = ok && si.lastnz == 2 && xq[0] == 0 && xq[32] == 0 && si.gg_ind == 0;
+            int32_t* tr = p.trace + (size_t)stream * LC3B_TRACE_WORDS;
+            for (int i = 0; i < LC3B_TRACE_WORDS; i++) tr[i] = 0;
+            tr[LC3B_TR_OK] = ok;
+            if (ok) {
+                tr[LC3B_TR_BW] = si.bw; tr[LC3B_TR_LASTNZ] = si.lastnz; tr[LC3B_TR_LSB_MODE] = si.lsb_mode;
+                tr[LC3B_TR_GG_IND] = si.gg_ind; tr[LC3B_TR_NUM_TNS] = si.num_tns; tr[LC3B_TR_RC_ORDER_IN0] = si.rc_in0;
+                tr[LC3B_TR_RC_ORDER_IN1] = si.rc_in1; tr[LC3B_TR_IND_LF] = si.ind_lf; tr[LC3B_TR_IND_HF] = si.ind_hf;
+                tr[LC3B_TR_LS_INDA] = si.ls_inda; tr[LC3B_TR_LS_INDB] = si.ls_indb; tr[LC3B_TR_IDX_A] = si.idx_a;
+                tr[LC3B_TR_IDX_B] = si.idx_b; tr[LC3B_TR_SUBMODE_LSB] = si.submode_lsb; tr[LC3B_TR_SUBMODE_MSB] = si.submode_msb;
+                tr[LC3B_TR_G_IND] = si.g_ind; tr[LC3B_TR_PITCH_PRESENT] = si.pitch_present; tr[LC3B_TR_LTPF_ACTIVE] = si.ltpf_active;
+                tr[LC3B_TR_PITCH_INDEX] = si.pitch_index; tr[LC3B_TR_NOISE_FACTOR] = si.noise_factor;
+                tr[LC3B_TR_RC_ORDER0] = rc_order0; tr[LC3B_TR_RC_ORDER1] = rc_order1;
+#pragma unroll
+                for (int i = 0; i < 16; i++) tr[LC3B_TR_RC_I0 + i] = rc_i[i];
+                // residual_bits.len(): bits actually consumed in the non-lsb branch, 0 in lsb mode (:160-209)
+                int n_nonzero_used = 0;
+                if (!si.lsb_mode) {
+                    int cnt = 0;
+                    for (int k = 0; k < si.lastnz && cnt < nres; k++) if (xq[k * 32] != 0) cnt++;
+                    n_nonzero_used = cnt;
+                }
+                tr[LC3B_TR_NRES] = n_nonzero_used;
+                tr[LC3B_TR_SEED] = (int32_t)(seed_acc & 0xffffu);
+                tr[LC3B_TR_IS_ZERO] = is_zero_frame;
+            }
+        }
+        if (p.trace_x) {
+            int32_t* tx = p.trace_x + (size_t)stream * ne;
+            for (int k = 0; k < ne; k++) tx[k] = (ok && k < si.lastnz) ? xq[k * 32] : 0;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------- kernel 1b: integers -> shaped spectrum
+// Dequantisation, residual refinement, noise filling, global gain, TNS lattice, SNS gains (reference D4-D8); one
+// thread per frame, every thread walks all ne lines, so the warp stays converged without any work sorting.
+template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
+__global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float* s_scf = (float*)smem;
+    float* s_tile = s_scf + 16 * ENT_THREADS;
+    int32_t* s_ring = (int32_t*)(s_tile + (ENT_THREADS / 32) * 16 * 33);
+    int32_t* s_band = s_ring + 8 * ENT_THREADS;
+    uint8_t* s_rows = (uint8_t*)(s_band + 68);
+
+    const DevConfig& c = *p.cfg;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int stream0 = blockIdx.x * ENT_THREADS;
+    const int ne = c.ne;
+
+    // hand-off record of this thread slot
+    const int32_t* ho = p.handoff + (size_t)(stream0 + tid) * HO_WORDS;
+    const int fid = ho[HO_FID];
+    const int stream = stream0 + fid;
+    const bool live = stream < p.n_streams;
+    const bool ok = ho[HO_OK] != 0;
+    SideInfoD si;
+    si.lastnz = ho[HO_LASTNZ]; si.lsb_mode = ho[HO_LSB_MODE]; si.gg_ind = ho[HO_GG_IND]; si.bw = ho[HO_BW];
+    si.num_tns = ho[HO_NUM_TNS]; si.noise_factor = ho[HO_NOISE_FACTOR];
+    si.ind_lf = ho[HO_IND_LF]; si.ind_hf = ho[HO_IND_HF]; si.submode_msb = ho[HO_SUBMODE_MSB]; si.submode_lsb = ho[HO_SUBMODE_LSB];
+    si.g_ind = ho[HO_G_IND]; si.ls_inda = ho[HO_LS_INDA]; si.ls_indb = ho[HO_LS_INDB]; si.idx_a = ho[HO_IDX_A]; si.idx_b = ho[HO_IDX_B];
+    si.ltpf_active = ho[HO_LTPF_ACTIVE]; si.pitch_index = ho[HO_PITCH_INDEX];
+    si.rc_in0 = si.rc_in1 = si.pitch_present = 0;
+    const int rc_order0 = ho[HO_RC_ORDER0], rc_order1 = ho[HO_RC_ORDER1];
+    const int nres = ho[HO_NRES];
+    const uint32_t seed_acc = (uint32_t)ho[HO_SEED];
+    int rc_i[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) rc_i[i] = ho[HO_RC_I + i];
+    Reader rd;
+    rd.buf = s_rows + fid * p.row_pitch;
+    rd.len = ho[HO_LEN];
+    rd.head = ho[HO_HEAD];
+    rd.tail = ho[HO_TAIL];
+    const int nbits = rd.len * 8;
+    int32_t* xq = p.xq + ((size_t)((stream0 + tid) >> 5) * ne) * 32 + lane;   // thread-private column, element k at xq[k * 32]
+
+    for (int i = tid; i < 65; i += ENT_THREADS) s_band[i] = p.cfg->band_idx[i];
+    // the frame bytes are only needed again for the residual bits (non-lsb mode); stage them when any frame of the CTA has some
+    const bool need_rows = ok && !si.lsb_mode && nres > 0;
+    if (__syncthreads_or(need_rows)) {
+        const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
+        const int nb = p.nbytes;
+        for (int i = tid; i < n_rows * nb; i += ENT_THREADS) {
+            int r = i / nb, b = i - r * nb;
+            s_rows[r * p.row_pitch + b] = p.frames[(size_t)(stream0 + r) * p.frame_stride + b];
+        }
+    }
+    __syncthreads();
+    {   // resume the tail reader mid-byte: (tail + tw_n) % 8 == 0
+        const int idx = rd.len - 1 - (rd.tail >> 3);
+        const uint32_t byte = (need_rows && idx >= 0 && idx < rd.len) ? rd.buf[idx] : 0u;
+        rd.tw = (uint64_t)(byte >> (rd.tail & 7));
+        rd.tw_n = 8 - (rd.tail & 7);
+    }
+
     // ---- pass 2: dequantise, noise fill, gain, TNS, SNS; spectrum -> inactive slot
     int slot = 0;
     if (live && p.fixed_slot < 0) slot = p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
@@ -677,7 +800,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
         }
     }
 
-    // ---- hand-off record, slot flip, status, inspection
+    // ---- hand-off record for the synthesis kernel, slot flip
     if (live) {
         int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
         sd[SD_OK] = ok;
@@ -686,38 +809,6 @@ __global__ void __launch_bounds__(ENT_THREADS, 4) entropy_kernel(EntropyParams p
         sd[SD_NBITS] = nbits;
         sd[SD_SLOT] = ok ? new_slot : slot;
         if (ok && p.fixed_slot < 0) p.sstate[(size_t)stream * SS_WORDS + SS_SLOT] = new_slot;
-        if (p.status_out) p.status_out[stream] = ok ? 0 : 1;
-        if (p.trace) {
-            int32_t* tr = p.trace + (size_t)stream * LC3B_TRACE_WORDS;
-            for (int i = 0; i < LC3B_TRACE_WORDS; i++) tr[i] = 0;
-            tr[LC3B_TR_OK] = ok;
-            if (ok) {
-                tr[LC3B_TR_BW] = si.bw; tr[LC3B_TR_LASTNZ] = si.lastnz; tr[LC3B_TR_LSB_MODE] = si.lsb_mode;
-                tr[LC3B_TR_GG_IND] = si.gg_ind; tr[LC3B_TR_NUM_TNS] = si.num_tns; tr[LC3B_TR_RC_ORDER_IN0] = si.rc_in0;
-                tr[LC3B_TR_RC_ORDER_IN1] = si.rc_in1; tr[LC3B_TR_IND_LF] = si.ind_lf; tr[LC3B_TR_IND_HF] = si.ind_hf;
-                tr[LC3B_TR_LS_INDA] = si.ls_inda; tr[LC3B_TR_LS_INDB] = si.ls_indb; tr[LC3B_TR_IDX_A] = si.idx_a;
-                tr[LC3B_TR_IDX_B] = si.idx_b; tr[LC3B_TR_SUBMODE_LSB] = si.submode_lsb; tr[LC3B_TR_SUBMODE_MSB] = si.submode_msb;
-                tr[LC3B_TR_G_IND] = si.g_ind; tr[LC3B_TR_PITCH_PRESENT] = si.pitch_present; tr[LC3B_TR_LTPF_ACTIVE] = si.ltpf_active;
-                tr[LC3B_TR_PITCH_INDEX] = si.pitch_index; tr[LC3B_TR_NOISE_FACTOR] = si.noise_factor;
-                tr[LC3B_TR_RC_ORDER0] = rc_order0; tr[LC3B_TR_RC_ORDER1] = rc_order1;
-#pragma unroll
-                for (int i = 0; i < 16; i++) tr[LC3B_TR_RC_I0 + i] = rc_i[i];
-                // residual_bits.len(): bits actually consumed in the non-lsb branch, 0 in lsb mode (:160-209)
-                int n_nonzero_used = 0;
-                if (!si.lsb_mode) {
-                    int cnt = 0;
-                    for (int k = 0; k < si.lastnz && cnt < nres; k++) if (xq[k * 32] != 0) cnt++;
-                    n_nonzero_used = cnt;
-                }
-                tr[LC3B_TR_NRES] = n_nonzero_used;
-                tr[LC3B_TR_SEED] = (int32_t)(seed_acc & 0xffffu);
-                tr[LC3B_TR_IS_ZERO] = is_zero_frame;
-            }
-        }
-        if (p.trace_x) {
-            int32_t* tx = p.trace_x + (size_t)stream * ne;
-            for (int k = 0; k < ne; k++) tx[k] = (ok && k < si.lastnz) ? xq[k * 32] : 0;
-        }
     }
 }
 
@@ -727,15 +818,19 @@ static int entropy_row_pitch(int nbytes) {
     return words * 4;
 }
 
-// dynamic shared memory limit, once per handle (lc3b_decoder_init) for the largest frame the handle accepts
+// dynamic shared memory limits, once per handle (lc3b_decoder_init) for the largest frame the handle accepts
 cudaError_t prepare_entropy(const DecoderState& st) {
-    const int smem = (int)entropy_smem_bytes(entropy_row_pitch(st.max_nbytes));
-    if (st.cfg.n_ms == LC3B_10MS) return cudaFuncSetAttribute(entropy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    return cudaFuncSetAttribute(entropy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int pitch = entropy_row_pitch(st.max_nbytes);
+    cudaError_t e = cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)entropy_smem_bytes(pitch));
+    if (e != cudaSuccess) return e;
+    const int smem = (int)dequant_smem_bytes(pitch);
+    if (st.cfg.n_ms == LC3B_10MS) return cudaFuncSetAttribute(dequant_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return cudaFuncSetAttribute(dequant_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
+// stages: bit 0 entropy_kernel (bitstream -> integers), bit 1 dequant_kernel (integers -> shaped spectrum)
 cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
-                           size_t frame_stride, int32_t* status_out, cudaStream_t stream) {
+                           size_t frame_stride, int32_t* status_out, int stages, cudaStream_t stream) {
     EntropyParams p;
     p.cfg = st.dcfg;
     p.frames = frames;
@@ -745,6 +840,7 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
     p.n_streams = st.n_streams;
     p.spec = st.spec;
     p.xq = st.xq;
+    p.handoff = st.handoff;
     p.side = st.side;
     p.sstate = st.sstate;
     p.status_out = status_out;
@@ -753,10 +849,13 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
     p.sym_lut = st.sym_lut;
     p.fixed_slot = st.fixed_slot;
     p.row_pitch = entropy_row_pitch(nbytes);
-    const size_t smem = entropy_smem_bytes(p.row_pitch);
     const int grid = (st.n_streams + ENT_THREADS - 1) / ENT_THREADS;
-    if (st.cfg.n_ms == LC3B_10MS) entropy_kernel<3><<<grid, ENT_THREADS, smem, stream>>>(p);
-    else entropy_kernel<2><<<grid, ENT_THREADS, smem, stream>>>(p);
+    if (stages & 1) entropy_kernel<<<grid, ENT_THREADS, entropy_smem_bytes(p.row_pitch), stream>>>(p);
+    if (stages & 2) {
+        const size_t smem = dequant_smem_bytes(p.row_pitch);
+        if (st.cfg.n_ms == LC3B_10MS) dequant_kernel<3><<<grid, ENT_THREADS, smem, stream>>>(p);
+        else dequant_kernel<2><<<grid, ENT_THREADS, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -8,7 +8,7 @@
 //   * the LTPF is an IIR across frame boundaries, but only while it is active (long_term_post_filter.rs:252)
 // so a call with F frames of S streams runs as S*F independent "units" through the expensive stages and touches the
 // time axis only where it must:
-//   1. entropy_kernel over the S*F units (the unchanged kernel 1; spectrum to a per-unit slot)
+//   1. entropy_kernel + dequant_kernel over the S*F units (the unchanged kernels; spectrum to a per-unit slot)
 //   2. plc_scan_kernel      thread per stream: walks the ok flags, assigns each concealed unit its source spectrum,
 //                           alpha and seed (the LCG is jumped ne steps at a time), updates the handle's PLC scalars
 //   3. imdct_multi_kernel   warp per unit: concealment scramble, DCT-IV (same FFT as kernel 2), window -> head / tail
@@ -23,7 +23,7 @@
 
 namespace lc3b {
 
-struct MultiLayout { size_t spec, xq, side, head, tail, xhat, last_good, total; };
+struct MultiLayout { size_t spec, xq, handoff, side, head, tail, xhat, last_good, total; };
 
 static MultiLayout multi_layout(const lc3b_config& c, int S, int F) {
     MultiLayout L;
@@ -33,6 +33,7 @@ static MultiLayout multi_layout(const lc3b_config& c, int S, int F) {
     const size_t nblk = ((V + 127) / 128) * 4;                    // 32-stream blocks, whole entropy CTAs
     L.spec = take(sizeof(float) * V * c.ne);
     L.xq = take(sizeof(int32_t) * nblk * c.ne * 32);
+    L.handoff = take(sizeof(int32_t) * nblk * 32 * HO_WORDS);
     L.side = take(sizeof(int32_t) * V * SIDE_WORDS);
     L.head = take(sizeof(float) * V * c.nf);
     L.tail = take(sizeof(float) * V * (c.nf - c.z));
@@ -428,11 +429,12 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     vs.n_streams = (int)V;
     vs.spec = (float*)(base + L.spec);
     vs.xq = (int32_t*)(base + L.xq);
+    vs.handoff = (int32_t*)(base + L.handoff);
     vs.side = (int32_t*)(base + L.side);
     vs.fixed_slot = 0;
     vs.trace = nullptr;
     vs.trace_x = nullptr;
-    cudaError_t e = launch_entropy(vs, frames, frame_nbytes, nbytes, frame_stride, status_out, stream);
+    cudaError_t e = launch_entropy(vs, frames, frame_nbytes, nbytes, frame_stride, status_out, 3, stream);
     if (e != cudaSuccess) return e;
     MultiParams p;
     p.cfg = st.dcfg; p.win = st.win; p.dtw = st.dtw; p.ftw = st.ftw;
