@@ -70,7 +70,7 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
     L.win = cv.take(sizeof(float) * 2 * c.nf);
     L.dtw = cv.take(sizeof(float2) * (c.nf / 2));
     L.ftw = cv.take(sizeof(float2) * (c.nf / 2));
-    L.sym_lut = cv.take(64 * 1024);
+    L.sym_lut = cv.take(64 * 32);
     L.spec = cv.take(sizeof(float) * 2 * ns * c.ne);
     L.xq = cv.take(sizeof(int32_t) * nblk * c.ne * 32);
     L.handoff = cv.take(sizeof(int32_t) * ((ns + 127) / 128) * 128 * HO_WORDS);   // every thread slot of whole entropy CTAs
@@ -152,13 +152,14 @@ __global__ void init_tables_kernel(DevConfig* cfg, float* win, float2* dtw, floa
     }
 }
 
-// symbol for every (probability model, quotient): largest val with cum[val] <= q (arithmetic_codec.rs:82-85)
+// coarse symbol table: for every (probability model, quotient / 32) the largest val with cum[val] <= 32 * bucket
+// (arithmetic_codec.rs:82-85); the entropy kernel refines from there against the cumulative table in shared memory
 __global__ void init_sym_lut_kernel(uint8_t* lut) {
     const int pki = blockIdx.x;
-    for (int q = threadIdx.x; q < 1024; q += blockDim.x) {
+    for (int b = threadIdx.x; b < 32; b += blockDim.x) {
         int val = 16;
-        while (LC3T_AC_SPEC_CUMFREQ[pki][val] > q) val--;
-        lut[pki * 1024 + q] = (uint8_t)val;
+        while (LC3T_AC_SPEC_CUMFREQ[pki][val] > 32 * b) val--;
+        lut[pki * 32 + b] = (uint8_t)val;
     }
 }
 
@@ -308,7 +309,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     if (e == cudaSuccess) e = prepare_multi(st);
     if (e == cudaSuccess) {
         init_tables_kernel<<<1, 256, 0, stream>>>(st.dcfg, st.win, st.dtw, st.ftw);
-        init_sym_lut_kernel<<<64, 256, 0, stream>>>(st.sym_lut);
+        init_sym_lut_kernel<<<64, 32, 0, stream>>>(st.sym_lut);
         init_streams_kernel<<<(n_streams + 255) / 256, 256, 0, stream>>>(st.sstate, n_streams);
         e = cudaGetLastError();
     }

@@ -65,7 +65,7 @@ struct DecoderState {
     float* win;          // [2*nf]
     float2* dtw;         // [n_fft]
     float2* ftw;         // [n_fft]
-    uint8_t* sym_lut;    // [64][1024] arithmetic-decoder symbol for (pki, quotient), built at init
+    uint8_t* sym_lut;    // [64][32] arithmetic-decoder symbol at the start of each 32-quotient bucket, built at init
     float* spec;         // [2][n_streams][ne]  double-buffered spectrum; the valid slot doubles as PLC "last good"
     int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (entropy -> dequantisation kernel)
     int32_t* handoff;    // [n_blocks32 * 32][HO_WORDS] decoded side information etc. (entropy -> dequantisation kernel)

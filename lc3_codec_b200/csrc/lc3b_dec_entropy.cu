@@ -41,7 +41,7 @@ struct EntropyParams {
     int32_t* status_out;  // nullable
     int32_t* trace;       // nullable
     int32_t* trace_x;     // nullable
-    const uint8_t* sym_lut;   // [64][1024] symbol for (pki, floor(low / (range >> 10)))
+    const uint8_t* sym_lut;   // [64][32] symbol at the start of each 32-quotient bucket (init_sym_lut_kernel)
     int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
     int row_pitch;        // bytes per staged frame row in shared memory
 };
@@ -143,13 +143,22 @@ __device__ __forceinline__ bool ac_decode(Reader& rd, AcState& st, const uint32_
     return ac_finish(rd, st, tmp, tab[val]);
 }
 
-// Spectral symbols: same search answered by a 64 x 1024 byte table (symbol for every quotient), see init_sym_lut_kernel.
+// Spectral symbols: the same search answered from shared memory.  A coarse table gives the symbol at the start of the
+// quotient's 32-wide bucket; the cumulative table (rows padded to SPEC_CF_STRIDE with 0xffff sentinels) is then walked
+// upward three entries at a time - independent loads, and almost always a single round.
+constexpr int SPEC_CF_STRIDE = 20;
 __device__ __forceinline__ bool ac_decode_spec(Reader& rd, AcState& st, const uint32_t* __restrict__ tab,
-                                               const uint8_t* __restrict__ lut, int& sym) {
+                                               const uint8_t* __restrict__ clut, int& sym) {
     const uint32_t tmp = st.range >> 10;
     if (st.low >= (tmp << 10)) return false;
     const uint32_t q = exact_quotient(st.low, tmp);                     // < 1024 by the test above
-    const int val = __ldg(lut + q);
+    int val = clut[q >> 5];
+    for (;;) {
+        const uint32_t c1 = tab[val + 1] & 0xffffu, c2 = tab[val + 2] & 0xffffu, c3 = tab[val + 3] & 0xffffu;
+        const int adv = (int)(c1 <= q) + (int)(c2 <= q) + (int)(c3 <= q);   // cum is non-decreasing
+        val += adv;
+        if (adv < 3) break;
+    }
     sym = val;
     return ac_finish(rd, st, tmp, tab[val]);
 }
@@ -289,7 +298,8 @@ static_assert(HO_RC_I + 16 == HO_WORDS, "hand-off record size");
 // shared-memory carve-ups (bytes), T = ENT_THREADS
 // entropy_kernel:
 //   lookup  4096            AC_SPEC_LOOKUP
-//   spec_cf 64*17*4         cum | freq << 16
+//   clut    2048            coarse symbol table (64 models x 32 quotient buckets)
+//   spec_cf 64*20*4         cum | freq << 16, rows padded with sentinels
 //   tns_cf  (2*8 + 8*17)*4  order tables then coef tables
 //   lev     7*T*4           lsb-mode save_lev flags, one bit per tuple
 //   sort    2*T*4           work-sorting keys and the resulting frame assignment
@@ -301,7 +311,7 @@ static_assert(HO_RC_I + 16 == HO_WORDS, "hand-off record size");
 //   band    68*4            I_fs band edges
 //   rows    T*row_pitch     staged frame bytes (residual bits)
 __host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
-    return 4096 + 64 * 17 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 2 * ENT_THREADS * 4 + (size_t)ENT_THREADS * row_pitch;
+    return 4096 + 2048 + 64 * 20 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 2 * ENT_THREADS * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 __host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
     return 16 * ENT_THREADS * 4 + (ENT_THREADS / 32) * 16 * 33 * 4 + 8 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
@@ -310,8 +320,9 @@ __host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
 __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* s_lookup = smem;
-    uint32_t* s_spec_cf = (uint32_t*)(smem + 4096);
-    uint32_t* s_tns_cf = s_spec_cf + 64 * 17;
+    uint8_t* s_clut = smem + 4096;
+    uint32_t* s_spec_cf = (uint32_t*)(smem + 4096 + 2048);
+    uint32_t* s_tns_cf = s_spec_cf + 64 * SPEC_CF_STRIDE;
     uint32_t* s_lev = s_tns_cf + (2 * 8 + 8 * 17);
     int32_t* s_key = (int32_t*)(s_lev + 7 * ENT_THREADS);
     int32_t* s_owner = s_key + ENT_THREADS;
@@ -324,8 +335,11 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
 
     // ---- stage tables and frame bytes
     for (int i = tid; i < 4096 / 4; i += ENT_THREADS) ((uint32_t*)s_lookup)[i] = ((const uint32_t*)LC3T_AC_SPEC_LOOKUP)[i];
-    for (int i = tid; i < 64 * 17; i += ENT_THREADS)
-        s_spec_cf[i] = (uint32_t)(uint16_t)(&LC3T_AC_SPEC_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_SPEC_FREQ[0][0])[i] << 16);
+    for (int i = tid; i < 2048 / 4; i += ENT_THREADS) ((uint32_t*)s_clut)[i] = ((const uint32_t*)p.sym_lut)[i];
+    for (int i = tid; i < 64 * SPEC_CF_STRIDE; i += ENT_THREADS) {
+        const int pk = i / SPEC_CF_STRIDE, j = i - pk * SPEC_CF_STRIDE;
+        s_spec_cf[i] = j < 17 ? ((uint32_t)(uint16_t)LC3T_AC_SPEC_CUMFREQ[pk][j] | ((uint32_t)(uint16_t)LC3T_AC_SPEC_FREQ[pk][j] << 16)) : 0xffffu;
+    }
     for (int i = tid; i < 2 * 8; i += ENT_THREADS)
         s_tns_cf[i] = (uint32_t)(uint16_t)(&LC3T_AC_TNS_ORDER_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_TNS_ORDER_FREQ[0][0])[i] << 16);
     for (int i = tid; i < 8 * 17; i += ENT_THREADS)
@@ -438,7 +452,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
             int t = ctx + rate_flag + ((k * 2) > (ne / 2) ? 256 : 0);
             const int pki = s_lookup[t + min(lev, 3) * 1024];
             int sym, bit;
-            if (!ac_decode_spec(rd, ac, s_spec_cf + pki * 17, p.sym_lut + pki * 1024, sym)) { ok = false; break; }
+            if (!ac_decode_spec(rd, ac, s_spec_cf + pki * SPEC_CF_STRIDE, s_clut + pki * 32, sym)) { ok = false; break; }
             if (sym >= 16) {                                            // escape: two more magnitude bits
                 if (!si.lsb_mode || lev > 0) {
                     if (!rd.tail_bool(bit)) { ok = false; break; }
