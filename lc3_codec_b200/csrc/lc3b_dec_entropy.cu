@@ -80,6 +80,19 @@ struct Reader {
         tail += 1;
         return true;
     }
+    // n (1 or 2) consecutive read_tail_bool calls at once: the bounds tests are monotonic in the bit position, so the
+    // n calls all succeed exactly when the last one does, and a failure of any of them discards the frame anyway
+    __device__ __forceinline__ bool tail_bools(int n, uint32_t& bits) {
+        const int byte_index = (tail + n - 1) >> 3;
+        if (len - head - byte_index + 2 < 0) return false;
+        if (byte_index >= len) return false;
+        if (tw_n < n) refill();
+        bits = (uint32_t)tw & ((1u << n) - 1u);
+        tw >>= n;
+        tw_n -= n;
+        tail += n;
+        return true;
+    }
     __device__ __forceinline__ bool tail_uint(int num_bits, uint32_t& out) {   // :63
         const int byte_index = tail >> 3, bit_index = tail & 7;
         const int add_bytes = (num_bits > 8 - bit_index && num_bits < 8) ? 2 : 1;
@@ -451,14 +464,14 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
         while (k < ntup) {
             int t = ctx + rate_flag + ((k * 2) > (ne / 2) ? 256 : 0);
             const int pki = s_lookup[t + min(lev, 3) * 1024];
-            int sym, bit;
+            int sym;
             if (!ac_decode_spec(rd, ac, s_spec_cf + pki * SPEC_CF_STRIDE, s_clut + pki * 32, sym)) { ok = false; break; }
             if (sym >= 16) {                                            // escape: two more magnitude bits
                 if (!si.lsb_mode || lev > 0) {
-                    if (!rd.tail_bool(bit)) { ok = false; break; }
-                    xa_ += bit << lev;
-                    if (!rd.tail_bool(bit)) { ok = false; break; }
-                    xb_ += bit << lev;
+                    uint32_t two;
+                    if (!rd.tail_bools(2, two)) { ok = false; break; }
+                    xa_ += (int)(two & 1u) << lev;
+                    xb_ += (int)(two >> 1) << lev;
                 }
                 lev++;
                 if (lev < 14) continue;                                 // QUIRK (ii): at lev == 14 the tuple ends with sym == 16
@@ -467,13 +480,12 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
             const int a = sym & 3, b = sym >> 2;
             xa_ += a << lev;
             xb_ += b << lev;
-            if (xa_ > 0) {
-                if (!rd.tail_bool(bit)) { ok = false; break; }
-                if (bit) xa_ = -xa_;
-            }
-            if (xb_ > 0) {
-                if (!rd.tail_bool(bit)) { ok = false; break; }
-                if (bit) xb_ = -xb_;
+            const int nsign = (xa_ > 0) + (xb_ > 0);
+            if (nsign > 0) {
+                uint32_t sg;
+                if (!rd.tail_bools(nsign, sg)) { ok = false; break; }
+                if (xa_ > 0) { if (sg & 1u) xa_ = -xa_; sg >>= 1; }
+                if (xb_ > 0 && (sg & 1u)) xb_ = -xb_;
             }
             xq[(2 * k) * 32] = xa_;
             xq[(2 * k + 1) * 32] = xb_;
