@@ -298,6 +298,34 @@ __device__ __forceinline__ float tns_lattice(float x, float (&st)[8], const floa
 
 constexpr int ENT_THREADS = 128;
 
+// Stage the CTA's frames into shared-memory rows (odd word pitch).  Dense input (frame_stride == nbytes, 16-byte
+// aligned block) is fetched with 16-byte loads and scattered byte by byte; otherwise byte by byte from the start.
+__device__ __forceinline__ void stage_rows(const EntropyParams& p, uint8_t* s_rows, int stream0, int tid) {
+    const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
+    const int nb = p.nbytes;
+    const int total = n_rows * nb;
+    const uint8_t* src = p.frames + (size_t)stream0 * p.frame_stride;
+    int done = 0;
+    if (p.frame_stride == (size_t)nb && (((uintptr_t)src) & 15) == 0) {
+        const int n16 = total >> 4;
+        for (int i = tid; i < n16; i += ENT_THREADS) {
+            const uint4 v = ((const uint4*)src)[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            int r = (16 * i) / nb, b = 16 * i - r * nb;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                s_rows[r * p.row_pitch + b] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+                if (++b == nb) { b = 0; r++; }
+            }
+        }
+        done = n16 << 4;
+    }
+    for (int i = done + tid; i < total; i += ENT_THREADS) {
+        const int r = i / nb, b = i - r * nb;
+        s_rows[r * p.row_pitch + b] = src[(size_t)r * p.frame_stride + b];
+    }
+}
+
 // Hand-off record entropy_kernel -> dequant_kernel, one per THREAD SLOT (stream0 + tid) because the integer spectrum
 // sits in that thread's lane-interleaved scratch column; HO_FID names the frame (row of the CTA) the slot decoded.
 enum {
@@ -359,12 +387,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
         s_tns_cf[16 + i] = (uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_CUMFREQ[0][0])[i] | ((uint32_t)(uint16_t)(&LC3T_AC_TNS_COEF_FREQ[0][0])[i] << 16);
     for (int i = tid; i < 7 * ENT_THREADS; i += ENT_THREADS) s_lev[i] = 0;
     {
-        const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
-        const int nb = p.nbytes;
-        for (int i = tid; i < n_rows * nb; i += ENT_THREADS) {
-            int r = i / nb, b = i - r * nb;
-            s_rows[r * p.row_pitch + b] = p.frames[(size_t)(stream0 + r) * p.frame_stride + b];
-        }
+        stage_rows(p, s_rows, stream0, tid);
     }
     __syncthreads();
 
@@ -636,12 +659,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     // the frame bytes are only needed again for the residual bits (non-lsb mode); stage them when any frame of the CTA has some
     const bool need_rows = ok && !si.lsb_mode && nres > 0;
     if (__syncthreads_or(need_rows)) {
-        const int n_rows = min(ENT_THREADS, p.n_streams - stream0);
-        const int nb = p.nbytes;
-        for (int i = tid; i < n_rows * nb; i += ENT_THREADS) {
-            int r = i / nb, b = i - r * nb;
-            s_rows[r * p.row_pitch + b] = p.frames[(size_t)(stream0 + r) * p.frame_stride + b];
-        }
+        stage_rows(p, s_rows, stream0, tid);
     }
     __syncthreads();
     {   // resume the tail reader mid-byte: (tail + tw_n) % 8 == 0
@@ -753,8 +771,6 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
         int res_used = 0;
-        int band = 0;
-        float gband = ok ? band_gain(0) : 0.0f;
         // The integers come back from the lane-interleaved scratch through a 16-slot per-thread ring filled by
         // cp.async PF lines ahead, so the L2 round trip never sits on the serial per-line chain.
         constexpr int PF = 6;
@@ -775,8 +791,12 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
             if (win[j + 1] != 0 && j < bw_stop) last_nz = j;
         }
         for (int e = W; e < W + PF; e++) issue(e);
-        int next_edge = s_band[1];
-        for (int k = 0; k < ne; k++) {
+        // lines are walked band by band (the last band runs to ne), so no per-line band-edge test is needed
+        int k = 0;
+        for (int band = 0; band < nb; band++) {
+        const float gband = ok ? band_gain(band) : 0.0f;
+        const int k_end = band + 1 < nb ? s_band[band + 1] : ne;
+        for (; k < k_end; k++) {
 #pragma unroll
             for (int j = 0; j < W; j++) win[j] = win[j + 1];
             {
@@ -805,7 +825,6 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
                     if (k < tns_e0) { if (rc_order0 > 0) v = tns_lattice(v, st, rc0, rc_order0); }
                     else if (rc_order1 > 0 && si.num_tns == 2) v = tns_lattice(v, st, rc1, rc_order1);
                 }
-                while (k >= next_edge && band + 1 < nb) { band++; next_edge = s_band[band + 1]; gband = band_gain(band); }
                 v = xm(v, gband);
             }
             // transpose through the warp tile, flush every 32 lines
@@ -823,6 +842,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
                 }
                 __syncwarp();
             }
+        }
         }
     }
 
