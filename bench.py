@@ -280,15 +280,30 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
         ms_total = timed(lambda i: dec.decode_frames(16, frames[i % F], lens, pcm), args.steps, args.warmup)
     ups = world * S * args.steps / (ms_total * 1e-3)
     host_in = frames.cpu().pin_memory()
-    host_out = torch.empty((S, 480), dtype=torch.int16).pin_memory()
-    dev_in = torch.empty((S, STRIDE), dtype=torch.uint8, device=dev)
+    host_lens = lens.cpu().pin_memory()
+    host_out = [dec.alloc_host_pcm() for _ in range(2)]
+    dec.set_host_pipelining(True)
+    e2e_steps = max(10, min(args.steps, 100))
 
     def e2e_step(i):
-        dev_in.copy_(host_in[i % F], non_blocking=True)
-        dec.decode_frames(16, dev_in, lens, pcm)
-        host_out.copy_(pcm, non_blocking=True)
-    e2e_steps = max(10, min(args.steps, 100))
-    ms_e2e = timed(e2e_step, e2e_steps, 3)
+        dec.decode_frames_host(16, host_in[i % F], host_lens, host_out[i & 1])
+    for i in range(3):
+        e2e_step(i)
+    dec.host_fence()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(e2e_steps):
+        e2e_step(3 + i)
+    dec.host_fence()
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    dec.set_host_pipelining(False)
     peak, peak_src = measured_peak()
     step_ms = ms_total / args.steps
     achieved = algo / (step_ms * 1e-3) / 1e9
@@ -299,14 +314,18 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": w["desc"], "name": "mixed", "streams_per_gpu": S,
-                       "parallelism": f"{world} x independent stream shards; 12 per-configuration decoders on 12 CUDA streams"},
+                       "parallelism": f"{world} x independent stream shards; 12 per-configuration decoders on 12 CUDA streams",
+                       "note": "e2e can exceed value: the host entry point lets the per-configuration streams run ahead across "
+                               "steps (joined once by host_fence); the device entry point joins them on the caller's stream every call"},
             "clocks": clk.summary(),
             "e2e": {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * STRIDE,
-                    "d2h_bytes_per_step": S * 480 * 2, "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "pinned-host rows copied in, Lc3MixedBatchDecoder.decode_frames, padded PCM rows copied out, every step"},
-            "gpu_launches": 24 * args.steps,
+                    "d2h_bytes_per_step": int(sum(c_ * n_ * 2 for (_, _, c_), n_ in zip(dec.buckets, dec.nf))),
+                    "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "Lc3MixedBatchDecoder.decode_frames_host (one lc3b_decode_frames_host per configuration on its own CUDA "
+                           "stream, host pipelining on, host_fence before the end event)"},
+            "gpu_launches": 36 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "whole step (12 configurations x 2 kernels on concurrent streams)", "kernel_ms": step_ms,
+                         "kernel": "whole step (12 configurations x 3 kernels on concurrent streams)", "kernel_ms": step_ms,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": algo},
             "cpu_baseline": cb}))
     if dist is not None:

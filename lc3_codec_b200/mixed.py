@@ -57,3 +57,36 @@ class Lc3MixedBatchDecoder:
             done = torch.cuda.Event()
             done.record(st)
             cur.wait_event(done)
+
+    # ------------------------------------------------------------------ host buffers
+    def alloc_host_pcm(self) -> list[torch.Tensor]:
+        """One dense pinned int16 [rows_b, nf_b] tensor per bucket (dense rows keep every PCM copy a single linear one)."""
+        return [torch.empty((count, nf), dtype=torch.int16).pin_memory() for (_, _, count), nf in zip(self.buckets, self.nf)]
+
+    def set_host_pipelining(self, on: bool) -> None:
+        for dec in self.decoders:
+            dec.set_host_pipelining(on)
+
+    def decode_frames_host(self, num_bits_per_audio_sample: int, frames: torch.Tensor, frame_nbytes: torch.Tensor,
+                           pcm_out: list[torch.Tensor]) -> None:
+        """Same call with HOST tensors (pinned): frames [S, stride] u8 and frame_nbytes [S] i32 in bucket order, pcm_out one
+        dense [rows_b, nf_b] tensor per bucket (alloc_host_pcm).  Buckets run on their own CUDA streams; with host
+        pipelining on, PCM copies overlap the other buckets' kernels and the next call.  Join with host_fence()."""
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for dec, st, (_, first, count), out in zip(self.decoders, self.streams, self.buckets, pcm_out):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                dec.decode_frames_host(num_bits_per_audio_sample, frames[first:first + count], out,
+                                       frame_nbytes=frame_nbytes[first:first + count], nbytes=frames.shape[1])
+
+    def host_fence(self) -> None:
+        """Make the current stream wait for every bucket's outstanding work (kernels and pipelined PCM copies)."""
+        cur = torch.cuda.current_stream(self.device)
+        for dec, st in zip(self.decoders, self.streams):
+            with torch.cuda.stream(st):
+                dec.host_fence()
+            done = torch.cuda.Event()
+            done.record(st)
+            cur.wait_event(done)

@@ -202,3 +202,42 @@ def test_mixed_rate_batch():
         exp = pcm_by[(fs, ms)][s // 12]
         nf = exp.shape[-1]
         assert np.abs(got[pos, :, :nf].astype(np.int32) - exp.astype(np.int32)).max() <= PCM_TOL, (fs, ms, s)
+
+
+def test_mixed_rate_batch_host_entry():
+    """Lc3MixedBatchDecoder.decode_frames_host: pinned host rows in, one dense pinned PCM tensor per configuration out,
+    pipelined copies; same PCM as the oracle."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from oracle import pyoracle as O
+    per, F = 10, 6
+    frames_by, pcm_by = {}, {}
+    for (fs, ms) in ALL_CONFIGS:
+        _, fr = corpus(fs, ms, MIXED_NBYTES[(fs, ms)], per, F)
+        frames_by[(fs, ms)] = fr
+        pcm_by[(fs, ms)] = O.decode_streams(fr, fs, ms)
+    stream_cfg = [ALL_CONFIGS[s % 12] for s in range(12 * per)]
+    dec = L.Lc3MixedBatchDecoder([(L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)) for fs, ms in stream_cfg],
+                                 max_nbytes=120, device="cuda:0")
+    dec.set_host_pipelining(True)
+    S = len(stream_cfg)
+    outs = [dec.alloc_host_pcm() for _ in range(F)]
+    rows_all = torch.zeros((F, S, 120), dtype=torch.uint8).pin_memory()
+    lens = torch.zeros(S, dtype=torch.int32).pin_memory()
+    for pos, s in enumerate(dec.order):
+        fs, ms = stream_cfg[s]
+        fr = frames_by[(fs, ms)][s // 12]
+        rows_all[:, pos, :fr.shape[1]] = torch.from_numpy(fr)
+        lens[pos] = fr.shape[1]
+    for f in range(F):
+        dec.decode_frames_host(16, rows_all[f], lens, outs[f])
+    dec.host_fence()
+    torch.cuda.synchronize()
+    for b, ((sf, fd), first, count) in enumerate(dec.buckets):
+        for r in range(count):
+            s = dec.order[first + r]
+            fs, ms = stream_cfg[s]
+            exp = pcm_by[(fs, ms)][s // 12]
+            got = np.stack([outs[f][b][r].numpy() for f in range(F)])
+            assert np.abs(got.astype(np.int32) - exp.astype(np.int32)).max() <= PCM_TOL, (fs, ms, s)
