@@ -17,7 +17,7 @@ static thread_local int g_enc_last_cuda_error = 0;
     } while (0)
 
 struct EncLayout {
-    size_t ecfg, win, dtw, ftw, perm, thist, xs_hist, x12, x6, estate, xf, e_b, ehand, xq, qhand, lsbs, stage_in,
+    size_t ecfg, win, dtw, ftw, perm, thist, xs_hist, x12, x6, estate, xf, e_b, ehand, xq, qhand, lsbs, bs_scratch, stage_in,
         stage_out, total;
 };
 
@@ -49,6 +49,7 @@ static EncLayout make_enc_layout(const lc3b_config& c, int n_streams, int max_nb
     L.xq = take(off, sizeof(int16_t) * ns * c.ne);
     L.qhand = take(off, sizeof(int32_t) * ns * QH_WORDS);
     L.lsbs = take(off, ns * 2 * c.ne);
+    L.bs_scratch = take(off, ns * sizeof(uint32_t) * (size_t)enc_bitstream_scratch_words(c.ne, max_nbytes));
     L.stage_in = take(off, sizeof(int16_t) * ns * c.nf * 2);   // double-buffered for the pipelined host path
     L.stage_out = take(off, ns * (size_t)max_nbytes);
     L.total = off;
@@ -227,6 +228,8 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
     st.xq = (int16_t*)(base + L.xq);
     st.qhand = (int32_t*)(base + L.qhand);
     st.lsbs = base + L.lsbs;
+    st.bs_scratch = (uint32_t*)(base + L.bs_scratch);
+    st.bs_words = enc_bitstream_scratch_words(c.ne, max_nbytes);
     st.stage_in = (int16_t*)(base + L.stage_in);
     st.stage_out = base + L.stage_out;
 

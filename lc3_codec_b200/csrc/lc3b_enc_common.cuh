@@ -60,12 +60,15 @@ struct EncoderState {
     int16_t* xq;           // [S][ne]       quantised spectrum
     int32_t* qhand;        // [S][QH_WORDS] decisions handed from kernel to kernel (lc3b_enc_quant.cu)
     uint8_t* lsbs;         // [S][ne]       deferred LSBs / sign bits in lsb_mode (bitstream_encoding.rs:22)
+    uint32_t* bs_scratch;  // [S][bs_words] bitstream hand-off: job record, tail bits, side bits, symbol queue, forward bytes
+    int bs_words;          //               32-bit words per stream of bs_scratch (for max_nbytes)
     int16_t* stage_in;     // [S][nf]       staging for the host entry point
     uint8_t* stage_out;    // [S][max_nbytes]
 };
 
 cudaError_t prepare_enc_analysis(const EncoderState& st);   // shared-memory limits of the kernels, once per handle
 cudaError_t prepare_enc_quant(const EncoderState& st);
+int enc_bitstream_scratch_words(int ne, int max_nbytes);   // per-stream size of EncoderState::bs_scratch
 // stages: bit 0 MDCT kernel, bit 1 attack detector + LTPF analysis kernel
 cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream);
 // stages: bit 0 SNS kernel (with the bandwidth detector), bit 1 TNS kernel, bit 2 quantise kernel, bit 3 bitstream kernel

@@ -42,8 +42,11 @@ struct QuantParams {
     int16_t* xq;
     int32_t* qhand;
     uint8_t* lsbs;
+    uint32_t* bs_scratch;
+    int bs_words;
     uint8_t* frames_out;
-    int w_bytes, side_words, sym_cap, out_words;     // per-warp shared-memory slice
+    int w_bytes, w_bytes_fin, side_words, sym_cap, out_words;     // per-warp shared-memory slices (prepare / finish kernels)
+    int inline_ac;     // small batches: the finish kernel runs the range coder itself (all lanes, same chain) and C2 is skipped
 };
 
 constexpr int QW = 4;                       // frames (warps) per CTA
@@ -1107,12 +1110,27 @@ __device__ __forceinline__ void bits_or(uint32_t* arr, int n_words, int pos, uin
     if (w + 1 < n_words && (uint32_t)(v >> 32) != 0) atomicOr(&arr[w + 1], (uint32_t)(v >> 32));
 }
 
-// Fast path of BitstreamEncoding::encode.  Returns false when the two ends of the frame meet (caller falls back).
-__device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_res, const int16_t* xq, uint32_t* side, int side_words,
-                                   uint32_t* tail, uint32_t* symq, int sym_cap, uint8_t* out, int out_words, int nbytes, int lane) {
+// Fast path of BitstreamEncoding::encode in three phases (enc_bitstream_kernel):
+//   A  bs_prepare_w   one warp per frame: side information, symbol queue (TNS symbols first), side bits, deferred LSBs
+//   B  ac_run_thread  one THREAD per frame: the range coder over the queue - a serial chain, so the frames of a CTA
+//                     share one warp for it instead of each spending a whole warp's issue slots on it
+//   C  bs_finish_w    one warp per frame: residual / LSB tail bits, collision test, merge of the two ends
+struct AcJob {
+    int nsym;          // queue length (TNS + spectral symbols); < 0: queue overflow, use the serial fallback
+    int spos;          // side bits written so far (header + per-tuple bits)
+    int nlsbs;         // deferred LSB entries (lsb_mode)
+    int nbits_ari;     // out: bitstream_encoding.rs:63-73 forecast taken BEFORE ac_enc_finish
+    int bp;            // out: forward bytes written, including ac_enc_finish
+    int bits;          // out: valid bits of the final partial byte
+    uint32_t last;     // out: value the final partial byte takes its top `bits` bits from
+    int pad;
+};
+
+__device__ void bs_prepare_w(const EncConfig& c, const SideHdr& h, const int16_t* xq, uint32_t* side, int side_words,
+                             uint32_t* tail, uint32_t* symq, int sym_cap, uint8_t* out, int out_words, AcJob* job, int lane) {
     const QRes& q = *h.q;
     const TnsRes& tns = *h.tns;
-    const int ne = c.ne, nbits = nbytes * 8;
+    const int ne = c.ne;
     WARP_STRIDE(i, side_words) side[i] = 0;
     WARP_STRIDE(i, out_words) ((uint32_t*)out)[i] = 0;
     if (q.lsb_mode) WARP_STRIDE(i, TAIL_WORDS) tail[i] = 0;
@@ -1150,10 +1168,27 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
     const uint32_t inc_a = warp_incl_scan(cnt_a, lane), inc_l = warp_incl_scan(cnt_l, lane);
     const uint32_t tot_a = __shfl_sync(FULL, inc_a, 31);
     const int nlsbs = (int)__shfl_sync(FULL, inc_l, 31);
-    const int nsym = (int)(tot_a & 0xffffu), nside_tup = (int)(tot_a >> 16);
-    if (nsym > sym_cap) return false;
+    int n_tns = 0;                                       // TNS symbols lead the queue (bitstream_encoding.rs:234-252)
+    for (int f = 0; f < tns.num_filters; f++) if (tns.rc_order[f] > 0) n_tns += 1 + tns.rc_order[f];
+    const int nsym = n_tns + (int)(tot_a & 0xffffu), nside_tup = (int)(tot_a >> 16);
+    if (nsym > sym_cap) {
+        if (lane == 0) job->nsym = -1;
+        __syncwarp();
+        return;
+    }
+    if (lane == 0) {
+        int o = 0;
+        for (int f = 0; f < tns.num_filters; f++) {
+            if (tns.rc_order[f] > 0) {
+                symq[o++] = (uint32_t)LC3T_AC_TNS_ORDER_CUMFREQ[tns.lpc_weighting][tns.rc_order[f] - 1] |
+                            ((uint32_t)LC3T_AC_TNS_ORDER_FREQ[tns.lpc_weighting][tns.rc_order[f] - 1] << 16);
+                for (int k = 0; k < tns.rc_order[f]; k++)
+                    symq[o++] = (uint32_t)LC3T_AC_TNS_COEF_CUMFREQ[k][tns.rc_i[k + 8 * f]] | ((uint32_t)LC3T_AC_TNS_COEF_FREQ[k][tns.rc_i[k + 8 * f]] << 16);
+            }
+        }
+    }
     {
-        int so = (int)((inc_a - cnt_a) & 0xffffu), bo = spos + (int)((inc_a - cnt_a) >> 16), lo = (int)(inc_l - cnt_l);
+        int so = n_tns + (int)((inc_a - cnt_a) & 0xffffu), bo = spos + (int)((inc_a - cnt_a) >> 16), lo = (int)(inc_l - cnt_l);
         int d2 = 0, d1 = 0;
         if (n0 >= 1 && n0 - 1 < ntt) d1 = tup_digit(tup_of(xw[n0 - 1]));
         if (n0 >= 2 && n0 - 2 < ntt) d2 = tup_digit(tup_of(xw[n0 - 2]));
@@ -1200,31 +1235,51 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
         }
     }
     spos += nside_tup;
+    if (lane == 0) { job->nsym = nsym; job->spos = spos; job->nlsbs = nlsbs; }
     __syncwarp();
-    // ---- the range coder proper: every lane runs the same chain, lane 0 stores the bytes
-    FwdSink w{out, nbytes, 0, lane};
+}
+
+// Phase B: the range coder proper (bitstream_encoding.rs:234-352, 354-429), one thread per frame.
+__device__ void ac_run_thread(const uint32_t* symq, uint8_t* out, int nbytes, AcJob* job) {
+    const int nsym = job->nsym;
+    if (nsym < 0) return;
+    FwdSink w{out, nbytes, 0, 0};
     AcEnc st{0, 0x00ffffffu, -1, 0, 0};
-    for (int f = 0; f < tns.num_filters; f++) {
-        if (tns.rc_order[f] > 0) {
-            ac_encode(st, w, LC3T_AC_TNS_ORDER_CUMFREQ[tns.lpc_weighting][tns.rc_order[f] - 1],
-                      LC3T_AC_TNS_ORDER_FREQ[tns.lpc_weighting][tns.rc_order[f] - 1]);
-            for (int k = 0; k < tns.rc_order[f]; k++)
-                ac_encode(st, w, LC3T_AC_TNS_COEF_CUMFREQ[k][tns.rc_i[k + 8 * f]], LC3T_AC_TNS_COEF_FREQ[k][tns.rc_i[k + 8 * f]]);
-        }
-    }
     uint32_t cf = symq[0];
     for (int i = 0; i < nsym; i++) {
-        const uint32_t nxt = symq[i + 1 < nsym ? i + 1 : i];
+        const uint32_t nxt = symq[i + 1];                 // the queue has one spare entry
         ac_encode(st, w, (int)(cf & 0xffffu), (int)(cf >> 16));
         cf = nxt;
     }
-    const int nbits_side = spos;
     int nbits_ari = w.bp * 8;
     nbits_ari += 25 - (31 - __clz(st.range));
     nbits_ari += 8;                                   // QUIRK: `carry >= 0` is always true (:67)
     if (st.carry_count > 0) nbits_ari += st.carry_count * 8;
-    int nres_enc = nbits - (nbits_side + nbits_ari);
+    job->nbits_ari = nbits_ari;
+    const int bits = ac_finish(st, w);                // the tail bits written in between never touch the coder's state
+    uint32_t last;
+    if (st.carry_count > 0) {
+        w.byte_forward((uint32_t)st.cache & 0xff);
+        while (st.carry_count > 1) { w.byte_forward(0xff); st.carry_count -= 1; }
+        last = 0xffu >> (8 - bits);
+    } else {
+        last = (uint32_t)st.cache;
+    }
+    job->bp = w.bp;
+    job->bits = bits;
+    job->last = last;
+}
+
+// Phase C: residual / LSB bits behind the side stream, collision test, final partial byte.  Returns false when the two
+// ends of the frame meet or the queue overflowed (caller falls back to the reference-order writer).
+__device__ bool bs_finish_w(const QRes& q, int n_res, uint32_t* side, int side_words, const uint32_t* tail, uint8_t* out,
+                            int nbytes, const AcJob* job, int lane) {
+    if (job->nsym < 0) return false;
+    const int nbits = nbytes * 8;
+    int spos = job->spos;
+    int nres_enc = nbits - (spos + job->nbits_ari);
     if (nres_enc < 0) nres_enc = 0;
+    const int nlsbs = job->nlsbs;
     const int m = q.lsb_mode ? (nres_enc < nlsbs ? nres_enc : nlsbs) : (n_res < nres_enc ? n_res : nres_enc);
     if (lane < TAIL_WORDS) {                          // tail bits [0, m) -> side stream at spos
         const int lo = lane * 32;
@@ -1234,18 +1289,10 @@ __device__ bool bitstream_encode_w(const EncConfig& c, const SideHdr& h, int n_r
         }
     }
     spos += m;
-    const int bits = ac_finish(st, w);
-    uint32_t last;
-    if (st.carry_count > 0) {
-        w.byte_forward((uint32_t)st.cache & 0xff);
-        while (st.carry_count > 1) { w.byte_forward(0xff); st.carry_count -= 1; }
-        last = 0xffu >> (8 - bits);
-    } else {
-        last = (uint32_t)st.cache;
-    }
-    if (w.bp >= nbytes || 8 * w.bp + bits + spos > nbits) return false;
+    const int bp = job->bp, bits = job->bits;
+    if (bp >= nbytes || 8 * bp + bits + spos > nbits) return false;
     __syncwarp();
-    if (lane == 0) out[w.bp] |= (uint8_t)(last & (0xff00u >> bits) & 0xffu);
+    if (lane == 0) out[bp] |= (uint8_t)(job->last & (0xff00u >> bits) & 0xffu);
     __syncwarp();
     return true;
 }
@@ -1344,67 +1391,142 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quantize_kernel(QuantParams p
     }
 }
 
-// Kernel C: residual bits, noise factor, bitstream.
-__global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams p) {
+// Bitstream stage = three kernels.  The per-stream hand-off lives in EncoderState::bs_scratch:
+//   [ job (8 words) | tail bits (TAIL_WORDS) | side bits (side_words) | symbol queue (sym_cap + 1) | forward bytes (out_words) ]
+// C1 enc_bs_prepare_kernel   warp per frame: residual bits, noise factor, side information, symbol queue, side bits
+// C2 enc_range_coder_kernel  THREAD per frame: the range coder is one serial chain per frame, so frames are the only
+//                            parallel axis; a warp per frame spent 6 k of its 12.8 k issue slots repeating it in 32 lanes
+// C3 enc_bs_finish_kernel    warp per frame: tail bits, collision test, merge of the two ends, coalesced output
+struct BsLayout { int job, tail, side, symq, fwd, words; };
+__host__ __device__ inline BsLayout bs_layout(int side_words, int sym_cap, int out_words) {
+    BsLayout L;
+    L.job = 0;
+    L.tail = 8;
+    L.side = L.tail + TAIL_WORDS;
+    L.symq = L.side + side_words;
+    L.fwd = L.symq + sym_cap + 1;
+    L.words = L.fwd + out_words;
+    return L;
+}
+static_assert(sizeof(AcJob) == 32, "AcJob is 8 words");
+
+__device__ __forceinline__ void load_results(const QuantParams& p, int stream, BwRes& bw, SnsRes& sns, TnsRes& tns, QRes& q,
+                                             SideHdr& h, int* rc_i, int lane) {
+    const int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
+    const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
+    if (lane < 16) rc_i[lane] = qh[QH_RC_I + lane];
+    bw = BwRes{qh[QH_BW], qh[QH_NBITS_BW]};
+    sns.ind_lf = qh[QH_IND_LF]; sns.ind_hf = qh[QH_IND_HF]; sns.shape_j = qh[QH_SHAPE_J]; sns.gind = qh[QH_GIND];
+    sns.ls_inda = qh[QH_LS_INDA]; sns.ls_indb = qh[QH_LS_INDB];
+    sns.joint = (uint64_t)(uint32_t)qh[QH_JOINT_LO] | ((uint64_t)(uint32_t)qh[QH_JOINT_HI] << 32);
+    tns.nbits_tns = qh[QH_NBITS_TNS]; tns.lpc_weighting = qh[QH_LPC_WEIGHTING]; tns.num_filters = qh[QH_NUM_FILTERS];
+    tns.rc_order[0] = qh[QH_ORDER0]; tns.rc_order[1] = qh[QH_ORDER1];
+    tns.rc_i = rc_i;
+    q.gg_ind = qh[QH_GG_IND]; q.nbits_spec = qh[QH_NBITS_SPEC]; q.nbits_lsb = qh[QH_NBITS_LSB]; q.nbits_trunc = qh[QH_NBITS_TRUNC];
+    q.lsb_mode = qh[QH_LSB_MODE]; q.rate_flag = qh[QH_RATE_FLAG]; q.lastnz_trunc = qh[QH_LASTNZ_TRUNC];
+    q.gg = __uint_as_float((uint32_t)qh[QH_GG]);
+    h.bw = &bw; h.sns = &sns; h.tns = &tns; h.q = &q;
+    h.pitch_present = eh[EH_PITCH_PRESENT]; h.ltpf_active = eh[EH_LTPF_ACTIVE]; h.pitch_index = eh[EH_PITCH_INDEX];
+    h.lg = 0;
+    while ((1 << h.lg) < p.cfg->ne / 2) h.lg++;
+}
+
+__global__ void __launch_bounds__(QNT_THREADS) enc_bs_prepare_kernel(QuantParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int stream = blockIdx.x * QW + wib;
-    if (stream >= p.n_streams) return;
+    if (stream >= p.n_streams) return;                            // warps are independent: no CTA-wide barrier below
     const int ne = c.ne;
     uint8_t* wb = smem + (size_t)wib * p.w_bytes;
     float* xf = (float*)wb;                                       // [NE_MAX]
     int16_t* xq = (int16_t*)(xf + NE_MAX);                        // [NE_MAX]
     int* rc_i = (int*)(xq + NE_MAX);                              // [16]
-    uint32_t* tail = (uint32_t*)(rc_i + 16);                      // [TAIL_WORDS]
+    AcJob* job = (AcJob*)(rc_i + 16);                             // 8 words
+    uint32_t* tail = (uint32_t*)(job + 1);                        // [TAIL_WORDS]
     uint32_t* side = tail + TAIL_WORDS;                           // [side_words]
-    uint32_t* symq = side + p.side_words;                         // [sym_cap]
-    uint8_t* out = (uint8_t*)(symq + p.sym_cap);                  // [out_words * 4]
-    const int nbytes = p.nbytes;
-    const int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
+    uint32_t* symq = side + p.side_words;                         // [sym_cap + 1]
+    uint8_t* out = (uint8_t*)(symq + p.sym_cap + 1);              // [out_words * 4] (zeroed here, filled by the range coder kernel)
     {
         const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
         WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
         const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
         WARP_STRIDE(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
-        if (lane < 16) rc_i[lane] = qh[QH_RC_I + lane];
         if (lane < TAIL_WORDS) tail[lane] = 0;
     }
-    __syncwarp();
-    const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
-    BwRes bw{qh[QH_BW], qh[QH_NBITS_BW]};
+    BwRes bw;
     SnsRes sns;
-    sns.ind_lf = qh[QH_IND_LF]; sns.ind_hf = qh[QH_IND_HF]; sns.shape_j = qh[QH_SHAPE_J]; sns.gind = qh[QH_GIND];
-    sns.ls_inda = qh[QH_LS_INDA]; sns.ls_indb = qh[QH_LS_INDB];
-    sns.joint = (uint64_t)(uint32_t)qh[QH_JOINT_LO] | ((uint64_t)(uint32_t)qh[QH_JOINT_HI] << 32);
     TnsRes tns;
-    tns.nbits_tns = qh[QH_NBITS_TNS]; tns.lpc_weighting = qh[QH_LPC_WEIGHTING]; tns.num_filters = qh[QH_NUM_FILTERS];
-    tns.rc_order[0] = qh[QH_ORDER0]; tns.rc_order[1] = qh[QH_ORDER1];
-    tns.rc_i = rc_i;
     QRes q;
-    q.gg_ind = qh[QH_GG_IND]; q.nbits_spec = qh[QH_NBITS_SPEC]; q.nbits_lsb = qh[QH_NBITS_LSB]; q.nbits_trunc = qh[QH_NBITS_TRUNC];
-    q.lsb_mode = qh[QH_LSB_MODE]; q.rate_flag = qh[QH_RATE_FLAG]; q.lastnz_trunc = qh[QH_LASTNZ_TRUNC];
-    q.gg = __uint_as_float((uint32_t)qh[QH_GG]);
-
+    SideHdr h;
+    load_results(p, stream, bw, sns, tns, q, h, rc_i, lane);
+    __syncwarp();
     int n_res = 0;
     if (!q.lsb_mode) n_res = residual_bits_w(ne, xf, xq, q.gg, q.nbits_spec - q.nbits_trunc + 4, tail, lane);
     __syncwarp();
-    const int nff = noise_factor_w(c, xf, xq, bw.bw, q.gg, lane);
+    h.nf_factor = noise_factor_w(c, xf, xq, bw.bw, q.gg, lane);
+    bs_prepare_w(c, h, xq, side, p.side_words, tail, symq, p.sym_cap, out, p.out_words, job, lane);
+    if (lane == 0) { job->pad = n_res | (h.nf_factor << 16); }
+    __syncwarp();
+    // hand-off: job | tail | side | queue (only the used part) are contiguous in the warp's slice
+    const BsLayout L = bs_layout(p.side_words, p.sym_cap, p.out_words);
+    uint32_t* g = p.bs_scratch + (size_t)stream * p.bs_words;
+    const int nq = job->nsym < 0 ? 0 : job->nsym + 1;
+    const uint32_t* src = (const uint32_t*)job;
+    WARP_STRIDE(i, L.symq + nq) g[i] = src[i];
+    WARP_STRIDE(i, p.out_words) g[L.fwd + i] = 0;
+}
 
+__global__ void __launch_bounds__(128) enc_range_coder_kernel(QuantParams p) {
+    const int stream = blockIdx.x * 128 + threadIdx.x;
+    if (stream >= p.n_streams) return;
+    const BsLayout L = bs_layout(p.side_words, p.sym_cap, p.out_words);
+    uint32_t* g = p.bs_scratch + (size_t)stream * p.bs_words;
+    ac_run_thread(g + L.symq, (uint8_t*)(g + L.fwd), p.nbytes, (AcJob*)g);
+}
+
+__global__ void __launch_bounds__(QNT_THREADS) enc_bs_finish_kernel(QuantParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EncConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int stream = blockIdx.x * QW + wib;
+    if (stream >= p.n_streams) return;
+    const int ne = c.ne, nbytes = p.nbytes;
+    const BsLayout L = bs_layout(p.side_words, p.sym_cap, p.out_words);
+    // warp slice: job | tail | side | forward bytes | rc_i | xq (fallback only)
+    uint32_t* wbase = (uint32_t*)(smem + (size_t)wib * p.w_bytes_fin);
+    AcJob* job = (AcJob*)wbase;
+    uint32_t* tail = wbase + L.tail;
+    uint32_t* side = wbase + L.side;
+    uint8_t* out = (uint8_t*)(wbase + L.symq);
+    int* rc_i = (int*)(wbase + L.symq + p.out_words);
+    int16_t* xq = (int16_t*)(rc_i + 16);
+    const uint32_t* g = p.bs_scratch + (size_t)stream * p.bs_words;
+    WARP_STRIDE(i, L.symq) wbase[i] = g[i];
+    WARP_STRIDE(i, p.out_words) ((uint32_t*)out)[i] = g[L.fwd + i];
+    BwRes bw;
+    SnsRes sns;
+    TnsRes tns;
+    QRes q;
     SideHdr h;
-    h.bw = &bw; h.sns = &sns; h.tns = &tns; h.q = &q;
-    h.pitch_present = eh[EH_PITCH_PRESENT]; h.ltpf_active = eh[EH_LTPF_ACTIVE]; h.pitch_index = eh[EH_PITCH_INDEX];
-    h.nf_factor = nff;
-    h.lg = 0;
-    while ((1 << h.lg) < ne / 2) h.lg++;
-    const bool ok = bitstream_encode_w(c, h, n_res, xq, side, p.side_words, tail, symq, p.sym_cap, out, p.out_words, nbytes, lane);
+    load_results(p, stream, bw, sns, tns, q, h, rc_i, lane);
+    __syncwarp();
+    const int n_res = job->pad & 0xffff;
+    h.nf_factor = job->pad >> 16;
+    if (p.inline_ac) {                                             // every lane runs the same chain and stores the same bytes
+        ac_run_thread(g + L.symq, out, nbytes, job);
+        __syncwarp();
+    }
+    const bool ok = bs_finish_w(q, n_res, side, p.side_words, tail, out, nbytes, job, lane);
     uint8_t* dst = p.frames_out + (size_t)stream * p.frame_stride;
     if (ok) {
         WARP_STRIDE(b, nbytes) {
             const int i = nbytes - 1 - b;
             dst[b] = out[b] | (uint8_t)(side[i >> 2] >> (8 * (i & 3)));
         }
-    } else {
+    } else {                                                       // reference-order rewrite of the whole frame by one lane
+        const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
+        WARP_STRIDE(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
         __syncwarp();
         if (lane == 0) bitstream_encode_serial(c, h, tail, n_res, xq, p.lsbs + (size_t)stream * 2 * ne, out, nbytes);
         __syncwarp();
@@ -1412,15 +1534,30 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bitstream_kernel(QuantParams 
     }
 }
 
-static size_t bitstream_warp_bytes(int ne, int nbytes, QuantParams* p) {
+static void bitstream_sizes(int ne, int nbytes, int* side_words, int* sym_cap, int* out_words) {
     const int nbits = nbytes * 8;
-    const int side_words = (nbits + 31) / 32 + 2;
-    const int sym_cap = ne / 2 + nbits / 2 + 32;      // tuples + escapes the truncation rule can admit (2 bits each at least)
-    const int out_words = (nbytes + 3) / 4 + 1;
-    size_t wbytes = sizeof(float) * NE_MAX + sizeof(int16_t) * NE_MAX + sizeof(int) * 16 +
-                    sizeof(uint32_t) * (size_t)(TAIL_WORDS + side_words + sym_cap + out_words);
+    *side_words = (nbits + 31) / 32 + 2;
+    *sym_cap = ne / 2 + nbits / 2 + 32 + 18;   // tuples + escapes the truncation rule can admit (2 bits each at least) + TNS
+    *out_words = (nbytes + 3) / 4 + 1;
+}
+int enc_bitstream_scratch_words(int ne, int max_nbytes) {
+    int sw, sc, ow;
+    bitstream_sizes(ne, max_nbytes, &sw, &sc, &ow);
+    return bs_layout(sw, sc, ow).words;
+}
+// shared-memory slice of one warp in the prepare kernel / the finish kernel
+static size_t bitstream_warp_bytes(int ne, int nbytes, QuantParams* p) {
+    int side_words, sym_cap, out_words;
+    bitstream_sizes(ne, nbytes, &side_words, &sym_cap, &out_words);
+    size_t wbytes = sizeof(float) * NE_MAX + sizeof(int16_t) * NE_MAX + sizeof(int) * 16 + sizeof(AcJob) +
+                    sizeof(uint32_t) * (size_t)(TAIL_WORDS + side_words + sym_cap + 1 + out_words);
     wbytes = (wbytes + 15) & ~(size_t)15;
-    if (p) { p->side_words = side_words; p->sym_cap = sym_cap; p->out_words = out_words; p->w_bytes = (int)wbytes; }
+    size_t fbytes = sizeof(uint32_t) * (size_t)(8 + TAIL_WORDS + side_words + out_words + 16) + sizeof(int16_t) * NE_MAX;
+    fbytes = (fbytes + 15) & ~(size_t)15;
+    if (p) {
+        p->side_words = side_words; p->sym_cap = sym_cap; p->out_words = out_words;
+        p->w_bytes = (int)wbytes; p->w_bytes_fin = (int)fbytes;
+    }
     return wbytes;
 }
 constexpr size_t SHAPE_SMEM = QW * sizeof(float) * (NE_MAX + S_FLOATS);
@@ -1432,7 +1569,7 @@ cudaError_t prepare_enc_quant(const EncoderState& st) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_tns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHAPE_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QUANTIZE_SMEM);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(enc_bitstream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(enc_bs_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(QW * bitstream_warp_bytes(st.cfg.ne, st.max_nbytes, nullptr)));
     return e;
 }
@@ -1450,13 +1587,22 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     p.xq = st.xq;
     p.qhand = st.qhand;
     p.lsbs = st.lsbs;
+    p.bs_scratch = st.bs_scratch;
+    p.bs_words = st.bs_words;
+    p.inline_ac = 0;
     p.frames_out = frames_out;
     const size_t wbytes = bitstream_warp_bytes(st.cfg.ne, nbytes, &p);
     const int grid = (p.n_streams + QW - 1) / QW;
     if (stages & 1) enc_sns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
     if (stages & 2) enc_tns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
     if (stages & 4) enc_quantize_kernel<<<grid, QNT_THREADS, QUANTIZE_SMEM, stream>>>(p);
-    if (stages & 8) enc_bitstream_kernel<<<grid, QNT_THREADS, QW * wbytes, stream>>>(p);
+    if (stages & 8) {
+        enc_bs_prepare_kernel<<<grid, QNT_THREADS, QW * wbytes, stream>>>(p);
+        // a thread-per-frame kernel needs ~12 k frames before its serial latency (~80 us) is amortised
+        p.inline_ac = p.n_streams < 12288 ? 1 : 0;
+        if (!p.inline_ac) enc_range_coder_kernel<<<(p.n_streams + 127) / 128, 128, 0, stream>>>(p);
+        enc_bs_finish_kernel<<<grid, QNT_THREADS, QW * (size_t)p.w_bytes_fin, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
