@@ -57,7 +57,7 @@ struct Carve {
 };
 
 struct Layout {
-    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, ola, ltpf_y, ltpf_xtail, side, sstate, stage_in, stage_out, stage_len,
+    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, ola, ltpf_y, ltpf_xtail, ltpf_x, side, sstate, stage_in, stage_out, stage_len,
         stage_status, total;
 };
 
@@ -76,7 +76,8 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
     L.handoff = cv.take(sizeof(int32_t) * ((ns + 127) / 128) * 128 * HO_WORDS);   // every thread slot of whole entropy CTAs
     L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
     L.ltpf_y = cv.take(sizeof(float) * ns * blocks * c.nf);
-    L.ltpf_xtail = cv.take(sizeof(float) * ns * 16);
+    L.ltpf_xtail = cv.take(sizeof(float) * ns * XTAIL_FLOATS);
+    L.ltpf_x = cv.take(sizeof(float) * ns * c.nf);
     L.side = cv.take(sizeof(int32_t) * ns * SIDE_WORDS);
     L.sstate = cv.take(sizeof(int32_t) * ns * SS_WORDS);
     L.stage_in = cv.take(ns * (size_t)max_nbytes);
@@ -289,6 +290,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     st.ola = (float*)(base + L.ola);
     st.ltpf_y = (float*)(base + L.ltpf_y);
     st.ltpf_xtail = (float*)(base + L.ltpf_xtail);
+    st.ltpf_x = (float*)(base + L.ltpf_x);
     st.side = (int32_t*)(base + L.side);
     st.sstate = (int32_t*)(base + L.sstate);
     st.stage_in = base + L.stage_in;

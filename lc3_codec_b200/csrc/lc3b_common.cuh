@@ -35,7 +35,9 @@ enum {
     SD_PLC_ALPHA,       // f32 bits: alpha to apply (concealed frames)
     SD_SLOT,            // which of the two spectrum slots holds the spectrum to transform
     SD_SRC,             // time-parallel path: unit whose spectrum to transform (-2 own, -1 the handle's last good slot)
+    SD_BLK,             // LTPF ring block synth_kernel wrote this frame's x_hat to (synth_kernel -> ltpf_kernel)
 };
+constexpr int XTAIL_FLOATS = 3 * 16;   // per stream: last 16 samples of x_hat of the frame in each ring block
 
 // Everything a kernel needs to know about the (fs, duration) configuration; lives in the workspace.
 struct DevConfig {
@@ -71,7 +73,8 @@ struct DecoderState {
     int32_t* handoff;    // [n_blocks32 * 32][HO_WORDS] decoded side information etc. (entropy -> dequantisation kernel)
     float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)
     float* ltpf_y;       // [n_streams][blocks*nf]  x_hat_ltpf_mem (long_term_post_filter.rs:30)
-    float* ltpf_xtail;   // [n_streams][16]  last samples of x_hat_mem (only l_num <= 10 are ever read back)
+    float* ltpf_xtail;   // [n_streams][3][16]  last samples of x_hat_mem per ring block (only l_num <= 10 are ever read back)
+    float* ltpf_x;       // [n_streams][nf]  x_hat of the current frame while its stream is inside an LTPF-active span
     int32_t* side;       // [n_streams][SIDE_WORDS]
     int32_t* sstate;     // [n_streams][8]  per-stream scalars, see SS_* below
     uint8_t* stage_in;   // [n_streams][max_nbytes] staging for the host-buffer entry point

@@ -18,7 +18,7 @@
 //                           LTPF ring, last good spectrum) exactly as F frame-by-frame calls would have
 // Arithmetic is the frame-by-frame path's, operation for operation, so both paths produce identical PCM.
 #include "lc3b_common.cuh"
-#include "lc3b_fft.cuh"
+#include "lc3b_imdct.cuh"
 #include "lc3b_math.cuh"
 
 namespace lc3b {
@@ -128,58 +128,59 @@ __global__ void __launch_bounds__(MW * 32) plc_scan_kernel(MultiParams p) {
 }
 
 // ---------------------------------------------------------------- 3. spectrum -> windowed time signal, per unit
+template <int NF, bool MS10>
 __global__ void __launch_bounds__(MW * 32) imdct_multi_kernel(MultiParams p) {
+    using G = FrameGeo<NF, MS10>;
+    constexpr int NE = G::NE, Z = G::Z, NP = G::NP, NPT = G::NPT;
     extern __shared__ __align__(16) uint8_t smem[];
-    const DevConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long v = (long long)blockIdx.x * MW + wid;
     if (v >= (long long)p.S * p.F) return;
-    const int nf = c.nf, ne = c.ne, z = c.z, N = c.n_fft, h = nf / 2;
     const int s = (int)(v / p.F);
-    float2* bufA = (float2*)(smem + (size_t)wid * ((size_t)2 * N * sizeof(float2) + (size_t)nf * 4));
-    float2* bufB = bufA + N;
-    float* X = (float*)(bufB + N);
+    float* P = (float*)smem + (size_t)wid * 2 * NF;
+    float* Q = P + NF;
 
     const int32_t* sd = p.side_v + (size_t)v * SIDE_WORDS;
     const int src = sd[SD_SRC];
     const float* sp;
-    if (src == -2) sp = p.spec_v + (size_t)v * ne;
-    else if (src >= 0) sp = p.spec_v + (size_t)src * ne;
-    else sp = p.spec + ((size_t)p.sstate[(size_t)s * SS_WORDS + SS_SLOT] * p.S + s) * ne;   // last good of earlier calls
+    if (src == -2) sp = p.spec_v + (size_t)v * NE;
+    else if (src >= 0) sp = p.spec_v + (size_t)src * NE;
+    else sp = p.spec + ((size_t)p.sstate[(size_t)s * SS_WORDS + SS_SLOT] * p.S + s) * NE;   // last good of earlier calls
     if (src == -2) {
-        for (int k4 = lane; k4 < nf / 4; k4 += 32)
-            ((float4*)X)[k4] = 4 * k4 < ne ? ((const float4*)sp)[k4] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int k0 = 0; k0 < NF / 4; k0 += 32) {
+            const int k4 = k0 + lane;
+            if (k0 + 32 <= NF / 4 || k4 < NF / 4)
+                ((float4*)P)[k4] = 4 * k4 < NE ? ((const float4*)sp)[k4] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
     } else {                                                      // packet_loss_concealment.rs:63-85
         const float alpha = u2f((uint32_t)sd[SD_PLC_ALPHA]);
         uint32_t sgen = (uint32_t)sd[SD_PLC_SEED];
         for (int i = 0; i <= lane; i++) sgen = (16831u + sgen * 12821u) & 0xFFFFu;
         uint32_t a32 = 1, c32 = 0;
         for (int i = 0; i < 32; i++) { c32 = (16831u + c32 * 12821u) & 0xFFFFu; a32 = (a32 * 12821u) & 0xFFFFu; }
-        for (int k = lane; k < nf; k += 32) {
+        for (int k = lane; k < NF; k += 32) {
             float val = 0.0f;
-            if (k < ne) {
+            if (k < NE) {
                 const float lg = sp[k];
                 val = sgen < 0x8000u ? xm(lg, alpha) : xm(lg, -alpha);
                 sgen = (a32 * sgen + c32) & 0xFFFFu;
             }
-            X[k] = val;
+            P[k] = val;
         }
     }
     __syncwarp();
-    dct_iv_warp(X, bufA, bufB, p.dtw, p.ftw, c.fft_radix, nf, N, lane);
-    auto t_at = [&](int m) -> float {                              // modified_dct.rs:97-136 (unfold)
-        if (m < h) return X[h + m];
-        if (m < nf) return -X[nf - 1 - (m - h)];
-        if (m < nf + h) return -X[h - 1 - (m - nf)];
-        return -X[m - 3 * h];
-    };
-    float* head = p.head + (size_t)v * nf;
-    float* tail = p.tail + (size_t)v * (nf - z);
-    for (int n = lane; n < nf; n += 32) {
-        const int m = n < nf - z ? z + n : nf + (n - (nf - z));
-        head[n] = xm(t_at(m), p.win[m]);
-    }
-    for (int n = lane; n < nf - z; n += 32) tail[n] = xm(t_at(nf + z + n), p.win[nf + z + n]);
+    const float* D = dct_iv_warp<NF>(P, Q, p.dtw, p.ftw, lane);
+    float hd[2 * NP], tl[2 * NPT];
+    imdct_unfold<NF, MS10>(D, p.win, lane, hd, tl);
+    float2* head = (float2*)(p.head + (size_t)v * NF);
+    float2* tail = (float2*)(p.tail + (size_t)v * (NF - Z));
+#pragma unroll
+    for (int j = 0; j < NP; j++)
+        if (64 * j + 64 <= NF || 64 * j + 2 * lane < NF) head[32 * j + lane] = make_float2(hd[2 * j], hd[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < NPT; j++)
+        if (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) tail[32 * j + lane] = make_float2(tl[2 * j], tl[2 * j + 1]);
 }
 
 __device__ __forceinline__ int16_t round_pcm(float v) {            // output_scaling.rs:13-26
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(MW * 32) ltpf_multi_kernel(MultiParams p, int 
     float* scratch = xt + 16;                                      // l_num + norm
     int32_t* ss = p.sstate + (size_t)s * SS_WORDS;
     float* yhist = p.ltpf_y + (size_t)s * p.hist_len;
-    float* xtail = p.ltpf_xtail + (size_t)s * 16;
+    float* xtail = p.ltpf_xtail + (size_t)s * XTAIL_FLOATS;      // [blocks][16], slot = ring block of the frame it closes
     const int blk0 = ss[SS_LTPF_BLK];
     const int prevw = ss[SS_LTPF_PREV];
     int prev_active = prevw & 1, prev_code = prevw >> 8, p_int_mem = ss[SS_LTPF_PINT], p_fr_mem = ss[SS_LTPF_PFR];
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(MW * 32) ltpf_multi_kernel(MultiParams p, int 
             }
             const float* xh = p.xhat + v * nf;
             for (int n = lane; n < nf; n += 32) X[n] = xh[n];
-            if (lane < 16) xt[lane] = f > 0 ? p.xhat[(v - 1) * nf + nf - 16 + lane] : xtail[lane];
+            if (lane < 16) xt[lane] = f > 0 ? p.xhat[(v - 1) * nf + nf - 16 + lane] : xtail[((blk0 + blocks - 1) % blocks) * 16 + lane];
             __syncwarp();
             // ---- long_term_post_filter.rs:252-343, as in synth_kernel
             auto cnum = [&](int cd, int k) -> float { return cd < 4 ? c.ltpf_num[cd][k] : 0.0f; };
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(MW * 32) ltpf_multi_kernel(MultiParams p, int 
         const float* src = have ? Y + bo : p.xhat + (v0 + g) * nf;
         for (int n = lane; n < nf; n += 32) yhist[bo + n] = src[n];
     }
-    if (lane < 16) xtail[lane] = p.xhat[(v0 + F - 1) * nf + nf - 16 + lane];
+    if (lane < 16) xtail[((blk0 + F - 1) % blocks) * 16 + lane] = p.xhat[(v0 + F - 1) * nf + nf - 16 + lane];
     {
         const float* t = p.tail + (v0 + F - 1) * (nf - z);
         float* ola = p.ola + (size_t)s * (nf - z);
@@ -407,12 +408,31 @@ static size_t ltpf_multi_warp_bytes(const lc3b_config& c) {
     return (b + 15) & ~(size_t)15;
 }
 
+namespace {
+struct PrepareImdct {
+    cudaError_t e = cudaSuccess;
+    template <int NF, bool MS10> void operator()() {
+        e = cudaFuncSetAttribute(imdct_multi_kernel<NF, MS10>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW * 2 * NF * 4);
+    }
+};
+struct LaunchImdct {
+    const MultiParams& p;
+    unsigned grid;
+    cudaStream_t stream;
+    template <int NF, bool MS10> void operator()() {
+        imdct_multi_kernel<NF, MS10><<<grid, MW * 32, MW * 2 * NF * 4, stream>>>(p);
+    }
+};
+}  // namespace
+
 cudaError_t prepare_multi(const DecoderState& st) {
     cudaError_t e = cudaFuncSetAttribute(ltpf_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(ltpf_multi_warp_bytes(st.cfg) * MW));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(imdct_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(MW * ((size_t)st.cfg.nf * 8 + (size_t)st.cfg.nf * 4)));
+    if (e == cudaSuccess) {
+        PrepareImdct pi;
+        if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, pi)) return cudaErrorInvalidValue;
+        e = pi.e;
+    }
     return e;
 }
 
@@ -447,8 +467,8 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     p.hist_len = (st.cfg.n_ms == LC3B_10MS ? 2 : 3) * st.cfg.nf;
     plc_scan_kernel<<<(S + MW - 1) / MW, MW * 32, 0, stream>>>(p);
     const unsigned grid_v = (unsigned)((V + MW - 1) / MW);
-    const size_t imdct_smem = MW * ((size_t)st.cfg.nf * 8 + (size_t)st.cfg.nf * 4);
-    imdct_multi_kernel<<<grid_v, MW * 32, imdct_smem, stream>>>(p);
+    LaunchImdct li{p, grid_v, stream};
+    if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, li)) return cudaErrorInvalidValue;
     ola_multi_kernel<<<grid_v, MW * 32, 0, stream>>>(p);
     const size_t lw = ltpf_multi_warp_bytes(st.cfg);
     ltpf_multi_kernel<<<(S + MW - 1) / MW, MW * 32, lw * MW, stream>>>(p, (int)lw);

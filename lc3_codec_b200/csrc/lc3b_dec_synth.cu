@@ -1,4 +1,4 @@
-// lc3b engine, decoder kernel 2 of 2: shaped spectrum -> PCM, one WARP per frame.
+// lc3b engine, decoder kernels 2 and 3: shaped spectrum -> PCM, one WARP per frame.
 //
 // Replaces, per stream, the second half of DecoderChannel::decode (src/decoder/lc3_decoder.rs:134-153):
 //   PacketLossConcealment::save / load_into   src/decoder/packet_loss_concealment.rs:50,63
@@ -6,13 +6,18 @@
 //                                             src/common/dct_iv.rs:49, src/common/kissfft.rs:78; window; overlap-add)
 //   LongTermPostFilter::run                   src/decoder/long_term_post_filter.rs:252 (five transition cases)
 //   output_scaling::scale_and_round           src/decoder/output_scaling.rs:13
-// Data-parallel work: 32 lanes walk the frame's lines/samples, all global traffic is stream-major and
-// coalesced (spectrum 4*ne B in, overlap memory 4*(nf-z) B in/out, LTPF history 4*nf B out, PCM 2*nf B out).
-// The FFT is a shared-memory Stockham autosort with radix-2/3/4/5 butterflies (a different factor order than
-// kissfft: the PCM contract is +-1 LSB, not bit equality).  The LTPF recursion only reaches back
-// p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are computed in parallel per step.
+//
+// synth_kernel<NF, MS10> (every stream): concealment, inverse MDCT (lc3b_imdct.cuh, frame length a template
+// constant), overlap-add, and the post filter's PASS-THROUGH case: x_hat goes to the LTPF history ring and, rounded,
+// to the PCM row.  Two consecutive samples per lane, so PCM leaves as 32-bit and f32 state as 64-bit accesses; all
+// global traffic is stream-major and coalesced (spectrum 4*ne B in, overlap memory 4*(nf-z) B in/out, LTPF history
+// 4*nf B out, PCM 2*nf B out).
+// ltpf_kernel (streams whose post filter is, or was in the previous frame, active): the IIR itself; for those streams
+// synth_kernel leaves x_hat in a side buffer (the ring block keeps the samples long pitch lags still reach), and this
+// kernel writes the filtered signal to the ring block and the PCM row.  The recursion only reaches back p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are
+// computed in parallel per step.  Streams outside such a span cost this kernel one flag load.
 #include "lc3b_common.cuh"
-#include "lc3b_fft.cuh"
+#include "lc3b_imdct.cuh"
 #include "lc3b_math.cuh"
 
 namespace lc3b {
@@ -26,49 +31,61 @@ struct SynthParams {
     float* ola;
     float* ltpf_y;
     float* ltpf_xtail;
-    const int32_t* side;
+    float* ltpf_x;       // [n_streams][nf] x_hat of streams inside an active span (synth_kernel -> ltpf_kernel)
+    int32_t* side;
     int32_t* sstate;
     int16_t* pcm_out;
     size_t pcm_stride;
     int n_streams;
     int hist_len;        // ltpf_blocks * nf
-    int y_floats;        // max(hist_len, 2 * nf): the FFT ping-pong buffers and the LTPF history share this space
-    int smem_per_warp;   // bytes
+    int pcm_pairs;       // PCM rows are 4-byte aligned: samples leave two at a time
+    int group;           // ltpf_kernel: streams looked after by one warp
+    int smem_per_warp;   // ltpf_kernel, bytes
 };
 
 constexpr int SYN_WARPS = 4;
 
+__device__ __forceinline__ int32_t round_pcm_i32(float v) {          // output_scaling.rs:13-26
+    int32_t q = v > 0.0f ? cast_i32(xa(v, 0.5f)) : cast_i32(xs(v, 0.5f));
+    return q > 32767 ? 32767 : q < -32768 ? -32768 : q;
+}
+
+template <int NF, bool MS10>
 __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
+    using G = FrameGeo<NF, MS10>;
+    constexpr int NE = G::NE, Z = G::Z, NP = G::NP, NPT = G::NPT;
     extern __shared__ __align__(16) uint8_t smem[];
-    const DevConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int stream = blockIdx.x * SYN_WARPS + wid;
-    if (stream >= p.n_streams) return;
-    const int nf = c.nf, ne = c.ne, z = c.z, N = c.n_fft, h = nf / 2;
+    if (stream >= p.n_streams) return;                            // warps are independent: no CTA-wide barrier below
 
-    uint8_t* base = smem + (size_t)wid * p.smem_per_warp;
-    float2* bufA = (float2*)base;                 // N complex
-    float2* bufB = bufA + N;                      // N complex
-    float* Y = (float*)base;                      // hist_len floats: LTPF circular history, over the (then dead) FFT buffers
-    float* X = (float*)base + p.y_floats;         // nf floats: spectrum in, then DCT-IV output, then time samples
-    float* scratch = X + nf;                      // l_num + norm floats: frozen history for transition case 5
+    float* P = (float*)smem + (size_t)wid * 2 * NF;               // spectrum in; FFT ping
+    float* Q = P + NF;                                            // FFT pong
 
-    const int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+    int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
     int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
     const int ok = sd[SD_OK];
     const int slot = sd[SD_SLOT];
-    const int nbits = sd[SD_NBITS];
-    const float* sp = p.spec + ((size_t)slot * p.n_streams + stream) * ne;
+    const int active = sd[SD_LTPF_ACTIVE];
+    const int prev_active = ss[SS_LTPF_PREV] & 1;
+    const int blk_idx = ss[SS_LTPF_BLK];
+    const float* sp = p.spec + ((size_t)slot * p.n_streams + stream) * NE;
+
+    // overlap memory: requested now, consumed after the FFT
+    float* ola = p.ola + (size_t)stream * (NF - Z);
+    float2 ola_r[NPT];
+#pragma unroll
+    for (int j = 0; j < NPT; j++)
+        ola_r[j] = (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) ? ((const float2*)ola)[32 * j + lane] : make_float2(0.0f, 0.0f);
 
     // ---- spectrum load, with concealment (packet_loss_concealment.rs:63-85) when the frame was bad
-    // overlap memory: requested now, consumed after the FFT (ceil(300 / 32) = 10 values per lane at most)
-    float* ola = p.ola + (size_t)stream * (nf - z);
-    float ola_r[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) { const int n = lane + 32 * j; ola_r[j] = n < nf - z ? ola[n] : 0.0f; }
     if (ok) {
-        for (int k4 = lane; k4 < nf / 4; k4 += 32)
-            ((float4*)X)[k4] = 4 * k4 < ne ? ((const float4*)sp)[k4] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int k0 = 0; k0 < NF / 4; k0 += 32) {
+            const int k4 = k0 + lane;
+            if (k0 + 32 <= NF / 4 || k4 < NF / 4)
+                ((float4*)P)[k4] = 4 * k4 < NE ? ((const float4*)sp)[k4] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         if (lane == 0) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
     } else {
         int lost = ss[SS_PLC_LOST];
@@ -81,89 +98,138 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
         for (int i = 0; i <= lane; i++) s = (16831u + s * 12821u) & 0xFFFFu;
         uint32_t a32 = 1, c32 = 0;                               // composition of 32 LCG steps
         for (int i = 0; i < 32; i++) { c32 = (16831u + c32 * 12821u) & 0xFFFFu; a32 = (a32 * 12821u) & 0xFFFFu; }
-        for (int k = lane; k < nf; k += 32) {
+        for (int k = lane; k < NF; k += 32) {
             float v = 0.0f;
-            if (k < ne) {
+            if (k < NE) {
                 const float lg = sp[k];
                 v = s < 0x8000u ? xm(lg, alpha) : xm(lg, -alpha);
-                if (k == ne - 1) ss[SS_PLC_SEED] = (int32_t)s;
+                if (k == NE - 1) ss[SS_PLC_SEED] = (int32_t)s;
                 s = (a32 * s + c32) & 0xFFFFu;
             }
-            X[k] = v;
+            P[k] = v;
         }
         if (lane == 0) { ss[SS_PLC_LOST] = lost + 1; ss[SS_PLC_ALPHA] = (int32_t)f2u(alpha); }
     }
     __syncwarp();
 
-    // ---- DCT-IV: pre-twiddle, N-point FFT, post-twiddle (dct_iv.rs:49-67)
-    dct_iv_warp(X, bufA, bufB, p.dtw, p.ftw, c.fft_radix, nf, N, lane);
+    // ---- DCT-IV, unfold, window (dct_iv.rs:49-67, modified_dct.rs:97-136)
+    const float* D = dct_iv_warp<NF>(P, Q, p.dtw, p.ftw, lane);
+    float head[2 * NP], tail[2 * NPT];
+    imdct_unfold<NF, MS10>(D, p.win, lane, head, tail);
 
-    // ---- unfold + window + overlap-add (modified_dct.rs:97-151); t[m] below is the reference's t_hat_mdct[m] / gain
-    auto t_at = [&](int m) -> float {
-        if (m < h) return X[h + m];
-        if (m < nf) return -X[nf - 1 - (m - h)];
-        if (m < nf + h) return -X[h - 1 - (m - nf)];
-        return -X[m - 3 * h];
-    };
-    float* T = (float*)bufA;                       // reuse: nf output samples fit in N complex
+    // ---- overlap-add (modified_dct.rs:138-151): two roundings, like the reference (and the time-parallel path)
 #pragma unroll
-    for (int j = 0; j < 15; j++) {
-        const int n = lane + 32 * j;
-        if (n < nf) {
-            float o;
-            if (n < nf - z) o = xa(j < 10 ? ola_r[j < 10 ? j : 0] : 0.0f, xm(t_at(z + n), p.win[z + n]));   // two roundings, like the reference (and the time-parallel path)
-            else o = t_at(nf + (n - (nf - z))) * p.win[nf + (n - (nf - z))];
-            T[n] = o;
+    for (int j = 0; j < NPT; j++) {
+        if (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) {
+            head[2 * j] = xa(ola_r[j].x, head[2 * j]);
+            head[2 * j + 1] = xa(ola_r[j].y, head[2 * j + 1]);
+            ((float2*)ola)[32 * j + lane] = make_float2(tail[2 * j], tail[2 * j + 1]);
         }
     }
-    __syncwarp();                                  // all reads of the old X-derived values for the first half are done
-    for (int n = lane; n < nf - z; n += 32) ola[n] = t_at(nf + z + n) * p.win[nf + z + n];
-    __syncwarp();
-    for (int n = lane; n < nf; n += 32) X[n] = T[n];   // X = x_hat (input of the post filter)
-    const float xtail_next = T[nf - 16 + (lane & 15)]; // last 16 samples of the filter INPUT, kept before Y reuses the buffer
-    __syncwarp();
 
-    // ---- long term post filter (long_term_post_filter.rs:252-343)
-    const int active = sd[SD_LTPF_ACTIVE];
-    const int prev = ss[SS_LTPF_PREV];
-    const int prev_active = prev & 1, prev_code = prev >> 8;
-    const int blocks = c.ltpf_blocks, l_num = c.ltpf_l_num, l_den = c.ltpf_l_den, norm = c.ltpf_norm, s2p5 = c.ltpf_s2p5;
-    const int blk = ss[SS_LTPF_BLK] * nf;
-    int p_int = 0, p_fr = 0, code = 4;
-    if (active) {                                  // compute_filter_parameters :164-190, compute_gains_params :142-161
-        const int pi = sd[SD_PITCH_INDEX];
-        int pit;
-        double pfr;
-        if (pi >= 440) { pit = pi - 283; pfr = 0.0; }
-        else if (pi >= 380) { pit = pi / 2 - 63; pfr = (double)(2 * pi - 4 * pit - 252); }
-        else { pit = pi / 4 + 32; pfr = (double)(pi + 128 - 4 * pit); }
-        const double pitch = (double)pit + pfr / 4.0;
-        const double pitch_fs = pitch * (8000.0 * ceil((double)c.fs / 8000.0) / 12800.0);
-        const int p_up = (int)((pitch_fs * 4.0) + 0.5);
-        p_int = p_up / 4;
-        p_fr = p_up - 4 * p_int;
-        const int t_nbits = c.n_ms == LC3B_7P5MS ? (int)round((double)nbits * 10.0 / 7.5) : nbits;
-        const int sf = c.fs_ind * 80;
-        code = t_nbits < 320 + sf ? 0 : t_nbits < 400 + sf ? 1 : t_nbits < 480 + sf ? 2 : t_nbits < 560 + sf ? 3 : 4;
+    // ---- post filter, pass-through case (long_term_post_filter.rs:252-343 with zero coefficients): history + PCM
+    // Inside an active span the ring block must keep its old content until the filter has run (long pitch lags reach
+    // around the ring into it), so x_hat waits in a side buffer for ltpf_kernel instead.
+    const bool in_span = active || prev_active;
+    float* yblk = in_span ? p.ltpf_x + (size_t)stream * NF : p.ltpf_y + (size_t)stream * p.hist_len + blk_idx * NF;
+    float* xtail = p.ltpf_xtail + (size_t)stream * XTAIL_FLOATS + blk_idx * 16;
+    int16_t* out = p.pcm_out + (size_t)stream * p.pcm_stride;
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+        const int n = 64 * j + 2 * lane;
+        if (64 * j + 64 <= NF || n < NF) {
+            const float a = head[2 * j], b = head[2 * j + 1];
+            ((float2*)yblk)[32 * j + lane] = make_float2(a, b);
+            if (n >= NF - 16) ((float2*)xtail)[(n - (NF - 16)) >> 1] = make_float2(a, b);   // x_hat tail for the next frame's filter
+            const int32_t qa = round_pcm_i32(a), qb = round_pcm_i32(b);
+            if (p.pcm_pairs) ((uint32_t*)out)[32 * j + lane] = ((uint32_t)qa & 0xffffu) | ((uint32_t)qb << 16);
+            else { out[n] = (int16_t)qa; out[n + 1] = (int16_t)qb; }
+        }
     }
-    const int p_int_mem = ss[SS_LTPF_PINT], p_fr_mem = ss[SS_LTPF_PFR];
-    float* yhist = p.ltpf_y + (size_t)stream * p.hist_len;
-    float* xtail = p.ltpf_xtail + (size_t)stream * 16;
+    if (lane == 0) {
+        sd[SD_BLK] = blk_idx;
+        int nb = blk_idx + 1;                                    // :334-337
+        if (nb > (MS10 ? 1 : 2)) nb = 0;
+        ss[SS_LTPF_BLK] = nb;
+        if (!in_span) {                                          // otherwise ltpf_kernel carries the filter state on
+            ss[SS_LTPF_PREV] = 4 << 8;
+            ss[SS_LTPF_PINT] = 0;
+            ss[SS_LTPF_PFR] = 0;
+        }
+    }
+}
 
-    if (!active && !prev_active) {                 // case 1: pass-through, history only
-        for (int n = lane; n < nf; n += 32) yhist[blk + n] = X[n];
-    } else {
+// ---------------------------------------------------------------- kernel 3: the post filter where it is not idle
+__global__ void __launch_bounds__(SYN_WARPS * 32) ltpf_kernel(SynthParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const DevConfig& c = *p.cfg;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int first = (blockIdx.x * SYN_WARPS + wid) * p.group;
+    if (first >= p.n_streams) return;
+    // which streams of this warp's group are inside an active span
+    uint32_t todo;
+    {
+        const int s = first + lane;
+        bool in_span = false;
+        if (lane < p.group && s < p.n_streams)
+            in_span = p.side[(size_t)s * SIDE_WORDS + SD_LTPF_ACTIVE] != 0 || (p.sstate[(size_t)s * SS_WORDS + SS_LTPF_PREV] & 1) != 0;
+        todo = __ballot_sync(0xffffffffu, in_span);
+    }
+    if (todo == 0) return;
+    const int nf = c.nf;
+    const int blocks = c.ltpf_blocks, l_num = c.ltpf_l_num, l_den = c.ltpf_l_den, norm = c.ltpf_norm, s2p5 = c.ltpf_s2p5;
+    float* Y = (float*)(smem + (size_t)wid * p.smem_per_warp);    // hist_len floats: LTPF circular history
+    float* X = Y + p.hist_len;                                    // nf floats: x_hat, the filter input
+    float* xt = X + nf;                                           // 16: x_hat tail of the previous frame
+    float* scratch = xt + 16;                                     // l_num + norm floats: frozen history for transition case 5
+
+    while (todo) {
+        const int stream = first + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+        int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
+        const int active = sd[SD_LTPF_ACTIVE];
+        const int nbits = sd[SD_NBITS];
+        const int blk_idx = sd[SD_BLK];
+        const int blk = blk_idx * nf;
+        const int prev = ss[SS_LTPF_PREV];
+        const int prev_active = prev & 1, prev_code = prev >> 8;
+        const int p_int_mem = ss[SS_LTPF_PINT], p_fr_mem = ss[SS_LTPF_PFR];
+        int p_int = 0, p_fr = 0, code = 4;
+        if (active) {                                  // compute_filter_parameters :164-190, compute_gains_params :142-161
+            const int pi = sd[SD_PITCH_INDEX];
+            int pit;
+            double pfr;
+            if (pi >= 440) { pit = pi - 283; pfr = 0.0; }
+            else if (pi >= 380) { pit = pi / 2 - 63; pfr = (double)(2 * pi - 4 * pit - 252); }
+            else { pit = pi / 4 + 32; pfr = (double)(pi + 128 - 4 * pit); }
+            const double pitch = (double)pit + pfr / 4.0;
+            const double pitch_fs = pitch * (8000.0 * ceil((double)c.fs / 8000.0) / 12800.0);
+            const int p_up = (int)((pitch_fs * 4.0) + 0.5);
+            p_int = p_up / 4;
+            p_fr = p_up - 4 * p_int;
+            const int t_nbits = c.n_ms == LC3B_7P5MS ? (int)round((double)nbits * 10.0 / 7.5) : nbits;
+            const int sf = c.fs_ind * 80;
+            code = t_nbits < 320 + sf ? 0 : t_nbits < 400 + sf ? 1 : t_nbits < 480 + sf ? 2 : t_nbits < 560 + sf ? 3 : 4;
+        }
+        float* yhist = p.ltpf_y + (size_t)stream * p.hist_len;
+        const float* xtail_prev = p.ltpf_xtail + (size_t)stream * XTAIL_FLOATS + (blk_idx == 0 ? blocks - 1 : blk_idx - 1) * 16;
+        __syncwarp();                                  // the previous stream's reads of the shared buffers are done
+        for (int n = lane; n < p.hist_len; n += 32) Y[n] = yhist[n];
+        if (lane < 16) xt[lane] = xtail_prev[lane];
+        __syncwarp();
+        for (int n = lane; n < nf; n += 32) X[n] = p.ltpf_x[(size_t)stream * nf + n];   // x_hat left by synth_kernel
+        __syncwarp();
+
         // coefficient sets: current (c_num, c_den) and previous (c_num_mem, c_den_mem); code 4 = all zero
         auto cnum = [&](int cd, int k) -> float { return cd < 4 ? c.ltpf_num[cd][k] : 0.0f; };
         auto cden = [&](int cd, int fr, int k) -> float { return cd < 4 ? c.ltpf_den[cd][fr][k] : 0.0f; };
         const int cur_code = active ? code : 4;     // inactive: zeroed coefficients (:196-201)
         const int mem_code = prev_active ? prev_code : 4;
-        for (int n = lane; n < p.hist_len; n += 32) Y[n] = yhist[n];
-        __syncwarp();
         auto wrapi = [&](int idx) -> int { return idx < 0 ? idx + p.hist_len : idx; };   // :244-250
         auto x_at = [&](int pos) -> float {          // x_hat_mem[wrap(pos)], pos relative to buffer start
             const int rel = pos - blk;               // >= -l_num
-            return rel >= 0 ? X[rel] : xtail[16 + rel];
+            return rel >= 0 ? X[rel] : xt[16 + rel];
         };
         // compute_filter / compute_filter_mem :380-415
         auto filt = [&](int start, int pint, int cd, int fr) -> float {
@@ -228,46 +294,48 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
             plain_from(s2p5);
         }
         __syncwarp();
-        for (int n = lane; n < nf; n += 32) { const float v = Y[blk + n]; yhist[blk + n] = v; X[n] = v; }
-    }
-    __syncwarp();
-    // x tail for the next frame: last 16 samples of this frame's x_hat (the filter INPUT; X may hold the output by now)
-    if (lane < 16) xtail[lane] = xtail_next;
-    if (lane == 0) {
-        ss[SS_LTPF_PREV] = (active ? 1 : 0) | ((active ? code : 4) << 8);
-        ss[SS_LTPF_PINT] = p_int;
-        ss[SS_LTPF_PFR] = p_fr;
-        int nb = ss[SS_LTPF_BLK] + 1;                // :334-337
-        if (nb * nf > (blocks - 1) * nf) nb = 0;
-        ss[SS_LTPF_BLK] = nb;
-    }
-
-    // ---- output_scaling.rs:13-26: round half away from zero, saturate
-    int16_t* out = p.pcm_out + (size_t)stream * p.pcm_stride;
-    for (int n = lane; n < nf; n += 32) {
-        const float v = X[n];
-        int32_t q = v > 0.0f ? cast_i32(xa(v, 0.5f)) : cast_i32(xs(v, 0.5f));
-        q = q > 32767 ? 32767 : q < -32768 ? -32768 : q;
-        out[n] = (int16_t)q;
+        int16_t* out = p.pcm_out + (size_t)stream * p.pcm_stride;
+        for (int n = lane; n < nf; n += 32) {
+            const float v = Y[blk + n];
+            yhist[blk + n] = v;
+            out[n] = (int16_t)round_pcm_i32(v);
+        }
+        if (lane == 0) {
+            ss[SS_LTPF_PREV] = (active ? 1 : 0) | ((active ? code : 4) << 8);
+            ss[SS_LTPF_PINT] = p_int;
+            ss[SS_LTPF_PFR] = p_fr;
+        }
     }
 }
 
-static size_t synth_warp_bytes(const lc3b_config& c, int* hist_len, int* y_floats) {
-    const int nf = c.nf, N = nf / 2;
+static size_t ltpf_warp_bytes(const lc3b_config& c) {
     const int blocks = c.n_ms == LC3B_10MS ? 2 : 3;
-    const int hl = blocks * nf;
-    // [FFT ping-pong buffers | LTPF history] + spectrum/time samples + case-5 scratch
-    const int yf = hl > 4 * N ? hl : 4 * N;
-    size_t per_warp = (size_t)yf * 4 + (size_t)nf * 4 + (size_t)(16 + nf / 3 + 16) * 4;
-    per_warp = (per_warp + 15) & ~(size_t)15;
-    if (hist_len) *hist_len = hl;
-    if (y_floats) *y_floats = yf;
-    return per_warp;
+    size_t b = (size_t)(blocks * c.nf + c.nf + 16 + 16 + c.nf / 3 + 16) * 4;
+    return (b + 15) & ~(size_t)15;
 }
+
+namespace {
+struct PrepareSynth {
+    cudaError_t e = cudaSuccess;
+    template <int NF, bool MS10> void operator()() {
+        e = cudaFuncSetAttribute(synth_kernel<NF, MS10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_WARPS * 2 * NF * 4);
+    }
+};
+struct LaunchSynth {
+    const SynthParams& p;
+    cudaStream_t stream;
+    template <int NF, bool MS10> void operator()() {
+        const int grid = (p.n_streams + SYN_WARPS - 1) / SYN_WARPS;
+        synth_kernel<NF, MS10><<<grid, SYN_WARPS * 32, SYN_WARPS * 2 * NF * 4, stream>>>(p);
+    }
+};
+}  // namespace
 
 cudaError_t prepare_synth(const DecoderState& st) {
-    return cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(synth_warp_bytes(st.cfg, nullptr, nullptr) * SYN_WARPS));
+    PrepareSynth ps;
+    if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ps)) return cudaErrorInvalidValue;
+    if (ps.e != cudaSuccess) return ps.e;
+    return cudaFuncSetAttribute(ltpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ltpf_warp_bytes(st.cfg) * SYN_WARPS));
 }
 
 cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream) {
@@ -280,15 +348,24 @@ cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_st
     p.ola = st.ola;
     p.ltpf_y = st.ltpf_y;
     p.ltpf_xtail = st.ltpf_xtail;
+    p.ltpf_x = st.ltpf_x;
     p.side = st.side;
     p.sstate = st.sstate;
     p.pcm_out = pcm_out;
     p.pcm_stride = pcm_stride;
     p.n_streams = st.n_streams;
-    const size_t per_warp = synth_warp_bytes(st.cfg, &p.hist_len, &p.y_floats);
-    p.smem_per_warp = (int)per_warp;
-    const int grid = (st.n_streams + SYN_WARPS - 1) / SYN_WARPS;
-    synth_kernel<<<grid, SYN_WARPS * 32, per_warp * SYN_WARPS, stream>>>(p);
+    p.hist_len = (st.cfg.n_ms == LC3B_10MS ? 2 : 3) * st.cfg.nf;
+    p.pcm_pairs = (((uintptr_t)pcm_out & 3) == 0 && (pcm_stride & 1) == 0) ? 1 : 0;
+    // ltpf_kernel: one warp per stream while that keeps the grid small, else a warp walks a group of streams
+    int group = 1;
+    while (group < 32 && st.n_streams / group > 16384) group *= 2;
+    p.group = group;
+    const size_t lw = ltpf_warp_bytes(st.cfg);
+    p.smem_per_warp = (int)lw;
+    LaunchSynth ls{p, stream};
+    if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ls)) return cudaErrorInvalidValue;
+    const int n_warps = (st.n_streams + group - 1) / group;
+    ltpf_kernel<<<(n_warps + SYN_WARPS - 1) / SYN_WARPS, SYN_WARPS * 32, lw * SYN_WARPS, stream>>>(p);
     return cudaGetLastError();
 }
 
