@@ -156,25 +156,10 @@ __device__ __forceinline__ bool ac_decode(Reader& rd, AcState& st, const uint32_
     return ac_finish(rd, st, tmp, tab[val]);
 }
 
-// Spectral symbols: the same search answered from shared memory.  A coarse table gives the symbol at the start of the
-// quotient's 32-wide bucket; the cumulative table (rows padded to SPEC_CF_STRIDE with 0xffff sentinels) is then walked
-// upward three entries at a time - independent loads, and almost always a single round.
+// Spectral symbols (decode_spectral_data below) answer the same search from shared memory: a coarse table gives the
+// symbol at the start of the quotient's 32-wide bucket; the cumulative table (rows padded to SPEC_CF_STRIDE with
+// 0xffff sentinels) is then walked upward three entries at a time - independent loads, and almost always one round.
 constexpr int SPEC_CF_STRIDE = 20;
-__device__ __forceinline__ bool ac_decode_spec(Reader& rd, AcState& st, const uint32_t* __restrict__ tab,
-                                               const uint8_t* __restrict__ clut, int& sym) {
-    const uint32_t tmp = st.range >> 10;
-    if (st.low >= (tmp << 10)) return false;
-    const uint32_t q = exact_quotient(st.low, tmp);                     // < 1024 by the test above
-    int val = clut[q >> 5];
-    for (;;) {
-        const uint32_t c1 = tab[val + 1] & 0xffffu, c2 = tab[val + 2] & 0xffffu, c3 = tab[val + 3] & 0xffffu;
-        const int adv = (int)(c1 <= q) + (int)(c2 <= q) + (int)(c3 <= q);   // cum is non-decreasing
-        val += adv;
-        if (adv < 3) break;
-    }
-    sym = val;
-    return ac_finish(rd, st, tmp, tab[val]);
-}
 
 // mpvq_deenum, spectral_noise_shaping.rs:155-235.  y lives in shared memory (per-thread column).
 __device__ void mpvq_deenum(int dim_in, int k_val_in, int ls_ind, uint32_t mpvq_ind, float* y, int ystride) {
@@ -479,47 +464,103 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
     }
     if (ok) {                                                          // decode_spectral_data :211
         // One arithmetic symbol per iteration for every lane (escape or final), instead of a per-tuple inner loop:
-        // lanes sit at different tuples/levels but all execute the same decode, which keeps the warp converged.
+        // lanes sit at different tuples/levels but all execute the same decode.  The body is straight-line code:
+        // renormalisation, the tail bits of the symbol (escape magnitude bits and/or signs, at most 4, peeked from
+        // the staged row without a bit window to refill) and the tuple bookkeeping are selects, and every failure
+        // of the reference's readers sets a sticky flag that ends the lane's loop - a frame that fails anywhere is
+        // discarded whole, so when exactly the flag is acted on does not matter.
         const int rate_flag = nbits > (160 + c.fs_ind * 160) ? 512 : 0;
+        const int half_ne = ne / 2;
+        const uint8_t* buf = rd.buf;
+        const int len = rd.len;
+        int head = rd.head, tail = rd.tail;
+        uint32_t low = ac.low, range = ac.range;
         int ctx = 0;
         const int ntup = si.lastnz >> 1;
         int k = 0, lev = 0, xa_ = 0, xb_ = 0;
-        while (k < ntup) {
-            int t = ctx + rate_flag + ((k * 2) > (ne / 2) ? 256 : 0);
-            const int pki = s_lookup[t + min(lev, 3) * 1024];
-            int sym;
-            if (!ac_decode_spec(rd, ac, s_spec_cf + pki * SPEC_CF_STRIDE, s_clut + pki * 32, sym)) { ok = false; break; }
-            if (sym >= 16) {                                            // escape: two more magnitude bits
-                if (!si.lsb_mode || lev > 0) {
-                    uint32_t two;
-                    if (!rd.tail_bools(2, two)) { ok = false; break; }
-                    xa_ += (int)(two & 1u) << lev;
-                    xb_ += (int)(two >> 1) << lev;
+        uint32_t lev_word = 0;                                          // save_lev flags of the current 32 tuples
+        bool bad = false;
+        while (k < ntup && !bad) {
+            const int t0 = ctx + rate_flag + ((k * 2) > half_ne ? 256 : 0);
+            const int pki = s_lookup[t0 + min(lev, 3) * 1024];
+            const uint32_t* tab = s_spec_cf + pki * SPEC_CF_STRIDE;
+            // ac_decode :67-97
+            const uint32_t tmp = range >> 10;
+            bad |= low >= (tmp << 10);                                  // AcRangeFlOutOfRange
+            const uint32_t q = min(exact_quotient(low, tmp), 1023u);
+            int val = s_clut[pki * 32 + (q >> 5)];
+            for (;;) {                                                  // almost always a single round
+                const uint32_t c1 = tab[val + 1] & 0xffffu, c2 = tab[val + 2] & 0xffffu, c3 = tab[val + 3] & 0xffffu;
+                const int adv = (int)(c1 <= q) + (int)(c2 <= q) + (int)(c3 <= q);   // cum is non-decreasing
+                val += adv;
+                if (!__any_sync(__activemask(), adv == 3)) break;
+            }
+            const uint32_t e = tab[val];
+            low -= tmp * (e & 0xffffu);
+            range = tmp * (e >> 16);
+            {   // renormalisation: range >= 64 here, so at most two bytes
+                const int nsh = (int)(range < 0x10000u) + (int)(range < 0x100u);
+                const uint32_t b0 = buf[head], b1 = buf[head + 1];
+                const uint32_t in = nsh == 2 ? ((b0 << 8) | b1) : b0;
+                low = nsh ? (((low << (8 * nsh)) & 0x00ffffffu) + in) : low;
+                range <<= 8 * nsh;
+                head += nsh;
+                bad |= head > len;                                      // read_head_byte past the end
+            }
+            // the next tail bits, LSB first (buffer_reader.rs:98): 9 usable bits after the in-byte shift
+            uint32_t w;
+            {
+                const int i0 = len - 1 - (tail >> 3);
+                const uint32_t y0 = buf[max(i0, 0)], y1 = buf[max(i0 - 1, 0)];
+                w = (y0 | (y1 << 8)) >> (tail & 7);
+            }
+            const bool esc = val >= 16;
+            const bool esc_bits = esc && (!si.lsb_mode || lev > 0);     // escape: two more magnitude bits
+            const uint32_t eb = esc_bits ? (w & 3u) : 0u;
+            const int n_esc = esc_bits ? 2 : 0;
+            xa_ += (int)(eb & 1u) << lev;
+            xb_ += (int)(eb >> 1) << lev;
+            const int lev2 = lev + (esc ? 1 : 0);
+            const bool fin = !esc || lev2 >= 14;                        // QUIRK (ii): at lev == 14 the tuple ends with sym == 16
+            const int a = val & 3, b = val >> 2;
+            if (fin) { xa_ += a << lev2; xb_ += b << lev2; }
+            const int nsign = fin ? (int)(xa_ > 0) + (int)(xb_ > 0) : 0;
+            const int nrd = n_esc + nsign;
+            if (nrd > 0) {                                              // bounds of the last read_tail_bool (:98-103)
+                const int byte_index = (tail + nrd - 1) >> 3;
+                bad |= (len - head - byte_index + 2 < 0) || (byte_index >= len);
+            }
+            tail += nrd;
+            uint32_t sg = w >> n_esc;
+            if (fin) {
+                if (xa_ > 0) { xa_ = (sg & 1u) ? -xa_ : xa_; sg >>= 1; }
+                if (xb_ > 0) xb_ = (sg & 1u) ? -xb_ : xb_;
+                if (!bad) {
+                    xq[(2 * k) * 32] = xa_;
+                    xq[(2 * k + 1) * 32] = xb_;
                 }
-                lev++;
-                if (lev < 14) continue;                                 // QUIRK (ii): at lev == 14 the tuple ends with sym == 16
+                seed_acc += (uint32_t)abs(xa_) * (uint32_t)(2 * k) + (uint32_t)abs(xb_) * (uint32_t)(2 * k + 1);
+                lev_word |= (si.lsb_mode && lev2 > 0) ? (1u << (k & 31)) : 0u;   // save_lev[k], QUIRK (i)
+                if ((k & 31) == 31 || k == ntup - 1) { s_lev[(k >> 5) * ENT_THREADS + tid] = lev_word; lev_word = 0; }
+                const int l = min(lev2, 3);
+                const int t1 = (l <= 1) ? 1 + (a + b) * (l + 1) : 12 + l;
+                ctx = (ctx & 15) * 16 + t1;
+                k++;
+                xa_ = 0;
+                xb_ = 0;
             }
-            if (si.lsb_mode && lev > 0) s_lev[(k >> 5) * ENT_THREADS + tid] |= 1u << (k & 31);   // save_lev[k], QUIRK (i)
-            const int a = sym & 3, b = sym >> 2;
-            xa_ += a << lev;
-            xb_ += b << lev;
-            const int nsign = (xa_ > 0) + (xb_ > 0);
-            if (nsign > 0) {
-                uint32_t sg;
-                if (!rd.tail_bools(nsign, sg)) { ok = false; break; }
-                if (xa_ > 0) { if (sg & 1u) xa_ = -xa_; sg >>= 1; }
-                if (xb_ > 0 && (sg & 1u)) xb_ = -xb_;
-            }
-            xq[(2 * k) * 32] = xa_;
-            xq[(2 * k + 1) * 32] = xb_;
-            seed_acc += (uint32_t)abs(xa_) * (uint32_t)(2 * k) + (uint32_t)abs(xb_) * (uint32_t)(2 * k + 1);
-            const int l = min(lev, 3);
-            t = (l <= 1) ? 1 + (a + b) * (l + 1) : 12 + l;
-            ctx = (ctx & 15) * 16 + t;
-            k++;
-            lev = 0;
-            xa_ = 0;
-            xb_ = 0;
+            lev = fin ? 0 : lev2;
+        }
+        ok = !bad;
+        ac.low = low;
+        ac.range = range;
+        rd.head = head;
+        rd.tail = tail;
+        {   // resume the windowed tail reader mid-byte: (tail + tw_n) % 8 == 0
+            const int idx = len - 1 - (tail >> 3);
+            const uint32_t byte = (idx >= 0 && idx < len) ? buf[idx] : 0u;
+            rd.tw = (uint64_t)(byte >> (tail & 7));
+            rd.tw_n = 8 - (tail & 7);
         }
     }
     if (ok) {                                                          // calc_num_residual_bits :390
