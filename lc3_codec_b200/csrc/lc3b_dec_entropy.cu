@@ -267,20 +267,6 @@ __device__ bool read_side_info(Reader& rd, const DevConfig& c, SideInfoD& s) {
     return true;
 }
 
-// One step of the inverse TNS lattice (temporal_noise_shaping.rs:58-71) with the state in registers.
-__device__ __forceinline__ float tns_lattice(float x, float (&st)[8], const float (&rc)[8], int order) {
-    float t = x;
-#pragma unroll
-    for (int j = 7; j >= 0; j--) {
-        if (j < order) {
-            t = xs(t, xm(rc[j], st[j]));
-            if (j + 1 < order) st[j + 1] = xa(xm(rc[j], t), st[j]);
-        }
-    }
-    st[0] = t;
-    return t;
-}
-
 constexpr int ENT_THREADS = 128;
 
 // Stage the CTA's frames into shared-memory rows (odd word pitch).  Dense input (frame_stride == nbytes, 16-byte
@@ -717,7 +703,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     float* s_y = s_scf + tid;                                          // PVQ vector / scale factors, stride T
     bool is_zero_frame = false;
     float gg = 0.0f, nf_level = 0.0f;
-    float rc0[8], rc1[8];
+    float rc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int bw_stop = 0, nf_start = 0, tns_s0 = 0, tns_e0 = 0, tns_e1 = 0;
     int lastnz = 0;
     if (ok) {
@@ -808,6 +794,9 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     const bool any_ok = __any_sync(0xffffffffu, ok);
     if (any_ok) {
         float st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // coefficient set in use
+        int ord = 0, om = 0;                     // this lane's order in use, the warp's largest
+        int tns_phase = 0, tns_next = ok ? tns_s0 : 0x7fffffff;   // next line at which this lane switches filters
         int32_t win[W + 1];                 // win[0] = x[k], win[j] = x[k + j]
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
@@ -849,25 +838,67 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
             }
             const int32_t xi = win[0];
             float v = (float)xi;
-            if (ok) {
-                if (!si.lsb_mode && xi != 0 && res_used < nres) {       // residual_spectrum.rs:13-39
-                    int bit = 0;
-                    rd.tail_bool(bit);                                  // cannot fail here, see DESIGN.md
-                    res_used++;
-                    if (bit) v = xi > 0 ? xa(v, 0.3125f) : xa(v, 0.1875f);
-                    else v = xi > 0 ? xs(v, 0.1875f) : xs(v, 0.3125f);
-                }
-                if (!is_zero_frame && k >= nf_start && k < bw_stop && last_nz < k - W) {   // noise_filling.rs:37-55
-                    nf_state = (13849 + nf_state * 31821) & 0xFFFF;
-                    v = nf_state < 0x8000 ? nf_level : -nf_level;
-                }
-                v = xm(v, gg);
-                if (k >= tns_s0 && k < tns_e1) {                        // QUIRK: lattice state carries across filters
-                    if (k < tns_e0) { if (rc_order0 > 0) v = tns_lattice(v, st, rc0, rc_order0); }
-                    else if (rc_order1 > 0 && si.num_tns == 2) v = tns_lattice(v, st, rc1, rc_order1);
-                }
-                v = xm(v, gband);
+            {   // residual_spectrum.rs:13-39: one tail bit per non-zero line while the budget lasts (it cannot run past
+                // the frame here); read straight from the staged row, no window to refill
+                const bool take = ok && !si.lsb_mode && xi != 0 && res_used < nres;
+                const int bidx = max(rd.len - 1 - (rd.tail >> 3), 0);
+                const uint32_t bit = take ? ((uint32_t)rd.buf[bidx] >> (rd.tail & 7)) & 1u : 0u;
+                const float up = xi > 0 ? 0.3125f : 0.1875f, down = xi > 0 ? -0.1875f : -0.3125f;
+                v = take ? xa(v, bit ? up : down) : v;
+                rd.tail += take ? 1 : 0;
+                res_used += take ? 1 : 0;
             }
+            {   // noise_filling.rs:37-55
+                const bool fill = ok && !is_zero_frame && k >= nf_start && k < bw_stop && last_nz < k - W;
+                const int nxt = (13849 + nf_state * 31821) & 0xFFFF;
+                nf_state = fill ? nxt : nf_state;
+                v = fill ? (nxt < 0x8000 ? nf_level : -nf_level) : v;
+            }
+            v = xm(v, gg);
+            // temporal_noise_shaping.rs:24-74.  Lanes sit in different filters (band edges depend on the bandwidth) with
+            // different orders; the coefficient set in use is switched per lane at its band edges, and the lattice runs
+            // the warp's largest order with per-lane selects, so the warp never splits over it.
+            {
+                const bool sw = k == tns_next;
+                if (__any_sync(0xffffffffu, sw)) {
+                    if (sw) {
+                        if (tns_phase == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) rc[i] = rc0[i];
+                            ord = rc_order0;
+                            tns_phase = 1;
+                            tns_next = tns_e0;
+                        } else if (tns_phase == 1 && tns_e0 < tns_e1) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) rc[i] = rc1[i];
+                            ord = si.num_tns == 2 ? rc_order1 : 0;
+                            tns_phase = 2;
+                            tns_next = tns_e1;
+                        } else {
+                            ord = 0;
+                            tns_next = 0x7fffffff;
+                        }
+                    }
+                    om = __reduce_max_sync(0xffffffffu, ord);
+                }
+                if (om > 0) {                                           // QUIRK: lattice state carries across filters
+                    float t = v;
+#pragma unroll
+                    for (int j = 7; j >= 0; j--) {
+                        if (j < om) {                                   // warp-uniform
+                            const float t2 = xs(t, xm(rc[j], st[j]));
+                            t = j < ord ? t2 : t;
+                            if (j + 1 < 8) {
+                                const float s2 = xa(xm(rc[j], t), st[j]);
+                                st[j + 1 < 8 ? j + 1 : 7] = j + 1 < ord ? s2 : st[j + 1 < 8 ? j + 1 : 7];
+                            }
+                        }
+                    }
+                    st[0] = ord > 0 ? t : st[0];
+                    v = t;
+                }
+            }
+            v = ok ? xm(v, gband) : v;
             // transpose through the warp tile, flush every 32 lines
             tile[(k & 15) * 33 + lane] = v;
             if ((k & 15) == 15 || k == ne - 1) {
