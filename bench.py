@@ -323,9 +323,9 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
                     "ms_per_step": ms_e2e / e2e_steps,
                     "api": "Lc3MixedBatchDecoder.decode_frames_host (one lc3b_decode_frames_host per configuration on its own CUDA "
                            "stream, host pipelining on, host_fence before the end event)"},
-            "gpu_launches": 36 * args.steps,
+            "gpu_launches": 48 * args.steps,    # 12 configurations x (entropy, dequant, synth, ltpf)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "whole step (12 configurations x 3 kernels on concurrent streams)", "kernel_ms": step_ms,
+                         "kernel": "whole step (12 configurations x 4 kernels on concurrent streams)", "kernel_ms": step_ms,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": algo},
             "cpu_baseline": cb}))
     if dist is not None:
@@ -454,7 +454,7 @@ def run_file(args, w, rank, local_rank, world, dev, dist):
                     "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames) on 4 chunks of 1024 "
                            "frames, device -> pinned host copy of chunk c on a second stream overlapping chunk c+1"},
-            "gpu_launches": 6 * args.steps,   # device-resident leg: one call per step
+            "gpu_launches": 6 * args.steps,   # device-resident leg: one call (six kernels) per step
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "whole call (entropy, dequant, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
                          "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes(w),
@@ -586,7 +586,9 @@ def main():
             enc.encode_frames(dev_pcm_in[i % F], frames_out)
             dec.decode_frames(16, frames_out, pcm_out)
 
-    launches_per_step = {"decode": 3, "encode": 6, "roundtrip": 9}[mode]
+    # decoder: entropy, dequant, synth, ltpf; encoder: mdct, ltpf, sns, tns, quantize, bs_prepare, [range_coder], bs_finish
+    enc_launches = 8 if S >= 12288 else 7          # small batches run the range coder inside bs_finish (lc3b_enc_quant.cu)
+    launches_per_step = {"decode": 4, "encode": enc_launches, "roundtrip": 4 + enc_launches}[mode]
 
     # ---- device-resident throughput (value) with clocks sampled during the timed region
     with ClockSampler(local_rank) as clk:
@@ -613,7 +615,8 @@ def main():
         # growing prefixes of the chain (masks 1, 3, 7, 15, 31, 63) and reported as differences
         prev = 0.0
         for mask, name in ((1, "lc3b::enc_mdct_kernel"), (3, "lc3b::enc_ltpf_kernel"), (7, "lc3b::enc_sns_kernel"),
-                           (15, "lc3b::enc_tns_kernel"), (31, "lc3b::enc_quantize_kernel"), (63, "lc3b::enc_bitstream_kernel")):
+                           (15, "lc3b::enc_tns_kernel"), (31, "lc3b::enc_quantize_kernel"),
+                           (63, "lc3b::enc_bs_prepare+range_coder+bs_finish")):
             enc.set_stage_mask(mask)
             t = timed(lambda i: enc.encode_frames(dev_pcm_in[i % F], frames_out), k_steps, 3) / k_steps
             kernels_ms[name] = max(t - prev, 0.0)
@@ -622,7 +625,7 @@ def main():
     if dec:
         if mode == "roundtrip":
             enc.encode_frames(dev_pcm_in[0], frames_out)           # valid bitstreams for the decoder-only timing
-        time_masks(dec, ("lc3b::entropy_kernel", "lc3b::dequant_kernel", "lc3b::synth_kernel"),
+        time_masks(dec, ("lc3b::entropy_kernel", "lc3b::dequant_kernel", "lc3b::synth_kernel+ltpf_kernel"),
                    lambda i: dec.decode_frames(16, dev_frames[i % F] if dev_frames is not None else frames_out, pcm_out))
     dom_name = max(kernels_ms, key=kernels_ms.get)
     dom_ms = kernels_ms[dom_name]
