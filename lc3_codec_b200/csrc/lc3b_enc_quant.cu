@@ -603,6 +603,14 @@ __device__ __forceinline__ Tup tup_of(uint32_t w) {
     t.b = t.b0 >> t.L;
     return t;
 }
+// bit i of x -> bit 2i (x < 2^16)
+__device__ __forceinline__ uint32_t spread_bits(uint32_t x) {
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
 __device__ __forceinline__ int tup_digit(const Tup& t) {
     const int l = t.L < 3 ? t.L : 3;
     return l <= 1 ? 1 + (int)(t.a + t.b) * (l + 1) : 12 + l;
@@ -617,14 +625,13 @@ __device__ BitCons compute_bit_consumption_w(int ne, int fs_ind, const int16_t* 
     bc.mode_flag = nbits >= (480 + fs_ind * 160);
     const uint32_t* xw = (const uint32_t*)xq;
     const int nt = ne >> 1;
-    const int CH = (nt + 31) >> 5;
-    const int n0 = lane * CH;
     int last = -1;
-#pragma unroll 1
-    for (int n = n0; n < n0 + CH; n++) if (n < nt && xw[n] != 0) last = n;
+    WARP_STRIDE(n, nt) if (xw[n] != 0) last = n;
     last = warp_max_i(last);
     const int lastnz = last < 0 ? 2 : 2 * last + 2;
     const int ntz = lastnz >> 1;
+    const int CH = (ntz + 31) >> 5;                       // the tuples that exist, spread evenly over the lanes
+    const int n0 = lane * CH;
     int d2 = 0, d1 = 0;                                   // digits of tuples n-2, n-1
     if (n0 >= 1 && n0 - 1 < ntz) d1 = tup_digit(tup_of(xw[n0 - 1]));
     if (n0 >= 2 && n0 - 2 < ntz) d2 = tup_digit(tup_of(xw[n0 - 2]));
@@ -635,13 +642,16 @@ __device__ BitCons compute_bit_consumption_w(int ne, int fs_ind, const int16_t* 
     for (int n = n0; n < n0 + CH; n++) if (n < n1) {
         const Tup t = tup_of(xw[n]);
         const int tc = d2 * 16 + d1 + bc.rate_flag + (2 * n > ne / 2 ? 256 : 0);
-#pragma unroll 1
-        for (int lev = 0; lev < t.L; lev++) {
-            const int pki = LC3T_AC_SPEC_LOOKUP[tc + (lev < 3 ? lev : 3) * 1024];
-            est += LC3T_AC_SPEC_BITS[pki][16];
-            if (lev == 0 && bc.mode_flag) lsb += 2; else est += 2 * 2048;
-        }
-        const int pki = LC3T_AC_SPEC_LOOKUP[tc + (t.L < 3 ? t.L : 3) * 1024];
+        // escape levels (:285-300): level lev uses the model of min(lev, 3), so levels 3.. all cost the same and the
+        // walk over levels closes into four terms (integer arithmetic: any order) - no lane-dependent trip count
+        const int L = t.L;
+        const int pk0 = LC3T_AC_SPEC_LOOKUP[tc], pk1 = LC3T_AC_SPEC_LOOKUP[tc + 1024];
+        const int pk2 = LC3T_AC_SPEC_LOOKUP[tc + 2048], pk3 = LC3T_AC_SPEC_LOOKUP[tc + 3072];
+        const uint32_t e0 = LC3T_AC_SPEC_BITS[pk0][16], e1 = LC3T_AC_SPEC_BITS[pk1][16] + 2 * 2048;
+        const uint32_t e2 = LC3T_AC_SPEC_BITS[pk2][16] + 2 * 2048, e3 = LC3T_AC_SPEC_BITS[pk3][16] + 2 * 2048;
+        est += (L > 0 ? e0 : 0u) + (L > 1 ? e1 : 0u) + (L > 2 ? e2 : 0u) + (L > 3 ? (uint32_t)(L - 3) * e3 : 0u);
+        if (L > 0) { if (bc.mode_flag) lsb += 2; else est += 2 * 2048; }
+        const int pki = L == 0 ? pk0 : L == 1 ? pk1 : L == 2 ? pk2 : pk3;
         est += LC3T_AC_SPEC_BITS[pki][t.a + 4 * t.b];
         if (t.a0 > 0) est += 2048;
         if (t.b0 > 0) est += 2048;
@@ -847,7 +857,7 @@ __device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, 
     const int bw_stop = d10 ? 80 * (bw_ind + 1) : 60 * (bw_ind + 1);
     const int nf_start = d10 ? 24 : 18, nf_width = d10 ? 3 : 2;
     const int nf_stop = c.ne < bw_stop ? c.ne : bw_stop;
-    int count = 0;
+    int count = 0;                                                // qualifying lines so far (warp-uniform)
     // nzm[r] = ballot of "xq[32 r + lane] != 0"; a line's window [k - w, hi] is then a bit range of at most 7 bits
     uint32_t nzm[13];
 #pragma unroll
@@ -855,9 +865,13 @@ __device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, 
         const int k = 32 * r + lane;
         nzm[r] = __ballot_sync(FULL, k < c.ne && xq[k] != 0);
     }
+    // The qualifying lines' |x| / gg are packed in line order into the front of xf (a line's value lands at or below
+    // its own index, and each round's reads are done before its writes), so the ordered sum only walks those.
 #pragma unroll
     for (int r = 0; r < 13; r++) {
         const int k = 32 * r + lane;
+        bool quiet = false;
+        float val = 0.0f;
         if (k >= nf_start && k < nf_stop) {
             const int hi = bw_stop - 1 < k + nf_width ? bw_stop - 1 : k + nf_width;
             const int lo = k - nf_width;
@@ -867,15 +881,17 @@ __device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, 
             const uint64_t lo64 = (uint64_t)wm | ((uint64_t)w0 << 32);
             const uint64_t hi64 = (uint64_t)w0 | ((uint64_t)wp << 32);
             const uint32_t win = rel < 32 ? (uint32_t)(lo64 >> rel) : (uint32_t)(hi64 >> (rel - 32));
-            const bool quiet = (win & ((1u << (hi - lo + 1)) - 1u)) == 0;
-            xf[k] = quiet ? fabsf(xf[k]) / gg : 0.0f;
-            count += quiet ? 1 : 0;
+            quiet = (win & ((1u << (hi - lo + 1)) - 1u)) == 0;
+            if (quiet) val = fabsf(xf[k]) / gg;
         }
+        const uint32_t qm = __ballot_sync(FULL, quiet);
+        __syncwarp();
+        if (quiet) xf[count + __popc(qm & ((1u << lane) - 1u))] = val;
+        count += __popc(qm);
     }
-    count = warp_sum_i(count);
     __syncwarp();
     float sum = 0.0f;
-    for (int k = nf_start; k < nf_stop; k++) sum += xf[k];
+    for (int i = 0; i < count; i++) sum += xf[i];
     const float level = count > 0 ? sum / (float)count : 0.0f;
     const float diff = 8.0f - 16.0f * level;
     if (diff >= 0.0f) {
@@ -1152,7 +1168,7 @@ __device__ void bs_prepare_w(const EncConfig& c, const SideHdr& h, const int16_t
     // ---- per-tuple preparation: symbols -> queue, side bits and deferred LSBs -> bit arrays
     const uint32_t* xw = (const uint32_t*)xq;
     const int ntt = q.lastnz_trunc >> 1;
-    const int CH = ((ne >> 1) + 31) >> 5;
+    const int CH = ntt > 0 ? (ntt + 31) >> 5 : 1;        // the tuples that exist, spread evenly over the lanes
     const int n0 = lane * CH;
     uint32_t cnt_a = 0, cnt_l = 0;                       // (symbols | side bits << 16), deferred LSB entries
     const int n1 = n0 + CH < ntt ? n0 + CH : ntt;
@@ -1197,19 +1213,27 @@ __device__ void bs_prepare_w(const EncConfig& c, const SideHdr& h, const int16_t
             {
                 const Tup t = tup_of(xw[n]);
                 const int tc = d2 * 16 + d1 + q.rate_flag + (2 * n > ne / 2 ? 256 : 0);
-                uint64_t sbits = 0;
-                int ns = 0;
-                uint32_t a = t.a0, b = t.b0, lsb0 = 0, lsb1 = 0;
-#pragma unroll 1
-                for (int lev = 0; lev < t.L; lev++) {
-                    const int pki = LC3T_AC_SPEC_LOOKUP[tc + (lev < 3 ? lev : 3) * 1024];
-                    symq[so++] = (uint32_t)LC3T_AC_SPEC_CUMFREQ[pki][16] | ((uint32_t)LC3T_AC_SPEC_FREQ[pki][16] << 16);
-                    if (q.lsb_mode && lev == 0) { lsb0 = a & 1; lsb1 = b & 1; }
-                    else { sbits |= (uint64_t)(a & 1) << ns; sbits |= (uint64_t)(b & 1) << (ns + 1); ns += 2; }
-                    a >>= 1;
-                    b >>= 1;
+                // escape levels (:262-283): one escape symbol per level from the model of min(lev, 3), and the level's
+                // two magnitude bits (a, b interleaved) as side bits - except level 0 in lsb mode, whose bits are deferred
+                const int L = t.L;
+                const int pk0 = LC3T_AC_SPEC_LOOKUP[tc], pk1 = LC3T_AC_SPEC_LOOKUP[tc + 1024];
+                const int pk2 = LC3T_AC_SPEC_LOOKUP[tc + 2048], pk3 = LC3T_AC_SPEC_LOOKUP[tc + 3072];
+                auto esc = [&](int pk) { return (uint32_t)LC3T_AC_SPEC_CUMFREQ[pk][16] | ((uint32_t)LC3T_AC_SPEC_FREQ[pk][16] << 16); };
+                if (L > 0) symq[so] = esc(pk0);
+                if (L > 1) symq[so + 1] = esc(pk1);
+                if (L > 2) symq[so + 2] = esc(pk2);
+                if (L > 3) {
+                    const uint32_t e3 = esc(pk3);
+                    for (int lev = 3; lev < L; lev++) symq[so + lev] = e3;
                 }
-                const int pki = LC3T_AC_SPEC_LOOKUP[tc + (t.L < 3 ? t.L : 3) * 1024];
+                so += L;
+                const int skip = (q.lsb_mode && L > 0) ? 1 : 0;
+                const uint32_t lsb0 = skip ? (t.a0 & 1u) : 0u, lsb1 = skip ? (t.b0 & 1u) : 0u;
+                const uint32_t lm = (1u << (L - skip)) - 1u;                       // L - skip <= 14
+                uint64_t sbits = (uint64_t)(spread_bits((t.a0 >> skip) & lm) | (spread_bits((t.b0 >> skip) & lm) << 1));
+                int ns = 2 * (L - skip);
+                const uint32_t a = t.a, b = t.b;
+                const int pki = L == 0 ? pk0 : L == 1 ? pk1 : L == 2 ? pk2 : pk3;
                 const int sym = (int)(a + 4 * b);
                 symq[so++] = (uint32_t)LC3T_AC_SPEC_CUMFREQ[pki][sym] | ((uint32_t)LC3T_AC_SPEC_FREQ[pki][sym] << 16);
                 uint32_t al = t.a0, bl = t.b0;
