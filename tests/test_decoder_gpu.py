@@ -144,6 +144,26 @@ def test_pipelined_host_entry_point():
     assert d.max() <= PCM_TOL
 
 
+def test_odd_pcm_stride_and_unaligned_rows():
+    """pcm_out rows at an odd sample pitch / 2-byte-aligned base take the kernels' scalar store path; same samples."""
+    import torch
+
+    import lc3_codec_b200 as L
+    for fs, ms, nb in ((48000, 10, 150), (16000, 7.5, 30)):
+        _, frames = corpus(fs, ms, nb, 40, 6)
+        ref = gpu_decode(fs, ms, frames, trace=False)[0]
+        sf, fd = L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)
+        ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(40, fd, sf, nb), dtype=torch.uint8, device="cuda:0")
+        dec = L.Lc3BatchDecoder(40, fd, sf, ws, nb)
+        nf = dec.nf
+        backing = torch.zeros(40 * (nf + 3) + 1, dtype=torch.int16, device="cuda:0")
+        out = backing[1:].view(40, nf + 3)[:, :nf + 1]         # base 2-byte aligned only, pitch nf + 3 (odd)
+        for f in range(6):
+            dec.decode_frames(16, torch.from_numpy(np.ascontiguousarray(frames[:, f])).cuda(), out)
+            assert np.array_equal(out[:, :nf].cpu().numpy(), ref[:, f])
+        assert int(out[:, nf].abs().max()) == 0                 # nothing written past nf
+
+
 def test_ragged_stream_counts():
     """Stream counts that are not multiples of the warp / CTA sizes."""
     for n in (1, 31, 33, 129):
