@@ -173,11 +173,17 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_mdct_kernel(AnalysisParams
     // ---- band energies (:140-152, divide inside the sum) and near-Nyquist flag (:154-178)
     float* e_b = p.e_b + (size_t)stream * 64;
     float* ebs = (float*)cx;                        // staging of the energies for the serial sums below
+    // the terms x^2 / width of all lines in parallel (the division is the expensive part), then one ordered sum per band
+    float* tq = (float*)tb;                         // the time buffer is dead by now; ne floats fit in its 2 nf int16
+    WARP_STRIDE(k, ne) {
+        const int b = c.band_of[k];
+        if (b != 255) tq[k] = wk[k] * wk[k] / (float)(c.band_idx[b + 1] - c.band_idx[b]);
+    }
+    __syncwarp();
     WARP_STRIDE(b, c.nb) {
         const int from = c.band_idx[b], to = c.band_idx[b + 1];
-        const float width = (float)(to - from);
         float e = 0.0f;
-        for (int k = from; k < to; k++) e += wk[k] * wk[k] / width;
+        for (int k = from; k < to; k++) e += tq[k];
         e_b[b] = e;
         ebs[b] = e;
     }

@@ -18,7 +18,7 @@
 //   * independent results go to different lanes (64 band energies, 32 codebook rows, 27 autocorrelation sums,
 //     100 four-line energies, 400 quantised lines, 200 two-tuples of the context walk);
 //   * a long ordered sum keeps its order: its terms are produced in parallel and one chain adds them;
-//   * the TNS lattice runs as a systolic pipeline, lane k holding stage k (same operations per sample);
+//   * the TNS analysis lattice is FIR: its stages run one after the other, each over all lines at once;
 //   * integer accumulations (bit estimates, ranks, offsets) are exact in any order and use warp scans;
 //   * the range coder consumes a queue of (cumulative, frequency) pairs the lanes prepared, and the backward
 //     side-bit stream is assembled by the lanes at prefix-summed offsets.
@@ -559,28 +559,54 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         nbits_tns += (int)ceilf((2048.0f + (float)ob + (float)cb) / 2048.0f);
     }
     r.nbits_tns = nbits_tns;
-    // forward lattice :285-310 as a systolic pipeline: lane k is stage k and keeps st[k]; sample n enters lane 0 at
-    // step n and leaves the last stage (lane order-1) at step n + order - 1.  The state survives from filter 0 to 1.
-    float st = 0.0f;
+    // forward lattice :313-341.  It is an FIR lattice: with f_0[n] = b_0[n] = x[n],
+    //   f_{k+1}[n] = f_k[n] + rc_k * b_k[n-1],   b_{k+1}[n] = rc_k * f_k[n] + b_k[n-1]     (st[k] is b_k[n-1])
+    // stage k+1 of every line only needs stage k of lines n and n-1, so the recursion over lines that the reference
+    // writes is not a dependence: the stages run one after the other, each over all lines at once, with exactly the
+    // reference's operations per line and stage.  A lane owns C consecutive lines (C odd: conflict-free shared-memory
+    // columns) in registers; b_k[n-1] of its first line comes from its neighbour, of the filter's first line from the
+    // state, which survives from filter 0 to filter 1 (b_k of filter 0's last line).
+    float st8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     for (int f = 0; f < tp.nf; f++) {
         const int order = r.rc_order[f];
         if (order == 0) continue;
-        const int po = order - 1;
-        const float rq = lane <= po ? rc_q[f * 8 + lane] : 0.0f;
         const int start = tp.start[f], N = tp.stop[f] - start;
-        float t_out = 0.0f, s_out = 0.0f;
-        for (int step = 0; step < N + po; step++) {
-            float t_in = __shfl_up_sync(FULL, t_out, 1), s_in = __shfl_up_sync(FULL, s_out, 1);
-            // lane 0 fetches the next sample; the other lanes read line 0, which the lattice never writes (start >= 9)
-            const float xin = x[lane == 0 ? start + (step < N ? step : N - 1) : 0];
-            if (lane == 0) { t_in = xin; s_in = xin; }
-            const int n = step - lane;
-            const bool act = lane <= po && n >= 0 && n < N;
-            const float tn = t_in + rq * st;              // every stage
-            const float st_tmp = rq * t_in + st;          // handed on by the inner stages
-            if (act) { t_out = tn; s_out = st_tmp; st = s_in; }
-            if (act && lane == po) x[start + n] = tn;
-            __syncwarp();                                  // orders lane 0's read of line `step` before its later overwrite
+        constexpr int CM = 13;                                     // ceil(388 / 32)
+        const int C = ((N + 31) >> 5) | 1;
+        const int n0 = lane * C;
+        float F[CM], B[CM];
+#pragma unroll
+        for (int i = 0; i < CM; i++) {
+            const int n = n0 + i;
+            F[i] = B[i] = (i < C && n < N) ? x[start + n] : 0.0f;
+        }
+        const int last_lane = (N - 1) / C, last_i = (N - 1) - last_lane * C;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k >= order) break;                                 // warp-uniform
+            const float rq = rc_q[f * 8 + k];
+            float b_last = 0.0f, b_end = 0.0f;                     // this lane's b_k of its last line / of line N-1
+#pragma unroll
+            for (int i = 0; i < CM; i++) {
+                if (i == C - 1) b_last = B[i];
+                if (i == last_i) b_end = B[i];
+            }
+            float up = __shfl_up_sync(FULL, b_last, 1);
+            if (lane == 0) up = st8[k];
+            st8[k] = __shfl_sync(FULL, b_end, last_lane);          // state left behind: b_k of the filter's last line
+#pragma unroll
+            for (int i = CM - 1; i >= 0; i--) {
+                const float prev = i == 0 ? up : B[i - 1];         // b_k[n-1]
+                const float fk = F[i];
+                B[i] = rq * fk + prev;
+                F[i] = fk + rq * prev;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CM; i++) {
+            const int n = n0 + i;
+            if (i < C && n < N) x[start + n] = F[i];
         }
         __syncwarp();
     }
@@ -1360,7 +1386,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_sns_kernel(QuantParams p) {
 }
 
 // Kernel A2: TNS analysis and filtering.
-__global__ void __launch_bounds__(QNT_THREADS) enc_tns_kernel(QuantParams p) {
+__global__ void __launch_bounds__(QNT_THREADS, 8) enc_tns_kernel(QuantParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
