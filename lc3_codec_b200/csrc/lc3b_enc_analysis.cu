@@ -310,38 +310,66 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
         __syncwarp();
     }
     float* x12n = x12 + c.delay + NMEM;             // where this frame's resampled samples go
-    WARP_STRIDE(n, len12) {        // resampling (:152-166)
-        float acc = 0.0f;
-        const int q15 = (15 * n) / up, r15 = (15 * n) % up;
-        // the reference walks k = -120/up ..= 120/up and skips taps with |up k - r15| >= 120: exactly the first one,
-        // and the last one when r15 == 0 (up divides 120)
-        // (up divides 120).  resamp_ph is the filter in phase-major order: ph[j] = h[up (j - kq + 1) - r15].
-        const int kq = 120 / up;
+    {   // resampling (:152-166).  Output n = lane + 32 i: its phase r15 = 15 n mod up does not depend on i (up divides
+        // 480), and its first input advances by 480 / up per i, so the lane's (up to four) outputs share each filter tap.
+        // The reference walks k = -120/up ..= 120/up and skips taps with |up k - r15| >= 120: exactly the first one, and
+        // the last one when r15 == 0 (up divides 120).  resamp_ph is the filter in phase-major order:
+        // ph[j] = h[up (j - kq + 1) - r15].
+        const int kq = 120 / up, q_step = 480 / up;
+        const int q15 = (15 * lane) / up, r15 = (15 * lane) % up;
         const float* xp = xs + q15 + 1;
         const float* ph = c.resamp_ph + r15 * (2 * kq);
+        const int n_out = len12 >> 5;                                  // 4 at 10 ms, 3 at 7.5 ms
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        const int last = n_out - 1;
+        const float* x3 = xp + last * q_step;                          // the fourth chain repeats the last one at 7.5 ms
 #pragma unroll 4
-        for (int j = 0; j < 2 * kq - 1; j++) acc += xp[j] * ph[j];
-        if (r15 != 0) acc += xp[2 * kq - 1] * ph[2 * kq - 1];
-        x12n[n] = acc * ((float)up * c.resamp_fac);
+        for (int j = 0; j < 2 * kq - 1; j++) {                         // warp-uniform trip count
+            const float h = ph[j];
+            a0 += xp[j] * h;
+            a1 += xp[q_step + j] * h;
+            a2 += xp[2 * q_step + j] * h;
+            a3 += x3[j] * h;
+        }
+        if (r15 != 0) {
+            const int j = 2 * kq - 1;
+            const float h = ph[j];
+            a0 += xp[j] * h;
+            a1 += xp[q_step + j] * h;
+            a2 += xp[2 * q_step + j] * h;
+            a3 += x3[j] * h;
+        }
+        const float sc = (float)up * c.resamp_fac;
+        x12n[lane] = a0 * sc;
+        x12n[lane + 32] = a1 * sc;
+        x12n[lane + 64] = a2 * sc;
+        if (n_out == 4) x12n[lane + 96] = a3 * sc;
     }
-    __syncwarp();
-    {   // 50 Hz high-pass biquad (:169-177): the recursive half (h50) is a serial chain on lane 0, the feed-forward
-        // half only needs h50[n], h50[n-1], h50[n-2] and runs on all lanes
+    // 50 Hz high-pass biquad (:169-177).  The recursive half (h50) is a serial chain: the chains of the CTA's frames run
+    // side by side on the first lanes of warp 0 instead of each spending its own warp's issue slots; the feed-forward
+    // half only needs h50[n], h50[n-1], h50[n-2] and runs on all lanes of the frame's own warp.
+    {
         const float m1_0 = __uint_as_float((uint32_t)es[ES_H50_M1]), m2_0 = __uint_as_float((uint32_t)es[ES_H50_M2]);
         float* h50s = wk;                            // len12 <= 128 floats (attack scratch is dead by now)
-        __syncwarp();
-        if (lane == 0) {
-            float m1 = m1_0, m2 = m2_0;
+        const int stream0 = blockIdx.x * ANA_WARPS;
+        const int n_live = min(ANA_WARPS, p.n_streams - stream0);   // warps of this CTA that have a frame (the others returned)
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+        if (wid == 0 && lane < n_live) {
+            uint8_t* ob = smem + (size_t)lane * p.smem_per_warp;      // warp `lane`'s slice: same carve-up as above
+            float* o_wk = (float*)ob;
+            const float* o_x12n = o_wk + 320 + 98 + 98 + 236 + c.delay + NMEM;
+            int32_t* o_es = p.estate + (size_t)(stream0 + lane) * ES_WORDS;
+            float m1 = __uint_as_float((uint32_t)o_es[ES_H50_M1]), m2 = __uint_as_float((uint32_t)o_es[ES_H50_M2]);
             for (int n = 0; n < len12; n++) {
-                const float h50 = x12n[n] - -1.9652933726226904f * m1 - 0.9658854605688177f * m2;
-                h50s[n] = h50;
+                const float h50 = o_x12n[n] - -1.9652933726226904f * m1 - 0.9658854605688177f * m2;
+                o_wk[n] = h50;
                 m2 = m1;
                 m1 = h50;
             }
-            es[ES_H50_M1] = (int32_t)__float_as_uint(m1);
-            es[ES_H50_M2] = (int32_t)__float_as_uint(m2);
+            o_es[ES_H50_M1] = (int32_t)__float_as_uint(m1);
+            o_es[ES_H50_M2] = (int32_t)__float_as_uint(m2);
         }
-        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
         WARP_STRIDE(n, len12) {
             const float h50 = h50s[n];
             const float m1 = n >= 1 ? h50s[n - 1] : m1_0;
