@@ -740,8 +740,10 @@ __device__ __noinline__ BitCons quantize_spectrum_w(const EncConfig& c, const fl
 }
 
 // SpectralQuantization::run :75-120.  e4: [ne/4] energies, T: [224] scratch (bisection terms, then per-tuple bit prefixes).
+constexpr size_t QUANTIZE_WARP_BYTES = sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX;   // xf | e4 | T | xq
 __device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const float* xf, int16_t* xq, float* e4, float* T,
-                                        int nbits, int nbits_bw, int nbits_tns, int nbits_ltpf, int lane) {
+                                        int nbits, int nbits_bw, int nbits_tns, int nbits_ltpf, int lane, int wib, int n_live,
+                                        uint8_t* smem_base) {
     const int ne = c.ne, fs_ind = c.fs_ind;
     int lg = 0;
     while ((1 << lg) < ne / 2) lg++;
@@ -811,14 +813,21 @@ __device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const f
             any_loud = any_loud || ball[r] != 0;
         }
         const bool is_zero = !any_loud;
-        __syncwarp();
-        float tmp = 0.0f;
-        for (int i = ne4 - 1; i >= (ne4 & ~3); i--) tmp += T[i];
-        for (int i4 = ne4 / 4 - 1; i4 >= 0; i4--) {
-            const float4 t4 = ((const float4*)T)[i4];
-            tmp += t4.w; tmp += t4.z; tmp += t4.y; tmp += t4.x;
+        // the ordered sum is one chain per frame: the chains of the CTA's frames run side by side on the first lanes of
+        // warp 0 (between two named barriers) instead of each being repeated by the 32 lanes of its own warp
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+        if (wib == 0 && lane < n_live) {
+            float* oT = (float*)(smem_base + (size_t)lane * QUANTIZE_WARP_BYTES) + NE_MAX + 100;   // warp `lane`'s T
+            float acc = 0.0f;
+            for (int i = ne4 - 1; i >= (ne4 & ~3); i--) acc += oT[i];
+            for (int i4 = ne4 / 4 - 1; i4 >= 0; i4--) {
+                const float4 t4 = ((const float4*)oT)[i4];
+                acc += t4.w; acc += t4.z; acc += t4.y; acc += t4.x;
+            }
+            oT[208] = acc;
         }
-        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+        const float tmp = T[208];
         if ((tmp > (float)nbits_spec_adj * 1.4f * 28.0f / 20.0f) && !is_zero) gg_ind += fac;
     }
     int gg_min = 0;
@@ -1420,7 +1429,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quantize_kernel(QuantParams p
     const int stream = blockIdx.x * QW + wib;
     if (stream >= p.n_streams) return;
     const int ne = c.ne;
-    uint8_t* wb = smem + (size_t)wib * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX);
+    uint8_t* wb = smem + (size_t)wib * QUANTIZE_WARP_BYTES;
     float* xf = (float*)wb;                                       // [NE_MAX]
     float* e4 = xf + NE_MAX;                                      // [100]
     float* T = e4 + 100;                                          // [224]
@@ -1431,7 +1440,9 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_quantize_kernel(QuantParams p
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     int32_t* es = p.estate + (size_t)stream * ES_WORDS;
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
-    const QRes q = spectral_quantization_w(c, es, xf, xq, e4, T, p.nbytes * 8, qh[QH_NBITS_BW], qh[QH_NBITS_TNS], eh[EH_NBITS_LTPF], lane);
+    const int n_live = min(QW, p.n_streams - blockIdx.x * QW);    // warps of this CTA that have a frame
+    const QRes q = spectral_quantization_w(c, es, xf, xq, e4, T, p.nbytes * 8, qh[QH_NBITS_BW], qh[QH_NBITS_TNS], eh[EH_NBITS_LTPF], lane,
+                                           wib, n_live, smem);
     uint32_t* gq = (uint32_t*)(p.xq + (size_t)stream * ne);
     WARP_STRIDE(i, ne / 2) gq[i] = ((const uint32_t*)xq)[i];
     if (lane == 0) {
@@ -1611,7 +1622,7 @@ static size_t bitstream_warp_bytes(int ne, int nbytes, QuantParams* p) {
     return wbytes;
 }
 constexpr size_t SHAPE_SMEM = QW * sizeof(float) * (NE_MAX + S_FLOATS);
-constexpr size_t QUANTIZE_SMEM = QW * (sizeof(float) * (NE_MAX + 100 + 224) + sizeof(int16_t) * NE_MAX);
+constexpr size_t QUANTIZE_SMEM = QW * QUANTIZE_WARP_BYTES;
 
 // dynamic shared memory limits, once per handle (lc3b_encoder_init) for the largest frame the handle accepts
 cudaError_t prepare_enc_quant(const EncoderState& st) {
