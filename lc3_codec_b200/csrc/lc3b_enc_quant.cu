@@ -166,6 +166,32 @@ __device__ __forceinline__ void add_unit_pulse_w(float ax, int n_max, int k, int
     }
 }
 
+// The same search as one thread's work (inputs in shared memory): the scan over candidates is a serial chain, so the
+// frames of a CTA run it side by side on the first lanes of warp 0 instead of each repeating it in 32 lanes.
+__device__ __forceinline__ void add_unit_pulse_1(const float* ax, int* cand, int n_max, int k, int k_max, float& corr_xy, float& energy_y) {
+    float corr_last = corr_xy, en_last = energy_y;
+#pragma unroll 1
+    for (int it = k; it < k_max; it++) {
+        int n_best = 0;
+        corr_xy = corr_last + ax[0];
+        float best_corr_sq = corr_xy * corr_xy;
+        float best_en = en_last + 2.0f * (float)cand[0] + 1.0f;
+#pragma unroll 1
+        for (int n_c = 1; n_c < n_max; n_c++) {
+            corr_xy = corr_last + ax[n_c];
+            energy_y = en_last + 2.0f * (float)cand[n_c] + 1.0f;
+            if (corr_xy * corr_xy * best_en > best_corr_sq * energy_y) {
+                n_best = n_c;
+                best_corr_sq = corr_xy * corr_xy;
+                best_en = energy_y;
+            }
+        }
+        corr_last += ax[n_best];
+        en_last += 2.0f * (float)cand[n_best] + 1.0f;
+        cand[n_best] += 1;
+    }
+}
+
 // normalize_candidate :629-648 (the squared norm is a sum of small integers: exact in any order)
 __device__ __forceinline__ float normalize_w(int y, bool in_range) {
     const int yy = in_range ? y : 0;
@@ -197,10 +223,11 @@ __device__ __noinline__ void mvpq_enum(uint64_t* index, int* lead_sign_ind, int 
 }
 
 // sns_run_quant :318-582.  In: lane n < 16 holds scf[n].  Out: lane n < 16 holds scfq[n].
-__device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane) {
+__device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, int wib, int n_live) {
     float* xqs = S + 208;                 // [4][16] normalised shapes
     float* t2s = S + 192;                 // [16] rotated residual
     int* ys = (int*)(S + 320);            // [4][16] pulse vectors
+    // exchange area of the pulse search (S + 272 .. 320): |t2rot| [16], pulse counts [16], corr / energy / first pulse
     const int n16 = lane & 15;
     // stage 1: lane i evaluates codebook row i of both halves
     float dlf = 0.0f, dhf = 0.0f;
@@ -235,9 +262,26 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane) {
             energy_y += (float)yn * (float)yn;
         }
     }
-    add_unit_pulse_w(ax, 16, k, 6, y3, corr_xy, energy_y, lane);
+    // add_unit_pulse :285-316, run for all frames of the CTA by warp 0 (see add_unit_pulse_1)
+    auto pulses = [&](int n_max, int k_from, int k_max, int& cand) {
+        float* xa = S + 272;
+        int* xc = (int*)(S + 288);
+        float* sc = S + 304;
+        if (lane < 16) { xa[lane] = ax; xc[lane] = cand; }
+        if (lane == 0) { sc[0] = corr_xy; sc[1] = energy_y; ((int*)sc)[2] = k_from; }
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+        if (wib == 0 && lane < n_live) {
+            float* oS = S + (size_t)lane * (NE_MAX + S_FLOATS);         // warp `lane`'s scratch (this is warp 0)
+            add_unit_pulse_1(oS + 272, (int*)(oS + 288), n_max, ((const int*)(oS + 304))[2], k_max, oS[304], oS[305]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+        if (lane < 16) cand = xc[lane];
+        corr_xy = sc[0];
+        energy_y = sc[1];
+    };
+    pulses(16, k, 6, y3);
     int y2 = y3;
-    add_unit_pulse_w(ax, 16, 6, 8, y2, corr_xy, energy_y, lane);
+    pulses(16, 6, 8, y2);
     int y1 = lane < 10 ? y2 : 0;
     int k1 = 8;
     for (int n = 10; n < 16; n++) {
@@ -249,7 +293,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane) {
             energy_y -= (float)yn * (float)yn;
         }
     }
-    add_unit_pulse_w(ax, 10, k1, 10, y1, corr_xy, energy_y, lane);
+    pulses(10, k1, 10, y1);
     int y0 = lane < 10 ? y1 : 0;
     {
         float max_abs_x = 0.0f;
@@ -327,7 +371,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane) {
 }
 
 // SpectralNoiseShaping::run :203-282.  S[0..64) holds the band energies on entry.
-__device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool attack, int lane) {
+__device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool attack, int lane, int wib, int n_live) {
     const float* W = SNS_W;
     float* eb = S;
     float* e = S + 64;
@@ -381,7 +425,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
         scf = att * (scf - sa);
     }
     SnsRes res;
-    const float scfq = sns_run_quant_w(scf, S, &res, lane);
+    const float scfq = sns_run_quant_w(scf, S, &res, lane, wib, n_live);
     // 16 -> 64 interpolation :85-98 of the decoder's twin, then the nb < 64 folding and g = 2^-scf
     float* it = S + 64;
     float* gs = S;
@@ -1383,7 +1427,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_sns_kernel(QuantParams p) {
     __syncwarp();
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     const BwRes bw = bandwidth_detect(c, S);
-    const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane);
+    const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane, wib, min(QW, p.n_streams - blockIdx.x * QW));
     WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     if (lane == 0) {
