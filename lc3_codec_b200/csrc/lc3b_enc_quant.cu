@@ -49,7 +49,7 @@ struct QuantParams {
     int inline_ac;     // small batches: the finish kernel runs the range coder itself (all lanes, same chain) and C2 is skipped
 };
 
-constexpr int QW = 4;                       // frames (warps) per CTA
+constexpr int QW = 8;                       // frames (warps) per CTA
 constexpr int QNT_THREADS = QW * 32;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NE_MAX = 400;
@@ -1439,7 +1439,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_sns_kernel(QuantParams p) {
 }
 
 // Kernel A2: TNS analysis and filtering.
-__global__ void __launch_bounds__(QNT_THREADS, 8) enc_tns_kernel(QuantParams p) {
+__global__ void __launch_bounds__(QNT_THREADS, 4) enc_tns_kernel(QuantParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
