@@ -137,37 +137,9 @@ __device__ BwRes bandwidth_detect(const EncConfig& c, const float* e_b) {
 }
 
 // ---------------------------------------------------------------- spectral_noise_shaping.rs
-// add_unit_pulse :285-316.  Lane n < n_max owns abs_x[n] and cand[n]; the best-candidate scan keeps the reference's
-// order (and its habit of leaving the LAST candidate's correlation/energy in the in-out arguments).
-__device__ __forceinline__ void add_unit_pulse_w(float ax, int n_max, int k, int k_max, int& cand, float& corr_xy, float& energy_y,
-                                                 int lane) {
-    float corr_last = corr_xy, en_last = energy_y;
-#pragma unroll 1
-    for (int it = k; it < k_max; it++) {
-        const float my_corr = corr_last + ax;
-        const float my_en = en_last + 2.0f * (float)cand + 1.0f;
-        int n_best = 0;
-        corr_xy = shf(my_corr, 0);
-        float best_corr_sq = corr_xy * corr_xy;
-        float best_en = shf(my_en, 0);
-#pragma unroll 1
-        for (int n_c = 1; n_c < n_max; n_c++) {
-            corr_xy = shf(my_corr, n_c);
-            energy_y = shf(my_en, n_c);
-            if (corr_xy * corr_xy * best_en > best_corr_sq * energy_y) {
-                n_best = n_c;
-                best_corr_sq = corr_xy * corr_xy;
-                best_en = energy_y;
-            }
-        }
-        corr_last += shf(ax, n_best);
-        en_last += 2.0f * (float)shi(cand, n_best) + 1.0f;
-        if (lane == n_best) cand += 1;
-    }
-}
-
-// The same search as one thread's work (inputs in shared memory): the scan over candidates is a serial chain, so the
-// frames of a CTA run it side by side on the first lanes of warp 0 instead of each repeating it in 32 lanes.
+// add_unit_pulse :285-316 as one thread's work (inputs in shared memory).  The best-candidate scan keeps the reference's
+// order (and its habit of leaving the LAST candidate's correlation/energy in the in-out arguments).  The scan is a serial
+// chain, so the frames of a CTA run it side by side on the first lanes of warp 0 instead of each repeating it in 32 lanes.
 __device__ __forceinline__ void add_unit_pulse_1(const float* ax, int* cand, int n_max, int k, int k_max, float& corr_xy, float& energy_y) {
     float corr_last = corr_xy, en_last = energy_y;
 #pragma unroll 1
