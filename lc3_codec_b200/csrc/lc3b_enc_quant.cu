@@ -239,6 +239,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
         float* xa = S + 272;
         int* xc = (int*)(S + 288);
         float* sc = S + 304;
+        __syncwarp();                                                    // the previous call's reads of the exchange area are done
         if (lane < 16) { xa[lane] = ax; xc[lane] = cand; }
         if (lane == 0) { sc[0] = corr_xy; sc[1] = energy_y; ((int*)sc)[2] = k_from; }
         asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
