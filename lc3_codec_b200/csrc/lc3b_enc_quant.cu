@@ -1383,12 +1383,14 @@ enum {
 static_assert(QH_GG < QH_WORDS, "hand-off record too small");
 
 // Kernel A1: bandwidth detector and SNS.  Spectrum in place in global memory, decisions into the hand-off record.
-__global__ void __launch_bounds__(QNT_THREADS) enc_sns_kernel(QuantParams p) {
+// Four frames per CTA here: the warps of a CTA wait at the pulse-search barriers, and with eight of them the wait showed.
+constexpr int SNS_WARPS = 4;
+__global__ void __launch_bounds__(SNS_WARPS * 32) enc_sns_kernel(QuantParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const EncConfig& c = *p.cfg;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int stream = blockIdx.x * QW + wib;
-    if (stream >= p.n_streams) return;                            // warps are independent: no CTA-wide barrier below
+    const int stream = blockIdx.x * SNS_WARPS + wib;
+    if (stream >= p.n_streams) return;                            // the warps that stay meet at named barriers sized for them
     const int ne = c.ne;
     float* xf = (float*)(smem + (size_t)wib * (sizeof(float) * (NE_MAX + S_FLOATS)));   // [NE_MAX]
     float* S = xf + NE_MAX;                                                             // [S_FLOATS]
@@ -1400,7 +1402,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_sns_kernel(QuantParams p) {
     __syncwarp();
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     const BwRes bw = bandwidth_detect(c, S);
-    const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane, wib, min(QW, p.n_streams - blockIdx.x * QW));
+    const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane, wib, min(SNS_WARPS, p.n_streams - blockIdx.x * SNS_WARPS));
     WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     if (lane == 0) {
@@ -1643,7 +1645,7 @@ constexpr size_t QUANTIZE_SMEM = QW * QUANTIZE_WARP_BYTES;
 
 // dynamic shared memory limits, once per handle (lc3b_encoder_init) for the largest frame the handle accepts
 cudaError_t prepare_enc_quant(const EncoderState& st) {
-    cudaError_t e = cudaFuncSetAttribute(enc_sns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHAPE_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(enc_sns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SHAPE_SMEM / QW * SNS_WARPS));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_tns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SHAPE_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(enc_quantize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QUANTIZE_SMEM);
     if (e == cudaSuccess)
@@ -1671,7 +1673,7 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     p.frames_out = frames_out;
     const size_t wbytes = bitstream_warp_bytes(st.cfg.ne, nbytes, &p);
     const int grid = (p.n_streams + QW - 1) / QW;
-    if (stages & 1) enc_sns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
+    if (stages & 1) enc_sns_kernel<<<(p.n_streams + SNS_WARPS - 1) / SNS_WARPS, SNS_WARPS * 32, SHAPE_SMEM / QW * SNS_WARPS, stream>>>(p);
     if (stages & 2) enc_tns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
     if (stages & 4) enc_quantize_kernel<<<grid, QNT_THREADS, QUANTIZE_SMEM, stream>>>(p);
     if (stages & 8) {
