@@ -599,9 +599,8 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         }
         const int last_lane = (N - 1) / C, last_i = (N - 1) - last_lane * C;
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k >= order) break;                                 // warp-uniform
+#pragma unroll 1                                                   // a rolled loop stays in the instruction cache
+        for (int k = 0; k < order; k++) {
             const float rq = rc_q[f * 8 + k];
             float b_last = 0.0f, b_end = 0.0f;                     // this lane's b_k of its last line / of line N-1
 #pragma unroll
