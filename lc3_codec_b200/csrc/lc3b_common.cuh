@@ -16,6 +16,10 @@
 // instruction issued twice, ncu thr/inst = 16).  Here every lane runs ceil(n/32) iterations with a predicated body.
 #define WARP_STRIDE(v, n) for (int v##_b = 0, v = lane; v##_b < (n); v##_b += 32, v += 32) if (v < (n))
 #define WARP_STRIDE_FROM(v, start, n) for (int v##_b = (start), v = (start) + lane; v##_b < (n); v##_b += 32, v += 32) if (v < (n))
+// The same loops kept rolled, for the kernels that run through a lot of code once per frame and are bound by instruction
+// fetch (ncu `no_instructions`: SNS and the bitstream stage): there code size matters more than the unrolled loads' overlap.
+#define WARP_STRIDE_R(v, n) _Pragma("unroll 1") WARP_STRIDE(v, n)
+#define WARP_STRIDE_FROM_R(v, start, n) _Pragma("unroll 1") WARP_STRIDE_FROM(v, start, n)
 
 namespace lc3b {
 

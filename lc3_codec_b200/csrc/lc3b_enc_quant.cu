@@ -349,7 +349,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     float* eb = S;
     float* e = S + 64;
     const int nb = c.nb, diff = 64 - nb;
-    WARP_STRIDE(b, 64) {
+    WARP_STRIDE_R(b, 64) {
         auto pad = [&](int j) -> float { return diff > 0 ? (j < 2 * diff ? eb[j >> 1] : eb[j - diff]) : eb[j]; };
         float v;
         if (b == 0) v = 0.75f * pad(0) + 0.25f * pad(1);
@@ -363,7 +363,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     total = (total / 64.0f) * powi_nt(10.0f, -4);
     const float floor_ = maxf_rs(powi_nt(2.0f, -32), total);
     __syncwarp();
-    WARP_STRIDE(b, 64) e[b] = log2f_msun(1.1920929e-07f + maxf_rs(e[b], floor_)) / 2.0f;
+    WARP_STRIDE_R(b, 64) e[b] = log2f_msun(1.1920929e-07f + maxf_rs(e[b], floor_)) / 2.0f;
     __syncwarp();
     const int n16 = lane & 15;
     float ds;
@@ -428,7 +428,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     __syncwarp();
     for (int j = 0; j < 2; j++) gs[lane + 32 * j] = exp2f_msun(-itv[j]);
     __syncwarp();
-    WARP_STRIDE(k, c.ne) {
+    WARP_STRIDE_R(k, c.ne) {
         const int b = c.band_of[k];
         if (b < nb) x[k] *= gs[b];
     }
@@ -1198,9 +1198,9 @@ __device__ void bs_prepare_w(const EncConfig& c, const SideHdr& h, const int16_t
     const QRes& q = *h.q;
     const TnsRes& tns = *h.tns;
     const int ne = c.ne;
-    WARP_STRIDE(i, side_words) side[i] = 0;
-    WARP_STRIDE(i, out_words) ((uint32_t*)out)[i] = 0;
-    if (q.lsb_mode) WARP_STRIDE(i, TAIL_WORDS) tail[i] = 0;
+    WARP_STRIDE_R(i, side_words) side[i] = 0;
+    WARP_STRIDE_R(i, out_words) ((uint32_t*)out)[i] = 0;
+    if (q.lsb_mode) WARP_STRIDE_R(i, TAIL_WORDS) tail[i] = 0;
     __syncwarp();
     int spos = 0;
     {
@@ -1394,7 +1394,7 @@ __global__ void __launch_bounds__(SNS_WARPS * 32) enc_sns_kernel(QuantParams p) 
     float* xf = (float*)(smem + (size_t)wib * (sizeof(float) * (NE_MAX + S_FLOATS)));   // [NE_MAX]
     float* S = xf + NE_MAX;                                                             // [S_FLOATS]
     float4* gx = (float4*)(p.xf + (size_t)stream * ne);
-    WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
+    WARP_STRIDE_R(i, ne / 4) ((float4*)xf)[i] = gx[i];
     const float* eb = p.e_b + (size_t)stream * 64;
     S[lane] = eb[lane];
     S[lane + 32] = eb[lane + 32];
@@ -1402,7 +1402,7 @@ __global__ void __launch_bounds__(SNS_WARPS * 32) enc_sns_kernel(QuantParams p) 
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     const BwRes bw = bandwidth_detect(c, S);
     const SnsRes sns = sns_encode_w(c, xf, S, eh[EH_ATTACK] != 0, lane, wib, min(SNS_WARPS, p.n_streams - blockIdx.x * SNS_WARPS));
-    WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
+    WARP_STRIDE_R(i, ne / 4) gx[i] = ((const float4*)xf)[i];
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     if (lane == 0) {
         qh[QH_BW] = bw.bw; qh[QH_NBITS_BW] = bw.nbits;
@@ -1528,9 +1528,9 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_prepare_kernel(QuantParams
     uint8_t* out = (uint8_t*)(symq + p.sym_cap + 1);              // [out_words * 4] (zeroed here, filled by the range coder kernel)
     {
         const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
-        WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
+        WARP_STRIDE_R(i, ne / 4) ((float4*)xf)[i] = gx[i];
         const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
-        WARP_STRIDE(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
+        WARP_STRIDE_R(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
         if (lane < TAIL_WORDS) tail[lane] = 0;
     }
     BwRes bw;
@@ -1552,8 +1552,8 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_prepare_kernel(QuantParams
     uint32_t* g = p.bs_scratch + (size_t)stream * p.bs_words;
     const int nq = job->nsym < 0 ? 0 : job->nsym + 1;
     const uint32_t* src = (const uint32_t*)job;
-    WARP_STRIDE(i, L.symq + nq) g[i] = src[i];
-    WARP_STRIDE(i, p.out_words) g[L.fwd + i] = 0;
+    WARP_STRIDE_R(i, L.symq + nq) g[i] = src[i];
+    WARP_STRIDE_R(i, p.out_words) g[L.fwd + i] = 0;
 }
 
 __global__ void __launch_bounds__(128) enc_range_coder_kernel(QuantParams p) {
@@ -1581,8 +1581,8 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_finish_kernel(QuantParams 
     int* rc_i = (int*)(wbase + L.symq + p.out_words);
     int16_t* xq = (int16_t*)(rc_i + 16);
     const uint32_t* g = p.bs_scratch + (size_t)stream * p.bs_words;
-    WARP_STRIDE(i, L.symq) wbase[i] = g[i];
-    WARP_STRIDE(i, p.out_words) ((uint32_t*)out)[i] = g[L.fwd + i];
+    WARP_STRIDE_R(i, L.symq) wbase[i] = g[i];
+    WARP_STRIDE_R(i, p.out_words) ((uint32_t*)out)[i] = g[L.fwd + i];
     BwRes bw;
     SnsRes sns;
     TnsRes tns;
@@ -1599,17 +1599,17 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_finish_kernel(QuantParams 
     const bool ok = bs_finish_w(q, n_res, side, p.side_words, tail, out, nbytes, job, lane);
     uint8_t* dst = p.frames_out + (size_t)stream * p.frame_stride;
     if (ok) {
-        WARP_STRIDE(b, nbytes) {
+        WARP_STRIDE_R(b, nbytes) {
             const int i = nbytes - 1 - b;
             dst[b] = out[b] | (uint8_t)(side[i >> 2] >> (8 * (i & 3)));
         }
     } else {                                                       // reference-order rewrite of the whole frame by one lane
         const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
-        WARP_STRIDE(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
+        WARP_STRIDE_R(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
         __syncwarp();
         if (lane == 0) bitstream_encode_serial(c, h, tail, n_res, xq, p.lsbs + (size_t)stream * 2 * ne, out, nbytes);
         __syncwarp();
-        WARP_STRIDE(b, nbytes) dst[b] = out[b];
+        WARP_STRIDE_R(b, nbytes) dst[b] = out[b];
     }
 }
 
