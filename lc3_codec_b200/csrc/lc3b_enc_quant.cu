@@ -118,9 +118,11 @@ __device__ BwRes bandwidth_detect(const EncConfig& c, const float* e_b) {
     const int* stop = (d10 ? STOP10 : STOP75)[n_bw - 1];
     const int* l = d10 ? L10 : L75;
     int bw = 0;
+#pragma unroll 1
     for (int k = n_bw - 1; k >= 0; k--) {
         const float width = (float)(stop[k] + 1 - start[k]);
         float quiet = 0.0f;
+#pragma unroll 1
         for (int n = start[k]; n <= stop[k]; n++) quiet += e_b[n] / width;
         if (quiet >= (float)QUIET[k]) { bw = k + 1; break; }
     }
@@ -128,6 +130,7 @@ __device__ BwRes bandwidth_detect(const EncConfig& c, const float* e_b) {
     float cutoff_max = 0.0f;
     const int l_bw = l[bw];
     const int from = start[bw] + 1 - l_bw, to = start[bw];
+#pragma unroll 1
     for (int n = from; n < to; n++) {
         const float cutoff = e_b[n - l_bw] / e_b[n];
         cutoff_max = maxf_rs(cutoff, cutoff_max);
@@ -203,6 +206,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
     const int n16 = lane & 15;
     // stage 1: lane i evaluates codebook row i of both halves
     float dlf = 0.0f, dhf = 0.0f;
+#pragma unroll 1
     for (int n = 0; n < 8; n++) {
         const float a = shf(scf_v, n), b = shf(scf_v, 8 + n);
         dlf += (a - LC3T_LFCB[lane][n]) * (a - LC3T_LFCB[lane][n]);
@@ -217,14 +221,17 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
     const float r1 = scf_v - st1;
     // stage 2 target: t2rot = r1 * D
     float t2rot = 0.0f;
+#pragma unroll 1
     for (int row = 0; row < 16; row++) t2rot += shf(r1, row) * LC3T_D[row][n16];
     const float ax = fabsf(t2rot);
     float abs_sum = 0.0f;
+#pragma unroll 1
     for (int n = 0; n < 16; n++) abs_sum += shf(ax, n);
     const float proj = (6.0f - 1.0f) / abs_sum;
     int y3 = cast_i32(floorf(ax * proj));
     float corr_xy = 0.0f, energy_y = 0.0f;
     int k = 0;
+#pragma unroll 1
     for (int n = 0; n < 16; n++) {
         const int yn = shi(y3, n);
         const float an = shf(ax, n);
@@ -257,6 +264,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
     pulses(16, 6, 8, y2);
     int y1 = lane < 10 ? y2 : 0;
     int k1 = 8;
+#pragma unroll 1
     for (int n = 10; n < 16; n++) {
         const int yn = shi(y2, n);
         const float an = shf(ax, n);
@@ -271,6 +279,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
     {
         float max_abs_x = 0.0f;
         int n_best = 0;
+#pragma unroll 1
         for (int n_c = 10; n_c < 16; n_c++) {
             const float an = shf(ax, n_c);
             if (an > max_abs_x) { max_abs_x = an; n_best = n_c; }
@@ -297,6 +306,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
     if (lane < 14) {
         g_c = gains[ci];
         d = 0.0f;
+#pragma unroll 1
         for (int n = 0; n < 16; n++) {
             const float diff = t2s[n] - g_c * xqs[cj * 16 + n];
             d += diff * diff;
@@ -335,6 +345,7 @@ __device__ float sns_run_quant_w(float scf_v, float* S, SnsRes* res, int lane, i
             break;
     }
     float factor = 0.0f;
+#pragma unroll 1
     for (int col = 0; col < 16; col++) factor += xqs[shape_j * 16 + col] * LC3T_D[n16][col];
     const float scfq = st1 + g_sel * factor;
     res->ind_lf = ind_lf; res->ind_hf = ind_hf; res->shape_j = shape_j; res->gind = gind;
@@ -359,6 +370,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     }
     __syncwarp();
     float total = 0.0f;
+#pragma unroll 1
     for (int b = 0; b < 64; b++) total += e[b];
     total = (total / 64.0f) * powi_nt(10.0f, -4);
     const float floor_ = maxf_rs(powi_nt(2.0f, -32), total);
@@ -369,16 +381,20 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     float ds;
     if (n16 == 0) {
         ds = W[0] * e[0];
+#pragma unroll 1
         for (int k = 1; k < 6; k++) ds += W[k] * e[k - 1];
     } else if (n16 == 15) {
         ds = W[5] * e[63];
+#pragma unroll 1
         for (int k = 0; k < 5; k++) ds += W[k] * e[60 + k - 1];
     } else {
         ds = 0.0f;
         const int from = 4 * n16 - 1;
+#pragma unroll 1
         for (int k = 0; k < 6; k++) ds += W[k] * e[from + k];
     }
     float tot = 0.0f;
+#pragma unroll 1
     for (int n = 0; n < 16; n++) tot += shf(ds, n);
     const float avg = tot / 16.0f;
     ds = 0.85f * (ds - avg);
@@ -386,12 +402,14 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     if (attack) {
         const int lo = n16 - 2 < 0 ? 0 : n16 - 2, hi = n16 + 2 > 15 ? 15 : n16 + 2;
         float s = shf(ds, lo);
+#pragma unroll 1
         for (int j = 1; j < 5; j++) {
             const float v = shf(ds, lo + j > 15 ? 15 : lo + j);
             if (lo + j <= hi) s += v;
         }
         scf = s / (float)(hi - lo + 1);
         float st = 0.0f;
+#pragma unroll 1
         for (int n = 0; n < 16; n++) st += shf(scf, n);
         const float sa = st / 16.0f;
         const float att = c.n_ms == LC3B_10MS ? 0.5f : 0.3f;
@@ -403,6 +421,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     float* it = S + 64;
     float* gs = S;
     const float s00 = shf(scfq, 0);
+#pragma unroll 1
     for (int j = 0; j < 2; j++) {
         const int b = lane + 32 * j;
         const int bb = b < 2 ? 2 : b;
@@ -416,6 +435,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
     }
     __syncwarp();
     float itv[2];
+#pragma unroll 1
     for (int j = 0; j < 2; j++) {
         const int b = lane + 32 * j;
         float v = it[b];
@@ -426,6 +446,7 @@ __device__ SnsRes sns_encode_w(const EncConfig& c, float* x, float* S, bool atta
         itv[j] = v;
     }
     __syncwarp();
+#pragma unroll 1
     for (int j = 0; j < 2; j++) gs[lane + 32 * j] = exp2f_msun(-itv[j]);
     __syncwarp();
     WARP_STRIDE_R(k, c.ne) {
