@@ -485,6 +485,10 @@ __device__ const TnsP TNS_T75[5] = {
     {2, {9, 150}, {150, 300}, {{9, 56, 103}, {150, 200, 250}}, {{56, 103, 150}, {200, 250, 300}}},
 };
 
+// An IEEE division is ~15 instructions inline; in straight-line register code that runs once per frame (Levinson-Durbin
+// below is unrolled over register arrays) a call is cheaper than the instruction fetch of 60 inlined copies.
+__device__ __noinline__ float fdiv_call(float a, float b) { return a / b; }
+
 // TemporalNoiseShaping::run :40-78.  Scratch: ac[2][27] at S, raw reflection coefficients at S+64,
 // results rc_i (int[16]) at S+256 and rc_q (float[16]) at S+272 (kept until the bitstream is written).
 __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, int nbits, bool near_nyquist, TnsRes& r, int lane) {
@@ -519,7 +523,7 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
 #pragma unroll
             for (int sb = 0; sb < 3; sb++) {
                 e_prod *= acf[sb * 9];
-                rk += acf[sb * 9 + k] / acf[sb * 9];
+                rk += fdiv_call(acf[sb * 9 + k], acf[sb * 9]);
             }
             rr[k] = (e_prod == 0.0f ? r0 : rk) * LAG[k];
         }
@@ -535,7 +539,7 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
             float rc = 0.0f;
 #pragma unroll
             for (int n = 0; n < k; n++) rc -= al[n] * rr[k - n];
-            if (e != 0.0f) rc /= e;
+            if (e != 0.0f) rc = fdiv_call(rc, e);
             a[0] = 1.0f;
 #pragma unroll
             for (int n = 1; n < k; n++) a[n] = al[n] + rc * al[k - n];
@@ -556,7 +560,7 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
 #pragma unroll
                 for (int n = 1; n < k; n++) {
                     float v = a[n] - rcq[k - 1] * a[k - n];
-                    v /= ee;
+                    v = fdiv_call(v, ee);
                     al[n] = v;
                 }
 #pragma unroll
