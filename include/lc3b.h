@@ -115,8 +115,8 @@ int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x);
 int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream);
 
 /* Profiling hook: which kernels lc3b_decode_frames launches (bit 0 = entropy kernel, bit 1 = dequantisation kernel,
- * bit 2 = synthesis kernel; default 7).  Lets bench.py time each kernel alone with CUDA events; results are only
- * meaningful with mask 7. */
+ * bit 2 = synthesis kernel and the post-filter kernel behind it; default 7).  Lets bench.py time each kernel alone
+ * with CUDA events; results are only meaningful with mask 7. */
 int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask);
 
 void lc3b_decoder_destroy(lc3b_decoder* h);
@@ -154,8 +154,8 @@ int lc3b_encoder_set_host_pipelining(lc3b_encoder* h, int on);
  * ltpf_active, nbits_ltpf), xq [S][ne] i16. */
 int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* hand, int16_t* xq, void* cuda_stream);
 /* Profiling hook, like lc3b_decoder_set_stage_mask: bit 0 = MDCT kernel, bit 1 = attack/LTPF analysis kernel,
- * bit 2 = SNS kernel (with the bandwidth detector), bit 3 = TNS kernel, bit 4 = quantise kernel, bit 5 = bitstream
- * kernel.  Default 63 (all). */
+ * bit 2 = SNS kernel (with the bandwidth detector), bit 3 = TNS kernel, bit 4 = quantise kernel, bit 5 = the
+ * bitstream stage (prepare, range coder, finish kernels).  Default 63 (all). */
 int lc3b_encoder_set_stage_mask(lc3b_encoder* h, int mask);
 void lc3b_encoder_destroy(lc3b_encoder* h);
 
