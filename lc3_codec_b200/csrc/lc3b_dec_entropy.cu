@@ -1,4 +1,4 @@
-// lc3b engine, decoder kernel 1 of 2: bitstream -> shaped spectrum, one THREAD per frame.
+// lc3b engine, decoder kernels 1a and 1b: bitstream -> shaped spectrum, one THREAD per frame.
 //
 // Replaces, per stream, the first half of DecoderChannel::decode (src/decoder/lc3_decoder.rs:73-135):
 //   side_info_reader::read            src/decoder/side_info_reader.rs:29

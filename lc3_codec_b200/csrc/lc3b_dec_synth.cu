@@ -14,8 +14,9 @@
 // 4*nf B out, PCM 2*nf B out).
 // ltpf_kernel (streams whose post filter is, or was in the previous frame, active): the IIR itself; for those streams
 // synth_kernel leaves x_hat in a side buffer (the ring block keeps the samples long pitch lags still reach), and this
-// kernel writes the filtered signal to the ring block and the PCM row.  The recursion only reaches back p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are
-// computed in parallel per step.  Streams outside such a span cost this kernel one flag load.
+// kernel writes the filtered signal to the ring block and the PCM row.  The recursion only reaches back
+// p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are computed in parallel per step.  Streams outside
+// such a span cost this kernel one flag load.
 #include "lc3b_common.cuh"
 #include "lc3b_imdct.cuh"
 #include "lc3b_math.cuh"
