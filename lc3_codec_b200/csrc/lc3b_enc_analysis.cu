@@ -123,11 +123,13 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_mdct_kernel(AnalysisParams
     int16_t* thist = p.thist + (size_t)stream * (nf - z);
 
     // ---- update_time_buffer (modified_dct.rs:126-138)
-    WARP_STRIDE(n, nf - z) tb[n] = thist[n];
-    WARP_STRIDE(n, nf) tb[nf - z + n] = in[n];
-    WARP_STRIDE(n, z) tb[2 * nf - z + n] = 0;
+    // samples move two at a time: nf, z and nf - z are even, the history rows are 4-byte aligned, the input row usually is
+    WARP_STRIDE(n, (nf - z) / 2) ((uint32_t*)tb)[n] = ((const uint32_t*)thist)[n];
+    if (((uintptr_t)in & 3) == 0) { WARP_STRIDE(n, nf / 2) ((uint32_t*)(tb + nf - z))[n] = ((const uint32_t*)in)[n]; }
+    else { WARP_STRIDE(n, nf) tb[nf - z + n] = in[n]; }
+    WARP_STRIDE(n, z / 2) ((uint32_t*)(tb + 2 * nf - z))[n] = 0u;
     __syncwarp();
-    WARP_STRIDE(n, nf - z) thist[n] = tb[nf + n];
+    WARP_STRIDE(n, (nf - z) / 2) ((uint32_t*)thist)[n] = ((const uint32_t*)(tb + nf))[n];
     // ---- window + fold (:73-97)
     {
         const int mid = 3 * half;
@@ -223,9 +225,25 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
     const int up = c.up, ns_keep = 240 / up;
     {   // x_s_extended (long_term_post_filter.rs:217-224): last 240/up samples of the previous frame, then this frame
         int16_t* xh = p.xs_hist + (size_t)stream * 64;
-        WARP_STRIDE(n, ns_keep) xs[n] = (float)xh[n];
-        WARP_STRIDE(n, nf) xs[ns_keep + n] = (float)x[n];
-        WARP_STRIDE(n, ns_keep) xh[n] = x[nf - ns_keep + n];
+        // two samples per load (ns_keep and nf are even; the history rows are 128 bytes apart, the input row usually aligned)
+        auto lo16 = [](uint32_t w) { return (float)(int16_t)(w & 0xffffu); };
+        auto hi16 = [](uint32_t w) { return (float)(int16_t)(w >> 16); };
+        WARP_STRIDE(n, ns_keep / 2) {
+            const uint32_t w = ((const uint32_t*)xh)[n];
+            xs[2 * n] = lo16(w);
+            xs[2 * n + 1] = hi16(w);
+        }
+        if (((uintptr_t)x & 3) == 0) {
+            WARP_STRIDE(n, nf / 2) {
+                const uint32_t w = ((const uint32_t*)x)[n];
+                xs[ns_keep + 2 * n] = lo16(w);
+                xs[ns_keep + 2 * n + 1] = hi16(w);
+            }
+            WARP_STRIDE(n, ns_keep / 2) ((uint32_t*)xh)[n] = ((const uint32_t*)(x + nf - ns_keep))[n];
+        } else {
+            WARP_STRIDE(n, nf) xs[ns_keep + n] = (float)x[n];
+            WARP_STRIDE(n, ns_keep) xh[n] = x[nf - ns_keep + n];
+        }
     }
     __syncwarp();
     const float* xcur = xs + ns_keep;                // this frame's samples in shared memory

@@ -7,7 +7,7 @@ Run on the B200 box: python -m pytest tests -m gpu
 import numpy as np
 import pytest
 
-from common import assert_encoder_parity, gpu_encode
+from common import assert_encoder_parity, corpus, gpu_encode
 from conftest import load_golden
 from tools.corpus import MIXED_NBYTES
 
@@ -71,6 +71,26 @@ def test_pipelined_host_entry_point():
         enc.encode_frames_host(host_in[f], host_out[f])      # no synchronisation between calls
     torch.cuda.synchronize()
     assert np.array_equal(host_out.numpy().transpose(1, 0, 2), o_frames)
+
+
+def test_odd_pcm_stride_and_unaligned_rows():
+    """pcm_in rows at an odd sample pitch / 2-byte-aligned base take the kernels' one-sample load path; same bytes."""
+    import torch
+
+    import lc3_codec_b200 as L
+    for fs, ms, nb in ((48000, 10, 120), (16000, 7.5, 30)):
+        pcm, o_frames = corpus(fs, ms, nb, 40, 6)
+        sf, fd = L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)
+        ws = torch.empty(L.Lc3BatchEncoder.calc_working_buffer_lengths(40, fd, sf, nb), dtype=torch.uint8, device="cuda:0")
+        enc = L.Lc3BatchEncoder(40, fd, sf, ws, nb)
+        nf = enc.nf
+        backing = torch.zeros(40 * (nf + 3) + 1, dtype=torch.int16, device="cuda:0")
+        view = backing[1:].view(40, nf + 3)[:, :nf]            # base 2-byte aligned only, pitch nf + 3 (odd)
+        out = torch.zeros((40, nb), dtype=torch.uint8, device="cuda:0")
+        for f in range(6):
+            view.copy_(torch.from_numpy(np.ascontiguousarray(pcm[:, f])).cuda())
+            enc.encode_frames(view, out)
+            assert np.array_equal(out.cpu().numpy(), o_frames[:, f])
 
 
 def test_8k_rejected_like_the_reference():
