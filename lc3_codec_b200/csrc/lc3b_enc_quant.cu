@@ -928,7 +928,8 @@ __device__ int residual_bits_w(int ne, const float* xf, const int16_t* xq, float
 
 // ---------------------------------------------------------------- noise_level_estimation.rs:21-55
 // The qualifying lines' |x|/gg replace the spectrum in place (0 elsewhere), then one chain adds them in line order.
-__device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, int bw_ind, float gg, int lane) {
+__device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, int bw_ind, float gg, int lane, int wib, int n_live,
+                              size_t warp_bytes) {
     const bool d10 = c.n_ms == LC3B_10MS;
     const int bw_stop = d10 ? 80 * (bw_ind + 1) : 60 * (bw_ind + 1);
     const int nf_start = d10 ? 24 : 18, nf_width = d10 ? 3 : 2;
@@ -965,9 +966,18 @@ __device__ int noise_factor_w(const EncConfig& c, float* xf, const int16_t* xq, 
         if (quiet) xf[count + __popc(qm & ((1u << lane) - 1u))] = val;
         count += __popc(qm);
     }
-    __syncwarp();
-    float sum = 0.0f;
-    for (int i = 0; i < count; i++) sum += xf[i];
+    // the ordered sum is one chain per frame: the CTA's chains run side by side on the first lanes of warp 0
+    if (lane == 0) ((int*)xf)[NE_MAX - 1] = count;                   // count <= ne - 24, so the last slot is free
+    asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+    if (wib == 0 && lane < n_live) {
+        float* oxf = (float*)((uint8_t*)xf + (size_t)lane * warp_bytes);   // warp `lane`'s spectrum buffer (this is warp 0)
+        const int n = ((const int*)oxf)[NE_MAX - 1];
+        float acc = 0.0f;
+        for (int i = 0; i < n; i++) acc += oxf[i];
+        oxf[NE_MAX - 2] = acc;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(n_live * 32) : "memory");
+    const float sum = xf[NE_MAX - 2];
     const float level = count > 0 ? sum / (float)count : 0.0f;
     const float diff = 8.0f - 16.0f * level;
     if (diff >= 0.0f) {
@@ -1553,9 +1563,10 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_prepare_kernel(QuantParams
     uint8_t* out = (uint8_t*)(symq + p.sym_cap + 1);              // [out_words * 4] (zeroed here, filled by the range coder kernel)
     {
         const float4* gx = (const float4*)(p.xf + (size_t)stream * ne);
-        WARP_STRIDE_R(i, ne / 4) ((float4*)xf)[i] = gx[i];
+        // (the kernel's first loads stay unrolled: all of them in flight at once)
+        WARP_STRIDE(i, ne / 4) ((float4*)xf)[i] = gx[i];
         const uint32_t* gq = (const uint32_t*)(p.xq + (size_t)stream * ne);
-        WARP_STRIDE_R(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
+        WARP_STRIDE(i, ne / 2) ((uint32_t*)xq)[i] = gq[i];
         if (lane < TAIL_WORDS) tail[lane] = 0;
     }
     BwRes bw;
@@ -1568,7 +1579,7 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_prepare_kernel(QuantParams
     int n_res = 0;
     if (!q.lsb_mode) n_res = residual_bits_w(ne, xf, xq, q.gg, q.nbits_spec - q.nbits_trunc + 4, tail, lane);
     __syncwarp();
-    h.nf_factor = noise_factor_w(c, xf, xq, bw.bw, q.gg, lane);
+    h.nf_factor = noise_factor_w(c, xf, xq, bw.bw, q.gg, lane, wib, min(QW, p.n_streams - blockIdx.x * QW), (size_t)p.w_bytes);
     bs_prepare_w(c, h, xq, side, p.side_words, tail, symq, p.sym_cap, out, p.out_words, job, lane);
     if (lane == 0) { job->pad = n_res | (h.nf_factor << 16); }
     __syncwarp();
