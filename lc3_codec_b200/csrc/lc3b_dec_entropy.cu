@@ -13,7 +13,8 @@
 // parallel axis is frames: lane = frame, a warp = 32 consecutive streams, all lanes walk the same line
 // index k so that the per-line traffic is coalesced:
 //   * the frame bytes of the CTA are staged once into shared memory (rows padded to an odd word count);
-//   * pass 1 (entropy) writes integers to a lane-interleaved scratch  xq[warp][k][lane]  (128 B per warp store);
+//   * pass 1 (entropy) writes integers to a lane-interleaved scratch  xq[warp][k / 4][lane][k % 4]  (a tuple is one
+//     8-byte store, four lines are one 16-byte load for pass 2; a warp's accesses are contiguous);
 //   * pass 2 (dequantise + noise fill + gain + TNS lattice + SNS gain) streams them back, and hands the
 //     f32 spectrum to a 32x33 shared tile per warp that is flushed as 128-byte row segments into the
 //     stream-major spectrum slot  spec[slot][stream][k].
@@ -109,6 +110,10 @@ struct Reader {
 };
 
 struct AcState { uint32_t low, range; };
+
+// Offset of line k in a thread's slice of the integer scratch xq[block32][k / 4][lane][k % 4] (int32 units, relative to
+// the thread's base pointer, which already carries lane * 4).
+__device__ __forceinline__ int xq_off(int k) { return (k >> 2) * 128 + (k & 3); }
 
 // q = floor(low / tmp) for low < 2^24, 64 <= tmp < 2^14: the float quotient is within 1 of the truth, fix it up exactly
 __device__ __forceinline__ uint32_t exact_quotient(uint32_t low, uint32_t tmp) {
@@ -319,14 +324,13 @@ static_assert(HO_RC_I + 16 == HO_WORDS, "hand-off record size");
 // dequant_kernel:
 //   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
 //   tile    (T/32)*16*33*4  per-warp transpose tile for the spectrum write-out (16 lines at a time)
-//   ring    8*T*4           per-thread prefetch ring (cp.async from the xq scratch)
 //   band    68*4            I_fs band edges
 //   rows    T*row_pitch     staged frame bytes (residual bits)
 __host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
     return 4096 + 2048 + 64 * 20 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 2 * ENT_THREADS * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 __host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
-    return 16 * ENT_THREADS * 4 + (ENT_THREADS / 32) * 16 * 33 * 4 + 8 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
+    return 16 * ENT_THREADS * 4 + (ENT_THREADS / 32) * 16 * 33 * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 
 __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p) {
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
     rd.tw = 0;
     rd.tw_n = 0;
     const int nbits = rd.len * 8;
-    int32_t* xq = p.xq + ((size_t)((stream0 + tid) >> 5) * ne) * 32 + lane;   // thread-private column, element k at xq[k * 32]
+    int32_t* xq = p.xq + ((size_t)((stream0 + tid) >> 5) * ne) * 32 + lane * 4;   // thread-private slice, line k at xq[xq_off(k)]
 
     SideInfoD si;
     bool ok = live && read_side_info(rd, c, si);
@@ -522,8 +526,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
                 if (xa_ > 0) { xa_ = (sg & 1u) ? -xa_ : xa_; sg >>= 1; }
                 if (xb_ > 0) xb_ = (sg & 1u) ? -xb_ : xb_;
                 if (!bad) {
-                    xq[(2 * k) * 32] = xa_;
-                    xq[(2 * k + 1) * 32] = xb_;
+                    *(int2*)(xq + xq_off(2 * k)) = make_int2(xa_, xb_);   // lines 2k, 2k + 1 share a 16-byte group
                 }
                 seed_acc += (uint32_t)abs(xa_) * (uint32_t)(2 * k) + (uint32_t)abs(xb_) * (uint32_t)(2 * k + 1);
                 lev_word |= (si.lsb_mode && lev2 > 0) ? (1u << (k & 31)) : 0u;   // save_lev[k], QUIRK (i)
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
                 left--;
                 if (bit) {
                     const int idx = k + j;
-                    int v = xq[idx * 32];
+                    int v = xq[xq_off(idx)];
                     if (v > 0) { v += 1; seed_acc += (uint32_t)idx; }
                     else if (v < 0) { v -= 1; seed_acc += (uint32_t)idx; }
                     else {
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
                         v = bit ? -1 : 1;
                         seed_acc += (uint32_t)idx;
                     }
-                    xq[idx * 32] = v;
+                    xq[xq_off(idx)] = v;
                 }
             }
         }
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
     if (live) {
         if (p.status_out) p.status_out[stream] = ok ? 0 : 1;
         if (p.trace) {
-            const bool is_zero_frame = ok && si.lastnz == 2 && xq[0] == 0 && xq[32] == 0 && si.gg_ind == 0;
+            const bool is_zero_frame = ok && si.lastnz == 2 && xq[0] == 0 && xq[1] == 0 && si.gg_ind == 0;
             int32_t* tr = p.trace + (size_t)stream * LC3B_TRACE_WORDS;
             for (int i = 0; i < LC3B_TRACE_WORDS; i++) tr[i] = 0;
             tr[LC3B_TR_OK] = ok;
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
                 int n_nonzero_used = 0;
                 if (!si.lsb_mode) {
                     int cnt = 0;
-                    for (int k = 0; k < si.lastnz && cnt < nres; k++) if (xq[k * 32] != 0) cnt++;
+                    for (int k = 0; k < si.lastnz && cnt < nres; k++) if (xq[xq_off(k)] != 0) cnt++;
                     n_nonzero_used = cnt;
                 }
                 tr[LC3B_TR_NRES] = n_nonzero_used;
@@ -632,7 +635,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
         }
         if (p.trace_x) {
             int32_t* tx = p.trace_x + (size_t)stream * ne;
-            for (int k = 0; k < ne; k++) tx[k] = (ok && k < si.lastnz) ? xq[k * 32] : 0;
+            for (int k = 0; k < ne; k++) tx[k] = (ok && k < si.lastnz) ? xq[xq_off(k)] : 0;
         }
     }
 }
@@ -646,8 +649,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     extern __shared__ __align__(16) uint8_t smem[];
     float* s_scf = (float*)smem;
     float* s_tile = s_scf + 16 * ENT_THREADS;
-    int32_t* s_ring = (int32_t*)(s_tile + (ENT_THREADS / 32) * 16 * 33);
-    int32_t* s_band = s_ring + 8 * ENT_THREADS;
+    int32_t* s_band = (int32_t*)(s_tile + (ENT_THREADS / 32) * 16 * 33);
     uint8_t* s_rows = (uint8_t*)(s_band + 68);
 
     const DevConfig& c = *p.cfg;
@@ -680,7 +682,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     rd.head = ho[HO_HEAD];
     rd.tail = ho[HO_TAIL];
     const int nbits = rd.len * 8;
-    int32_t* xq = p.xq + ((size_t)((stream0 + tid) >> 5) * ne) * 32 + lane;   // thread-private column, element k at xq[k * 32]
+    int32_t* xq = p.xq + ((size_t)((stream0 + tid) >> 5) * ne) * 32 + lane * 4;   // thread-private slice, line k at xq[xq_off(k)]
 
     for (int i = tid; i < 65; i += ENT_THREADS) s_band[i] = p.cfg->band_idx[i];
     // the frame bytes are only needed again for the residual bits (non-lsb mode); stage them when any frame of the CTA has some
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     int lastnz = 0;
     if (ok) {
         lastnz = si.lastnz;
-        const int x0 = xq[0], x1 = xq[32];
+        const int x0 = xq[0], x1 = xq[1];
         is_zero_frame = si.lastnz == 2 && x0 == 0 && x1 == 0 && si.gg_ind == 0;
         {                                                              // global_gain.rs:15-25
             const int fs = c.fs_ind + 1;
@@ -801,26 +803,33 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
         int res_used = 0;
-        // The integers come back from the lane-interleaved scratch through a 16-slot per-thread ring filled by
-        // cp.async PF lines ahead, so the L2 round trip never sits on the serial per-line chain.
-        constexpr int PF = 6;
-        int32_t* ring = s_ring + tid;                                  // slot e at ring[(e & 7) * ENT_THREADS]
-        const int n_valid = ok ? lastnz : 0;                           // lines >= lastnz are zero and never fetched
-        auto issue = [&](int e) {
-            if (e < n_valid) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (e & 7) * ENT_THREADS);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(xq + e * 32));
+        // The integers come back four lines at a time (one 16-byte load per thread and group), one group ahead of the
+        // group in use, so the L2 round trip never sits on the serial per-line chain; the group in use is shifted down
+        // one element per line.  Groups beyond the frame's lastnz are not fetched (their lines read as zero).
+        const int n_valid = ok ? lastnz : 0;
+        const int4* xg = (const int4*)xq;                              // group g of this thread at xg[g * 32]
+        const int4 zero4 = make_int4(0, 0, 0, 0);
+        int4 g = 0 < n_valid ? xg[0] : zero4;
+        int4 gn = 4 < n_valid ? xg[32] : zero4;
+        int jpos = 0;                                                  // next line to pop
+        auto pop = [&]() -> int32_t {
+            const int32_t v = jpos < n_valid ? g.x : 0;
+            g.x = g.y; g.y = g.z; g.z = g.w;
+            jpos++;
+            if ((jpos & 3) == 0) {                                     // warp-uniform: every lane pops the same line
+                g = gn;
+                const int nxt = jpos + 4;
+                gn = nxt < n_valid ? xg[(nxt >> 2) * 32] : zero4;
             }
-            asm volatile("cp.async.commit_group;\n" ::);
+            return v;
         };
 #pragma unroll
         for (int j = 0; j <= W; j++) win[j] = 0;
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            win[j + 1] = j < n_valid ? xq[j * 32] : 0;
+            win[j + 1] = pop();
             if (win[j + 1] != 0 && j < bw_stop) last_nz = j;
         }
-        for (int e = W; e < W + PF; e++) issue(e);
         // lines are walked band by band (the last band runs to ne), so no per-line band-edge test is needed
         int k = 0;
         for (int band = 0; band < nb; band++) {
@@ -831,9 +840,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
             for (int j = 0; j < W; j++) win[j] = win[j + 1];
             {
                 const int j = k + W;
-                issue(j + PF);
-                asm volatile("cp.async.wait_group %0;\n" ::"n"(PF));
-                win[W] = j < n_valid ? ring[(j & 7) * ENT_THREADS] : 0;
+                win[W] = pop();
                 if (win[W] != 0 && j < bw_stop) last_nz = j;
             }
             const int32_t xi = win[0];
