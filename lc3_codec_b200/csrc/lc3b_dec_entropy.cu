@@ -15,9 +15,8 @@
 //   * the frame bytes of the CTA are staged once into shared memory (rows padded to an odd word count);
 //   * pass 1 (entropy) writes integers to a lane-interleaved scratch  xq[warp][k / 4][lane][k % 4]  (a tuple is one
 //     8-byte store, four lines are one 16-byte load for pass 2; a warp's accesses are contiguous);
-//   * pass 2 (dequantise + noise fill + gain + TNS lattice + SNS gain) streams them back, and hands the
-//     f32 spectrum to a 32x33 shared tile per warp that is flushed as 128-byte row segments into the
-//     stream-major spectrum slot  spec[slot][stream][k].
+//   * pass 2 (dequantise + noise fill + gain + TNS lattice + SNS gain) streams them back and writes the f32
+//     spectrum four lines at a time (16 bytes per thread) into the stream-major slot  spec[slot][stream][k].
 // The spectrum slot written is the stream's INACTIVE one; it becomes the active slot (= PLC "last good",
 // packet_loss_concealment.rs:50) only if the frame decoded without error, so concealment needs no copy.
 // All f32 arithmetic uses contraction-proof ops in the reference's order: the spectrum is bit-exact.
@@ -210,7 +209,6 @@ struct SideInfoD {
 // side_info_reader.rs:29-200
 __device__ bool read_side_info(Reader& rd, const DevConfig& c, SideInfoD& s) {
     uint32_t v;
-    int b;
     s.bw = 0;
     if (c.nbits_bw > 0) {
         if (!rd.tail_uint(c.nbits_bw, v)) return false;
@@ -323,14 +321,13 @@ static_assert(HO_RC_I + 16 == HO_WORDS, "hand-off record size");
 //   rows    T*row_pitch     staged frame bytes
 // dequant_kernel:
 //   scf     16*T*4          per-thread SNS scale factors (also the PVQ vector while de-enumerating)
-//   tile    (T/32)*16*33*4  per-warp transpose tile for the spectrum write-out (16 lines at a time)
 //   band    68*4            I_fs band edges
 //   rows    T*row_pitch     staged frame bytes (residual bits)
 __host__ __device__ inline size_t entropy_smem_bytes(int row_pitch) {
     return 4096 + 2048 + 64 * 20 * 4 + (2 * 8 + 8 * 17) * 4 + 7 * ENT_THREADS * 4 + 2 * ENT_THREADS * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 __host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
-    return 16 * ENT_THREADS * 4 + (ENT_THREADS / 32) * 16 * 33 * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
+    return 16 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 
 __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p) {
@@ -648,12 +645,11 @@ template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
 __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* s_scf = (float*)smem;
-    float* s_tile = s_scf + 16 * ENT_THREADS;
-    int32_t* s_band = (int32_t*)(s_tile + (ENT_THREADS / 32) * 16 * 33);
+    int32_t* s_band = (int32_t*)(s_scf + 16 * ENT_THREADS);
     uint8_t* s_rows = (uint8_t*)(s_band + 68);
 
     const DevConfig& c = *p.cfg;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int stream0 = blockIdx.x * ENT_THREADS;
     const int ne = c.ne;
 
@@ -787,7 +783,6 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
         return exp2_raw_fm(s);
     };
 
-    float* tile = s_tile + wid * 16 * 33;
     // rows of one warp belong to arbitrary streams of the CTA (work sorting) and may sit in different slots
     // (a slot only flips on a good frame): every row is addressed through its own stream id and slot
     const size_t slot_stride = (size_t)p.n_streams * ne;
@@ -799,6 +794,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
         float rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // coefficient set in use
         int ord = 0, om = 0;                     // this lane's order in use, the warp's largest
         int tns_phase = 0, tns_next = ok ? tns_s0 : 0x7fffffff;   // next line at which this lane switches filters
+        float4 vq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // the finished lines of the current group of four
         int32_t win[W + 1];                 // win[0] = x[k], win[j] = x[k + j]
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
@@ -906,21 +902,10 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
                 }
             }
             v = ok ? xm(v, gband) : v;
-            // transpose through the warp tile, flush every 32 lines
-            tile[(k & 15) * 33 + lane] = v;
-            if ((k & 15) == 15 || k == ne - 1) {
-                __syncwarp();
-                // 16 lines x 32 rows: two rows per pass, each half-warp writes one row's 64-byte segment
-                const int k0 = k & ~15, cnt = (k & 15) + 1;
-                const int hl = lane & 15, hw = lane >> 4;
-                for (int r2 = 0; r2 < 32; r2 += 2) {
-                    const int r = r2 + hw;
-                    const bool row_ok = __shfl_sync(0xffffffffu, (int)ok, r);
-                    const long long row_off = __shfl_sync(0xffffffffu, my_row_off_ll, r);
-                    if (row_ok && hl < cnt) p.spec[row_off + k0 + hl] = tile[hl * 33 + r];
-                }
-                __syncwarp();
-            }
+            // four finished lines leave as one 16-byte store into the thread's own stream-major row (the two halves of
+            // a 32-byte sector are written four lines apart and meet in L2)
+            if ((k & 3) == 0) vq.x = v; else if ((k & 3) == 1) vq.y = v; else if ((k & 3) == 2) vq.z = v; else vq.w = v;
+            if ((k & 3) == 3 && ok) *(float4*)(p.spec + my_row_off_ll + (k & ~3)) = vq;
         }
         }
     }
