@@ -123,6 +123,18 @@ __device__ __forceinline__ uint32_t exact_quotient(uint32_t low, uint32_t tmp) {
     return q;
 }
 
+// The spectral loop's version: min(floor(low / tmp), 1023) or 1024 with fewer integer-pipe operations.  low and tmp are
+// exact in f32; the reciprocal estimate (relative error < 2^-21.4 after the multiply) scaled by 1 - 2^-20 lies below the
+// true quotient by less than 0.002 whenever that quotient is below 1024, so its truncation is q or q - 1 and one
+// upward fix-up suffices.  Quotients >= 1024 only occur on frames the caller has already marked bad.
+__device__ __forceinline__ uint32_t quotient_spec(uint32_t low, uint32_t tmp) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)tmp));
+    uint32_t q = min((uint32_t)__fmul_rn(__fmul_rn((float)low, r), 0.99999904632568359375f), 1023u);
+    if (low - q * tmp >= tmp) q += 1;
+    return q;
+}
+
 __device__ __forceinline__ bool ac_finish(Reader& rd, AcState& st, uint32_t tmp, uint32_t e) {
     st.low -= tmp * (e & 0xffffu);
     st.range = tmp * (e >> 16);
@@ -474,7 +486,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
             // ac_decode :67-97
             const uint32_t tmp = range >> 10;
             bad |= low >= (tmp << 10);                                  // AcRangeFlOutOfRange
-            const uint32_t q = min(exact_quotient(low, tmp), 1023u);
+            const uint32_t q = quotient_spec(low, tmp);
             int val = s_clut[pki * 32 + (q >> 5)];
             for (;;) {                                                  // almost always a single round
                 const uint32_t c1 = tab[val + 1] & 0xffffu, c2 = tab[val + 2] & 0xffffu, c3 = tab[val + 3] & 0xffffu;
