@@ -574,6 +574,10 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
         // save_lev[] is only ever written for tuple indices < lastnz/2 and is zero beyond, so the walk can stop there.
         for (int k = 0; k < (si.lastnz >> 1) && !stop; k += 2) {
             if (!((s_lev[(k >> 5) * ENT_THREADS + tid] >> (k & 31)) & 1u)) continue;
+            // lines k and k + 1 (k even) are one 8-byte half of a group: one load, one store, instead of a dependent
+            // round trip to L2 per refined line
+            int2 vv = *(const int2*)(xq + xq_off(k));
+            bool touched = false;
 #pragma unroll
             for (int j = 0; j < 2; j++) {                               // read_res_bit :346
                 if (stop) break;
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
                 left--;
                 if (bit) {
                     const int idx = k + j;
-                    int v = xq[xq_off(idx)];
+                    int v = j == 0 ? vv.x : vv.y;
                     if (v > 0) { v += 1; seed_acc += (uint32_t)idx; }
                     else if (v < 0) { v -= 1; seed_acc += (uint32_t)idx; }
                     else {
@@ -593,9 +597,11 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
                         v = bit ? -1 : 1;
                         seed_acc += (uint32_t)idx;
                     }
-                    xq[xq_off(idx)] = v;
+                    if (j == 0) vv.x = v; else vv.y = v;
+                    touched = true;
                 }
             }
+            if (touched) *(int2*)(xq + xq_off(k)) = vv;
         }
     }
 
