@@ -193,12 +193,51 @@ def cpu_baseline(w, target_s: float = 8.0):
                       "C++ restatement of lc3-codec (the Rust reference cannot be built here)"}
 
 
+def cpu_baseline_mixed(target_s: float = 8.0):
+    """Oracle on all host cores over the twelve configurations of the mixed-rate batch, equal stream counts each (as in
+    the batch): total frames / total time."""
+    from oracle import pyoracle as O
+    from tools.corpus import MIXED_NBYTES, make_pcm
+    cores = O.ncores()
+    n = max(cores * 8, 64)
+    samples = []
+    for (fs, ms), nb in sorted(MIXED_NBYTES.items()):
+        nf = O.config(fs, ms)["nf"]
+        if fs == 8000:                  # no 8 kHz encoder in the reference: the committed oracle-encoded fixture
+            fr = np.load(ROOT / "tests" / "golden" / f"bench_mixed_8k_{str(ms).replace('.', 'p')}ms.npy")
+            fr = np.ascontiguousarray(fr[np.arange(n) % fr.shape[0]])
+        else:
+            fr = O.encode_streams(make_pcm(n, 8, fs, nf), fs, ms, nb)
+        samples.append((fs, ms, np.ascontiguousarray(np.tile(fr, (1, 8, 1)))))
+    for fs, ms, fr in samples:
+        O.decode_streams(fr, fs, ms, nthreads=cores)                # warm
+    t0, units, reps = time.perf_counter(), 0, 0
+    while time.perf_counter() - t0 < target_s:
+        for fs, ms, fr in samples:
+            O.decode_streams(fr, fs, ms, nthreads=cores)
+            units += fr.shape[0] * fr.shape[1]
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": units / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x (12 configurations x {n} streams x 64 frames), {dt:.1f} s, one thread per core, "
+                      "C++ restatement of lc3-codec (the Rust reference cannot be built here)"}
+
+
 def run_reference(args, w, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     if rank != 0:
         return
     from oracle import pyoracle as O
     cores = O.ncores()
+    if w["mode"] == "mixed":                 # twelve configurations: the cpu_baseline leg's own loop, bounded in time
+        cb = cpu_baseline_mixed(target_s=min(30.0, 0.1 * max(args.steps, 10)))
+        emit(({"impl": "reference", "metric": w["metric"], "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": w["desc"], "note": "CPU path; bounded sample, see cpu_baseline.sample"},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     frames, pcm = cpu_sample(w, cores)
     for _ in range(args.warmup):
         cpu_run(w, frames, pcm, cores)
@@ -335,7 +374,7 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
     step_ms = ms_total / args.steps
     achieved = algo / (step_ms * 1e-3) / 1e9
     if rank == 0:
-        cb = None
+        cb = cpu_baseline_mixed() if (world == 1 and not args.no_cpu_baseline) else None
         emit(({
             "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
