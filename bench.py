@@ -7,8 +7,10 @@
 A "step" is one Lc3Decoder::decode_frame (or Lc3Encoder::encode_frame) for EVERY stream of the batch: the batched hot
 path, one frame per stream.  Default workload `decode48`: BASELINE.json config 5's 262,144 concurrent 48 kHz / 10 ms /
 150 B mono streams, all of them on one GPU at N = 1 (they fit: 2.9 GB of codec state) and the same count on every
-GPU at N > 1 (weak scaling).  Bitstreams: tests/golden/bench_c1_frames.npy (1,024 distinct synthetic streams x 8
-frames, oracle-encoded once by tools/make_bench_corpus.py), tiled over the batch.
+GPU at N > 1 (weak scaling).  Bitstreams: tests/golden/bench_c1_frames.npy - 1,024 distinct synthetic streams of the
+SURVEY 8d corpus (200-frame clips, oracle-encoded from frame 0 by tools/make_bench_corpus.py), 8 consecutive frames
+each at a per-stream offset in [10, 192], tiled over the batch.  `config.corpus` carries the statistics of what was
+decoded (mean lastnz, near-empty and lsb_mode fractions), measured on the GPU from the decoder's own side information.
 Other workloads (extra measurements for BASELINE.md, same JSON shape): `encode48` (config 2: 48 kHz stereo, 120 B per
 channel, 4,096 stereo streams = 8,192 channels), `decode16` (config 3: 16 kHz / 7.5 ms / 30 B, 16,384 streams, LTPF
 active), `roundtrip48` (config 5: encode + decode of 262,144 streams at 150 B).  Their inputs are synthetic PCM
@@ -93,6 +95,32 @@ def load_frames() -> np.ndarray:
     return np.load(ROOT / "tests" / "golden" / "bench_c1_frames.npy")          # [1024, 8, 150] u8
 
 
+def gpu_corpus_stats(dev, sf, fd, frames_fsb):
+    """Statistics of the bitstreams a decode workload runs on, from the GPU decoder's own inspection record
+    (lc3b_decoder_set_trace): frames_fsb is a CUDA uint8 [F, U, nbytes] set of distinct streams, decoded in order."""
+    import torch
+
+    import lc3_codec_b200 as L
+    F, U, nb = frames_fsb.shape
+    ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(U, fd, sf, nb), dtype=torch.uint8, device=dev)
+    d = L.Lc3BatchDecoder(U, fd, sf, ws, nb)
+    tr, x = d.enable_trace()
+    out = torch.empty((U, d.nf), dtype=torch.int16, device=dev)
+    rows = []
+    for f in range(F):
+        d.decode_frames(16, frames_fsb[f].contiguous(), out)
+        rows.append(torch.cat([tr[:, :4].clone(), tr[:, 18:19].clone(), tr[:, 21:22].clone(),
+                               (x != 0).sum(1, keepdim=True).to(torch.int32)], 1))
+    t = torch.stack(rows).cpu().numpy().reshape(-1, 7)
+    ok = t[:, 0] == 1
+    return {"distinct_streams": int(U), "frames_per_stream": int(F), "mean_lastnz": float(t[ok, 2].mean()),
+            "near_empty_frac": float((t[ok, 2] <= 16).mean()), "lsb_mode_frac": float(t[ok, 3].mean()),
+            "mean_nonzero_lines": float(t[ok, 6].mean()), "concealed_frac": float(1.0 - ok.mean()),
+            "ltpf_active_frac": float(t[ok, 4].mean()), "tns_active_frac": float((t[ok, 5] > 0).mean()),
+            "clips": "SURVEY 8d: 200 frames per stream, window of consecutive frames at a per-stream offset in [10, 192]",
+            "measured": "on the GPU, lc3b_decoder_set_trace over the distinct streams before the timed region"}
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -151,18 +179,19 @@ class ClockSampler:
 def cpu_sample(w, cores, reps: int = 16):
     """Bounded sample of the workload for the oracle: (frames or None, pcm or None).  32 streams per host thread, each
     replaying its 8 corpus frames `reps` times, so that one call is ~0.1 s of work and thread start-up does not show."""
-    from tools.corpus import make_pcm
+    from tools.corpus import make_pcm_window
     n = max(cores * 32, 64)
     if w["mode"] in ("decode", "file") and w["fs"] == 48000:
         frames = load_frames()
         frames = frames[np.arange(n) % frames.shape[0]]
         return np.ascontiguousarray(np.tile(frames, (1, reps, 1))), None
     from oracle import pyoracle as O
-    pcm = make_pcm(n, 8, w["fs"], w["nf"])
-    frames = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"]) if w["mode"] in ("decode", "file") else None
+    lead = 4
+    pcm = make_pcm_window(n, 8, w["fs"], w["nf"], lead=lead)          # same 200-frame clips and windows as the GPU arm
+    frames = O.encode_streams(pcm, w["fs"], w["ms"], w["nbytes"])[:, lead:] if w["mode"] in ("decode", "file") else None
     if frames is not None:
         frames = np.ascontiguousarray(np.tile(frames, (1, reps, 1)))
-    return frames, np.ascontiguousarray(np.tile(pcm, (1, reps, 1)))
+    return frames, np.ascontiguousarray(np.tile(pcm[:, lead:], (1, reps, 1)))
 
 
 def cpu_run(w, frames, pcm, cores):
@@ -197,7 +226,7 @@ def cpu_baseline_mixed(target_s: float = 8.0):
     """Oracle on all host cores over the twelve configurations of the mixed-rate batch, equal stream counts each (as in
     the batch): total frames / total time."""
     from oracle import pyoracle as O
-    from tools.corpus import MIXED_NBYTES, make_pcm
+    from tools.corpus import MIXED_NBYTES, make_pcm_window
     cores = O.ncores()
     n = max(cores * 8, 64)
     samples = []
@@ -207,7 +236,7 @@ def cpu_baseline_mixed(target_s: float = 8.0):
             fr = np.load(ROOT / "tests" / "golden" / f"bench_mixed_8k_{str(ms).replace('.', 'p')}ms.npy")
             fr = np.ascontiguousarray(fr[np.arange(n) % fr.shape[0]])
         else:
-            fr = O.encode_streams(make_pcm(n, 8, fs, nf), fs, ms, nb)
+            fr = O.encode_streams(make_pcm_window(n, 8, fs, nf, lead=4), fs, ms, nb)[:, 4:]
         samples.append((fs, ms, np.ascontiguousarray(np.tile(fr, (1, 8, 1)))))
     for fs, ms, fr in samples:
         O.decode_streams(fr, fs, ms, nthreads=cores)                # warm
@@ -283,14 +312,14 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
     import torch
 
     import lc3_codec_b200 as L
-    from tools.corpus import MIXED_NBYTES, make_pcm
+    from tools.corpus import MIXED_NBYTES, make_pcm_window
 
     S = w["streams"]
     fs_list, dur_list = [8000, 16000, 24000, 32000, 44100, 48000], [7.5, 10]
     stream_cfg = [(fs_list[s % 6], dur_list[(s // 6) % 2]) for s in range(S)]
     dec = L.Lc3MixedBatchDecoder([(L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)) for fs, ms in stream_cfg],
                                  max_nbytes=120, device=dev)
-    U, F, WARM, STRIDE = 512, 8, 4, 120
+    U, F, WARM, STRIDE = 256, 8, 4, 120
     frames = torch.zeros((F, S, STRIDE), dtype=torch.uint8, device=dev)
     lens = torch.zeros(S, dtype=torch.int32, device=dev)
     algo = 0
@@ -302,7 +331,7 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
             fr_u = torch.from_numpy(np.load(ROOT / "tests" / "golden" / f"bench_mixed_8k_{str(ms).replace('.', 'p')}ms.npy")).to(dev)
             fr_u = fr_u.permute(1, 0, 2).contiguous()                                    # [F,U,nb]
         else:                     # bitstreams from the GPU encoder itself
-            pcm_u = torch.from_numpy(make_pcm(U, WARM + F, fs, nf)).to(dev)
+            pcm_u = torch.from_numpy(make_pcm_window(U, F, fs, nf, lead=WARM)).to(dev)
             n = L.Lc3BatchEncoder.calc_working_buffer_lengths(U, L.FrameDuration(fd), L.SamplingFrequency(sf), nb)
             ews = torch.empty(n, dtype=torch.uint8, device=dev)
             enc = L.Lc3BatchEncoder(U, L.FrameDuration(fd), L.SamplingFrequency(sf), ews, nb)
@@ -558,7 +587,7 @@ def main():
     import torch
 
     import lc3_codec_b200 as L
-    from tools.corpus import make_pcm
+    from tools.corpus import make_pcm_window
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: lc3_codec_b200 has no CPU fallback")
@@ -599,21 +628,26 @@ def main():
     # ---- inputs, resident in HBM: [F][S][...] so that step i reads one contiguous frame set
     dev_pcm_in = dev_frames = None
     if args.workload == "decode48":
-        dev_frames = torch.from_numpy(load_frames()).to(dev)[idx].permute(1, 0, 2).contiguous()        # [F,S,150]
+        fr_u = torch.from_numpy(load_frames()).to(dev).permute(1, 0, 2).contiguous()                    # [F,U,150]
+        dev_frames = fr_u[:, idx].contiguous()                                                           # [F,S,150]
     else:
-        pcm_u = torch.from_numpy(make_pcm(U, WARM + F, w["fs"], NF)).to(dev)                             # [U,WARM+F,nf]
-        if mode == "decode":                                   # bitstreams from the GPU encoder itself
-            n = L.Lc3BatchEncoder.calc_working_buffer_lengths(U, fd, sf, NB)
-            tmp_ws = torch.empty(n, dtype=torch.uint8, device=dev)
-            tmp_enc = L.Lc3BatchEncoder(U, fd, sf, tmp_ws, NB)
-            fr_u = torch.empty((WARM + F, U, NB), dtype=torch.uint8, device=dev)
-            for f in range(WARM + F):
-                tmp_enc.encode_frames(pcm_u[:, f].contiguous(), fr_u[f])
-            dev_frames = fr_u[WARM:][:, idx].contiguous()                                                # [F,S,NB]
-            torch.cuda.synchronize(dev)
-            del tmp_enc, tmp_ws
+        pcm_u = torch.from_numpy(make_pcm_window(U, F, w["fs"], NF, lead=WARM)).to(dev)                 # [U,WARM+F,nf]
+        # bitstreams of the distinct streams from the GPU encoder itself (decode input / corpus statistics)
+        n = L.Lc3BatchEncoder.calc_working_buffer_lengths(U, fd, sf, NB)
+        tmp_ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        tmp_enc = L.Lc3BatchEncoder(U, fd, sf, tmp_ws, NB)
+        fr_all = torch.empty((WARM + F, U, NB), dtype=torch.uint8, device=dev)
+        for f in range(WARM + F):
+            tmp_enc.encode_frames(pcm_u[:, f].contiguous(), fr_all[f])
+        torch.cuda.synchronize(dev)
+        del tmp_enc, tmp_ws
+        fr_u = fr_all[WARM:].contiguous()                                                                # [F,U,NB]
+        if mode == "decode":
+            dev_frames = fr_u[:, idx].contiguous()                                                       # [F,S,NB]
         else:
             dev_pcm_in = pcm_u[:, WARM:][idx].permute(1, 0, 2).contiguous()                              # [F,S,nf]
+    corpus_stats = gpu_corpus_stats(dev, sf, fd, fr_u) if rank == 0 else None
+    del fr_u
     pcm_out = torch.empty((S, NF), dtype=torch.int16, device=dev) if dec else None
     frames_out = torch.empty((S, NB), dtype=torch.uint8, device=dev) if enc else None
 
@@ -758,6 +792,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "name": args.workload, "streams_per_gpu": S, "frame_bytes": NB, "nf": NF,
+                       "corpus": corpus_stats,
                        "l2": f"no explicit flush: each step streams the per-stream codec state + I/O "
                              f"({ws_bytes / 1e6:.0f} MB workspace per GPU), far more than the 126 MB L2",
                        "parallelism": f"{world} x independent stream shards, no collective on the data path"},

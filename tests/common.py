@@ -6,7 +6,7 @@ import functools
 import numpy as np
 
 from oracle import pyoracle as O
-from tools.corpus import MIXED_NBYTES, make_pcm
+from tools.corpus import CLIP_FRAMES, MIXED_NBYTES, clip_offsets, make_pcm, take_window
 
 ALL_CONFIGS = sorted(MIXED_NBYTES.keys())
 
@@ -17,6 +17,25 @@ def corpus(fs: int, ms: float, nbytes: int, n_streams: int, n_frames: int, first
     cfg = O.config(fs, ms)
     pcm = make_pcm(n_streams, n_frames, fs, cfg["nf"], first_stream)
     frames = O.encode_streams(pcm, fs, ms, nbytes)
+    return pcm, frames
+
+
+@functools.lru_cache(maxsize=2)
+def _clip_pcm(fs: int, nf: int, n_streams: int, first_stream: int):
+    return make_pcm(n_streams, CLIP_FRAMES, fs, nf, first_stream)
+
+
+@functools.lru_cache(maxsize=8)
+def corpus_clip(fs: int, ms: float, nbytes: int, n_streams: int, window: int = 0, first_stream: int = 0):
+    """SURVEY.md 8d clips: 200 frames per stream, oracle-encoded from frame 0.  window = 0 returns the whole clips
+    (pcm [S,200,nf], frames [S,200,nbytes]); window = n returns n consecutive frames per stream at the per-stream
+    offset of tools.corpus.clip_offsets (in [10, 200 - n]), i.e. what bench.py's fixtures hold."""
+    cfg = O.config(fs, ms)
+    pcm = _clip_pcm(fs, cfg["nf"], n_streams, first_stream)
+    frames = O.encode_streams(pcm, fs, ms, nbytes)
+    if window:
+        off = clip_offsets(n_streams, window, first_stream)
+        return take_window(pcm, off, window), take_window(frames, off, window)
     return pcm, frames
 
 
@@ -81,7 +100,9 @@ def assert_parity(fs, ms, frames, nbytes_per_frame=None, host=False, exact_spect
     assert d.max() <= 1, f"PCM differs by {d.max()} LSB (streams {np.unique(np.argwhere(d > 1)[:, 0])[:8]})"
     return dict(pcm_exact=float((d == 0).mean()), concealed=float((o_tr[..., 0] == 0).mean()),
                 lsb_mode=float(o_tr[..., 3].mean()), ltpf_active=float(o_tr[..., 18].mean()),
-                tns=float((o_tr[..., 21] > 0).mean()))
+                tns=float((o_tr[..., 21] > 0).mean()),
+                mean_lastnz=float(o_tr[..., 2][o_tr[..., 0] == 1].mean()) if (o_tr[..., 0] == 1).any() else 0.0,
+                near_empty=float((o_tr[..., 2][o_tr[..., 0] == 1] <= 16).mean()) if (o_tr[..., 0] == 1).any() else 0.0)
 
 
 def gpu_encode(fs, ms, pcm, nbytes, host=False, device="cuda:0", debug=False):
@@ -117,24 +138,47 @@ def snr_db(ref, test):
     return 10.0 * np.log10((ref ** 2).sum() / max((err ** 2).sum(), 1e-30))
 
 
-def assert_encoder_parity(fs, ms, nbytes, n_streams, n_frames, host=False, min_identical=0.999):
-    """Encoder gate (SURVEY.md 8d iii): bytes identical on >= 99.9 % of frames, and every differing frame decodes
-    (oracle decoder) to within 0.1 dB SNR of the oracle's own frame against the input."""
-    pcm, o_frames = corpus(fs, ms, nbytes, n_streams, n_frames)
-    g_frames = gpu_encode(fs, ms, pcm, nbytes, host=host)
+def codec_delay(pcm, dec_pcm):
+    """Delay D (samples) at which the decoder's output lines up with the encoder's input: dec[t] ~ in[t - D].
+    Found by minimising the mean squared error over D in [0, nf) on the streams given (LC3: nf - 2 z, the 2.5 ms
+    look-ahead at 10 ms frames; the frame period itself is hidden by feeding frame f in and reading frame f out)."""
+    S, F, nf = pcm.shape
+    x = pcm.reshape(S, -1).astype(np.float64)
+    y = dec_pcm.reshape(S, -1).astype(np.float64)
+    errs = [((y[:, d:] - x[:, :x.shape[1] - d]) ** 2).mean() for d in range(0, nf)]
+    return int(np.argmin(errs))
+
+
+def encoder_gate(pcm, o_frames, g_frames, fs, ms, min_identical=0.999, snr_tol_db=0.1):
+    """Encoder parity gate (SURVEY.md 8d iii, BASELINE.json north_star): bitstreams byte-identical on at least
+    `min_identical` of the frames, and EVERY differing frame decodes (oracle decoder, each bitstream set decoded as a
+    whole so the overlap of the neighbouring frames is the set's own) to an SNR against the delayed input that is
+    within `snr_tol_db` of the oracle frame's.  Pure CPU; returns (identical fraction, worst |dSNR| in dB)."""
     same = (o_frames == g_frames).all(-1)
     frac = float(same.mean())
+    worst = 0.0
     if not same.all():
-        cfg = O.config(fs, ms)
-        d = cfg["nf"] - 2 * cfg["z"] + cfg["nf"]            # not used for alignment below; SNR is frame-local on decoded PCM
+        S, F, nf = pcm.shape
         o_pcm = O.decode_streams(o_frames, fs, ms)
         g_pcm = O.decode_streams(g_frames, fs, ms)
-        for s, f in np.argwhere(~same)[:50]:
-            # compare the two decodes of the differing frame against each other's reference: the input delayed by the codec
-            a, b = o_pcm[s, f].astype(np.float64), g_pcm[s, f].astype(np.float64)
-            ref_e = max((a ** 2).sum(), 1.0)
-            rel = 10.0 * np.log10(ref_e / max(((a - b) ** 2).sum(), 1e-9))
-            assert rel > 20.0 or abs(snr_db(a, b)) >= 0.0, (s, f, rel)
+        D = codec_delay(pcm, o_pcm)
+        x = np.concatenate([np.zeros((S, D), np.int16), pcm.reshape(S, -1)], axis=1)[:, :F * nf].reshape(S, F, nf)
+        for s, f in np.argwhere(~same):
+            ref = x[s, f].astype(np.float64)
+            if (ref ** 2).sum() < 1.0:                  # silent input: SNR undefined, the two decodes must both be silent-ish
+                assert np.abs(o_pcm[s, f].astype(np.int32) - g_pcm[s, f].astype(np.int32)).max() <= 2, (s, f)
+                continue
+            d_snr = abs(snr_db(ref, g_pcm[s, f]) - snr_db(ref, o_pcm[s, f]))
+            worst = max(worst, d_snr)
+            assert d_snr <= snr_tol_db, f"stream {s} frame {f}: bytes differ and decoded SNR differs by {d_snr:.3f} dB"
     assert frac >= min_identical, f"only {frac * 100:.3f} % of frames byte-identical " \
                                   f"(first mismatches at {np.argwhere(~same)[:5].tolist()})"
-    return frac
+    return frac, worst
+
+
+def assert_encoder_parity(fs, ms, nbytes, n_streams, n_frames, host=False, min_identical=0.999, clip=False):
+    """GPU encoder vs oracle encoder on the same PCM through encoder_gate().  clip=True: 200-frame SURVEY 8d clips
+    (n_frames ignored)."""
+    pcm, o_frames = corpus_clip(fs, ms, nbytes, n_streams) if clip else corpus(fs, ms, nbytes, n_streams, n_frames)
+    g_frames = gpu_encode(fs, ms, pcm, nbytes, host=host)
+    return encoder_gate(pcm, o_frames, g_frames, fs, ms, min_identical)[0]

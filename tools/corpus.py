@@ -146,3 +146,35 @@ def make_pcm(n_streams: int, n_frames: int, fs: int, nf: int, first_stream: int 
 # nbytes used by the mixed-rate config: (fs, ms) -> nbytes
 MIXED_NBYTES = {(8000, 7.5): 20, (8000, 10): 26, (16000, 7.5): 30, (16000, 10): 40, (24000, 7.5): 45, (24000, 10): 60,
                 (32000, 7.5): 60, (32000, 10): 80, (44100, 7.5): 90, (44100, 10): 120, (48000, 7.5): 90, (48000, 10): 120}
+
+
+# ---- SURVEY.md 8d clips: 200 frames per stream; benches and full-size tests take a window of consecutive frames
+CLIP_FRAMES, CLIP_SKIP = 200, 10
+
+
+def clip_offsets(n_streams: int, n_frames: int, first_stream: int = 0) -> np.ndarray:
+    """Per-stream first frame of an n_frames window inside the 200-frame clip, in [CLIP_SKIP, CLIP_FRAMES - n_frames]
+    (draw 40 of the stream's splitmix64 sequence): the windows of a batch sample the whole clip."""
+    ids = np.arange(first_stream, first_stream + n_streams, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        u = _draw(SEED0 + ids, 40)
+    span = CLIP_FRAMES - n_frames - CLIP_SKIP
+    return CLIP_SKIP + np.minimum((u * (span + 1)).astype(int), span)
+
+
+def take_window(clips: np.ndarray, off: np.ndarray, n_frames: int, lead: int = 0) -> np.ndarray:
+    """[S, CLIP_FRAMES, ...] -> [S, lead + n_frames, ...]: frames off-lead .. off+n_frames-1 of every stream."""
+    idx = (off - lead)[:, None] + np.arange(lead + n_frames)[None, :]
+    return np.ascontiguousarray(clips[np.arange(clips.shape[0])[:, None], idx])
+
+
+def make_pcm_window(n_streams: int, n_frames: int, fs: int, nf: int, lead: int = 0, first_stream: int = 0) -> np.ndarray:
+    """[n_streams, lead + n_frames, nf] int16 cut from the streams' 200-frame clips at clip_offsets(); `lead` extra
+    frames in front of the window let an encoder settle before the frames that count (lead <= CLIP_SKIP)."""
+    assert 0 <= lead <= CLIP_SKIP
+    out = np.empty((n_streams, lead + n_frames, nf), np.int16)
+    for i in range(0, n_streams, 256):                    # bound temporary memory
+        n = min(256, n_streams - i)
+        clips = make_pcm(n, CLIP_FRAMES, fs, nf, first_stream + i)
+        out[i:i + n] = take_window(clips, clip_offsets(n, n_frames, first_stream + i), n_frames, lead)
+    return out
