@@ -65,6 +65,9 @@ WORKLOADS = {
 }
 
 
+for _k, _v in WORKLOADS.items():
+    _v["name"] = _k
+
 _JSON_FD = None
 
 
@@ -307,7 +310,7 @@ def bind_to_gpu_numa_node(local_rank):
         pass
 
 
-def run_mixed(args, w, rank, local_rank, world, dev, dist):
+def run_mixed(args, w, rank, local_rank, world, dev, dist, quick=False):
     """BASELINE config 4: twelve configurations in one batch through Lc3MixedBatchDecoder."""
     import torch
 
@@ -374,9 +377,11 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
     with ClockSampler(local_rank) as clk:
         ms_total = timed(lambda i: dec.decode_frames(16, frames[i % F], lens, pcm), args.steps, args.warmup)
     ups = world * S * args.steps / (ms_total * 1e-3)
+    if quick:
+        return {"quick": True, "value": ups, "unit": "frames/s", "ms_per_step": ms_total / args.steps, "streams_per_gpu": S}
     host_in = frames.cpu().pin_memory()
     host_lens = lens.cpu().pin_memory()
-    host_out = [dec.alloc_host_pcm() for _ in range(2)]
+    host_out = [dec.alloc_host_pcm() for _ in range(2)]      # one dense pinned buffer per call in flight
     dec.set_host_pipelining(True)
     e2e_steps = max(10, min(args.steps, 100))
 
@@ -402,32 +407,30 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist):
     peak, peak_src = measured_peak()
     step_ms = ms_total / args.steps
     achieved = algo / (step_ms * 1e-3) / 1e9
-    if rank == 0:
-        cb = cpu_baseline_mixed() if (world == 1 and not args.no_cpu_baseline) else None
-        emit(({
-            "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": w["desc"], "name": "mixed", "streams_per_gpu": S,
-                       "parallelism": f"{world} x independent stream shards; 12 per-configuration decoders on 12 CUDA streams",
-                       "note": "e2e can exceed value: the host entry point lets the per-configuration streams run ahead across "
-                               "steps (joined once by host_fence); the device entry point joins them on the caller's stream every call"},
-            "clocks": clk.summary(),
-            "e2e": {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * STRIDE,
-                    "d2h_bytes_per_step": int(sum(c_ * n_ * 2 for (_, _, c_), n_ in zip(dec.buckets, dec.nf))),
-                    "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "Lc3MixedBatchDecoder.decode_frames_host (one lc3b_decode_frames_host per configuration on its own CUDA "
-                           "stream, host pipelining on, host_fence before the end event)"},
-            "gpu_launches": 48 * args.steps,    # 12 configurations x (entropy, dequant, synth, ltpf)
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "whole step (12 configurations x 4 kernels on concurrent streams)", "kernel_ms": step_ms,
-                         "peak_source": peak_src, "algorithmic_bytes_per_step": algo},
-            "cpu_baseline": cb}))
-    if dist is not None:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    cb = cpu_baseline_mixed() if (world == 1 and not args.no_cpu_baseline) else None
+    return {
+        "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "name": "mixed", "streams_per_gpu": S,
+                   "parallelism": f"{world} x independent stream shards; one lc3b_mixed_decode_frames call per step = 1 entropy + "
+                                  "2 dequantisation + 12 synthesis + 12 post-filter kernels as one CUDA graph"},
+        "clocks": clk.summary(),
+        "e2e": {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * STRIDE,
+                "d2h_bytes_per_step": int(sum(c_ * n_ * 2 for (_, _, c_), n_ in zip(dec.buckets, dec.nf))),
+                "ms_per_step": ms_e2e / e2e_steps,
+                "api": "lc3b_mixed_decode_frames_host (Lc3MixedBatchDecoder.decode_frames_host): one H2D copy, one graph, one "
+                       "dense D2H copy per step, host pipelining on, host_fence before the end event"},
+        "gpu_launches": 27 * args.steps,    # entropy + 2 dequant + 12 x (synth, ltpf), issued as one graph per step
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "whole step (27 kernels, one graph)", "kernel_ms": step_ms,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": algo},
+        "cpu_baseline": cb}
 
 
-def run_file(args, w, rank, local_rank, world, dev, dist):
+def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
     """few streams, many frames - one time-parallel call per step, with the frame-by-frame path beside it."""
     import torch
 
@@ -533,31 +536,30 @@ def run_file(args, w, rank, local_rank, world, dev, dist):
     peak, peak_src = measured_peak()
     step_ms = ms_total / args.steps
     achieved = algo_bytes(w) * S * F / (step_ms * 1e-3) / 1e9
-    if rank == 0:
-        cb = cpu_baseline(w) if (world == 1 and not args.no_cpu_baseline) else None
-        emit(({
-            "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": w["desc"], "name": "file48", "streams_per_gpu": S, "frames_per_call": F,
-                       "frame_by_frame_value": fb_ups,
-                       "frame_by_frame_note": f"same handle, {fb_frames} lc3b_decode_frames calls of {S} streams each",
-                       "l2": f"per-unit scratch {scratch.numel() / 1e6:.0f} MB per call, far more than the 126 MB L2",
-                       "parallelism": f"{world} x independent stream shards, no collective on the data path"},
-            "clocks": clk.summary(),
-            "e2e": {"value": world * S * F * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * F * NB,
-                    "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames) on 4 chunks of 1024 "
-                           "frames, device -> pinned host copy of chunk c on a second stream overlapping chunk c+1"},
-            "gpu_launches": 6 * args.steps,   # device-resident leg: one call (six kernels) per step
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "whole call (entropy, dequant, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
-                         "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes(w),
-                         "note": "issue/latency bound like the frame-by-frame kernels (DESIGN.md section 5)"},
-            "cpu_baseline": cb,
-        }))
-    if dist is not None:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    cb = cpu_baseline(w) if (world == 1 and not args.no_cpu_baseline) else None
+    return {
+        "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "name": "file48", "streams_per_gpu": S, "frames_per_call": F,
+                   "frame_by_frame_value": fb_ups,
+                   "frame_by_frame_note": f"same handle, {fb_frames} lc3b_decode_frames calls of {S} streams each",
+                   "l2": f"per-unit scratch {scratch.numel() / 1e6:.0f} MB per call, far more than the 126 MB L2",
+                   "parallelism": f"{world} x independent stream shards, no collective on the data path"},
+        "clocks": clk.summary(),
+        "e2e": {"value": world * S * F * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * F * NB,
+                "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
+                "api": "pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames) on 4 chunks of 1024 "
+                       "frames, device -> pinned host copy of chunk c on a second stream overlapping chunk c+1"},
+        "gpu_launches": 6 * args.steps,   # device-resident leg: one call (six kernels) per step
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "whole call (entropy, dequant, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
+                     "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes(w),
+                     "note": "issue/latency bound like the frame-by-frame kernels (DESIGN.md section 5)"},
+        "cpu_baseline": cb,
+    }
 
 
 def main():
@@ -568,26 +570,29 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="decode48", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the named workload's)")
+    ap.add_argument("--total-streams", type=int, default=0, help="strong scaling: this many streams in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the small-batch workloads reported under `secondary`")
     ap.add_argument("--quick", action="store_true", help="device-resident loop only (for ncu captures; not a bench value)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3)
     w = dict(WORKLOADS[args.workload])
-    if args.streams:
-        w["streams"] = args.streams
-
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    scaling = "weak"
+    if args.streams:
+        w["streams"] = args.streams
+    if args.total_streams:
+        from lc3_codec_b200.sharding import shard_range
+        w["streams"] = shard_range(args.total_streams, rank, world)[1]
+        scaling = "strong"
     if args.impl == "reference":
         run_reference(args, w, rank)
         return
 
     import torch
-
-    import lc3_codec_b200 as L
-    from tools.corpus import make_pcm_window
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: lc3_codec_b200 has no CPU fallback")
@@ -599,16 +604,45 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    if w["mode"] == "mixed":
-        run_mixed(args, w, rank, local_rank, world, dev, dist)
-        return
-    if w["mode"] == "file":
-        run_file(args, w, rank, local_rank, world, dev, dist)
-        return
+    runner = {"mixed": run_mixed, "file": run_file}.get(w["mode"], run_codec)
+    out = runner(args, w, rank, local_rank, world, dev, dist, quick=args.quick)
+    if out is not None and not args.quick:
+        out["scaling"] = scaling
+        if scaling == "strong":
+            out["config"]["total_streams"] = args.total_streams
+        # The small-batch configurations of BASELINE.json at their stated sizes (configs 2, 3, 4), device-resident, so that
+        # the driver's record of the default command carries them: latency-bound territory, see DESIGN.md section 8.
+        if world == 1 and args.workload == "decode48" and not args.no_secondary:
+            sec = {}
+            sargs = argparse.Namespace(**vars(args))
+            sargs.steps, sargs.warmup = 200, 10
+            for name in ("decode16", "mixed", "encode48"):
+                ws = dict(WORKLOADS[name])
+                fn = {"mixed": run_mixed}.get(ws["mode"], run_codec)
+                try:
+                    r = fn(sargs, ws, rank, local_rank, world, dev, dist, quick=True)
+                    sec[name] = {"workload": ws["desc"], "streams": ws["streams"], "ms_per_step": r["ms_per_step"],
+                                 "value": r["value"], "unit": "channel-frames/s" if name == "encode48" else "frames/s"}
+                except Exception as e:                      # the headline must not die with a secondary measurement
+                    sec[name] = {"error": repr(e)}
+            out["secondary"] = sec
+    if out is not None and rank == 0:
+        emit(out)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_codec(args, w, rank, local_rank, world, dev, dist, quick=False):
+    """decode / encode / roundtrip workloads of one (fs, duration, nbytes) configuration."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from tools.corpus import make_pcm_window
+
     S, NB, NF, mode = w["streams"], w["nbytes"], w["nf"], w["mode"]
     sf, fd = L.SamplingFrequency.from_hz(w["fs"]), L.FrameDuration.from_ms(w["ms"])
     stream = torch.cuda.current_stream(dev)
-    U, F, WARM = 1024, 8, 4
+    U, F, WARM = (256 if quick and w["name"] != "decode48" else 1024), 8, 4       # distinct streams, frames each, encoder lead-in
     # rank r owns streams [r*S, (r+1)*S) of the job; stream s replays corpus stream s mod U
     idx = torch.from_numpy((np.arange(S) + rank * S) % U).to(dev)
 
@@ -627,7 +661,7 @@ def main():
 
     # ---- inputs, resident in HBM: [F][S][...] so that step i reads one contiguous frame set
     dev_pcm_in = dev_frames = None
-    if args.workload == "decode48":
+    if w["name"] == "decode48":
         fr_u = torch.from_numpy(load_frames()).to(dev).permute(1, 0, 2).contiguous()                    # [F,U,150]
         dev_frames = fr_u[:, idx].contiguous()                                                           # [F,S,150]
     else:
@@ -696,10 +730,8 @@ def main():
         ms_total = timed(step_dev, args.steps, args.warmup)
     clocks = clk.summary()
     ups = world * S * args.steps / (ms_total * 1e-3)
-    if args.quick:
-        if rank == 0:
-            emit(({"quick": True, "value": ups, "unit": "frames/s", "ms_per_step": ms_total / args.steps}))
-        return
+    if quick:
+        return {"quick": True, "value": ups, "unit": "frames/s", "ms_per_step": ms_total / args.steps, "streams_per_gpu": S}
 
     # ---- per-kernel time, each kernel alone (profiling hooks), same inputs
     k_steps = max(20, min(args.steps, 100))
@@ -740,7 +772,7 @@ def main():
     if traffic_file.exists():
         try:
             t = json.loads(traffic_file.read_text())
-            per_frame = t.get("dram_bytes_per_stream_frame", {}).get(args.workload, {}).get(dom_name)
+            per_frame = t.get("dram_bytes_per_stream_frame", {}).get(w["name"], {}).get(dom_name)
             if per_frame is not None:                  # ncu figure is per stream-frame; one launch covers S of them
                 roofline["traffic"] = per_frame * S
                 roofline["traffic_source"] = t.get("source")
@@ -783,7 +815,9 @@ def main():
     e2e = {"value": world * S * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "api": api}
 
-    if rank == 0:
+    if rank != 0:
+        return None
+    if True:
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(w)
@@ -791,7 +825,7 @@ def main():
             "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "name": args.workload, "streams_per_gpu": S, "frame_bytes": NB, "nf": NF,
+            "config": {"workload": w["desc"], "name": w["name"], "streams_per_gpu": S, "frame_bytes": NB, "nf": NF,
                        "corpus": corpus_stats,
                        "l2": f"no explicit flush: each step streams the per-stream codec state + I/O "
                              f"({ws_bytes / 1e6:.0f} MB workspace per GPU), far more than the 126 MB L2",
@@ -799,9 +833,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
             "cpu_baseline": cb,
         }
-        emit(out)
-    if dist is not None:
-        dist.destroy_process_group()
+        return out
 
 
 if __name__ == "__main__":

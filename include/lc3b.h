@@ -114,12 +114,68 @@ int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x);
  * copied into `out` (device) on `cuda_stream`.  For stage-level parity tests. */
 int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream);
 
+/* How a call's kernels are issued: 0 = one launch per kernel on `cuda_stream`; 1 = the whole call as ONE CUDA graph
+ * launch (graphs are cached per handle and keyed by the call's arguments; a caller cycling through a few buffer sets
+ * replays instantiated graphs, anything else patches an executable graph in place).  Default: 1 for handles of at most
+ * 131 072 streams (launch-sensitive), else 0; LC3B_GRAPH=0/1 in the environment overrides the default.  Results are
+ * identical either way.  graph_stats: cache hits / in-place updates / instantiations so far (any pointer may be NULL). */
+int lc3b_decoder_set_graph_mode(lc3b_decoder* h, int mode);
+/* Which dequantisation kernel runs: 0 = by batch size (default: one warp per frame up to 98 304 streams, one thread per
+ * frame above), 1 = warp per frame, 2 = thread per frame.  Bit-identical results; the choice only matters for speed. */
+int lc3b_decoder_set_dequant_mode(lc3b_decoder* h, int mode);
+int lc3b_decoder_graph_stats(const lc3b_decoder* h, uint64_t* hits, uint64_t* updates, uint64_t* builds);
+
 /* Profiling hook: which kernels lc3b_decode_frames launches (bit 0 = entropy kernel, bit 1 = dequantisation kernel,
  * bit 2 = synthesis kernel and the post-filter kernel behind it; default 7).  Lets bench.py time each kernel alone
  * with CUDA events; results are only meaningful with mask 7. */
 int lc3b_decoder_set_stage_mask(lc3b_decoder* h, int mask);
 
 void lc3b_decoder_destroy(lc3b_decoder* h);
+
+/* ------------------------------------------------------------------ mixed-rate decoder (BASELINE config 4)
+ * Lc3Decoder::new takes ONE frame duration and ONE sampling frequency for all its channels
+ * (src/decoder/lc3_decoder.rs:181), so a mixed population of streams is a set of reference decoders.  This handle is
+ * that set - up to twelve (sampling frequency, frame duration) configurations - driven as one batch: one entropy
+ * launch over every stream, one dequantisation launch per frame duration, one synthesis + post-filter launch per
+ * configuration, the whole call issued as one CUDA graph.
+ *
+ * Row order: streams are bucketed by configuration, buckets sorted by (sampling_frequency, frame_duration), streams of a
+ * bucket in their original order.  lc3b_mixed_decoder_layout returns that order (`order[row]` = original stream id;
+ * nullable) and the bucket table; the caller lays the rows of `frames`, `frame_nbytes`, `pcm_out`, `status_out` out in
+ * that order, so every bucket is a contiguous row range and nothing is gathered or scattered on the device. */
+typedef struct lc3b_mixed_decoder lc3b_mixed_decoder;
+typedef struct lc3b_mixed_bucket {
+    int32_t sampling_frequency, frame_duration;   /* LC3B_HZ*, LC3B_7P5MS / LC3B_10MS */
+    int32_t first_row, n_rows;                    /* rows [first_row, first_row + n_rows) of the caller's buffers */
+    int32_t nf, reserved;                         /* samples per frame of this bucket */
+    uint64_t host_pcm_offset;                     /* lc3b_mixed_decode_frames_host: int16 offset of the bucket's dense PCM */
+} lc3b_mixed_bucket;
+#define LC3B_MIXED_MAX_BUCKETS 12
+int lc3b_mixed_decoder_layout(int n_streams, const int32_t* sampling_frequency, const int32_t* frame_duration, int32_t* order,
+                              lc3b_mixed_bucket* buckets /* [LC3B_MIXED_MAX_BUCKETS] */, int32_t* n_buckets,
+                              uint64_t* host_pcm_elems);
+/* Lc3Decoder::calc_working_buffer_lengths / Lc3Decoder::new for the whole set (sampling_frequency[s], frame_duration[s]
+ * describe ORIGINAL stream s; host arrays, only read during the call). */
+int lc3b_mixed_decoder_workspace_bytes(int n_streams, const int32_t* sampling_frequency, const int32_t* frame_duration,
+                                       int max_nbytes, size_t* device_bytes);
+int lc3b_mixed_decoder_init(lc3b_mixed_decoder** out, int n_streams, const int32_t* sampling_frequency,
+                            const int32_t* frame_duration, int max_nbytes, int device, void* dev_workspace,
+                            size_t workspace_bytes, void* cuda_stream);
+/* One Lc3Decoder::decode_frame per stream (rows in bucket order, see above).  frame_nbytes is required (device
+ * int32[n_streams]: configurations differ in frame length; 0 = lost frame); `nbytes` bounds it (<= max_nbytes, <= frame_stride).
+ * pcm_out rows have one common pitch `pcm_stride` >= the largest nf; a row of bucket b receives nf_b samples. */
+int lc3b_mixed_decode_frames(lc3b_mixed_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                             int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
+                             void* cuda_stream);
+/* Same with HOST buffers.  pcm_out is DENSE per bucket: bucket b's rows are [n_rows][nf_b] int16 at element offset
+ * host_pcm_offset (lc3b_mixed_decoder_layout), host_pcm_elems in total - so the read-back is one linear copy. */
+int lc3b_mixed_decode_frames_host(lc3b_mixed_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
+                                  int nbytes, size_t frame_stride, int16_t* pcm_out, int32_t* status_out, void* cuda_stream);
+int lc3b_mixed_decoder_set_host_pipelining(lc3b_mixed_decoder* h, int on);   /* as lc3b_decoder_set_host_pipelining */
+int lc3b_mixed_decoder_host_fence(lc3b_mixed_decoder* h, void* cuda_stream);
+int lc3b_mixed_decoder_set_graph_mode(lc3b_mixed_decoder* h, int mode);      /* default 1 (graph) */
+int lc3b_mixed_decoder_set_dequant_mode(lc3b_mixed_decoder* h, int mode);    /* as lc3b_decoder_set_dequant_mode */
+void lc3b_mixed_decoder_destroy(lc3b_mixed_decoder* h);
 
 /* ------------------------------------------------------------------ encoder */
 typedef struct lc3b_encoder lc3b_encoder;
@@ -149,6 +205,7 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
  * overlaps the kernels of call i.  Results are ordered on `cuda_stream` as before (the bitstream copy stays on it);
  * the caller's PCM buffer must stay valid until the call's work has drained, as with any asynchronous copy. */
 int lc3b_encoder_set_host_pipelining(lc3b_encoder* h, int on);
+int lc3b_encoder_set_graph_mode(lc3b_encoder* h, int mode);   /* as lc3b_decoder_set_graph_mode */
 /* Test hook: device copies of the last encode's intermediates (any pointer may be NULL): xf [S][ne] f32 (quantiser
  * input, after SNS and TNS), e_b [S][64] f32, hand [S][8] i32 (near_nyquist, attack, pitch_index, pitch_present,
  * ltpf_active, nbits_ltpf), xq [S][ne] i16. */
@@ -158,6 +215,45 @@ int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* han
  * bitstream stage (prepare, range coder, finish kernels).  Default 63 (all). */
 int lc3b_encoder_set_stage_mask(lc3b_encoder* h, int mask);
 void lc3b_encoder_destroy(lc3b_encoder* h);
+
+/* ------------------------------------------------------------------ one batch over the GPUs of a box
+ * Streams never interact (DecoderChannel / EncoderChannel own all state, src/decoder/lc3_decoder.rs:62-69,
+ * src/encoder/lc3_encoder.rs:42-60), so a batch shards by stream id with nothing to exchange: stream s belongs to
+ * shard floor(s * G / N) - a contiguous block of rows per GPU; no collective, no peer access.
+ * A sharded handle owns per GPU: a decoder / encoder handle on its own device workspace (allocated once, at create;
+ * nothing afterwards), a CUDA stream and one host thread that issues that GPU's copies and launches.  The calls take
+ * HOST buffers of the whole batch (pin them: lc3b_host_alloc, or cudaHostAlloc with the portable flag), hand every
+ * thread its row range and return at once; *_wait joins all outstanding calls, after which the outputs are valid and the
+ * first error of any shard is returned.  Calls must come from one thread at a time; frames of a stream stay in order.
+ *   devices   n_devices CUDA device indices, or NULL for 0 .. n_devices-1
+ *   *_shard   which device and rows [first_stream, first_stream + n_streams) a shard covers */
+typedef struct lc3b_sharded_decoder lc3b_sharded_decoder;
+int lc3b_sharded_decoder_create(lc3b_sharded_decoder** out, int n_streams, int frame_duration, int sampling_frequency,
+                                int max_nbytes, const int* devices, int n_devices);
+int lc3b_sharded_decoder_n_shards(const lc3b_sharded_decoder* h);
+int lc3b_sharded_decoder_shard(const lc3b_sharded_decoder* h, int shard, int* device, int* first_stream, int* n_streams);
+/* arguments as lc3b_decode_frames_host, for all n_streams rows */
+int lc3b_sharded_decode_frames_host(lc3b_sharded_decoder* h, int bits_per_sample, const uint8_t* frames,
+                                    const int32_t* frame_nbytes, int nbytes, size_t frame_stride, int16_t* pcm_out,
+                                    size_t pcm_stride, int32_t* status_out);
+int lc3b_sharded_decoder_wait(lc3b_sharded_decoder* h);
+void lc3b_sharded_decoder_destroy(lc3b_sharded_decoder* h);
+
+typedef struct lc3b_sharded_encoder lc3b_sharded_encoder;
+int lc3b_sharded_encoder_create(lc3b_sharded_encoder** out, int n_streams, int frame_duration, int sampling_frequency,
+                                int max_nbytes, const int* devices, int n_devices);
+int lc3b_sharded_encoder_n_shards(const lc3b_sharded_encoder* h);
+int lc3b_sharded_encoder_shard(const lc3b_sharded_encoder* h, int shard, int* device, int* first_stream, int* n_streams);
+/* arguments as lc3b_encode_frames_host, for all n_streams rows */
+int lc3b_sharded_encode_frames_host(lc3b_sharded_encoder* h, const int16_t* pcm_in, size_t pcm_stride, uint8_t* frames_out,
+                                    int nbytes, size_t frame_stride);
+int lc3b_sharded_encoder_wait(lc3b_sharded_encoder* h);
+void lc3b_sharded_encoder_destroy(lc3b_sharded_encoder* h);
+
+/* Pinned (page-locked, portable across devices) host memory for the host-buffer entry points, for callers that do
+ * not link the CUDA runtime themselves. */
+int lc3b_host_alloc(void** out, size_t bytes);
+void lc3b_host_free(void* p);
 
 /* Self-test hooks: the engine's own f32 transcendentals (csrc/lc3b_math.cuh, msun-style) evaluated
  * on the host (no GPU needed) or on the device, so tests can compare them with the oracle's.

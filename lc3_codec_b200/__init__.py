@@ -8,3 +8,4 @@ from .native import FrameDuration, Lc3bError, SamplingFrequency, lib, lib_path  
 from .decoder import Lc3BatchDecoder, Lc3DecoderError  # noqa: F401
 from .encoder import Lc3BatchEncoder  # noqa: F401
 from .mixed import Lc3MixedBatchDecoder  # noqa: F401
+from .sharding import Lc3ShardedBatchDecoder, Lc3ShardedBatchEncoder  # noqa: F401

@@ -4,22 +4,27 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+
 #include "lc3b_common.cuh"
+#include "lc3b_handles.cuh"
 #include "lc3b_math.cuh"
 #include "lc3_tables.h"
 
 namespace lc3b {
 
 static thread_local int g_last_cuda_error = 0;
-static int cuda_fail(cudaError_t e) {
+int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return LC3B_ERR_CUDA;
 }
-#define CU(x)                                      \
-    do {                                           \
-        cudaError_t _e = (x);                      \
-        if (_e != cudaSuccess) return cuda_fail(_e); \
-    } while (0)
+#define CU(x) LC3B_CU(x)
+
+int default_graph_mode(int n_streams) {
+    const char* env = getenv("LC3B_GRAPH");
+    if (env && (env[0] == '0' || env[0] == '1')) return env[0] - '0';
+    return n_streams <= 131072 ? 1 : 0;
+}
 
 // common/config.rs:42-100
 static bool make_config(int sf, int fd, lc3b_config* c) {
@@ -61,7 +66,7 @@ struct Layout {
         stage_status, total;
 };
 
-static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
+static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes, bool staging = true) {
     Carve cv;
     Layout L;
     const size_t ns = (size_t)n_streams, nblk = (ns + 31) / 32;
@@ -80,10 +85,11 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes) {
     L.ltpf_x = cv.take(sizeof(float) * ns * c.nf);
     L.side = cv.take(sizeof(int32_t) * ns * SIDE_WORDS);
     L.sstate = cv.take(sizeof(int32_t) * ns * SS_WORDS);
-    L.stage_in = cv.take(ns * (size_t)max_nbytes);
-    L.stage_out = cv.take(sizeof(int16_t) * ns * c.nf * 2);   // double-buffered for the pipelined host path
-    L.stage_len = cv.take(sizeof(int32_t) * ns);
-    L.stage_status = cv.take(sizeof(int32_t) * ns);
+    // staging for the host-buffer entry point (a mixed-rate handle stages for all of its buckets at once instead)
+    L.stage_in = cv.take(staging ? ns * (size_t)max_nbytes : 0);
+    L.stage_out = cv.take(staging ? sizeof(int16_t) * ns * c.nf * 2 : 0);   // double-buffered for the pipelined host path
+    L.stage_len = cv.take(staging ? sizeof(int32_t) * ns : 0);
+    L.stage_status = cv.take(staging ? sizeof(int32_t) * ns : 0);
     L.total = cv.off;
     return L;
 }
@@ -204,6 +210,15 @@ static void fill_host_config(const lc3b_config& c, DevConfig* d) {
     if (c.n_ms == LC3B_10MS) { d->ltpf_blocks = 2; d->ltpf_norm = c.nf / 4; } else { d->ltpf_blocks = 3; d->ltpf_norm = c.nf / 3; }
     d->ltpf_s2p5 = c.fs == 44100 ? 48000 / 400 : c.fs / 400;
     for (int k = 0; k < 400; k++) d->gg_table[k] = powf_msun(10.0f, xd((float)(k - 245), 28.0f));   // global_gain.rs:19-20
+    {                                                          // noise_filling.rs:49 composed n times
+        uint32_t a = 1, cc = 0;
+        d->nf_lcg[0] = (1u << 16);
+        for (int n = 1; n <= MAX_NE; n++) {
+            a = (a * 31821u) & 0xffffu;
+            cc = (cc * 31821u + 13849u) & 0xffffu;
+            d->nf_lcg[n] = (a << 16) | cc;
+        }
+    }
     const float step = (float)(M_PI / 17.0);                   // temporal_noise_shaping.rs:38-45
     for (int k = 0; k < 17; k++) d->tns_sin[k] = (float)sin((double)xm(step, (float)(k - 8)));
 }
@@ -228,17 +243,6 @@ __global__ void math_kernel(int which, const float* x, const float* y, float* ou
 
 using namespace lc3b;
 
-struct lc3b_decoder {
-    DecoderState st;
-    int stage_mask;
-    // optional pipelining of the host entry point: PCM leaves on an internal copy stream from a double-buffered
-    // staging area, so the device->host copy of call i overlaps the kernels of call i+1
-    int pipelined;
-    int buf;
-    cudaStream_t copy_stream;
-    cudaEvent_t compute_done[2], d2h_done[2];
-    bool d2h_pending[2];
-};
 
 extern "C" {
 
@@ -252,26 +256,44 @@ int lc3b_config_new(int sampling_frequency, int frame_duration, lc3b_config* out
 
 int lc3b_decoder_workspace_bytes(int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
                                  size_t* device_bytes) {
-    lc3b_config c;
-    if (!device_bytes || n_streams <= 0 || max_nbytes <= 0 || max_nbytes > MAX_NBYTES ||
-        !make_config(sampling_frequency, frame_duration, &c))
-        return LC3B_ERR_INVALID_ARG;
-    *device_bytes = make_layout(c, n_streams, max_nbytes).total;
-    return LC3B_OK;
+    return lc3b::decoder_workspace_bytes(n_streams, frame_duration, sampling_frequency, max_nbytes, true, device_bytes);
 }
 
 int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
                       int device, void* dev_workspace, size_t workspace_bytes, void* cuda_stream) {
+    return lc3b::decoder_init(out, n_streams, frame_duration, sampling_frequency, max_nbytes, device, dev_workspace,
+                              workspace_bytes, cuda_stream, true);
+}
+
+}  // extern "C"
+
+namespace lc3b {
+
+bool config_new(int sf, int fd, lc3b_config* c) { return make_config(sf, fd, c); }
+
+int decoder_workspace_bytes(int n_streams, int frame_duration, int sampling_frequency, int max_nbytes, bool staging,
+                            size_t* device_bytes) {
+    lc3b_config c;
+    if (!device_bytes || n_streams <= 0 || max_nbytes <= 0 || max_nbytes > MAX_NBYTES ||
+        !make_config(sampling_frequency, frame_duration, &c))
+        return LC3B_ERR_INVALID_ARG;
+    *device_bytes = make_layout(c, n_streams, max_nbytes, staging).total;
+    return LC3B_OK;
+}
+
+int decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int sampling_frequency, int max_nbytes,
+                 int device, void* dev_workspace, size_t workspace_bytes, void* cuda_stream, bool staging) {
     lc3b_config c;
     if (!out || !dev_workspace || n_streams <= 0 || max_nbytes <= 0 || max_nbytes > MAX_NBYTES ||
         !make_config(sampling_frequency, frame_duration, &c))
         return LC3B_ERR_INVALID_ARG;
-    const Layout L = make_layout(c, n_streams, max_nbytes);
+    const Layout L = make_layout(c, n_streams, max_nbytes, staging);
     if (workspace_bytes < L.total || ((uintptr_t)dev_workspace & 255) != 0) return LC3B_ERR_WORKSPACE;
+    DeviceGuard guard;                        // the caller's current device is restored on return
     CU(cudaSetDevice(device));
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     uint8_t* base = (uint8_t*)dev_workspace;
-    lc3b_decoder* h = (lc3b_decoder*)calloc(1, sizeof(lc3b_decoder));
+    lc3b_decoder* h = new (std::nothrow) lc3b_decoder();
     if (!h) return LC3B_ERR_INVALID_ARG;
     DecoderState& st = h->st;
     st.cfg = c;
@@ -300,6 +322,7 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
     st.trace = nullptr;
     st.trace_x = nullptr;
     st.fixed_slot = -1;
+    st.dequant_mode = 0;
 
     DevConfig hc;
     fill_host_config(c, &hc);
@@ -316,21 +339,27 @@ int lc3b_decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
-        free(h);
+        delete h;
         return cuda_fail(e);
     }
-    h->stage_mask = 7;
-    h->pipelined = 0;
-    h->buf = 0;
-    h->copy_stream = nullptr;
-    h->d2h_pending[0] = h->d2h_pending[1] = false;
+    h->graph_mode = default_graph_mode(n_streams);
     *out = h;
     return LC3B_OK;
 }
 
+}  // namespace lc3b
+
+extern "C" {
+
 int lc3b_decoder_set_host_pipelining(lc3b_decoder* h, int on) {
     if (!h) return LC3B_ERR_INVALID_ARG;
+    if (!on && h->pipelined) {
+        // copies still in flight read the staging halves the next (unpipelined) call writes: let them land first
+        for (int i = 0; i < 2; i++)
+            if (h->d2h_pending[i]) { CU(cudaEventSynchronize(h->d2h_done[i])); h->d2h_pending[i] = false; }
+    }
     if (on && !h->copy_stream) {
+        DeviceGuard guard;
         CU(cudaSetDevice(h->st.device));
         CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -344,12 +373,30 @@ int lc3b_decoder_set_host_pipelining(lc3b_decoder* h, int on) {
 
 int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream) {
     if (!h) return LC3B_ERR_INVALID_ARG;
-    for (int i = 0; i < 2; i++) {
-        if (h->d2h_pending[i]) {
-            CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->d2h_done[i], 0));
-            h->d2h_pending[i] = false;
-        }
-    }
+    // d2h_pending stays set: a later decode on ANOTHER stream than the one fenced here must still wait for the
+    // staging half it overwrites (waiting twice on a completed event costs nothing)
+    for (int i = 0; i < 2; i++)
+        if (h->d2h_pending[i]) CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->d2h_done[i], 0));
+    return LC3B_OK;
+}
+
+int lc3b_decoder_set_graph_mode(lc3b_decoder* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return LC3B_ERR_INVALID_ARG;
+    h->graph_mode = mode;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_set_dequant_mode(lc3b_decoder* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return LC3B_ERR_INVALID_ARG;
+    h->st.dequant_mode = mode;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_graph_stats(const lc3b_decoder* h, uint64_t* hits, uint64_t* updates, uint64_t* builds) {
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    if (hits) *hits = h->graphs.hits;
+    if (updates) *updates = h->graphs.updates;
+    if (builds) *builds = h->graphs.builds;
     return LC3B_OK;
 }
 
@@ -387,6 +434,17 @@ int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x) {
     return LC3B_OK;
 }
 
+// one decode_frame per stream: the call's kernels as a plan, issued directly or as a cached graph
+static cudaError_t run_decode(lc3b_decoder* h, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes, size_t frame_stride,
+                              int16_t* pcm_out, size_t pcm_stride, int32_t* status_out, int stage_mask, cudaStream_t stream) {
+    LaunchPlan plan;
+    if (stage_mask & 3) plan_entropy(plan, h->st, frames, frame_nbytes, nbytes, frame_stride, status_out, stage_mask & 3);
+    if (stage_mask & 4) {
+        if (plan_synth(plan, h->st, pcm_out, pcm_stride, plan.n - 1) < 0) return cudaErrorInvalidValue;
+    }
+    return h->graph_mode ? plan_launch_graph(h->graphs, plan, stream) : plan_launch_direct(plan, stream);
+}
+
 int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,
                        int nbytes, size_t frame_stride, int16_t* pcm_out, size_t pcm_stride, int32_t* status_out,
                        void* cuda_stream) {
@@ -396,8 +454,7 @@ int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* fram
     if (nbytes < 0 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (h->stage_mask & 3) CU(launch_entropy(st, frames, frame_nbytes, nbytes, frame_stride, status_out, h->stage_mask & 3, stream));
-    if (h->stage_mask & 4) CU(launch_synth(st, pcm_out, pcm_stride, stream));
+    CU(run_decode(h, frames, frame_nbytes, nbytes, frame_stride, pcm_out, pcm_stride, status_out, h->stage_mask, stream));
     return LC3B_OK;
 }
 
@@ -416,8 +473,6 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
     if (frame_stride == (size_t)nbytes) CU(cudaMemcpyAsync(st.stage_in, frames, ns * (size_t)nbytes, cudaMemcpyHostToDevice, stream));
     else CU(cudaMemcpy2DAsync(st.stage_in, (size_t)nbytes, frames, frame_stride, (size_t)nbytes, ns, cudaMemcpyHostToDevice, stream));
     if (frame_nbytes) CU(cudaMemcpyAsync(st.stage_len, frame_nbytes, sizeof(int32_t) * ns, cudaMemcpyHostToDevice, stream));
-    CU(launch_entropy(st, st.stage_in, frame_nbytes ? st.stage_len : nullptr, nbytes, (size_t)nbytes,
-                      status_out ? st.stage_status : nullptr, 3, stream));
     const size_t out_elems = ns * (size_t)st.cfg.nf;
     int16_t* stage = st.stage_out + (h->pipelined ? (size_t)h->buf * out_elems : 0);
     cudaStream_t out_stream = stream;
@@ -426,7 +481,8 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
         if (h->d2h_pending[h->buf]) CU(cudaStreamWaitEvent(stream, h->d2h_done[h->buf], 0));
         out_stream = h->copy_stream;
     }
-    CU(launch_synth(st, stage, (size_t)st.cfg.nf, stream));
+    CU(run_decode(h, st.stage_in, frame_nbytes ? st.stage_len : nullptr, nbytes, (size_t)nbytes, stage, (size_t)st.cfg.nf,
+                  status_out ? st.stage_status : nullptr, 7, stream));
     if (h->pipelined) {
         CU(cudaEventRecord(h->compute_done[h->buf], stream));
         CU(cudaStreamWaitEvent(out_stream, h->compute_done[h->buf], 0));
@@ -461,7 +517,7 @@ void lc3b_decoder_destroy(lc3b_decoder* h) {
         for (int i = 0; i < 2; i++) { cudaEventDestroy(h->compute_done[i]); cudaEventDestroy(h->d2h_done[i]); }
         cudaStreamDestroy(h->copy_stream);
     }
-    free(h);
+    delete h;
 }
 
 int lc3b_selftest_math_host(int which, const float* x, const float* y, float* out, int n) {

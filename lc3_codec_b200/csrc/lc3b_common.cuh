@@ -55,6 +55,7 @@ struct DevConfig {
     float tns_sin[17];                   // sin(pi/17 * (i - 8)) (temporal_noise_shaping.rs:44)
     float ltpf_num[4][12];               // 0.85 * gain * TAB_LTPF_NUM[gain_ind][k]  (long_term_post_filter.rs:232-236)
     float ltpf_den[4][4][16];            // gain * TAB_LTPF_DEN[pitch_frac][k], first index = gain_ind
+    uint32_t nf_lcg[MAX_NE + 1];         // noise-filling LCG jumped n steps: s_n = ((v >> 16) * s_0 + (v & 0xffff)) & 0xffff (noise_filling.rs:49)
     // per-config float tables appended after this struct in the workspace:
     //   win  [2*nf]   gain * w[2nf-1-m]   (modified_dct.rs:89 and :131-134 folded together)
     //   dtw  [n_fft]  DCT-IV twiddles exp(-i*pi*(8n+1)/(8*nf)) as float2 (dct_iv.rs:30-35)
@@ -66,6 +67,7 @@ struct DecoderState {
     lc3b_config cfg;
     int n_streams, n_blocks32, max_nbytes, device;
     int fixed_slot;      // -1: double-buffered spectrum slots tracked in sstate; >= 0: always write that slot (time-parallel path)
+    int dequant_mode;    // 0 auto, 1 warp-per-frame dequantisation kernel, 2 thread-per-frame (lc3b_decoder_set_dequant_mode)
     // device pointers (carved from the caller's workspace)
     DevConfig* dcfg;
     float* win;          // [2*nf]
@@ -102,6 +104,62 @@ enum {
     SS_LTPF_BLK,        // block_start_index / nf
     SS_WORDS = 8
 };
+
+// Parameters of the entropy / dequantisation kernels (one struct, passed by value)
+struct EntropyParams {
+    const DevConfig* cfg;
+    const uint8_t* frames;
+    const int32_t* frame_nbytes;
+    int nbytes;
+    size_t frame_stride;
+    int n_streams;
+    float* spec;          // [2][n_streams][ne]
+    int32_t* xq;          // [n_blocks32][ne][32]
+    int32_t* handoff;     // [n_blocks32 * 32][HO_WORDS] entropy kernel -> dequantisation kernel
+    int32_t* side;        // [n_streams][SIDE_WORDS]
+    int32_t* sstate;      // [n_streams][SS_WORDS]
+    int32_t* status_out;  // nullable
+    int32_t* trace;       // nullable
+    int32_t* trace_x;     // nullable
+    const uint8_t* sym_lut;   // [64][32] symbol at the start of each 32-quotient bucket (init_sym_lut_kernel)
+    int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
+    int row_pitch;        // bytes per staged frame row in shared memory
+};
+
+// Mixed-rate batches: one (fs, duration) bucket = a contiguous row range of the caller's buffers with its own state.
+// `ep` carries the bucket's static pointers; the per-call ones are patched in by the kernel (mixed_select).
+struct MixedBucket {
+    EntropyParams ep;
+    int first_row;        // first row of the bucket in the caller's (bucket-ordered) buffers
+    int first_cta;        // first CTA of the bucket in this table's launch
+};
+struct MixedParams {
+    const MixedBucket* buckets;   // device
+    int n_buckets;
+    const uint8_t* frames;
+    const int32_t* frame_nbytes;
+    int nbytes;
+    size_t frame_stride;
+    int32_t* status_out;
+    int row_pitch;
+};
+struct MixedTables {              // device tables + launch sizes: every bucket, the 10 ms ones, the 7.5 ms ones
+    const MixedBucket *all, *b10, *b75;
+    int n_all, n_10, n_75;
+    int cta_all, cta_10, cta_75;
+    int n_streams, dequant_mode;
+};
+
+struct LaunchPlan;
+int entropy_row_pitch(int nbytes);
+bool use_dequant_warp(int n_streams, int mode);   // mode: 0 auto (by batch size), 1 warp-per-frame, 2 thread-per-frame
+EntropyParams entropy_params(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                             size_t frame_stride, int32_t* status_out);
+void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                  size_t frame_stride, int32_t* status_out, int stages);
+void plan_entropy_mixed(LaunchPlan& plan, const MixedTables& t, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                        size_t frame_stride, int32_t* status_out, int* node_d10, int* node_d75);
+int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, int dep);
 
 cudaError_t prepare_entropy(const DecoderState& st);   // shared-memory limits of the kernels, once per handle
 cudaError_t prepare_synth(const DecoderState& st);

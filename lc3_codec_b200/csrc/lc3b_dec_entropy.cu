@@ -20,31 +20,16 @@
 // The spectrum slot written is the stream's INACTIVE one; it becomes the active slot (= PLC "last good",
 // packet_loss_concealment.rs:50) only if the frame decoded without error, so concealment needs no copy.
 // All f32 arithmetic uses contraction-proof ops in the reference's order: the spectrum is bit-exact.
+#include <stdlib.h>
+#include <string.h>
+
 #include "lc3b_common.cuh"
 #include "lc3b_math.cuh"
+#include "lc3b_plan.cuh"
 #include "lc3_tables.h"
 
 namespace lc3b {
 
-struct EntropyParams {
-    const DevConfig* cfg;
-    const uint8_t* frames;
-    const int32_t* frame_nbytes;
-    int nbytes;
-    size_t frame_stride;
-    int n_streams;
-    float* spec;          // [2][n_streams][ne]
-    int32_t* xq;          // [n_blocks32][ne][32]
-    int32_t* handoff;     // [n_blocks32 * 32][HO_WORDS] entropy kernel -> dequantisation kernel
-    int32_t* side;        // [n_streams][SIDE_WORDS]
-    int32_t* sstate;      // [n_streams][SS_WORDS]
-    int32_t* status_out;  // nullable
-    int32_t* trace;       // nullable
-    int32_t* trace_x;     // nullable
-    const uint8_t* sym_lut;   // [64][32] symbol at the start of each 32-quotient bucket (init_sym_lut_kernel)
-    int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
-    int row_pitch;        // bytes per staged frame row in shared memory
-};
 
 // ---------------------------------------------------------------- bit reader over one staged frame (buffer_reader.rs)
 struct Reader {
@@ -342,8 +327,7 @@ __host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
     return 16 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 
-__global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ void entropy_body(const EntropyParams& p, const int block, uint8_t* smem) {
     uint8_t* s_lookup = smem;
     uint8_t* s_clut = smem + 4096;
     uint32_t* s_spec_cf = (uint32_t*)(smem + 4096 + 2048);
@@ -355,7 +339,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
 
     const DevConfig& c = *p.cfg;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int stream0 = blockIdx.x * ENT_THREADS;
+    const int stream0 = block * ENT_THREADS;
     const int ne = c.ne;
 
     // ---- stage tables and frame bytes
@@ -656,19 +640,52 @@ __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(EntropyParams p
 }
 
 
+__global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(const __grid_constant__ EntropyParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    entropy_body(p, blockIdx.x, smem);
+}
+
+// Mixed-rate batches (BASELINE config 4; lc3b_mixed_*): ONE launch covers every (fs, duration) bucket.  A CTA finds its
+// bucket in a small device table, patches the per-call pointers into that bucket's parameter block (rows of the caller's
+// buffers are in bucket order, so a bucket is a contiguous row range) and runs the single-configuration body on it.
+__device__ __forceinline__ void mixed_select(const MixedParams& m, EntropyParams* s_p, int* s_block) {
+    if (threadIdx.x == 0) {
+        int b = 0;
+        while (b + 1 < m.n_buckets && (int)blockIdx.x >= m.buckets[b + 1].first_cta) b++;
+        const MixedBucket& bk = m.buckets[b];
+        EntropyParams q = bk.ep;
+        q.frames = m.frames + (size_t)bk.first_row * m.frame_stride;
+        q.frame_nbytes = m.frame_nbytes ? m.frame_nbytes + bk.first_row : nullptr;
+        q.nbytes = m.nbytes;
+        q.frame_stride = m.frame_stride;
+        q.status_out = m.status_out ? m.status_out + bk.first_row : nullptr;
+        q.row_pitch = m.row_pitch;
+        *s_p = q;
+        *s_block = (int)blockIdx.x - bk.first_cta;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ENT_THREADS, 6) entropy_mixed_kernel(const __grid_constant__ MixedParams m) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ EntropyParams s_p;
+    __shared__ int s_block;
+    mixed_select(m, &s_p, &s_block);
+    entropy_body(s_p, s_block, smem);
+}
+
 // ---------------------------------------------------------------- kernel 1b: integers -> shaped spectrum
 // Dequantisation, residual refinement, noise filling, global gain, TNS lattice, SNS gains (reference D4-D8); one
 // thread per frame, every thread walks all ne lines, so the warp stays converged without any work sorting.
 template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
-__global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ void dequant_body(const EntropyParams& p, const int block, uint8_t* smem) {
     float* s_scf = (float*)smem;
     int32_t* s_band = (int32_t*)(s_scf + 16 * ENT_THREADS);
     uint8_t* s_rows = (uint8_t*)(s_band + 68);
 
     const DevConfig& c = *p.cfg;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int stream0 = blockIdx.x * ENT_THREADS;
+    const int stream0 = block * ENT_THREADS;
     const int ne = c.ne;
 
     // hand-off record of this thread slot
@@ -940,7 +957,329 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(EntropyParams p
     }
 }
 
-static int entropy_row_pitch(int nbytes) {
+template <int W>
+__global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(const __grid_constant__ EntropyParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    dequant_body<W>(p, blockIdx.x, smem);
+}
+
+template <int W>
+__global__ void __launch_bounds__(ENT_THREADS, 5) dequant_mixed_kernel(const __grid_constant__ MixedParams m) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ EntropyParams s_p;
+    __shared__ int s_block;
+    mixed_select(m, &s_p, &s_block);
+    dequant_body<W>(s_p, s_block, smem);
+}
+
+// ---------------------------------------------------------------- kernel 1b', one WARP per frame (small batches)
+// The thread-per-frame dequant_kernel needs ~100 k frames to fill the GPU: every frame's ne lines are one thread's serial
+// loop (0.07 ms at 16 384 streams of 120 lines whatever the occupancy).  Below DQW_MAX_STREAMS streams this variant is
+// launched instead: a warp owns a frame, a lane the lines k = lane, lane + 32, ...
+//   * residual refinement and noise filling are per-line decisions whose only serial part is a COUNT (the i-th non-zero
+//     line takes the i-th residual bit; the i-th filled line takes the LCG's i-th output): ballot + popcount give the
+//     rank, and the LCG is jumped to any rank with the composed multiplier / increment table DevConfig::nf_lcg;
+//   * the noise-filling window test (no non-zero integer within +-W lines) is a mask test on the ballots of three rows;
+//   * the TNS lattice is a true recurrence over lines: the frames of a CTA run it side by side on the first lanes of
+//     warp 0, between two barriers, each on its own shared-memory row (the select-based lattice of dequant_kernel);
+//   * SNS scale factors: PVQ de-enumeration on one lane, the 16 x 16 rotation on 16 lanes, band gains on 64.
+// Every f32 operation per line is dequant_kernel's, in its order: the spectrum is bit-identical (tested).
+constexpr int DQW_WARPS = 8;
+constexpr int DQW_PITCH = MAX_NE + 1;             // odd row pitch: the lattice lanes hit distinct banks
+struct DqwFrame {                                  // per-frame values handed from phase A to the lattice and phase C
+    float rc0[8], rc1[8];
+    float scf[16], y[16];
+    float gband[64];
+    int ok, ord0, ord1, s0, e0, e1, new_slot, stream;
+};
+__host__ __device__ inline size_t dequant_warp_smem_bytes() {
+    return sizeof(float) * DQW_WARPS * DQW_PITCH + sizeof(DqwFrame) * DQW_WARPS + MAX_NE;
+}
+
+__device__ __forceinline__ float sns_interp64(const float* scf, int j) {             // spectral_noise_shaping.rs:85-98
+    if (j < 2) return scf[0];
+    if (j >= 62) {
+        const float d = xs(scf[15], scf[14]);
+        return xa(scf[15], xm(j == 62 ? 0.125f : 0.375f, d));
+    }
+    const int n = (j - 2) >> 2, r = (j - 2) & 3;
+    const float fn = scf[n], d = xs(scf[n + 1], fn);
+    const float w = r == 0 ? 0.125f : r == 1 ? 0.375f : r == 2 ? 0.625f : 0.875f;
+    return xa(fn, xm(w, d));
+}
+
+__device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const int block, uint8_t* smem) {
+    float* s_v = (float*)smem;                                         // [DQW_WARPS][DQW_PITCH]
+    DqwFrame* s_f = (DqwFrame*)(s_v + DQW_WARPS * DQW_PITCH);
+    uint8_t* s_band_of = (uint8_t*)(s_f + DQW_WARPS);                  // line -> band
+
+    const DevConfig& c = *p.cfg;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ne = c.ne, nb = c.nb;
+    const int W = c.n_ms == LC3B_10MS ? 3 : 2;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (int k = tid; k < ne; k += DQW_WARPS * 32) {                   // the last band runs to ne
+        int lo = 0, hi = nb - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (c.band_idx[mid] <= k) lo = mid; else hi = mid - 1;
+        }
+        s_band_of[k] = (uint8_t)lo;
+    }
+
+    // ---- hand-off record of this warp's thread slot (the entropy kernel's tid)
+    const int n_slots = ((p.n_streams + ENT_THREADS - 1) / ENT_THREADS) * ENT_THREADS;
+    const int slot = block * DQW_WARPS + wid;
+    const bool have = slot < n_slots;
+    int h0 = 0, h1 = 0;
+    if (have) {
+        const int32_t* ho = p.handoff + (size_t)slot * HO_WORDS;
+        h0 = ho[lane];
+        if (lane < HO_WORDS - 32) h1 = ho[32 + lane];
+    }
+    auto field = [&](int i) -> int { return i < 32 ? __shfl_sync(0xffffffffu, h0, i) : __shfl_sync(0xffffffffu, h1, i - 32); };
+    const int fid = field(HO_FID);
+    const int stream = (slot / ENT_THREADS) * ENT_THREADS + fid;
+    const bool live = have && stream < p.n_streams;
+    const bool ok = live && field(HO_OK) != 0;
+    const int lastnz = field(HO_LASTNZ), lsb_mode = field(HO_LSB_MODE), gg_ind = field(HO_GG_IND), bw = field(HO_BW);
+    const int num_tns = field(HO_NUM_TNS), noise_factor = field(HO_NOISE_FACTOR);
+    const int rc_order0 = field(HO_RC_ORDER0), rc_order1 = field(HO_RC_ORDER1);
+    const int nres = field(HO_NRES), tail = field(HO_TAIL), len = field(HO_LEN);
+    const uint32_t seed0 = (uint32_t)field(HO_SEED) & 0xffffu;
+    const int nbits = len * 8;
+    DqwFrame& F = s_f[wid];
+    float* sv = s_v + wid * DQW_PITCH;
+
+    int slot_cur = 0;
+    if (live && p.fixed_slot < 0) slot_cur = p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
+    const int new_slot = p.fixed_slot >= 0 ? p.fixed_slot : slot_cur ^ 1;
+    if (lane == 0) {
+        F.ok = ok ? 1 : 0;
+        F.ord0 = F.ord1 = 0;
+        F.new_slot = new_slot;
+        F.stream = stream;
+    }
+    constexpr int NR = (MAX_NE + 31) / 32;                             // rows of 32 lines
+    if (ok) {                                                          // warp-uniform
+        const bool d10 = c.n_ms == LC3B_10MS;
+        const int bw_stop = d10 ? 80 * (bw + 1) : 60 * (bw + 1);
+        const int nf_start = d10 ? 24 : 18;
+        float gg;
+        {                                                              // global_gain.rs:15-25
+            const int fs = c.fs_ind + 1;
+            const int gg_off = -min(nbits / (10 * fs), 115) - 105 - 5 * fs;
+            gg = c.gg_table[gg_ind + gg_off + 245];
+        }
+        const float nf_level = xd(xs(8.0f, (float)noise_factor), 16.0f);
+        // ---- integers of this frame: thread slot's lane-interleaved scratch column
+        const int32_t* xq = p.xq + ((size_t)(slot >> 5) * ne) * 32 + (slot & 31) * 4;
+        int32_t x[NR];
+        uint32_t nzb[NR];                                              // non-zero lines below bw_stop, one bit per line
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+            const int k = 32 * j + lane;
+            x[j] = (32 * j < ne && k < lastnz) ? xq[xq_off(k)] : 0;    // lastnz <= ne
+            nzb[j] = __ballot_sync(0xffffffffu, x[j] != 0 && k < bw_stop);
+        }
+        const bool is_zero_frame = lastnz == 2 && (__ballot_sync(0xffffffffu, x[0] != 0) & 3u) == 0 && gg_ind == 0;
+        const uint8_t* fr = p.frames + (size_t)stream * p.frame_stride;
+        int res_base = 0, fill_base = 0;
+#pragma unroll
+        for (int j = 0; j < NR; j++) {
+            if (32 * j < ne) {                                         // warp-uniform
+                const int k = 32 * j + lane;
+                const int32_t xi = x[j];
+                float v = (float)xi;
+                {   // residual_spectrum.rs:13-39: the i-th non-zero line takes the i-th tail bit while the budget lasts
+                    const uint32_t m = __ballot_sync(0xffffffffu, xi != 0);
+                    const int rank = res_base + __popc(m & lt_mask);
+                    res_base += __popc(m);
+                    const bool take = !lsb_mode && xi != 0 && rank < nres;
+                    const int pos = tail + rank;
+                    const int bidx = max(len - 1 - (pos >> 3), 0);
+                    const uint32_t bit = take ? ((uint32_t)fr[bidx] >> (pos & 7)) & 1u : 0u;
+                    const float up = xi > 0 ? 0.3125f : 0.1875f, down = xi > 0 ? -0.1875f : -0.3125f;
+                    v = take ? xa(v, bit ? up : down) : v;
+                }
+                {   // noise_filling.rs:37-55: lines whose +-W neighbourhood holds no non-zero integer
+                    const uint32_t lo = j > 0 ? nzb[j > 0 ? j - 1 : 0] : 0u, mid = nzb[j], hi = j + 1 < NR ? nzb[j + 1 < NR ? j + 1 : j] : 0u;
+                    const uint64_t a = ((uint64_t)mid << 32) | lo, b = ((uint64_t)hi << 32) | mid;
+                    const uint32_t wm = (1u << (W + 1)) - 1u;
+                    const uint32_t near = ((uint32_t)(a >> (32 + lane - W)) | (uint32_t)(b >> lane)) & wm;
+                    const bool fill = !is_zero_frame && k >= nf_start && k < bw_stop && near == 0;
+                    const uint32_t fm = __ballot_sync(0xffffffffu, fill);
+                    const int n = fill_base + __popc(fm & lt_mask) + 1;     // this line takes the LCG's n-th output
+                    fill_base += __popc(fm);
+                    const uint32_t ac = c.nf_lcg[fill ? n : 0];
+                    const uint32_t st = ((ac >> 16) * seed0 + (ac & 0xffffu)) & 0xffffu;
+                    v = fill ? (st < 0x8000u ? nf_level : -nf_level) : v;
+                }
+                v = xm(v, gg);
+                if (k < ne) sv[k] = v;
+            }
+        }
+        // ---- TNS parameters for the lattice lanes (temporal_noise_shaping.rs:83-138; QUIRK: index 0 -> rc = 0.0)
+        if (lane < 16) {
+            const int ri = field(HO_RC_I + lane);
+            const float r = ri != 0 ? c.tns_sin[ri] : 0.0f;
+            if (lane < 8) F.rc0[lane] = r; else F.rc1[lane - 8] = r;
+        } else {
+            (void)field(HO_RC_I + (lane & 15));                        // the shuffle needs every lane
+        }
+        if (lane == 0) {
+            F.s0 = d10 ? 12 : 9;
+            if (bw < 3) { F.e0 = bw_stop; F.e1 = bw_stop; }
+            else { F.e0 = bw_stop / 2; F.e1 = bw_stop; }
+            F.ord0 = rc_order0;
+            F.ord1 = (bw >= 3 && num_tns == 2) ? rc_order1 : 0;
+        }
+        // ---- SNS scale factors (spectral_noise_shaping.rs:21-98)
+        const int ind_lf = field(HO_IND_LF), ind_hf = field(HO_IND_HF), submode_msb = field(HO_SUBMODE_MSB);
+        const int submode_lsb = field(HO_SUBMODE_LSB), g_ind = field(HO_G_IND), ls_inda = field(HO_LS_INDA);
+        const int ls_indb = field(HO_LS_INDB), idx_a = field(HO_IDX_A), idx_b = field(HO_IDX_B);
+        const int shape_j = (submode_msb << 1) + submode_lsb;
+        if (lane == 0) {
+            switch (shape_j) {
+                case 0:
+                    mpvq_deenum(10, 10, ls_inda, (uint32_t)idx_a, F.y, 1);
+                    mpvq_deenum(6, 1, ls_indb, (uint32_t)idx_b, F.y + 10, 1);
+                    break;
+                case 1:
+                    mpvq_deenum(10, 10, ls_inda, (uint32_t)idx_a, F.y, 1);
+                    for (int i = 10; i < 16; i++) F.y[i] = 0.0f;
+                    break;
+                case 2: mpvq_deenum(16, 8, ls_inda, (uint32_t)idx_a, F.y, 1); break;
+                default: mpvq_deenum(16, 6, ls_inda, (uint32_t)idx_a, F.y, 1); break;
+            }
+        }
+        __syncwarp();
+        if (lane < 16) {
+            const float* gains = shape_j == 0 ? LC3T_SNS_VQ_REG_ADJ_GAINS : shape_j == 1 ? LC3T_SNS_VQ_REG_LF_ADJ_GAINS
+                                 : shape_j == 2 ? LC3T_SNS_VQ_NEAR_ADJ_GAINS : LC3T_SNS_VQ_FAR_ADJ_GAINS;
+            float y[16];
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) { y[i] = F.y[i]; sum = xa(sum, xm(y[i], y[i])); }
+            const float y_norm = sqrtf(sum);
+            float g = gains[g_ind];
+            if (y_norm != 0.0f) g = xd(g, y_norm);
+            float factor = 0.0f;
+#pragma unroll
+            for (int col = 0; col < 16; col++) factor = xa(factor, xm(y[col], LC3T_D[lane][col]));
+            const float st1 = lane < 8 ? LC3T_LFCB[ind_lf][lane] : LC3T_HFCB[ind_hf][lane - 8];
+            F.scf[lane] = xa(st1, xm(g, factor));
+        }
+        __syncwarp();
+        const int n2 = 64 - nb;
+        for (int b = lane; b < nb; b += 32) {                          // :100-123 incl. the nb < 64 folding
+            float sc;
+            if (n2 != 0) sc = b < n2 ? xd(xa(sns_interp64(F.scf, 2 * b), sns_interp64(F.scf, 2 * b + 1)), 2.0f) : sns_interp64(F.scf, b + n2);
+            else sc = sns_interp64(F.scf, b);
+            F.gband[b] = exp2_raw_fm(sc);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: the TNS lattices of the CTA's frames, one lane each (temporal_noise_shaping.rs:24-74)
+    if (wid == 0) {
+        const bool mine = lane < DQW_WARPS && s_f[lane < DQW_WARPS ? lane : 0].ok;
+        const DqwFrame& G = s_f[lane < DQW_WARPS ? lane : 0];
+        const bool any_tns = mine && (G.ord0 > 0 || G.ord1 > 0);
+        if (__any_sync(0xffffffffu, any_tns)) {
+            float* row = s_v + (lane < DQW_WARPS ? lane : 0) * DQW_PITCH;
+            float st[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int ord = 0, om = 0, phase = 0;
+            int next = any_tns ? G.s0 : 0x7fffffff;
+            const int k_lo = __reduce_min_sync(0xffffffffu, any_tns ? G.s0 : 0x7fffffff);
+            const int k_hi = __reduce_max_sync(0xffffffffu, any_tns ? G.e1 : 0);
+            for (int k = k_lo; k < k_hi; k++) {
+                const bool sw = k == next;
+                if (__any_sync(0xffffffffu, sw)) {
+                    if (sw) {
+                        if (phase == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) rc[i] = G.rc0[i];
+                            ord = G.ord0; phase = 1; next = G.e0;
+                        } else if (phase == 1 && G.e0 < G.e1) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) rc[i] = G.rc1[i];
+                            ord = G.ord1; phase = 2; next = G.e1;
+                        } else { ord = 0; next = 0x7fffffff; }
+                    }
+                    om = __reduce_max_sync(0xffffffffu, ord);
+                }
+                if (om > 0) {                                          // QUIRK: lattice state carries across filters
+                    const bool act = ord > 0;
+                    float t = act ? row[k] : 0.0f;
+#pragma unroll
+                    for (int j = 7; j >= 0; j--) {
+                        if (j < om) {                                  // warp-uniform
+                            const float t2 = xs(t, xm(rc[j], st[j]));
+                            t = j < ord ? t2 : t;
+                            if (j + 1 < 8) {
+                                const float s2 = xa(xm(rc[j], t), st[j]);
+                                st[j + 1 < 8 ? j + 1 : 7] = j + 1 < ord ? s2 : st[j + 1 < 8 ? j + 1 : 7];
+                            }
+                        }
+                    }
+                    st[0] = act ? t : st[0];
+                    if (act) row[k] = t;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: SNS gains, spectrum -> inactive slot (coalesced rows), hand-off record for the synthesis kernel
+    if (ok) {
+        float* dst = p.spec + ((size_t)new_slot * p.n_streams + stream) * ne;
+        for (int k = lane; k < ne; k += 32) dst[k] = xm(sv[k], F.gband[s_band_of[k]]);
+    }
+    const int ltpf_active = field(HO_LTPF_ACTIVE), pitch_index = field(HO_PITCH_INDEX);
+    if (live && lane == 0) {
+        int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+        sd[SD_OK] = ok;
+        sd[SD_LTPF_ACTIVE] = ok ? ltpf_active : 0;
+        sd[SD_PITCH_INDEX] = ok ? pitch_index : 0;
+        sd[SD_NBITS] = nbits;
+        sd[SD_SLOT] = ok ? new_slot : slot_cur;
+        if (ok && p.fixed_slot < 0) p.sstate[(size_t)stream * SS_WORDS + SS_SLOT] = new_slot;
+    }
+}
+
+__global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_kernel(const __grid_constant__ EntropyParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    dequant_warp_body(p, blockIdx.x, smem);
+}
+
+// mixed-rate variant: CTAs of a bucket are numbered in units of DQW_WARPS thread slots (16 per entropy CTA)
+__global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_mixed_kernel(const __grid_constant__ MixedParams m) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ EntropyParams s_p;
+    __shared__ int s_block;
+    if (threadIdx.x == 0) {
+        constexpr int PER = ENT_THREADS / DQW_WARPS;
+        int b = 0;
+        while (b + 1 < m.n_buckets && (int)blockIdx.x >= m.buckets[b + 1].first_cta * PER) b++;
+        const MixedBucket& bk = m.buckets[b];
+        EntropyParams q = bk.ep;
+        q.frames = m.frames + (size_t)bk.first_row * m.frame_stride;
+        q.frame_nbytes = m.frame_nbytes ? m.frame_nbytes + bk.first_row : nullptr;
+        q.nbytes = m.nbytes;
+        q.frame_stride = m.frame_stride;
+        q.status_out = m.status_out ? m.status_out + bk.first_row : nullptr;
+        q.row_pitch = m.row_pitch;
+        s_p = q;
+        s_block = (int)blockIdx.x - bk.first_cta * PER;
+    }
+    __syncthreads();
+    dequant_warp_body(s_p, s_block, smem);
+}
+
+
+int entropy_row_pitch(int nbytes) {
     int words = (nbytes + 3) / 4 + 1;
     if ((words & 1) == 0) words++;                 // odd word pitch: lanes land on distinct banks
     return words * 4;
@@ -949,17 +1288,22 @@ static int entropy_row_pitch(int nbytes) {
 // dynamic shared memory limits, once per handle (lc3b_decoder_init) for the largest frame the handle accepts
 cudaError_t prepare_entropy(const DecoderState& st) {
     const int pitch = entropy_row_pitch(st.max_nbytes);
-    cudaError_t e = cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)entropy_smem_bytes(pitch));
-    if (e != cudaSuccess) return e;
-    const int smem = (int)dequant_smem_bytes(pitch);
-    if (st.cfg.n_ms == LC3B_10MS) return cudaFuncSetAttribute(dequant_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    return cudaFuncSetAttribute(dequant_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int es = (int)entropy_smem_bytes(pitch), ds = (int)dequant_smem_bytes(pitch);
+    cudaError_t e = cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, es);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(entropy_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, es);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_mixed_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_mixed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dequant_warp_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_warp_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dequant_warp_smem_bytes());
+    return e;
 }
 
-// stages: bit 0 entropy_kernel (bitstream -> integers), bit 1 dequant_kernel (integers -> shaped spectrum)
-cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
-                           size_t frame_stride, int32_t* status_out, int stages, cudaStream_t stream) {
+EntropyParams entropy_params(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                             size_t frame_stride, int32_t* status_out) {
     EntropyParams p;
+    memset(&p, 0, sizeof(p));                      // padding bytes are part of the graph cache key
     p.cfg = st.dcfg;
     p.frames = frames;
     p.frame_nbytes = frame_nbytes;
@@ -977,14 +1321,80 @@ cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const 
     p.sym_lut = st.sym_lut;
     p.fixed_slot = st.fixed_slot;
     p.row_pitch = entropy_row_pitch(nbytes);
-    const int grid = (st.n_streams + ENT_THREADS - 1) / ENT_THREADS;
-    if (stages & 1) entropy_kernel<<<grid, ENT_THREADS, entropy_smem_bytes(p.row_pitch), stream>>>(p);
+    return p;
+}
+
+// stages: bit 0 entropy_kernel (bitstream -> integers), bit 1 dequant_kernel (integers -> shaped spectrum)
+void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                  size_t frame_stride, int32_t* status_out, int stages) {
+    const EntropyParams p = entropy_params(st, frames, frame_nbytes, nbytes, frame_stride, status_out);
+    const unsigned grid = (unsigned)((st.n_streams + ENT_THREADS - 1) / ENT_THREADS);
+    if (stages & 1) plan.add(entropy_kernel, grid, ENT_THREADS, entropy_smem_bytes(p.row_pitch), p);
     if (stages & 2) {
-        const size_t smem = dequant_smem_bytes(p.row_pitch);
-        if (st.cfg.n_ms == LC3B_10MS) dequant_kernel<3><<<grid, ENT_THREADS, smem, stream>>>(p);
-        else dequant_kernel<2><<<grid, ENT_THREADS, smem, stream>>>(p);
+        if (use_dequant_warp(st.n_streams, st.dequant_mode)) {
+            plan.add(dequant_warp_kernel, grid * (ENT_THREADS / DQW_WARPS), DQW_WARPS * 32, dequant_warp_smem_bytes(), p);
+        } else {
+            const size_t smem = dequant_smem_bytes(p.row_pitch);
+            if (st.cfg.n_ms == LC3B_10MS) plan.add(dequant_kernel<3>, grid, ENT_THREADS, smem, p);
+            else plan.add(dequant_kernel<2>, grid, ENT_THREADS, smem, p);
+        }
     }
-    return cudaGetLastError();
+}
+
+// Which dequantisation kernel a batch of n streams gets: warp-per-frame below DQW_MAX_STREAMS (it finishes a small batch
+// in a fraction of the thread-per-frame kernel's serial latency but costs more issue slots per frame), thread-per-frame
+// above.  lc3b_decoder_set_dequant_mode (or LC3B_DEQUANT=warp|thread in the environment) forces one; tests run both.
+constexpr int DQW_MAX_STREAMS = 98304;
+bool use_dequant_warp(int n_streams, int mode) {
+    static const int forced = [] {
+        const char* e = getenv("LC3B_DEQUANT");
+        return !e ? 0 : (e[0] == 'w' ? 1 : e[0] == 't' ? 2 : 0);
+    }();
+    if (mode == 0) mode = forced;
+    if (mode) return mode == 1;
+    return n_streams <= DQW_MAX_STREAMS;
+}
+
+cudaError_t launch_entropy(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                           size_t frame_stride, int32_t* status_out, int stages, cudaStream_t stream) {
+    LaunchPlan plan;
+    plan_entropy(plan, st, frames, frame_nbytes, nbytes, frame_stride, status_out, stages);
+    return plan_launch_direct(plan, stream);
+}
+
+// Mixed-rate call: one entropy launch over all buckets, one dequantisation launch per frame duration present.
+// Returns the node index of the 10 ms and of the 7.5 ms dequantisation launch (-1 if absent) for the synthesis nodes
+// to depend on.
+void plan_entropy_mixed(LaunchPlan& plan, const MixedTables& t, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
+                        size_t frame_stride, int32_t* status_out, int* node_d10, int* node_d75) {
+    MixedParams m;
+    memset(&m, 0, sizeof(m));
+    m.frames = frames;
+    m.frame_nbytes = frame_nbytes;
+    m.nbytes = nbytes;
+    m.frame_stride = frame_stride;
+    m.status_out = status_out;
+    m.row_pitch = entropy_row_pitch(nbytes);
+    m.buckets = t.all;
+    m.n_buckets = t.n_all;
+    const int e = plan.add(entropy_mixed_kernel, (unsigned)t.cta_all, ENT_THREADS, entropy_smem_bytes(m.row_pitch), m, -1);
+    const size_t smem = dequant_smem_bytes(m.row_pitch);
+    *node_d10 = *node_d75 = -1;
+    if (use_dequant_warp(t.n_streams, t.dequant_mode)) {               // one launch for both frame durations (W is a run-time value there)
+        *node_d10 = *node_d75 = plan.add(dequant_warp_mixed_kernel, (unsigned)(t.cta_all * (ENT_THREADS / DQW_WARPS)), DQW_WARPS * 32,
+                                         dequant_warp_smem_bytes(), m, e);
+        return;
+    }
+    if (t.n_10 > 0) {
+        m.buckets = t.b10;
+        m.n_buckets = t.n_10;
+        *node_d10 = plan.add(dequant_mixed_kernel<3>, (unsigned)t.cta_10, ENT_THREADS, smem, m, e);
+    }
+    if (t.n_75 > 0) {
+        m.buckets = t.b75;
+        m.n_buckets = t.n_75;
+        *node_d75 = plan.add(dequant_mixed_kernel<2>, (unsigned)t.cta_75, ENT_THREADS, smem, m, e);
+    }
 }
 
 }  // namespace lc3b

@@ -17,9 +17,12 @@
 // kernel writes the filtered signal to the ring block and the PCM row.  The recursion only reaches back
 // p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are computed in parallel per step.  Streams outside
 // such a span cost this kernel one flag load.
+#include <string.h>
+
 #include "lc3b_common.cuh"
 #include "lc3b_imdct.cuh"
 #include "lc3b_math.cuh"
+#include "lc3b_plan.cuh"
 
 namespace lc3b {
 
@@ -322,12 +325,13 @@ struct PrepareSynth {
         e = cudaFuncSetAttribute(synth_kernel<NF, MS10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_WARPS * 2 * NF * 4);
     }
 };
-struct LaunchSynth {
+struct PlanSynth {
+    LaunchPlan& plan;
     const SynthParams& p;
-    cudaStream_t stream;
+    int dep, node;
     template <int NF, bool MS10> void operator()() {
         const int grid = (p.n_streams + SYN_WARPS - 1) / SYN_WARPS;
-        synth_kernel<NF, MS10><<<grid, SYN_WARPS * 32, SYN_WARPS * 2 * NF * 4, stream>>>(p);
+        node = plan.add(synth_kernel<NF, MS10>, (unsigned)grid, SYN_WARPS * 32, SYN_WARPS * 2 * NF * 4, p, dep);
     }
 };
 }  // namespace
@@ -339,8 +343,10 @@ cudaError_t prepare_synth(const DecoderState& st) {
     return cudaFuncSetAttribute(ltpf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ltpf_warp_bytes(st.cfg) * SYN_WARPS));
 }
 
-cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream) {
+// Adds the synthesis kernel (after node `dep`, -1 = none) and the post-filter kernel behind it; returns the last node.
+int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, int dep) {
     SynthParams p;
+    memset(&p, 0, sizeof(p));
     p.cfg = st.dcfg;
     p.win = st.win;
     p.dtw = st.dtw;
@@ -363,11 +369,16 @@ cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_st
     p.group = group;
     const size_t lw = ltpf_warp_bytes(st.cfg);
     p.smem_per_warp = (int)lw;
-    LaunchSynth ls{p, stream};
-    if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ls)) return cudaErrorInvalidValue;
+    PlanSynth ps{plan, p, dep, -1};
+    if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ps)) return -1;
     const int n_warps = (st.n_streams + group - 1) / group;
-    ltpf_kernel<<<(n_warps + SYN_WARPS - 1) / SYN_WARPS, SYN_WARPS * 32, lw * SYN_WARPS, stream>>>(p);
-    return cudaGetLastError();
+    return plan.add(ltpf_kernel, (unsigned)((n_warps + SYN_WARPS - 1) / SYN_WARPS), SYN_WARPS * 32, lw * SYN_WARPS, p, ps.node);
+}
+
+cudaError_t launch_synth(const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, cudaStream_t stream) {
+    LaunchPlan plan;
+    if (plan_synth(plan, st, pcm_out, pcm_stride, -1) < 0) return cudaErrorInvalidValue;
+    return plan_launch_direct(plan, stream);
 }
 
 }  // namespace lc3b

@@ -12,7 +12,10 @@
 // biquad, the block-energy envelope, the decision logic) run on lane 0.  The FFT is kissfft's own decimation-in-time
 // schedule (same factor order 4,4,..,2,3,5, same butterflies, same twiddle products) executed level by level with
 // the butterflies of a level spread over the lanes, so the spectrum is bit-identical to the reference's.
+#include <string.h>
+
 #include "lc3b_enc_common.cuh"
+#include "lc3b_plan.cuh"
 #include "lc3b_math.cuh"
 #include "lc3_tables.h"
 
@@ -610,8 +613,9 @@ cudaError_t prepare_enc_analysis(const EncoderState& st) {
     return e;
 }
 
-cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream) {
+void plan_enc_analysis(LaunchPlan& plan, const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages) {
     AnalysisParams p;
+    memset(&p, 0, sizeof(p));
     p.cfg = st.ecfg;
     p.win = st.win;
     p.dtw = st.dtw;
@@ -633,14 +637,19 @@ cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size
     if (stages & 1) {
         const size_t per_warp = mdct_warp_bytes(st.cfg.nf);
         p.smem_per_warp = (int)per_warp;
-        enc_mdct_kernel<<<grid, ANA_WARPS * 32, per_warp * ANA_WARPS, stream>>>(p);
+        plan.add(enc_mdct_kernel, (unsigned)grid, ANA_WARPS * 32, per_warp * ANA_WARPS, p);
     }
     if (stages & 2) {
         const size_t per_warp = ltpf_warp_bytes(st.cfg);
         p.smem_per_warp = (int)per_warp;
-        enc_ltpf_kernel<<<grid, ANA_WARPS * 32, per_warp * ANA_WARPS, stream>>>(p);
+        plan.add(enc_ltpf_kernel, (unsigned)grid, ANA_WARPS * 32, per_warp * ANA_WARPS, p);
     }
-    return cudaGetLastError();
+}
+
+cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream) {
+    LaunchPlan plan;
+    plan_enc_analysis(plan, st, pcm, pcm_stride, nbytes, stages);
+    return plan_launch_direct(plan, stream);
 }
 
 }  // namespace lc3b

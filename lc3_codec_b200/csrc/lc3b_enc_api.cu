@@ -3,18 +3,17 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+
 #include "lc3b_enc_common.cuh"
+#include "lc3b_handles.cuh"
 #include "lc3b_math.cuh"
 #include "lc3_tables.h"
 
 namespace lc3b {
 
-static thread_local int g_enc_last_cuda_error = 0;
-#define CU(x)                                                                  \
-    do {                                                                       \
-        cudaError_t _e = (x);                                                  \
-        if (_e != cudaSuccess) { g_enc_last_cuda_error = (int)_e; return LC3B_ERR_CUDA; } \
-    } while (0)
+// CUDA failures of the encoder land in the same thread-local slot as the decoder's (lc3b_last_cuda_error)
+#define CU(x) LC3B_CU(x)
 
 struct EncLayout {
     size_t ecfg, win, dtw, ftw, perm, thist, xs_hist, x12, x6, estate, xf, e_b, ehand, xq, qhand, lsbs, bs_scratch, stage_in,
@@ -169,15 +168,26 @@ static void fill_enc_config(const lc3b_config& c, EncConfig* d, float2* dtw, flo
 using namespace lc3b;
 
 struct lc3b_encoder {
-    EncoderState st;
-    int stage_mask;
+    EncoderState st{};
+    int stage_mask = 63;
+    int graph_mode = 0;                 // 0 = one launch per kernel, 1 = one cached CUDA graph per call (lc3b_plan.cuh)
+    GraphCache graphs;
     // optional pipelining of the host entry point: PCM arrives on an internal copy stream into a double-buffered
     // staging area, so the upload of call i+1 overlaps the kernels of call i
-    int pipelined, buf;
-    cudaStream_t copy_stream;
-    cudaEvent_t h2d_done[2], consumed[2];
-    bool consumed_valid[2];
+    int pipelined = 0, buf = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    bool consumed_valid[2] = {false, false};
 };
+
+// the kernels of one encode_frame per stream as a plan: stage mask bits 0-1 analysis, bits 2-5 quantisation / bitstream
+static cudaError_t run_encode(lc3b_encoder* h, const int16_t* pcm, size_t pcm_stride, uint8_t* frames_out, int nbytes,
+                              size_t frame_stride, int mask, cudaStream_t stream) {
+    LaunchPlan plan;
+    if (mask & 3) plan_enc_analysis(plan, h->st, pcm, pcm_stride, nbytes, mask & 3);
+    if (mask & 60) plan_enc_quant(plan, h->st, frames_out, nbytes, frame_stride, mask >> 2);
+    return h->graph_mode ? plan_launch_graph(h->graphs, plan, stream) : plan_launch_direct(plan, stream);
+}
 
 extern bool lc3b_make_config(int sf, int fd, lc3b_config* c);
 
@@ -202,10 +212,11 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
         return LC3B_ERR_INVALID_ARG;
     const EncLayout L = make_enc_layout(c, n_streams, max_nbytes);
     if (workspace_bytes < L.total || ((uintptr_t)dev_workspace & 255) != 0) return LC3B_ERR_WORKSPACE;
+    DeviceGuard guard;                        // the caller's current device is restored on return
     CU(cudaSetDevice(device));
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     uint8_t* base = (uint8_t*)dev_workspace;
-    lc3b_encoder* h = (lc3b_encoder*)calloc(1, sizeof(lc3b_encoder));
+    lc3b_encoder* h = new (std::nothrow) lc3b_encoder();
     if (!h) return LC3B_ERR_INVALID_ARG;
     EncoderState& st = h->st;
     st.cfg = c;
@@ -255,15 +266,10 @@ int lc3b_encoder_init(lc3b_encoder** out, int n_streams, int frame_duration, int
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
-        free(h);
-        g_enc_last_cuda_error = (int)e;
-        return LC3B_ERR_CUDA;
+        delete h;
+        return cuda_fail(e);
     }
-    h->stage_mask = 63;
-    h->pipelined = 0;
-    h->buf = 0;
-    h->copy_stream = nullptr;
-    h->consumed_valid[0] = h->consumed_valid[1] = false;
+    h->graph_mode = default_graph_mode(n_streams);
     *out = h;
     return LC3B_OK;
 }
@@ -282,9 +288,7 @@ int lc3b_encode_frames(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_stride
     // underflows calc_bit_budget (spectral_quantization.rs:133) - both are panics there, invalid arguments here
     if (nbytes < 20 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (h->stage_mask & 3) CU(launch_enc_analysis(st, pcm_in, pcm_stride, nbytes, h->stage_mask & 3, stream));
-    if (h->stage_mask & 60) CU(launch_enc_quant(st, frames_out, nbytes, frame_stride, h->stage_mask >> 2, stream));
+    CU(run_encode(h, pcm_in, pcm_stride, frames_out, nbytes, frame_stride, h->stage_mask, (cudaStream_t)cuda_stream));
     return LC3B_OK;
 }
 
@@ -310,13 +314,13 @@ int lc3b_encode_frames_host(lc3b_encoder* h, const int16_t* pcm_in, size_t pcm_s
         CU(cudaEventRecord(h->h2d_done[h->buf], in_stream));
         CU(cudaStreamWaitEvent(stream, h->h2d_done[h->buf], 0));
     }
-    CU(launch_enc_analysis(st, stage, nf, nbytes, 3, stream));
+    // one plan for the whole call; the staging buffer counts as consumed when the call's kernels have run
+    CU(run_encode(h, stage, nf, st.stage_out, nbytes, (size_t)nbytes, 63, stream));
     if (h->pipelined) {
         CU(cudaEventRecord(h->consumed[h->buf], stream));
         h->consumed_valid[h->buf] = true;
         h->buf ^= 1;
     }
-    CU(launch_enc_quant(st, st.stage_out, nbytes, (size_t)nbytes, 15, stream));
     if (frame_stride == (size_t)nbytes) CU(cudaMemcpyAsync(frames_out, st.stage_out, ns * (size_t)nbytes, cudaMemcpyDeviceToHost, stream));
     else CU(cudaMemcpy2DAsync(frames_out, frame_stride, st.stage_out, (size_t)nbytes, (size_t)nbytes, ns, cudaMemcpyDeviceToHost, stream));
     return LC3B_OK;
@@ -336,9 +340,16 @@ int lc3b_encoder_debug_read(lc3b_encoder* h, float* xf, float* e_b, int32_t* han
     return LC3B_OK;
 }
 
+int lc3b_encoder_set_graph_mode(lc3b_encoder* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return LC3B_ERR_INVALID_ARG;
+    h->graph_mode = mode;
+    return LC3B_OK;
+}
+
 int lc3b_encoder_set_host_pipelining(lc3b_encoder* h, int on) {
     if (!h) return LC3B_ERR_INVALID_ARG;
     if (on && !h->copy_stream) {
+        DeviceGuard guard;
         CU(cudaSetDevice(h->st.device));
         CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -357,7 +368,7 @@ void lc3b_encoder_destroy(lc3b_encoder* h) {
         for (int i = 0; i < 2; i++) { cudaEventDestroy(h->h2d_done[i]); cudaEventDestroy(h->consumed[i]); }
         cudaStreamDestroy(h->copy_stream);
     }
-    free(h);
+    delete h;
 }
 
 }  // extern "C"

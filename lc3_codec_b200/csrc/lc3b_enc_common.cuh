@@ -73,5 +73,9 @@ int enc_bitstream_scratch_words(int ne, int max_nbytes);   // per-stream size of
 cudaError_t launch_enc_analysis(const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages, cudaStream_t stream);
 // stages: bit 0 SNS kernel (with the bandwidth detector), bit 1 TNS kernel, bit 2 quantise kernel, bit 3 bitstream kernel
 cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream);
+// the same launches written into a plan (lc3b_plan.cuh) instead of issued
+struct LaunchPlan;
+void plan_enc_analysis(LaunchPlan& plan, const EncoderState& st, const int16_t* pcm, size_t pcm_stride, int nbytes, int stages);
+void plan_enc_quant(LaunchPlan& plan, const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages);
 
 }  // namespace lc3b

@@ -25,7 +25,10 @@
 // The reference writes both ends of the frame interleaved; when they never meet the result is the OR of the two
 // streams, which is what the fast path builds.  A frame whose two ends collide (the encoder overspent its budget)
 // is re-encoded by one lane with the reference's interleaved write order (bitstream_encode_serial).
+#include <string.h>
+
 #include "lc3b_enc_common.cuh"
+#include "lc3b_plan.cuh"
 #include "lc3b_math.cuh"
 #include "lc3_tables.h"
 
@@ -1689,8 +1692,9 @@ cudaError_t prepare_enc_quant(const EncoderState& st) {
     return e;
 }
 
-cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream) {
+void plan_enc_quant(LaunchPlan& plan, const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages) {
     QuantParams p;
+    memset(&p, 0, sizeof(p));
     p.cfg = st.ecfg;
     p.n_streams = st.n_streams;
     p.nbytes = nbytes;
@@ -1708,17 +1712,22 @@ cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nb
     p.frames_out = frames_out;
     const size_t wbytes = bitstream_warp_bytes(st.cfg.ne, nbytes, &p);
     const int grid = (p.n_streams + QW - 1) / QW;
-    if (stages & 1) enc_sns_kernel<<<(p.n_streams + SNS_WARPS - 1) / SNS_WARPS, SNS_WARPS * 32, SHAPE_SMEM / QW * SNS_WARPS, stream>>>(p);
-    if (stages & 2) enc_tns_kernel<<<grid, QNT_THREADS, SHAPE_SMEM, stream>>>(p);
-    if (stages & 4) enc_quantize_kernel<<<grid, QNT_THREADS, QUANTIZE_SMEM, stream>>>(p);
+    if (stages & 1) plan.add(enc_sns_kernel, (unsigned)((p.n_streams + SNS_WARPS - 1) / SNS_WARPS), SNS_WARPS * 32, SHAPE_SMEM / QW * SNS_WARPS, p);
+    if (stages & 2) plan.add(enc_tns_kernel, (unsigned)grid, QNT_THREADS, SHAPE_SMEM, p);
+    if (stages & 4) plan.add(enc_quantize_kernel, (unsigned)grid, QNT_THREADS, QUANTIZE_SMEM, p);
     if (stages & 8) {
-        enc_bs_prepare_kernel<<<grid, QNT_THREADS, QW * wbytes, stream>>>(p);
+        plan.add(enc_bs_prepare_kernel, (unsigned)grid, QNT_THREADS, QW * wbytes, p);
         // a thread-per-frame kernel needs ~12 k frames before its serial latency (~80 us) is amortised
         p.inline_ac = p.n_streams < 12288 ? 1 : 0;
-        if (!p.inline_ac) enc_range_coder_kernel<<<(p.n_streams + 127) / 128, 128, 0, stream>>>(p);
-        enc_bs_finish_kernel<<<grid, QNT_THREADS, QW * (size_t)p.w_bytes_fin, stream>>>(p);
+        if (!p.inline_ac) plan.add(enc_range_coder_kernel, (unsigned)((p.n_streams + 127) / 128), 128, 0, p);
+        plan.add(enc_bs_finish_kernel, (unsigned)grid, QNT_THREADS, QW * (size_t)p.w_bytes_fin, p);
     }
-    return cudaGetLastError();
+}
+
+cudaError_t launch_enc_quant(const EncoderState& st, uint8_t* frames_out, int nbytes, size_t frame_stride, int stages, cudaStream_t stream) {
+    LaunchPlan plan;
+    plan_enc_quant(plan, st, frames_out, nbytes, frame_stride, stages);
+    return plan_launch_direct(plan, stream);
 }
 
 }  // namespace lc3b

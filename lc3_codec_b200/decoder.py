@@ -158,8 +158,28 @@ class Lc3BatchDecoder:
         if rc:
             raise Lc3bError(rc, "lc3b_decoder_host_fence")
 
+    def set_graph_mode(self, on: bool) -> None:
+        """Issue every call as ONE cached CUDA graph launch (True) or one launch per kernel (False); include/lc3b.h."""
+        rc = native.lib().lc3b_decoder_set_graph_mode(self._h, int(bool(on)))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_set_graph_mode")
+
+    def set_dequant_mode(self, mode: int) -> None:
+        """0 = dequantisation kernel chosen by batch size, 1 = warp per frame, 2 = thread per frame (identical results)."""
+        rc = native.lib().lc3b_decoder_set_dequant_mode(self._h, mode)
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_set_dequant_mode")
+
+    def graph_stats(self) -> dict:
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        rc = native.lib().lc3b_decoder_graph_stats(self._h, C.byref(a), C.byref(b), C.byref(c))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_graph_stats")
+        return {"hits": a.value, "updates": b.value, "builds": c.value}
+
     def set_stage_mask(self, mask: int) -> None:
-        """Profiling hook: 1 = entropy kernel only, 2 = synthesis kernel only, 3 = both (default)."""
+        """Profiling hook (lc3b_decoder_set_stage_mask): bit 0 = entropy kernel, bit 1 = dequantisation kernel, bit 2 =
+        synthesis + post-filter kernels; default 7 (all).  Results are only meaningful with mask 7."""
         rc = native.lib().lc3b_decoder_set_stage_mask(self._h, mask)
         if rc:
             raise Lc3bError(rc, "lc3b_decoder_set_stage_mask")

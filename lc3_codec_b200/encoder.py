@@ -83,8 +83,15 @@ class Lc3BatchEncoder:
         if rc != 0:
             raise Lc3bError(rc, "lc3b_encoder_set_host_pipelining")
 
+    def set_graph_mode(self, on: bool) -> None:
+        """Issue every call as ONE cached CUDA graph launch (True) or one launch per kernel (False); include/lc3b.h."""
+        rc = native.lib().lc3b_encoder_set_graph_mode(self._h, int(bool(on)))
+        if rc:
+            raise Lc3bError(rc, "lc3b_encoder_set_graph_mode")
+
     def set_stage_mask(self, mask: int) -> None:
-        """Profiling hook: 1 = analysis kernel only, 2 = quantisation kernel only, 3 = both (default)."""
+        """Profiling hook (lc3b_encoder_set_stage_mask): bit 0 = MDCT kernel, bit 1 = attack / LTPF analysis kernel,
+        bit 2 = SNS kernel, bit 3 = TNS kernel, bit 4 = quantise kernel, bit 5 = bitstream stage; default 63 (all)."""
         rc = native.lib().lc3b_encoder_set_stage_mask(self._h, mask)
         if rc:
             raise Lc3bError(rc, "lc3b_encoder_set_stage_mask")

@@ -29,7 +29,11 @@ class FrameDuration(enum.IntEnum):          # src/common/config.rs:12
 
     @staticmethod
     def from_ms(ms: float) -> "FrameDuration":
-        return FrameDuration.TenMs if float(ms) == 10.0 else FrameDuration.SevenPointFiveMs
+        if float(ms) == 10.0:
+            return FrameDuration.TenMs
+        if float(ms) == 7.5:
+            return FrameDuration.SevenPointFiveMs
+        raise ValueError(f"LC3 frame durations are 7.5 and 10 ms, not {ms}")
 
 
 class Lc3bError(RuntimeError):
@@ -53,7 +57,20 @@ EXPORTS = ["lc3b_config_new", "lc3b_last_cuda_error", "lc3b_version", "lc3b_deco
            "lc3b_selftest_math_host",
            "lc3b_selftest_math_device", "lc3b_encoder_workspace_bytes", "lc3b_encoder_init", "lc3b_encode_frames",
            "lc3b_encode_frames_host", "lc3b_encoder_set_host_pipelining", "lc3b_encoder_debug_read", "lc3b_encoder_set_stage_mask",
-           "lc3b_encoder_destroy"]
+           "lc3b_encoder_destroy", "lc3b_decoder_set_graph_mode", "lc3b_decoder_graph_stats", "lc3b_decoder_set_dequant_mode", "lc3b_mixed_decoder_set_dequant_mode", "lc3b_encoder_set_graph_mode",
+           "lc3b_mixed_decoder_layout", "lc3b_mixed_decoder_workspace_bytes", "lc3b_mixed_decoder_init", "lc3b_mixed_decode_frames",
+           "lc3b_mixed_decode_frames_host", "lc3b_mixed_decoder_set_host_pipelining", "lc3b_mixed_decoder_host_fence",
+           "lc3b_mixed_decoder_set_graph_mode", "lc3b_mixed_decoder_destroy",
+           "lc3b_sharded_decoder_create", "lc3b_sharded_decoder_n_shards", "lc3b_sharded_decoder_shard",
+           "lc3b_sharded_decode_frames_host", "lc3b_sharded_decoder_wait", "lc3b_sharded_decoder_destroy",
+           "lc3b_sharded_encoder_create", "lc3b_sharded_encoder_n_shards", "lc3b_sharded_encoder_shard",
+           "lc3b_sharded_encode_frames_host", "lc3b_sharded_encoder_wait", "lc3b_sharded_encoder_destroy",
+           "lc3b_host_alloc", "lc3b_host_free"]
+
+
+class MixedBucket(C.Structure):             # lc3b_mixed_bucket
+    _fields_ = [("sampling_frequency", C.c_int32), ("frame_duration", C.c_int32), ("first_row", C.c_int32),
+                ("n_rows", C.c_int32), ("nf", C.c_int32), ("reserved", C.c_int32), ("host_pcm_offset", C.c_uint64)]
 
 _lib = None
 
@@ -94,6 +111,34 @@ def lib() -> C.CDLL:
         L.lc3b_encoder_set_host_pipelining.argtypes = [vp, i32]
         L.lc3b_encoder_destroy.argtypes = [vp]
         L.lc3b_encoder_destroy.restype = None
+        u64p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+        L.lc3b_decoder_set_graph_mode.argtypes = [vp, i32]
+        L.lc3b_decoder_set_dequant_mode.argtypes = [vp, i32]
+        L.lc3b_mixed_decoder_set_dequant_mode.argtypes = [vp, i32]
+        L.lc3b_decoder_graph_stats.argtypes = [vp, u64p, u64p, u64p]
+        L.lc3b_encoder_set_graph_mode.argtypes = [vp, i32]
+        L.lc3b_mixed_decoder_layout.argtypes = [i32, vp, vp, vp, C.POINTER(MixedBucket), i32p, u64p]
+        L.lc3b_mixed_decoder_workspace_bytes.argtypes = [i32, vp, vp, i32, C.POINTER(sz)]
+        L.lc3b_mixed_decoder_init.argtypes = [C.POINTER(vp), i32, vp, vp, i32, i32, vp, sz, vp]
+        L.lc3b_mixed_decode_frames.argtypes = [vp, i32, vp, vp, i32, sz, vp, sz, vp, vp]
+        L.lc3b_mixed_decode_frames_host.argtypes = [vp, i32, vp, vp, i32, sz, vp, vp, vp]
+        L.lc3b_mixed_decoder_set_host_pipelining.argtypes = [vp, i32]
+        L.lc3b_mixed_decoder_host_fence.argtypes = [vp, vp]
+        L.lc3b_mixed_decoder_set_graph_mode.argtypes = [vp, i32]
+        L.lc3b_mixed_decoder_destroy.argtypes = [vp]
+        L.lc3b_mixed_decoder_destroy.restype = None
+        for kind in ("decoder", "encoder"):
+            getattr(L, f"lc3b_sharded_{kind}_create").argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32p, i32]
+            getattr(L, f"lc3b_sharded_{kind}_n_shards").argtypes = [vp]
+            getattr(L, f"lc3b_sharded_{kind}_shard").argtypes = [vp, i32, i32p, i32p, i32p]
+            getattr(L, f"lc3b_sharded_{kind}_wait").argtypes = [vp]
+            getattr(L, f"lc3b_sharded_{kind}_destroy").argtypes = [vp]
+            getattr(L, f"lc3b_sharded_{kind}_destroy").restype = None
+        L.lc3b_sharded_decode_frames_host.argtypes = [vp, i32, vp, vp, i32, sz, vp, sz, vp]
+        L.lc3b_sharded_encode_frames_host.argtypes = [vp, vp, sz, vp, i32, sz]
+        L.lc3b_host_alloc.argtypes = [C.POINTER(vp), sz]
+        L.lc3b_host_free.argtypes = [vp]
+        L.lc3b_host_free.restype = None
         L.lc3b_selftest_math_host.argtypes = [i32, vp, vp, vp, i32]
         L.lc3b_selftest_math_device.argtypes = [i32, vp, vp, vp, i32, vp]
         _lib = L

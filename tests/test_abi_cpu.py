@@ -134,3 +134,59 @@ def test_msun_accuracy_vs_float64(oracle):
     assert ulp_err(run(0, np.full(n, 10.0, np.float32), y), np.power(10.0, y.astype(np.float64))) < 1.0
     x = (np.float32(np.pi / 17.0) * np.arange(-8, 9, dtype=np.float32)).astype(np.float32)
     assert np.array_equal(run(5, x), np.sin(x.astype(np.float64)).astype(np.float32))   # sinf: f64 kernels, correctly rounded here
+
+
+def test_mixed_layout_is_bucket_ordered(L):
+    """lc3b_mixed_decoder_layout (host only): buckets sorted by (sampling frequency, duration), streams of a bucket in
+    original order, dense host PCM offsets; bad enums rejected."""
+    import ctypes as C
+
+    import numpy as np
+    from lc3_codec_b200 import native
+    rng = np.random.default_rng(2)
+    n = 1000
+    sf = rng.integers(0, 6, n).astype(np.int32)
+    fd = rng.integers(0, 2, n).astype(np.int32)
+    order = np.zeros(n, np.int32)
+    buckets = (native.MixedBucket * 12)()
+    nb, elems = C.c_int32(0), C.c_uint64(0)
+    assert L.lib().lc3b_mixed_decoder_layout(n, sf.ctypes.data, fd.ctypes.data, order.ctypes.data, buckets, C.byref(nb), C.byref(elems)) == 0
+    assert sorted(order.tolist()) == list(range(n))
+    keys = [(int(sf[s]), int(fd[s]), int(s)) for s in order]
+    assert keys == sorted(keys)
+    row, off = 0, 0
+    for b in buckets[:nb.value]:
+        assert b.first_row == row and b.host_pcm_offset == off
+        cfg = native.config(b.sampling_frequency, b.frame_duration)
+        assert b.nf == cfg.nf and all(sf[s] == b.sampling_frequency and fd[s] == b.frame_duration for s in order[row:row + b.n_rows])
+        row += b.n_rows
+        off += b.n_rows * b.nf
+    assert row == n and off == elems.value
+    sf[5] = 6
+    assert L.lib().lc3b_mixed_decoder_layout(n, sf.ctypes.data, fd.ctypes.data, None, None, None, None) == 2
+    size = C.c_size_t(0)
+    sf[5] = 0
+    assert L.lib().lc3b_mixed_decoder_workspace_bytes(n, sf.ctypes.data, fd.ctypes.data, 120, C.byref(size)) == 0 and size.value > 0
+    assert L.lib().lc3b_mixed_decoder_workspace_bytes(n, sf.ctypes.data, fd.ctypes.data, 401, C.byref(size)) == 2
+
+
+def test_new_entry_points_reject_null_handles(L):
+    lib = L.lib()
+    assert lib.lc3b_decoder_set_graph_mode(None, 1) == 2
+    assert lib.lc3b_encoder_set_graph_mode(None, 1) == 2
+    assert lib.lc3b_mixed_decode_frames(None, 16, None, None, 10, 10, None, 480, None, None) == 2
+    assert lib.lc3b_mixed_decoder_host_fence(None, None) == 2
+    assert lib.lc3b_sharded_decoder_wait(None) == 2 and lib.lc3b_sharded_encoder_wait(None) == 2
+    assert lib.lc3b_sharded_decoder_n_shards(None) == 0
+    assert lib.lc3b_sharded_decode_frames_host(None, 16, None, None, 10, 10, None, 480, None) == 2
+    lib.lc3b_mixed_decoder_destroy(None)
+    lib.lc3b_sharded_decoder_destroy(None)
+    lib.lc3b_sharded_encoder_destroy(None)
+    lib.lc3b_host_free(None)
+
+
+def test_frame_duration_from_ms_rejects_other_values(L):
+    assert L.FrameDuration.from_ms(7.5) == L.FrameDuration.SevenPointFiveMs and L.FrameDuration.from_ms(10) == L.FrameDuration.TenMs
+    for bad in (5, 2.5, 0, 20):
+        with pytest.raises(ValueError):
+            L.FrameDuration.from_ms(bad)

@@ -225,8 +225,8 @@ def test_mixed_rate_batch():
 
 
 def test_mixed_rate_batch_host_entry():
-    """Lc3MixedBatchDecoder.decode_frames_host: pinned host rows in, one dense pinned PCM tensor per configuration out,
-    pipelined copies; same PCM as the oracle."""
+    """lc3b_mixed_decode_frames_host: pinned host rows in, ONE dense pinned PCM buffer out (per-bucket views), pipelined
+    copies, status flags; same PCM as the oracle.  Run with the graph executor and with plain launches."""
     import torch
 
     import lc3_codec_b200 as L
@@ -238,26 +238,164 @@ def test_mixed_rate_batch_host_entry():
         frames_by[(fs, ms)] = fr
         pcm_by[(fs, ms)] = O.decode_streams(fr, fs, ms)
     stream_cfg = [ALL_CONFIGS[s % 12] for s in range(12 * per)]
+    for graph in (True, False):
+        dec = L.Lc3MixedBatchDecoder([(L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)) for fs, ms in stream_cfg],
+                                     max_nbytes=120, device="cuda:0")
+        dec.set_graph_mode(graph)
+        dec.set_host_pipelining(True)
+        S = len(stream_cfg)
+        outs = [dec.alloc_host_pcm() for _ in range(F)]
+        status = torch.full((F, S), -1, dtype=torch.int32).pin_memory()
+        rows_all = torch.zeros((F, S, 120), dtype=torch.uint8).pin_memory()
+        lens = torch.zeros(S, dtype=torch.int32).pin_memory()
+        for pos, s in enumerate(dec.order):
+            fs, ms = stream_cfg[s]
+            fr = frames_by[(fs, ms)][s // 12]
+            rows_all[:, pos, :fr.shape[1]] = torch.from_numpy(fr)
+            lens[pos] = fr.shape[1]
+        for f in range(F):
+            dec.decode_frames_host(16, rows_all[f], lens, outs[f], status_out=status[f])
+        dec.host_fence()
+        torch.cuda.synchronize()
+        assert int(status.abs().max()) == 0
+        views = [dec.host_pcm_views(o) for o in outs]
+        for b, ((sf, fd), first, count) in enumerate(dec.buckets):
+            for r in range(count):
+                s = dec.order[first + r]
+                fs, ms = stream_cfg[s]
+                exp = pcm_by[(fs, ms)][s // 12]
+                got = np.stack([views[f][b][r].numpy() for f in range(F)])
+                assert np.abs(got.astype(np.int32) - exp.astype(np.int32)).max() <= PCM_TOL, (fs, ms, s, graph)
+
+
+def test_mixed_rate_matches_single_configuration_handles_bitwise():
+    """The mixed-rate kernels run the single-configuration bodies: a bucket's PCM must equal, bit for bit, what an
+    ordinary lc3b_decode_frames handle produces for the same streams (ragged bucket sizes, lost frames included)."""
+    import torch
+
+    import lc3_codec_b200 as L
+    sizes = {(48000, 10): 130, (16000, 7.5): 33, (24000, 10): 1, (44100, 7.5): 129, (8000, 10): 40, (32000, 7.5): 64}
+    F = 8
+    stream_cfg, local = [], []
+    for i in range(max(sizes.values())):
+        for cfg, n in sizes.items():
+            if i < n:
+                stream_cfg.append(cfg)
+                local.append(i)
+    frames_by = {cfg: corpus(cfg[0], cfg[1], MIXED_NBYTES[cfg], n, F)[1] for cfg, n in sizes.items()}
+    rng = np.random.default_rng(3)
+    lost = {cfg: rng.random((n, F)) < 0.1 for cfg, n in sizes.items()}
+    ref = {}
+    for cfg, fr in frames_by.items():
+        lens = np.where(lost[cfg], 0, fr.shape[2]).astype(np.int32)
+        ref[cfg] = gpu_decode(cfg[0], cfg[1], fr, lens, trace=False)
     dec = L.Lc3MixedBatchDecoder([(L.SamplingFrequency.from_hz(fs), L.FrameDuration.from_ms(ms)) for fs, ms in stream_cfg],
                                  max_nbytes=120, device="cuda:0")
-    dec.set_host_pipelining(True)
     S = len(stream_cfg)
-    outs = [dec.alloc_host_pcm() for _ in range(F)]
-    rows_all = torch.zeros((F, S, 120), dtype=torch.uint8).pin_memory()
-    lens = torch.zeros(S, dtype=torch.int32).pin_memory()
-    for pos, s in enumerate(dec.order):
-        fs, ms = stream_cfg[s]
-        fr = frames_by[(fs, ms)][s // 12]
-        rows_all[:, pos, :fr.shape[1]] = torch.from_numpy(fr)
-        lens[pos] = fr.shape[1]
     for f in range(F):
-        dec.decode_frames_host(16, rows_all[f], lens, outs[f])
-    dec.host_fence()
-    torch.cuda.synchronize()
-    for b, ((sf, fd), first, count) in enumerate(dec.buckets):
-        for r in range(count):
-            s = dec.order[first + r]
-            fs, ms = stream_cfg[s]
-            exp = pcm_by[(fs, ms)][s // 12]
-            got = np.stack([outs[f][b][r].numpy() for f in range(F)])
-            assert np.abs(got.astype(np.int32) - exp.astype(np.int32)).max() <= PCM_TOL, (fs, ms, s)
+        rows = np.zeros((S, 128), np.uint8)
+        lens = np.zeros(S, np.int32)
+        for pos, s in enumerate(dec.order):
+            cfg = stream_cfg[s]
+            fr = frames_by[cfg][local[s], f]
+            rows[pos, :len(fr)] = fr
+            lens[pos] = 0 if lost[cfg][local[s], f] else len(fr)
+        out = torch.zeros((S, 480), dtype=torch.int16, device="cuda:0")
+        st = torch.full((S,), -1, dtype=torch.int32, device="cuda:0")
+        dec.decode_frames(16, torch.from_numpy(rows).cuda(), torch.from_numpy(lens).cuda(), out, status_out=st)
+        got, gst = out.cpu().numpy(), st.cpu().numpy()
+        for pos, s in enumerate(dec.order):
+            cfg = stream_cfg[s]
+            pcm, _, _, _, status = ref[cfg]
+            nf = pcm.shape[-1]
+            assert np.array_equal(got[pos, :nf], pcm[local[s], f]), (cfg, s, f)
+            assert gst[pos] == status[local[s], f]
+
+
+def test_graph_executor_equals_plain_launches():
+    """lc3b_decoder_set_graph_mode: the cached-graph executor replays / patches graphs as the caller's buffers rotate;
+    PCM and status are identical to plain launches, and the cache statistics show replays and in-place updates."""
+    import torch
+
+    import lc3_codec_b200 as L
+    _, frames = corpus(16000, 7.5, 30, 96, 40)
+    S, F, nb = frames.shape
+    sf, fd = L.SamplingFrequency.Hz16000, L.FrameDuration.SevenPointFiveMs
+    outs = []
+    for graph in (False, True):
+        ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(S, fd, sf, nb), dtype=torch.uint8, device="cuda:0")
+        dec = L.Lc3BatchDecoder(S, fd, sf, ws, nb)
+        dec.set_graph_mode(graph)
+        ring = [torch.zeros((S, nb), dtype=torch.uint8, device="cuda:0") for _ in range(3)]     # caller rotates 3 input buffers
+        fresh = []                                                                                # ... then uses new ones every call
+        pcm = torch.zeros((F, S, dec.nf), dtype=torch.int16, device="cuda:0")
+        for f in range(F):
+            if f < 20:
+                buf = ring[f % 3]
+            else:
+                buf = torch.zeros((S, nb), dtype=torch.uint8, device="cuda:0")
+                fresh.append(buf)
+            buf.copy_(torch.from_numpy(np.ascontiguousarray(frames[:, f])))
+            dec.decode_frames(16, buf, pcm[f])
+        torch.cuda.synchronize()
+        outs.append(pcm.cpu().numpy())
+        if graph:
+            st = dec.graph_stats()
+            assert st["hits"] + st["updates"] + st["builds"] == F and st["builds"] <= 24, st
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_sharded_decoder_two_shards_on_one_gpu():
+    """lc3b_sharded_decoder_*: one host-buffer call for the whole batch, one thread + stream + workspace per shard.
+    Two shards on device 0 exercise the row arithmetic and the worker threads on a single-GPU box."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from oracle import pyoracle as O
+    _, frames = corpus(48000, 10, 100, 101, 12)
+    S, F, nb = frames.shape
+    rng = np.random.default_rng(5)
+    lens = np.where(rng.random((S, F)) < 0.1, 0, nb).astype(np.int32)
+    dec = L.Lc3ShardedBatchDecoder(S, L.FrameDuration.TenMs, L.SamplingFrequency.Hz48000, nb, devices=[0, 0])
+    sh = dec.shards()
+    assert [d for d, _, _ in sh] == [0, 0] and sh[0][1] == 0 and sh[0][2] + sh[1][2] == S and sh[1][1] == sh[0][2]
+    host_in = torch.from_numpy(np.ascontiguousarray(frames.transpose(1, 0, 2))).pin_memory()
+    host_len = torch.from_numpy(np.ascontiguousarray(lens.T)).pin_memory()
+    host_out = torch.zeros((F, S, 480), dtype=torch.int16).pin_memory()
+    status = torch.full((F, S), -1, dtype=torch.int32).pin_memory()
+    for f in range(F):
+        dec.decode_frames_host(16, host_in[f], host_out[f], frame_nbytes=host_len[f], status_out=status[f])
+    dec.wait()
+    o_pcm, o_tr, _, _ = O.decode_streams(frames, 48000, 10, lens, trace=True)
+    d = np.abs(host_out.numpy().transpose(1, 0, 2).astype(np.int32) - o_pcm.astype(np.int32))
+    assert d.max() <= PCM_TOL
+    assert np.array_equal(status.numpy().T, 1 - o_tr[..., 0])
+    with pytest.raises(L.Lc3DecoderError):
+        dec.decode_frames_host(24, host_in[0], host_out[0])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_both_dequantisation_kernels_against_the_oracle(mode):
+    """lc3b_decoder_set_dequant_mode: the warp-per-frame kernel (small batches) and the thread-per-frame kernel (large
+    batches) each meet the full parity bar - shaped spectrum bit exact - on every kind of frame: high-rate frames with
+    lsb_mode, TNS with one and two filters, 7.5 ms (window 2), 8 kHz / 7.5 ms (nb = 60 folding), lost frames, garbage."""
+    rng = np.random.default_rng(17)
+    for fs, ms, nb, S, F in ((48000, 10, 150, 70, 24), (48000, 10, 400, 33, 8), (16000, 7.5, 30, 129, 30), (8000, 7.5, 20, 40, 20),
+                             (32000, 7.5, 60, 64, 16), (24000, 10, 60, 31, 16), (44100, 10, 120, 32, 12)):
+        _, frames = corpus(fs, ms, nb, S, F)
+        lens = np.where(rng.random((S, F)) < 0.06, 0, nb).astype(np.int32)
+        stats = assert_parity(fs, ms, frames, lens, dequant_mode=mode, graph=bool(mode & 1))
+        assert stats["concealed"] > 0.0
+    for fs, ms, nb in ((48000, 10, 150), (16000, 7.5, 30), (8000, 10, 26)):
+        frames = rng.integers(0, 256, size=(96, 10, nb), dtype=np.uint8)
+        assert_parity(fs, ms, frames, dequant_mode=mode)
+
+
+def test_dequantisation_kernels_agree_bitwise_at_batch_sizes_around_the_switch():
+    """Same streams through mode 1 and mode 2 at 4 096 streams: identical spectra and PCM (tiled corpus)."""
+    _, base = corpus(48000, 10, 150, 128, 6)
+    frames = np.tile(base, (32, 1, 1))
+    a = gpu_decode(48000, 10, frames, dequant_mode=1)
+    b = gpu_decode(48000, 10, frames, dequant_mode=2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[4], b[4])

@@ -109,3 +109,30 @@ def test_round_trip_gpu_encode_gpu_decode():
     g_pcm = gpu_decode(48000, 10, g_frames, trace=False)[0]
     o_pcm = O.decode_streams(o_frames, 48000, 10)
     assert np.abs(g_pcm.astype(np.int32) - o_pcm.astype(np.int32)).max() <= 1
+
+
+def test_sharded_encoder_and_graph_executor():
+    """lc3b_sharded_encoder_* (two shards on device 0, host buffers for the whole batch) and lc3b_encoder_set_graph_mode:
+    bytes identical to the oracle encoder either way."""
+    import torch
+
+    import lc3_codec_b200 as L
+    pcm, o_frames = corpus(48000, 10, 120, 75, 10)
+    S, F, nf = pcm.shape
+    enc = L.Lc3ShardedBatchEncoder(S, L.FrameDuration.TenMs, L.SamplingFrequency.Hz48000, 120, devices=[0, 0])
+    host_in = torch.from_numpy(np.ascontiguousarray(pcm.transpose(1, 0, 2))).pin_memory()
+    host_out = torch.zeros((F, S, 120), dtype=torch.uint8).pin_memory()
+    for f in range(F):
+        enc.encode_frames_host(host_in[f], host_out[f])
+    enc.wait()
+    assert np.array_equal(host_out.numpy().transpose(1, 0, 2), o_frames)
+    for graph in (True, False):
+        sf, fd = L.SamplingFrequency.Hz48000, L.FrameDuration.TenMs
+        ws = torch.empty(L.Lc3BatchEncoder.calc_working_buffer_lengths(S, fd, sf, 120), dtype=torch.uint8, device="cuda:0")
+        e1 = L.Lc3BatchEncoder(S, fd, sf, ws, 120)
+        e1.set_graph_mode(graph)
+        out = torch.zeros((F, S, 120), dtype=torch.uint8, device="cuda:0")
+        x = torch.from_numpy(np.ascontiguousarray(pcm.transpose(1, 0, 2))).cuda()
+        for f in range(F):
+            e1.encode_frames(x[f], out[f])
+        assert np.array_equal(out.cpu().numpy().transpose(1, 0, 2), o_frames), graph

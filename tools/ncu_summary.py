@@ -45,7 +45,13 @@ def main():
             "registers": int(g("launch__registers_per_thread")),
             "smem_per_block": int(g("launch__shared_mem_per_block_dynamic", 0) + g("launch__shared_mem_per_block_static", 0)),
             "warp_inst": g("smsp__inst_executed.sum"),
-            "thread_inst_per_warp_inst": g("smsp__thread_inst_executed.sum") / max(g("smsp__inst_executed.sum"), 1.0),
+            "thread_inst_per_warp_inst": g("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "thread_inst_pred_on_per_warp_inst": g("smsp__thread_inst_executed_pred_on_per_inst_executed.ratio"),
+            "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "pipe_alu_pct": g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "pipe_fma_pct": g("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "pipe_lsu_pct": g("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+            "dram_pct_of_peak": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
             "l2_hit_pct": g("lts__t_sector_hit_rate.pct"),
             "stalls": {k2: v / tot for k2, v in top},
         })
