@@ -653,6 +653,7 @@ def run_codec(args, w, rank, local_rank, world, dev, dist, quick=False):
         ws_bytes += n
         dec_ws = torch.empty(n, dtype=torch.uint8, device=dev)
         dec = L.Lc3BatchDecoder(S, fd, sf, dec_ws, NB)
+        dec.set_min_nbytes(NB)           # every frame of this workload is NB bytes: at 150 B the post filter's history is dead state
     if mode in ("encode", "roundtrip"):
         n = L.Lc3BatchEncoder.calc_working_buffer_lengths(S, fd, sf, NB)
         ws_bytes += n

@@ -120,6 +120,15 @@ int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream);
  * 131 072 streams (launch-sensitive), else 0; LC3B_GRAPH=0/1 in the environment overrides the default.  Results are
  * identical either way.  graph_stats: cache hits / in-place updates / instantiations so far (any pointer may be NULL). */
 int lc3b_decoder_set_graph_mode(lc3b_decoder* h, int mode);
+/* A promise about the frames this handle will see: every submitted frame is at least `min_nbytes` long or is a lost
+ * frame (length 0).  Default 0 (no promise).  When the promised length rules the long-term post filter out for every
+ * frame the handle accepts - the reference's gain table ends in the row (0.0, 0) once the frame carries 560 + 80 * fs_ind
+ * bits per 10 ms (src/decoder/long_term_post_filter.rs:142-161), e.g. 110 bytes at 48 kHz / 10 ms - the decoder stops
+ * keeping the filter's 20 / 22.5 ms output history (it can never be read again), which removes a quarter of the
+ * synthesis kernel's memory traffic, and does not launch the post-filter kernel.  Results are bit-identical for every frame that
+ * keeps the promise; a non-empty frame shorter than min_nbytes is treated as a lost frame (concealed), and a call whose
+ * fixed `nbytes` is below it returns LC3B_ERR_INVALID_ARG.  Set it before the first decode. */
+int lc3b_decoder_set_min_nbytes(lc3b_decoder* h, int min_nbytes);
 /* Which dequantisation kernel runs: 0 = by batch size (default: one warp per frame up to 98 304 streams, one thread per
  * frame above), 1 = warp per frame, 2 = thread per frame.  Bit-identical results; the choice only matters for speed. */
 int lc3b_decoder_set_dequant_mode(lc3b_decoder* h, int mode);
@@ -237,6 +246,7 @@ int lc3b_sharded_decode_frames_host(lc3b_sharded_decoder* h, int bits_per_sample
                                     const int32_t* frame_nbytes, int nbytes, size_t frame_stride, int16_t* pcm_out,
                                     size_t pcm_stride, int32_t* status_out);
 int lc3b_sharded_decoder_wait(lc3b_sharded_decoder* h);
+int lc3b_sharded_decoder_set_min_nbytes(lc3b_sharded_decoder* h, int min_nbytes);   /* lc3b_decoder_set_min_nbytes on every shard */
 void lc3b_sharded_decoder_destroy(lc3b_sharded_decoder* h);
 
 typedef struct lc3b_sharded_encoder lc3b_sharded_encoder;

@@ -106,6 +106,7 @@ struct Lc3File {
     // `reference_quirk` reproduces that count; otherwise every complete frame period is counted.
     size_t frame_periods(size_t file_len, bool reference_quirk = false) const {
         const size_t period = num_channels * nbytes;
+        if (period == 0) return 0;
         size_t n = file_len / period;
         if (reference_quirk && n > 0 && n * period == file_len) n -= 1;
         return n;

@@ -62,7 +62,7 @@ struct Carve {
 };
 
 struct Layout {
-    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, ola, ltpf_y, ltpf_xtail, ltpf_x, side, sstate, stage_in, stage_out, stage_len,
+    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, gband, tns_list, ola, ltpf_y, ltpf_xtail, ltpf_x, side, sstate, stage_in, stage_out, stage_len,
         stage_status, total;
 };
 
@@ -79,6 +79,8 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes, b
     L.spec = cv.take(sizeof(float) * 2 * ns * c.ne);
     L.xq = cv.take(sizeof(int32_t) * nblk * c.ne * 32);
     L.handoff = cv.take(sizeof(int32_t) * ((ns + 127) / 128) * 128 * HO_WORDS);   // every thread slot of whole entropy CTAs
+    L.gband = cv.take(sizeof(float) * ((ns + 127) / 128) * 128 * 64);
+    L.tns_list = cv.take(sizeof(int32_t) * (1 + ((ns + 127) / 128) * 128));
     L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
     L.ltpf_y = cv.take(sizeof(float) * ns * blocks * c.nf);
     L.ltpf_xtail = cv.take(sizeof(float) * ns * XTAIL_FLOATS);
@@ -309,6 +311,8 @@ int decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int samp
     st.spec = (float*)(base + L.spec);
     st.xq = (int32_t*)(base + L.xq);
     st.handoff = (int32_t*)(base + L.handoff);
+    st.gband = (float*)(base + L.gband);
+    st.tns_list = (int32_t*)(base + L.tns_list);
     st.ola = (float*)(base + L.ola);
     st.ltpf_y = (float*)(base + L.ltpf_y);
     st.ltpf_xtail = (float*)(base + L.ltpf_xtail);
@@ -323,6 +327,13 @@ int decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int samp
     st.trace_x = nullptr;
     st.fixed_slot = -1;
     st.dequant_mode = 0;
+    st.no_ltpf = 0;
+    st.min_nbytes = 0;
+    st.sm_count = 148;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) st.sm_count = sms;
+    }
 
     DevConfig hc;
     fill_host_config(c, &hc);
@@ -383,6 +394,21 @@ int lc3b_decoder_host_fence(lc3b_decoder* h, void* cuda_stream) {
 int lc3b_decoder_set_graph_mode(lc3b_decoder* h, int mode) {
     if (!h || mode < 0 || mode > 1) return LC3B_ERR_INVALID_ARG;
     h->graph_mode = mode;
+    return LC3B_OK;
+}
+
+// long_term_post_filter.rs:142-161: the filter's gain is the table row (0.0, 0) once the (10 ms-equivalent) frame bits reach
+// 560 + 80 * fs_ind - from there on is_active can be set in the bitstream but the filter passes its input through
+static bool ltpf_impossible(const lc3b_config& c, int nbytes) {
+    const int nbits = nbytes * 8;
+    const int t_nbits = c.n_ms == LC3B_7P5MS ? (int)round((double)nbits * 10.0 / 7.5) : nbits;
+    return t_nbits >= 560 + c.fs_ind * 80;
+}
+
+int lc3b_decoder_set_min_nbytes(lc3b_decoder* h, int min_nbytes) {
+    if (!h || min_nbytes < 0 || min_nbytes > h->st.max_nbytes) return LC3B_ERR_INVALID_ARG;
+    h->st.min_nbytes = min_nbytes;
+    h->st.no_ltpf = (min_nbytes > 0 && ltpf_impossible(h->st.cfg, min_nbytes)) ? 1 : 0;
     return LC3B_OK;
 }
 
@@ -453,6 +479,7 @@ int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* fram
     const DecoderState& st = h->st;
     if (nbytes < 0 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
+    if (!frame_nbytes && nbytes < st.min_nbytes) return LC3B_ERR_INVALID_ARG;       // lc3b_decoder_set_min_nbytes
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     CU(run_decode(h, frames, frame_nbytes, nbytes, frame_stride, pcm_out, pcm_stride, status_out, h->stage_mask, stream));
     return LC3B_OK;
@@ -466,6 +493,7 @@ int lc3b_decode_frames_host(lc3b_decoder* h, int bits_per_sample, const uint8_t*
     const DecoderState& st = h->st;
     if (nbytes < 0 || nbytes > st.max_nbytes || (size_t)nbytes > frame_stride || pcm_stride < (size_t)st.cfg.nf)
         return LC3B_ERR_INVALID_ARG;
+    if (!frame_nbytes && nbytes < st.min_nbytes) return LC3B_ERR_INVALID_ARG;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const size_t ns = (size_t)st.n_streams;
     // frames: one strided copy packs the rows to pitch `nbytes`
@@ -536,14 +564,16 @@ int lc3b_selftest_math_device(int which, const float* x, const float* y, float* 
 }  // extern "C"
 
 namespace lc3b {
-__global__ void gather_spectrum_kernel(const float* spec, const int32_t* side, float* out, int n_streams, int ne) {
+// after any decode call (frame by frame or time-parallel) the stream's SS_SLOT names the slot of its last good spectrum,
+// which is also what the last frame's IMDCT read unless that frame was concealed (then: the spectrum it was faded from)
+__global__ void gather_spectrum_kernel(const float* spec, const int32_t* sstate, float* out, int n_streams, int ne) {
     const int s = blockIdx.x;
-    const int slot = side[(size_t)s * SIDE_WORDS + SD_SLOT];
+    const int slot = sstate[(size_t)s * SS_WORDS + SS_SLOT];
     const float* sp = spec + ((size_t)slot * n_streams + s) * ne;
     for (int k = threadIdx.x; k < ne; k += blockDim.x) out[(size_t)s * ne + k] = sp[k];
 }
 }  // namespace lc3b
 
 void lc3b_gather_spectrum(const lc3b::DecoderState& st, float* out, cudaStream_t stream) {
-    lc3b::gather_spectrum_kernel<<<st.n_streams, 128, 0, stream>>>(st.spec, st.side, out, st.n_streams, st.cfg.ne);
+    lc3b::gather_spectrum_kernel<<<st.n_streams, 128, 0, stream>>>(st.spec, st.sstate, out, st.n_streams, st.cfg.ne);
 }

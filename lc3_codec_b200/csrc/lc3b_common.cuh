@@ -67,6 +67,9 @@ struct DecoderState {
     lc3b_config cfg;
     int n_streams, n_blocks32, max_nbytes, device;
     int fixed_slot;      // -1: double-buffered spectrum slots tracked in sstate; >= 0: always write that slot (time-parallel path)
+    int no_ltpf;         // 1: every frame the handle accepts is too long for the post filter to be active (gain row (0.0, 0))
+    int min_nbytes;      // promised minimum frame length (0 = none), lc3b_decoder_set_min_nbytes
+    int sm_count;        // multiprocessors of the handle's device (persistent kernels size their grids with it)
     int dequant_mode;    // 0 auto, 1 warp-per-frame dequantisation kernel, 2 thread-per-frame (lc3b_decoder_set_dequant_mode)
     // device pointers (carved from the caller's workspace)
     DevConfig* dcfg;
@@ -77,6 +80,8 @@ struct DecoderState {
     float* spec;         // [2][n_streams][ne]  double-buffered spectrum; the valid slot doubles as PLC "last good"
     int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (entropy -> dequantisation kernel)
     int32_t* handoff;    // [n_blocks32 * 32][HO_WORDS] decoded side information etc. (entropy -> dequantisation kernel)
+    float* gband;        // [thread slots][64] SNS band gains, dequant_warp_kernel -> tns_list_kernel
+    int32_t* tns_list;   // [1 + thread slots] count + thread slots of the frames tns_list_kernel has to finish
     float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)
     float* ltpf_y;       // [n_streams][blocks*nf]  x_hat_ltpf_mem (long_term_post_filter.rs:30)
     float* ltpf_xtail;   // [n_streams][3][16]  last samples of x_hat_mem per ring block (only l_num <= 10 are ever read back)
@@ -122,7 +127,10 @@ struct EntropyParams {
     int32_t* trace;       // nullable
     int32_t* trace_x;     // nullable
     const uint8_t* sym_lut;   // [64][32] symbol at the start of each 32-quotient bucket (init_sym_lut_kernel)
+    float* gband;         // [thread slots][64] SNS band gains of frames waiting for the lattice kernel
+    int32_t* tns_list;    // [1 + thread slots]: count, then the thread slots of frames with an active TNS filter
     int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
+    int min_nbytes;           // frames shorter than this (but not empty) break the handle's promise and are treated as lost
     int row_pitch;        // bytes per staged frame row in shared memory
 };
 

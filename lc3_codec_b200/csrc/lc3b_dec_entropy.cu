@@ -341,6 +341,7 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
     const int tid = threadIdx.x, lane = tid & 31;
     const int stream0 = block * ENT_THREADS;
     const int ne = c.ne;
+    if (block == 0 && tid == 0) p.tns_list[0] = 0;                     // list of TNS-active frames, filled by dequant_warp_kernel
 
     // ---- stage tables and frame bytes
     for (int i = tid; i < 4096 / 4; i += ENT_THREADS) ((uint32_t*)s_lookup)[i] = ((const uint32_t*)LC3T_AC_SPEC_LOOKUP)[i];
@@ -368,6 +369,7 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
         if (s_me < p.n_streams) {
             int len = p.frame_nbytes ? p.frame_nbytes[s_me] : p.nbytes;
             len = min(max(len, 0), p.nbytes);
+            if (len < p.min_nbytes) len = 0;
             Reader pr;
             pr.buf = s_rows + tid * p.row_pitch;
             pr.len = len; pr.head = 0; pr.tail = 0; pr.tw = 0; pr.tw_n = 0;
@@ -397,6 +399,7 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
     rd.len = live ? (p.frame_nbytes ? p.frame_nbytes[stream] : p.nbytes) : 0;
     if (rd.len > p.nbytes) rd.len = p.nbytes;
     if (rd.len < 0) rd.len = 0;
+    if (rd.len < p.min_nbytes) rd.len = 0;                              // shorter than the handle's promised minimum: treated as lost
     rd.head = 0;
     rd.tail = 0;
     rd.tw = 0;
@@ -972,28 +975,25 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_mixed_kernel(const __g
     dequant_body<W>(s_p, s_block, smem);
 }
 
-// ---------------------------------------------------------------- kernel 1b', one WARP per frame (small batches)
+// ---------------------------------------------------------------- kernels 1b' / 1b'': the small-batch dequantisation
 // The thread-per-frame dequant_kernel needs ~100 k frames to fill the GPU: every frame's ne lines are one thread's serial
-// loop (0.07 ms at 16 384 streams of 120 lines whatever the occupancy).  Below DQW_MAX_STREAMS streams this variant is
-// launched instead: a warp owns a frame, a lane the lines k = lane, lane + 32, ...
-//   * residual refinement and noise filling are per-line decisions whose only serial part is a COUNT (the i-th non-zero
-//     line takes the i-th residual bit; the i-th filled line takes the LCG's i-th output): ballot + popcount give the
-//     rank, and the LCG is jumped to any rank with the composed multiplier / increment table DevConfig::nf_lcg;
-//   * the noise-filling window test (no non-zero integer within +-W lines) is a mask test on the ballots of three rows;
-//   * the TNS lattice is a true recurrence over lines: the frames of a CTA run it side by side on the first lanes of
-//     warp 0, between two barriers, each on its own shared-memory row (the select-based lattice of dequant_kernel);
-//   * SNS scale factors: PVQ de-enumeration on one lane, the 16 x 16 rotation on 16 lanes, band gains on 64.
+// loop (0.07 ms at 16 384 streams of 120 lines whatever the occupancy).  Below DQW_MAX_STREAMS streams the same work is
+// split along what is really serial:
+//   dequant_warp_kernel (one WARP per frame, a lane owns the lines k = lane, lane + 32, ...): everything but the lattice.
+//     * residual refinement and noise filling are per-line decisions whose only serial part is a COUNT (the i-th
+//       non-zero line takes the i-th residual bit; the i-th filled line takes the LCG's i-th output): ballot + popcount
+//       give the rank, and the LCG is jumped to any rank with the composed multiplier / increment table
+//       DevConfig::nf_lcg;
+//     * the noise-filling window test (no non-zero integer within +-W lines) is a mask test on the ballots of three rows;
+//     * SNS scale factors: PVQ de-enumeration on one lane, the 16 x 16 rotation on 16 lanes, band gains on 64;
+//     * frames without TNS leave finished; a frame with an active TNS filter leaves its gain-scaled lines and its 64
+//       band gains, and appends itself to a list;
+//   tns_list_kernel (one THREAD per listed frame): the TNS lattice - a true recurrence over lines - then the SNS gains,
+//     in place on the frame's spectrum row, with dequant_kernel's select-based lattice so the warp never splits.
 // Every f32 operation per line is dequant_kernel's, in its order: the spectrum is bit-identical (tested).
 constexpr int DQW_WARPS = 8;
-constexpr int DQW_PITCH = MAX_NE + 1;             // odd row pitch: the lattice lanes hit distinct banks
-struct DqwFrame {                                  // per-frame values handed from phase A to the lattice and phase C
-    float rc0[8], rc1[8];
-    float scf[16], y[16];
-    float gband[64];
-    int ok, ord0, ord1, s0, e0, e1, new_slot, stream;
-};
 __host__ __device__ inline size_t dequant_warp_smem_bytes() {
-    return sizeof(float) * DQW_WARPS * DQW_PITCH + sizeof(DqwFrame) * DQW_WARPS + MAX_NE;
+    return sizeof(float) * DQW_WARPS * (64 + 16 + 16) + MAX_NE;
 }
 
 __device__ __forceinline__ float sns_interp64(const float* scf, int j) {             // spectral_noise_shaping.rs:85-98
@@ -1009,9 +1009,10 @@ __device__ __forceinline__ float sns_interp64(const float* scf, int j) {        
 }
 
 __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const int block, uint8_t* smem) {
-    float* s_v = (float*)smem;                                         // [DQW_WARPS][DQW_PITCH]
-    DqwFrame* s_f = (DqwFrame*)(s_v + DQW_WARPS * DQW_PITCH);
-    uint8_t* s_band_of = (uint8_t*)(s_f + DQW_WARPS);                  // line -> band
+    float* s_gband = (float*)smem;                                     // [DQW_WARPS][64]
+    float* s_scf = s_gband + DQW_WARPS * 64;                           // [DQW_WARPS][16]
+    float* s_y = s_scf + DQW_WARPS * 16;                               // [DQW_WARPS][16]
+    uint8_t* s_band_of = (uint8_t*)(s_y + DQW_WARPS * 16);             // line -> band
 
     const DevConfig& c = *p.cfg;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1027,45 +1028,42 @@ __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const 
         }
         s_band_of[k] = (uint8_t)lo;
     }
+    __syncthreads();                                                   // the only CTA-wide step: warps are independent below
 
     // ---- hand-off record of this warp's thread slot (the entropy kernel's tid)
     const int n_slots = ((p.n_streams + ENT_THREADS - 1) / ENT_THREADS) * ENT_THREADS;
     const int slot = block * DQW_WARPS + wid;
-    const bool have = slot < n_slots;
-    int h0 = 0, h1 = 0;
-    if (have) {
-        const int32_t* ho = p.handoff + (size_t)slot * HO_WORDS;
-        h0 = ho[lane];
-        if (lane < HO_WORDS - 32) h1 = ho[32 + lane];
-    }
-    auto field = [&](int i) -> int { return i < 32 ? __shfl_sync(0xffffffffu, h0, i) : __shfl_sync(0xffffffffu, h1, i - 32); };
+    if (slot >= n_slots) return;
+    const int32_t* ho = p.handoff + (size_t)slot * HO_WORDS;
+    const int h0 = ho[lane];
+    const int h1 = lane < HO_WORDS - 32 ? ho[32 + lane] : 0;
+    // both shuffles are executed by every lane whatever i is (a lane-dependent i must not split the warp around them)
+    auto field = [&](int i) -> int {
+        const int a = __shfl_sync(0xffffffffu, h0, i & 31), b = __shfl_sync(0xffffffffu, h1, i & 31);
+        return i < 32 ? a : b;
+    };
     const int fid = field(HO_FID);
     const int stream = (slot / ENT_THREADS) * ENT_THREADS + fid;
-    const bool live = have && stream < p.n_streams;
+    const bool live = stream < p.n_streams;
     const bool ok = live && field(HO_OK) != 0;
     const int lastnz = field(HO_LASTNZ), lsb_mode = field(HO_LSB_MODE), gg_ind = field(HO_GG_IND), bw = field(HO_BW);
     const int num_tns = field(HO_NUM_TNS), noise_factor = field(HO_NOISE_FACTOR);
     const int rc_order0 = field(HO_RC_ORDER0), rc_order1 = field(HO_RC_ORDER1);
     const int nres = field(HO_NRES), tail = field(HO_TAIL), len = field(HO_LEN);
     const uint32_t seed0 = (uint32_t)field(HO_SEED) & 0xffffu;
+    const int ltpf_active = field(HO_LTPF_ACTIVE), pitch_index = field(HO_PITCH_INDEX);
     const int nbits = len * 8;
-    DqwFrame& F = s_f[wid];
-    float* sv = s_v + wid * DQW_PITCH;
 
     int slot_cur = 0;
     if (live && p.fixed_slot < 0) slot_cur = p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
     const int new_slot = p.fixed_slot >= 0 ? p.fixed_slot : slot_cur ^ 1;
-    if (lane == 0) {
-        F.ok = ok ? 1 : 0;
-        F.ord0 = F.ord1 = 0;
-        F.new_slot = new_slot;
-        F.stream = stream;
-    }
     constexpr int NR = (MAX_NE + 31) / 32;                             // rows of 32 lines
     if (ok) {                                                          // warp-uniform
         const bool d10 = c.n_ms == LC3B_10MS;
         const int bw_stop = d10 ? 80 * (bw + 1) : 60 * (bw + 1);
         const int nf_start = d10 ? 24 : 18;
+        // does any TNS filter of this frame do anything?  (phase 2 exists only for bw >= 3, temporal_noise_shaping.rs:83-138)
+        const bool has_tns = rc_order0 > 0 || (bw >= 3 && num_tns == 2 && rc_order1 > 0);
         float gg;
         {                                                              // global_gain.rs:15-25
             const int fs = c.fs_ind + 1;
@@ -1073,6 +1071,59 @@ __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const 
             gg = c.gg_table[gg_ind + gg_off + 245];
         }
         const float nf_level = xd(xs(8.0f, (float)noise_factor), 16.0f);
+        // ---- SNS scale factors (spectral_noise_shaping.rs:21-98) -> 64 band gains
+        float* scf = s_scf + wid * 16;
+        float* yv = s_y + wid * 16;
+        float* gband = s_gband + wid * 64;
+        {
+            const int ind_lf = field(HO_IND_LF), ind_hf = field(HO_IND_HF), submode_msb = field(HO_SUBMODE_MSB);
+            const int submode_lsb = field(HO_SUBMODE_LSB), g_ind = field(HO_G_IND), ls_inda = field(HO_LS_INDA);
+            const int ls_indb = field(HO_LS_INDB), idx_a = field(HO_IDX_A), idx_b = field(HO_IDX_B);
+            const int shape_j = (submode_msb << 1) + submode_lsb;
+            if (lane == 0) {
+                switch (shape_j) {
+                    case 0:
+                        mpvq_deenum(10, 10, ls_inda, (uint32_t)idx_a, yv, 1);
+                        mpvq_deenum(6, 1, ls_indb, (uint32_t)idx_b, yv + 10, 1);
+                        break;
+                    case 1:
+                        mpvq_deenum(10, 10, ls_inda, (uint32_t)idx_a, yv, 1);
+                        for (int i = 10; i < 16; i++) yv[i] = 0.0f;
+                        break;
+                    case 2: mpvq_deenum(16, 8, ls_inda, (uint32_t)idx_a, yv, 1); break;
+                    default: mpvq_deenum(16, 6, ls_inda, (uint32_t)idx_a, yv, 1); break;
+                }
+            }
+            __syncwarp();
+            if (lane < 16) {
+                const float* gains = shape_j == 0 ? LC3T_SNS_VQ_REG_ADJ_GAINS : shape_j == 1 ? LC3T_SNS_VQ_REG_LF_ADJ_GAINS
+                                     : shape_j == 2 ? LC3T_SNS_VQ_NEAR_ADJ_GAINS : LC3T_SNS_VQ_FAR_ADJ_GAINS;
+                float y[16];
+                float sum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) { y[i] = yv[i]; sum = xa(sum, xm(y[i], y[i])); }
+                const float y_norm = sqrtf(sum);
+                float g = gains[g_ind];
+                if (y_norm != 0.0f) g = xd(g, y_norm);
+                float factor = 0.0f;
+#pragma unroll
+                for (int col = 0; col < 16; col++) factor = xa(factor, xm(y[col], LC3T_D[lane][col]));
+                const float st1 = lane < 8 ? LC3T_LFCB[ind_lf][lane] : LC3T_HFCB[ind_hf][lane - 8];
+                scf[lane] = xa(st1, xm(g, factor));
+            }
+            __syncwarp();
+            const int n2 = 64 - nb;
+            for (int b0 = 0; b0 < 64; b0 += 32) {                      // :100-123 incl. the nb < 64 folding
+                const int b = b0 + lane;
+                if (b < nb) {
+                    float sc;
+                    if (n2 != 0) sc = b < n2 ? xd(xa(sns_interp64(scf, 2 * b), sns_interp64(scf, 2 * b + 1)), 2.0f) : sns_interp64(scf, b + n2);
+                    else sc = sns_interp64(scf, b);
+                    gband[b] = exp2_raw_fm(sc);
+                }
+            }
+            __syncwarp();
+        }
         // ---- integers of this frame: thread slot's lane-interleaved scratch column
         const int32_t* xq = p.xq + ((size_t)(slot >> 5) * ne) * 32 + (slot & 31) * 4;
         int32_t x[NR];
@@ -1085,6 +1136,7 @@ __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const 
         }
         const bool is_zero_frame = lastnz == 2 && (__ballot_sync(0xffffffffu, x[0] != 0) & 3u) == 0 && gg_ind == 0;
         const uint8_t* fr = p.frames + (size_t)stream * p.frame_stride;
+        float* dst = p.spec + ((size_t)new_slot * p.n_streams + stream) * ne;
         int res_base = 0, fill_base = 0;
 #pragma unroll
         for (int j = 0; j < NR; j++) {
@@ -1117,127 +1169,16 @@ __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const 
                     v = fill ? (st < 0x8000u ? nf_level : -nf_level) : v;
                 }
                 v = xm(v, gg);
-                if (k < ne) sv[k] = v;
+                if (k < ne) dst[k] = has_tns ? v : xm(v, gband[s_band_of[k]]);   // coalesced row
             }
         }
-        // ---- TNS parameters for the lattice lanes (temporal_noise_shaping.rs:83-138; QUIRK: index 0 -> rc = 0.0)
-        if (lane < 16) {
-            const int ri = field(HO_RC_I + lane);
-            const float r = ri != 0 ? c.tns_sin[ri] : 0.0f;
-            if (lane < 8) F.rc0[lane] = r; else F.rc1[lane - 8] = r;
-        } else {
-            (void)field(HO_RC_I + (lane & 15));                        // the shuffle needs every lane
-        }
-        if (lane == 0) {
-            F.s0 = d10 ? 12 : 9;
-            if (bw < 3) { F.e0 = bw_stop; F.e1 = bw_stop; }
-            else { F.e0 = bw_stop / 2; F.e1 = bw_stop; }
-            F.ord0 = rc_order0;
-            F.ord1 = (bw >= 3 && num_tns == 2) ? rc_order1 : 0;
-        }
-        // ---- SNS scale factors (spectral_noise_shaping.rs:21-98)
-        const int ind_lf = field(HO_IND_LF), ind_hf = field(HO_IND_HF), submode_msb = field(HO_SUBMODE_MSB);
-        const int submode_lsb = field(HO_SUBMODE_LSB), g_ind = field(HO_G_IND), ls_inda = field(HO_LS_INDA);
-        const int ls_indb = field(HO_LS_INDB), idx_a = field(HO_IDX_A), idx_b = field(HO_IDX_B);
-        const int shape_j = (submode_msb << 1) + submode_lsb;
-        if (lane == 0) {
-            switch (shape_j) {
-                case 0:
-                    mpvq_deenum(10, 10, ls_inda, (uint32_t)idx_a, F.y, 1);
-                    mpvq_deenum(6, 1, ls_indb, (uint32_t)idx_b, F.y + 10, 1);
-                    break;
-                case 1:
-                    mpvq_deenum(10, 10, ls_inda, (uint32_t)idx_a, F.y, 1);
-                    for (int i = 10; i < 16; i++) F.y[i] = 0.0f;
-                    break;
-                case 2: mpvq_deenum(16, 8, ls_inda, (uint32_t)idx_a, F.y, 1); break;
-                default: mpvq_deenum(16, 6, ls_inda, (uint32_t)idx_a, F.y, 1); break;
-            }
-        }
-        __syncwarp();
-        if (lane < 16) {
-            const float* gains = shape_j == 0 ? LC3T_SNS_VQ_REG_ADJ_GAINS : shape_j == 1 ? LC3T_SNS_VQ_REG_LF_ADJ_GAINS
-                                 : shape_j == 2 ? LC3T_SNS_VQ_NEAR_ADJ_GAINS : LC3T_SNS_VQ_FAR_ADJ_GAINS;
-            float y[16];
-            float sum = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 16; i++) { y[i] = F.y[i]; sum = xa(sum, xm(y[i], y[i])); }
-            const float y_norm = sqrtf(sum);
-            float g = gains[g_ind];
-            if (y_norm != 0.0f) g = xd(g, y_norm);
-            float factor = 0.0f;
-#pragma unroll
-            for (int col = 0; col < 16; col++) factor = xa(factor, xm(y[col], LC3T_D[lane][col]));
-            const float st1 = lane < 8 ? LC3T_LFCB[ind_lf][lane] : LC3T_HFCB[ind_hf][lane - 8];
-            F.scf[lane] = xa(st1, xm(g, factor));
-        }
-        __syncwarp();
-        const int n2 = 64 - nb;
-        for (int b = lane; b < nb; b += 32) {                          // :100-123 incl. the nb < 64 folding
-            float sc;
-            if (n2 != 0) sc = b < n2 ? xd(xa(sns_interp64(F.scf, 2 * b), sns_interp64(F.scf, 2 * b + 1)), 2.0f) : sns_interp64(F.scf, b + n2);
-            else sc = sns_interp64(F.scf, b);
-            F.gband[b] = exp2_raw_fm(sc);
+        if (has_tns) {                                                 // the lattice kernel finishes this frame
+            float* gb = p.gband + (size_t)slot * 64;
+            gb[lane] = lane < nb ? gband[lane] : 0.0f;
+            gb[32 + lane] = 32 + lane < nb ? gband[32 + lane] : 0.0f;
+            if (lane == 0) p.tns_list[1 + atomicAdd(p.tns_list, 1)] = slot;
         }
     }
-    __syncthreads();
-
-    // ---- phase B: the TNS lattices of the CTA's frames, one lane each (temporal_noise_shaping.rs:24-74)
-    if (wid == 0) {
-        const bool mine = lane < DQW_WARPS && s_f[lane < DQW_WARPS ? lane : 0].ok;
-        const DqwFrame& G = s_f[lane < DQW_WARPS ? lane : 0];
-        const bool any_tns = mine && (G.ord0 > 0 || G.ord1 > 0);
-        if (__any_sync(0xffffffffu, any_tns)) {
-            float* row = s_v + (lane < DQW_WARPS ? lane : 0) * DQW_PITCH;
-            float st[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            int ord = 0, om = 0, phase = 0;
-            int next = any_tns ? G.s0 : 0x7fffffff;
-            const int k_lo = __reduce_min_sync(0xffffffffu, any_tns ? G.s0 : 0x7fffffff);
-            const int k_hi = __reduce_max_sync(0xffffffffu, any_tns ? G.e1 : 0);
-            for (int k = k_lo; k < k_hi; k++) {
-                const bool sw = k == next;
-                if (__any_sync(0xffffffffu, sw)) {
-                    if (sw) {
-                        if (phase == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) rc[i] = G.rc0[i];
-                            ord = G.ord0; phase = 1; next = G.e0;
-                        } else if (phase == 1 && G.e0 < G.e1) {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) rc[i] = G.rc1[i];
-                            ord = G.ord1; phase = 2; next = G.e1;
-                        } else { ord = 0; next = 0x7fffffff; }
-                    }
-                    om = __reduce_max_sync(0xffffffffu, ord);
-                }
-                if (om > 0) {                                          // QUIRK: lattice state carries across filters
-                    const bool act = ord > 0;
-                    float t = act ? row[k] : 0.0f;
-#pragma unroll
-                    for (int j = 7; j >= 0; j--) {
-                        if (j < om) {                                  // warp-uniform
-                            const float t2 = xs(t, xm(rc[j], st[j]));
-                            t = j < ord ? t2 : t;
-                            if (j + 1 < 8) {
-                                const float s2 = xa(xm(rc[j], t), st[j]);
-                                st[j + 1 < 8 ? j + 1 : 7] = j + 1 < ord ? s2 : st[j + 1 < 8 ? j + 1 : 7];
-                            }
-                        }
-                    }
-                    st[0] = act ? t : st[0];
-                    if (act) row[k] = t;
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase C: SNS gains, spectrum -> inactive slot (coalesced rows), hand-off record for the synthesis kernel
-    if (ok) {
-        float* dst = p.spec + ((size_t)new_slot * p.n_streams + stream) * ne;
-        for (int k = lane; k < ne; k += 32) dst[k] = xm(sv[k], F.gband[s_band_of[k]]);
-    }
-    const int ltpf_active = field(HO_LTPF_ACTIVE), pitch_index = field(HO_PITCH_INDEX);
     if (live && lane == 0) {
         int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
         sd[SD_OK] = ok;
@@ -1249,20 +1190,130 @@ __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const 
     }
 }
 
+// The listed frames' lattices, one thread each: temporal_noise_shaping.rs:24-74 then the SNS gains, four lines at a time
+// in place on the frame's row (the row is the slot dequant_warp_kernel just wrote and made current).
+__device__ __forceinline__ void tns_list_body(const EntropyParams& p, const int block) {
+    // band gains of the CTA's frames, [band][thread] (a thread walks its own column: no bank conflicts), and the band edges:
+    // the walk along the bands must not wait for global memory at every band change
+    __shared__ float s_g[64 * ENT_THREADS];
+    __shared__ int s_edge[65];
+    const DevConfig& c = *p.cfg;
+    const int tid = (int)threadIdx.x;
+    const int i = block * ENT_THREADS + tid;
+    const int count = p.tns_list[0];
+    if (block * ENT_THREADS >= count) return;                          // whole CTA beyond the list
+    const bool mine = i < count;
+    const int slot = mine ? p.tns_list[1 + i] : 0;
+    const int32_t* ho = p.handoff + (size_t)slot * HO_WORDS;
+    const int ne = c.ne, nb = c.nb;
+    for (int b = tid; b < 65; b += ENT_THREADS) s_edge[b] = b < nb ? c.band_idx[b] : 0x7fffffff;   // the last band runs to ne
+    if (mine) {
+        const float4* gb4 = (const float4*)(p.gband + (size_t)slot * 64);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float4 g4 = gb4[q];
+            s_g[(4 * q + 0) * ENT_THREADS + tid] = g4.x;
+            s_g[(4 * q + 1) * ENT_THREADS + tid] = g4.y;
+            s_g[(4 * q + 2) * ENT_THREADS + tid] = g4.z;
+            s_g[(4 * q + 3) * ENT_THREADS + tid] = g4.w;
+        }
+    }
+    int ord0 = 0, ord1 = 0, s0 = 0x7fffffff, e0 = 0, e1 = 0;
+    float rc0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rc1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float* row = p.spec;
+    if (mine) {
+        const int stream = (slot / ENT_THREADS) * ENT_THREADS + ho[HO_FID];
+        const int bw = ho[HO_BW];
+        const bool d10 = c.n_ms == LC3B_10MS;
+        const int bw_stop = d10 ? 80 * (bw + 1) : 60 * (bw + 1);
+        s0 = d10 ? 12 : 9;
+        if (bw < 3) { e0 = bw_stop; e1 = bw_stop; }
+        else { e0 = bw_stop / 2; e1 = bw_stop; }
+        ord0 = ho[HO_RC_ORDER0];
+        ord1 = ho[HO_NUM_TNS] == 2 ? ho[HO_RC_ORDER1] : 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {                                  // QUIRK: index 0 -> rc = 0.0
+            const int a = ho[HO_RC_I + j], b = ho[HO_RC_I + 8 + j];
+            rc0[j] = a != 0 ? c.tns_sin[a] : 0.0f;
+            rc1[j] = b != 0 ? c.tns_sin[b] : 0.0f;
+        }
+        const int cur = p.fixed_slot >= 0 ? p.fixed_slot : p.sstate[(size_t)stream * SS_WORDS + SS_SLOT];
+        row = p.spec + ((size_t)cur * p.n_streams + stream) * ne;
+    }
+    __syncthreads();
+    float st[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int ord = 0, om = 0, phase = 0, next = s0;
+    int band = 0, band_end = mine ? s_edge[1] : 0x7fffffff;
+    float gcur = mine ? s_g[tid] : 0.0f;
+    const int n4 = ne >> 2;                                            // ne is a multiple of 4 in every configuration
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 cur4 = mine ? ((const float4*)row)[0] : zero4;
+    float4 nxt4 = (mine && 1 < n4) ? ((const float4*)row)[1] : zero4;
+    for (int g = 0; g < n4; g++) {
+        const float4 nn4 = (mine && g + 2 < n4) ? ((const float4*)row)[g + 2] : zero4;     // two groups ahead of the lattice
+        float vv[4] = {cur4.x, cur4.y, cur4.z, cur4.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int k = 4 * g + e;
+            float v = vv[e];
+            const bool sw = k == next;
+            if (__any_sync(0xffffffffu, sw)) {
+                if (sw) {
+                    if (phase == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) rc[j] = rc0[j];
+                        ord = ord0; phase = 1; next = e0;
+                    } else if (phase == 1 && e0 < e1) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) rc[j] = rc1[j];
+                        ord = ord1; phase = 2; next = e1;
+                    } else { ord = 0; next = 0x7fffffff; }
+                }
+                om = __reduce_max_sync(0xffffffffu, ord);
+            }
+            if (om > 0) {                                              // QUIRK: lattice state carries across filters
+                float t = v;
+#pragma unroll
+                for (int j = 7; j >= 0; j--) {
+                    if (j < om) {                                      // warp-uniform
+                        const float t2 = xs(t, xm(rc[j], st[j]));
+                        t = j < ord ? t2 : t;
+                        if (j + 1 < 8) {
+                            const float s2 = xa(xm(rc[j], t), st[j]);
+                            st[j + 1 < 8 ? j + 1 : 7] = j + 1 < ord ? s2 : st[j + 1 < 8 ? j + 1 : 7];
+                        }
+                    }
+                }
+                st[0] = ord > 0 ? t : st[0];
+                v = t;
+            }
+            while (k >= band_end) {                                    // next band; zero-width bands are skipped
+                band++;
+                band_end = s_edge[band + 1 < 64 ? band + 1 : 64];
+                gcur = s_g[band * ENT_THREADS + tid];
+            }
+            vv[e] = xm(v, gcur);
+        }
+        if (mine) ((float4*)row)[g] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        cur4 = nxt4;
+        nxt4 = nn4;
+    }
+}
+
 __global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_kernel(const __grid_constant__ EntropyParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     dequant_warp_body(p, blockIdx.x, smem);
 }
+__global__ void __launch_bounds__(ENT_THREADS) tns_list_kernel(const __grid_constant__ EntropyParams p) {
+    tns_list_body(p, blockIdx.x);
+}
 
-// mixed-rate variant: CTAs of a bucket are numbered in units of DQW_WARPS thread slots (16 per entropy CTA)
-__global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_mixed_kernel(const __grid_constant__ MixedParams m) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ EntropyParams s_p;
-    __shared__ int s_block;
+// mixed-rate variants.  per_cta_slots: thread slots one CTA covers (DQW_WARPS for the warp kernel, ENT_THREADS for the list
+// kernel); a bucket's first_cta counts entropy CTAs of ENT_THREADS slots.
+__device__ __forceinline__ void mixed_select_scaled(const MixedParams& m, EntropyParams* s_p, int* s_block, int per_entropy_cta) {
     if (threadIdx.x == 0) {
-        constexpr int PER = ENT_THREADS / DQW_WARPS;
         int b = 0;
-        while (b + 1 < m.n_buckets && (int)blockIdx.x >= m.buckets[b + 1].first_cta * PER) b++;
+        while (b + 1 < m.n_buckets && (int)blockIdx.x >= m.buckets[b + 1].first_cta * per_entropy_cta) b++;
         const MixedBucket& bk = m.buckets[b];
         EntropyParams q = bk.ep;
         q.frames = m.frames + (size_t)bk.first_row * m.frame_stride;
@@ -1271,13 +1322,24 @@ __global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_mixed_kernel(cons
         q.frame_stride = m.frame_stride;
         q.status_out = m.status_out ? m.status_out + bk.first_row : nullptr;
         q.row_pitch = m.row_pitch;
-        s_p = q;
-        s_block = (int)blockIdx.x - bk.first_cta * PER;
+        *s_p = q;
+        *s_block = (int)blockIdx.x - bk.first_cta * per_entropy_cta;
     }
     __syncthreads();
+}
+__global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_mixed_kernel(const __grid_constant__ MixedParams m) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ EntropyParams s_p;
+    __shared__ int s_block;
+    mixed_select_scaled(m, &s_p, &s_block, ENT_THREADS / DQW_WARPS);
     dequant_warp_body(s_p, s_block, smem);
 }
-
+__global__ void __launch_bounds__(ENT_THREADS) tns_list_mixed_kernel(const __grid_constant__ MixedParams m) {
+    __shared__ EntropyParams s_p;
+    __shared__ int s_block;
+    mixed_select_scaled(m, &s_p, &s_block, 1);
+    tns_list_body(s_p, s_block);
+}
 
 int entropy_row_pitch(int nbytes) {
     int words = (nbytes + 3) / 4 + 1;
@@ -1319,7 +1381,10 @@ EntropyParams entropy_params(const DecoderState& st, const uint8_t* frames, cons
     p.trace = st.trace;
     p.trace_x = st.trace_x;
     p.sym_lut = st.sym_lut;
+    p.gband = st.gband;
+    p.tns_list = st.tns_list;
     p.fixed_slot = st.fixed_slot;
+    p.min_nbytes = st.min_nbytes;
     p.row_pitch = entropy_row_pitch(nbytes);
     return p;
 }
@@ -1333,6 +1398,7 @@ void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frame
     if (stages & 2) {
         if (use_dequant_warp(st.n_streams, st.dequant_mode)) {
             plan.add(dequant_warp_kernel, grid * (ENT_THREADS / DQW_WARPS), DQW_WARPS * 32, dequant_warp_smem_bytes(), p);
+            plan.add(tns_list_kernel, grid, ENT_THREADS, 0, p);
         } else {
             const size_t smem = dequant_smem_bytes(p.row_pitch);
             if (st.cfg.n_ms == LC3B_10MS) plan.add(dequant_kernel<3>, grid, ENT_THREADS, smem, p);
@@ -1381,8 +1447,9 @@ void plan_entropy_mixed(LaunchPlan& plan, const MixedTables& t, const uint8_t* f
     const size_t smem = dequant_smem_bytes(m.row_pitch);
     *node_d10 = *node_d75 = -1;
     if (use_dequant_warp(t.n_streams, t.dequant_mode)) {               // one launch for both frame durations (W is a run-time value there)
-        *node_d10 = *node_d75 = plan.add(dequant_warp_mixed_kernel, (unsigned)(t.cta_all * (ENT_THREADS / DQW_WARPS)), DQW_WARPS * 32,
-                                         dequant_warp_smem_bytes(), m, e);
+        const int a = plan.add(dequant_warp_mixed_kernel, (unsigned)(t.cta_all * (ENT_THREADS / DQW_WARPS)), DQW_WARPS * 32,
+                               dequant_warp_smem_bytes(), m, e);
+        *node_d10 = *node_d75 = plan.add(tns_list_mixed_kernel, (unsigned)t.cta_all, ENT_THREADS, 0, m, a);
         return;
     }
     if (t.n_10 > 0) {

@@ -23,7 +23,7 @@
 
 namespace lc3b {
 
-struct MultiLayout { size_t spec, xq, handoff, side, head, tail, xhat, last_good, total; };
+struct MultiLayout { size_t spec, xq, handoff, gband, tns_list, side, head, tail, xhat, last_good, total; };
 
 static MultiLayout multi_layout(const lc3b_config& c, int S, int F) {
     MultiLayout L;
@@ -34,6 +34,8 @@ static MultiLayout multi_layout(const lc3b_config& c, int S, int F) {
     L.spec = take(sizeof(float) * V * c.ne);
     L.xq = take(sizeof(int32_t) * nblk * c.ne * 32);
     L.handoff = take(sizeof(int32_t) * nblk * 32 * HO_WORDS);
+    L.gband = take(sizeof(float) * nblk * 32 * 64);             // small unit counts take the warp-per-frame dequantisation
+    L.tns_list = take(sizeof(int32_t) * (1 + nblk * 32));
     L.side = take(sizeof(int32_t) * V * SIDE_WORDS);
     L.head = take(sizeof(float) * V * c.nf);
     L.tail = take(sizeof(float) * V * (c.nf - c.z));
@@ -450,6 +452,8 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     vs.spec = (float*)(base + L.spec);
     vs.xq = (int32_t*)(base + L.xq);
     vs.handoff = (int32_t*)(base + L.handoff);
+    vs.gband = (float*)(base + L.gband);
+    vs.tns_list = (int32_t*)(base + L.tns_list);
     vs.side = (int32_t*)(base + L.side);
     vs.fixed_slot = 0;
     vs.trace = nullptr;

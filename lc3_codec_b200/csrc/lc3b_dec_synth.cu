@@ -17,6 +17,7 @@
 // kernel writes the filtered signal to the ring block and the PCM row.  The recursion only reaches back
 // p_int - l_den/2 >= 18 samples, so up to 32 consecutive outputs are computed in parallel per step.  Streams outside
 // such a span cost this kernel one flag load.
+#include <stdlib.h>
 #include <string.h>
 
 #include "lc3b_common.cuh"
@@ -45,17 +46,24 @@ struct SynthParams {
     int pcm_pairs;       // PCM rows are 4-byte aligned: samples leave two at a time
     int group;           // ltpf_kernel: streams looked after by one warp
     int smem_per_warp;   // ltpf_kernel, bytes
+    int no_ltpf;         // the handle's minimum frame length rules the post filter out: no history is kept (lc3b_decoder_set_min_nbytes)
 };
 
 constexpr int SYN_WARPS = 4;
+constexpr int PIPE_WARPS = 8;    // warps per CTA of the persistent synthesis kernel (they share the CTA's copy of the tables)
+// per warp: two stage buffers + one pong buffer of nf floats and two mbarriers; per CTA: DCT-IV and FFT twiddles (nf/2 float2
+// each) and the window (2 nf floats reserved)
+static inline size_t synth_smem_bytes(int nf) { return (size_t)PIPE_WARPS * 3 * nf * 4 + (size_t)4 * nf * 4 + (size_t)PIPE_WARPS * 2 * 8; }
 
 __device__ __forceinline__ int32_t round_pcm_i32(float v) {          // output_scaling.rs:13-26
     int32_t q = v > 0.0f ? cast_i32(xa(v, 0.5f)) : cast_i32(xs(v, 0.5f));
     return q > 32767 ? 32767 : q < -32768 ? -32768 : q;
 }
 
+// The non-persistent form of the same kernel (one warp = one frame, spectrum through ordinary loads): kept selectable
+// (LC3B_SYNTH=classic) for A/B measurements against the TMA-pipelined persistent kernel below.
 template <int NF, bool MS10>
-__global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
+__global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __grid_constant__ SynthParams p) {
     using G = FrameGeo<NF, MS10>;
     constexpr int NE = G::NE, Z = G::Z, NP = G::NP, NPT = G::NPT;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -143,14 +151,16 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
         const int n = 64 * j + 2 * lane;
         if (64 * j + 64 <= NF || n < NF) {
             const float a = head[2 * j], b = head[2 * j + 1];
-            ((float2*)yblk)[32 * j + lane] = make_float2(a, b);
-            if (n >= NF - 16) ((float2*)xtail)[(n - (NF - 16)) >> 1] = make_float2(a, b);   // x_hat tail for the next frame's filter
+            if (!p.no_ltpf) {
+                ((float2*)yblk)[32 * j + lane] = make_float2(a, b);
+                if (n >= NF - 16) ((float2*)xtail)[(n - (NF - 16)) >> 1] = make_float2(a, b);   // x_hat tail for the next frame's filter
+            }
             const int32_t qa = round_pcm_i32(a), qb = round_pcm_i32(b);
             if (p.pcm_pairs) ((uint32_t*)out)[32 * j + lane] = ((uint32_t)qa & 0xffffu) | ((uint32_t)qb << 16);
             else { out[n] = (int16_t)qa; out[n + 1] = (int16_t)qb; }
         }
     }
-    if (lane == 0) {
+    if (lane == 0 && !p.no_ltpf) {
         sd[SD_BLK] = blk_idx;
         int nb = blk_idx + 1;                                    // :334-337
         if (nb > (MS10 ? 1 : 2)) nb = 0;
@@ -160,6 +170,209 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_kernel(SynthParams p) {
             ss[SS_LTPF_PINT] = 0;
             ss[SS_LTPF_PFR] = 0;
         }
+    }
+}
+
+
+// ---- 1-D bulk copies global -> shared through the TMA unit, completion on an mbarrier (PTX cp.async.bulk, sm_90+)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LC3B_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LC3B_DONE;\n"
+        "bra LC3B_WAIT;\n"
+        "LC3B_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// generic-proxy accesses of a buffer are ordered before the async-proxy (TMA) writes issued afterwards
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// What the kernel needs to know about a frame before it can fetch its spectrum: a handful of words per stream.
+struct FrameHead {
+    int ok, slot, active, prev_active, blk_idx;
+};
+__device__ __forceinline__ FrameHead load_head(const SynthParams& p, int stream) {
+    const int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+    const int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
+    FrameHead h;
+    h.ok = sd[SD_OK];
+    h.slot = sd[SD_SLOT];
+    h.active = sd[SD_LTPF_ACTIVE];
+    h.prev_active = ss[SS_LTPF_PREV] & 1;
+    h.blk_idx = ss[SS_LTPF_BLK];
+    return h;
+}
+
+// synth_kernel: PERSISTENT, one warp per frame at a time.  A warp walks the frames w, w + W, w + 2W, ... (W = warps in
+// the grid); while it transforms frame i the TMA unit already fetches the spectrum of frame i + 1 into the warp's other
+// stage buffer (cp.async.bulk + mbarrier: no registers, no issue slots), and the side words of frame i + 2 are on
+// their way, so a warp never waits for HBM latency once it is running.  Per warp: two stage buffers of nf floats (the
+// spectrum arrives in the first ne, the rest stays zero; the stage buffer then serves as the FFT's ping buffer) and
+// one pong buffer.
+template <int NF, bool MS10>
+__global__ void __launch_bounds__(PIPE_WARPS * 32, 4) synth_kernel(const __grid_constant__ SynthParams p) {
+    using G = FrameGeo<NF, MS10>;
+    constexpr int NE = G::NE, Z = G::Z, NP = G::NP, NPT = G::NPT, N = NF / 2;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n_warps = gridDim.x * PIPE_WARPS;
+    int stream = blockIdx.x * PIPE_WARPS + wid;
+
+    // the CTA's copy of the transform tables: a persistent CTA pays for it once and every later access is a shared-memory load
+    float2* s_dtw = (float2*)((float*)smem + (size_t)PIPE_WARPS * 3 * NF);
+    float2* s_ftw = s_dtw + N;
+    float* s_win = (float*)(s_ftw + N);                           // win[Z .. 2 NF): the part the unfold reads, indexed from 0
+    for (int i = threadIdx.x; i < N; i += PIPE_WARPS * 32) { s_dtw[i] = p.dtw[i]; s_ftw[i] = p.ftw[i]; }
+    for (int i = threadIdx.x; i < 2 * NF - Z; i += PIPE_WARPS * 32) s_win[i] = p.win[Z + i];
+    __syncthreads();
+    if (stream >= p.n_streams) return;                            // warps are independent from here on: no CTA-wide barrier below
+
+    float* S0 = (float*)smem + (size_t)wid * 3 * NF;              // stage buffers (spectrum in; FFT ping)
+    float* Q = S0 + 2 * NF;                                       // FFT pong
+    uint64_t* bars = (uint64_t*)(s_win + 2 * NF) + 2 * wid;
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    for (int k = lane; k < 2 * NF; k += 32) S0[k] = 0.0f;         // the zero padding beyond ne (both stages)
+    __syncwarp();
+    fence_proxy_async();
+
+    auto fetch = [&](int st, int s, const FrameHead& h) {         // spectrum of stream s -> stage st
+        if (lane == 0) {
+            const float* sp = p.spec + ((size_t)h.slot * p.n_streams + s) * NE;
+            mbar_expect_tx(&bars[st], NE * 4);
+            bulk_g2s(S0 + st * NF, sp, NE * 4, &bars[st]);
+        }
+    };
+    FrameHead head = load_head(p, stream);
+    fetch(0, stream, head);
+    int nstream = stream + n_warps;
+    FrameHead nhead = head;
+    if (nstream < p.n_streams) nhead = load_head(p, nstream);
+    uint32_t phase0 = 0, phase1 = 0;
+
+    for (int it = 0; stream < p.n_streams; it++) {
+        const int st = it & 1;
+        float* P = S0 + st * NF;
+        // ---- next frame: its spectrum starts moving now, the side words of the one after are requested
+        const int n2stream = nstream + n_warps;
+        FrameHead n2head = nhead;
+        if (nstream < p.n_streams) {
+            // the other stage buffer was this warp's FFT ping buffer one frame ago: restore its zero tail, then hand it to the TMA
+            float* O = S0 + (st ^ 1) * NF;
+            if (it > 0) {
+                for (int k = NE + lane; k < NF; k += 32) O[k] = 0.0f;
+                __syncwarp();
+                fence_proxy_async();
+            }
+            fetch(st ^ 1, nstream, nhead);
+            if (n2stream < p.n_streams) n2head = load_head(p, n2stream);
+        }
+
+        int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
+        int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
+        const int ok = head.ok, active = head.active, prev_active = head.prev_active, blk_idx = head.blk_idx;
+
+        // overlap memory: requested now, consumed after the FFT
+        float* ola = p.ola + (size_t)stream * (NF - Z);
+        float2 ola_r[NPT];
+#pragma unroll
+        for (int j = 0; j < NPT; j++)
+            ola_r[j] = (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) ? ((const float2*)ola)[32 * j + lane] : make_float2(0.0f, 0.0f);
+
+        // ---- the spectrum has landed in P; concealment (packet_loss_concealment.rs:63-85) when the frame was bad
+        mbar_wait(&bars[st], st ? phase1 : phase0);
+        if (st) phase1 ^= 1; else phase0 ^= 1;
+        if (ok) {
+            if (lane == 0) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
+        } else {
+            int lost = ss[SS_PLC_LOST];
+            float alpha = u2f((uint32_t)ss[SS_PLC_ALPHA]);
+            uint32_t seed = (uint32_t)ss[SS_PLC_SEED];
+            __syncwarp();                                            // every lane has read the state before any lane updates it
+            if (lost >= 4) alpha = xm(alpha, lost < 8 ? 0.9f : 0.85f);
+            // lane's first line is k = lane: LCG advanced lane+1 times; then jump 32 steps at a time
+            uint32_t s = seed;
+            for (int i = 0; i <= lane; i++) s = (16831u + s * 12821u) & 0xFFFFu;
+            uint32_t a32 = 1, c32 = 0;                               // composition of 32 LCG steps
+            for (int i = 0; i < 32; i++) { c32 = (16831u + c32 * 12821u) & 0xFFFFu; a32 = (a32 * 12821u) & 0xFFFFu; }
+            for (int k = lane; k < NE; k += 32) {
+                const float lg = P[k];
+                P[k] = s < 0x8000u ? xm(lg, alpha) : xm(lg, -alpha);
+                if (k == NE - 1) ss[SS_PLC_SEED] = (int32_t)s;
+                s = (a32 * s + c32) & 0xFFFFu;
+            }
+            if (lane == 0) { ss[SS_PLC_LOST] = lost + 1; ss[SS_PLC_ALPHA] = (int32_t)f2u(alpha); }
+            __syncwarp();
+        }
+
+        // ---- DCT-IV, unfold, window (dct_iv.rs:49-67, modified_dct.rs:97-136)
+        const float* D = dct_iv_warp<NF>(P, Q, s_dtw, s_ftw, lane);
+        float head_s[2 * NP], tail[2 * NPT];
+        imdct_unfold<NF, MS10>(D, s_win - Z, lane, head_s, tail);
+        __syncwarp();                                                // every lane is done reading P / Q before they are reused
+
+        // ---- overlap-add (modified_dct.rs:138-151): two roundings, like the reference (and the time-parallel path)
+#pragma unroll
+        for (int j = 0; j < NPT; j++) {
+            if (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) {
+                head_s[2 * j] = xa(ola_r[j].x, head_s[2 * j]);
+                head_s[2 * j + 1] = xa(ola_r[j].y, head_s[2 * j + 1]);
+                ((float2*)ola)[32 * j + lane] = make_float2(tail[2 * j], tail[2 * j + 1]);
+            }
+        }
+
+        // ---- post filter, pass-through case (long_term_post_filter.rs:252-343 with zero coefficients): history + PCM
+        // Inside an active span the ring block must keep its old content until the filter has run (long pitch lags reach
+        // around the ring into it), so x_hat waits in a side buffer for ltpf_kernel instead.  When the handle's promised
+        // minimum frame length rules the filter out for good (p.no_ltpf), the history is never read and is not kept.
+        const bool in_span = active || prev_active;
+        float* yblk = in_span ? p.ltpf_x + (size_t)stream * NF : p.ltpf_y + (size_t)stream * p.hist_len + blk_idx * NF;
+        float* xtail = p.ltpf_xtail + (size_t)stream * XTAIL_FLOATS + blk_idx * 16;
+        int16_t* out = p.pcm_out + (size_t)stream * p.pcm_stride;
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            const int n = 64 * j + 2 * lane;
+            if (64 * j + 64 <= NF || n < NF) {
+                const float a = head_s[2 * j], b = head_s[2 * j + 1];
+                if (!p.no_ltpf) {
+                    ((float2*)yblk)[32 * j + lane] = make_float2(a, b);
+                    if (n >= NF - 16) ((float2*)xtail)[(n - (NF - 16)) >> 1] = make_float2(a, b);   // x_hat tail for the next frame's filter
+                }
+                const int32_t qa = round_pcm_i32(a), qb = round_pcm_i32(b);
+                if (p.pcm_pairs) ((uint32_t*)out)[32 * j + lane] = ((uint32_t)qa & 0xffffu) | ((uint32_t)qb << 16);
+                else { out[n] = (int16_t)qa; out[n + 1] = (int16_t)qb; }
+            }
+        }
+        if (lane == 0 && !p.no_ltpf) {
+            sd[SD_BLK] = blk_idx;
+            int nb = blk_idx + 1;                                    // :334-337
+            if (nb > (MS10 ? 1 : 2)) nb = 0;
+            ss[SS_LTPF_BLK] = nb;
+            if (!in_span) {                                          // otherwise ltpf_kernel carries the filter state on
+                ss[SS_LTPF_PREV] = 4 << 8;
+                ss[SS_LTPF_PINT] = 0;
+                ss[SS_LTPF_PFR] = 0;
+            }
+        }
+        stream = nstream;
+        head = nhead;
+        nstream = n2stream;
+        nhead = n2head;
     }
 }
 
@@ -322,16 +535,29 @@ namespace {
 struct PrepareSynth {
     cudaError_t e = cudaSuccess;
     template <int NF, bool MS10> void operator()() {
-        e = cudaFuncSetAttribute(synth_kernel<NF, MS10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_WARPS * 2 * NF * 4);
+        e = cudaFuncSetAttribute(synth_kernel<NF, MS10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)synth_smem_bytes(NF));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(synth_classic_kernel<NF, MS10>, cudaFuncAttributeMaxDynamicSharedMemorySize, SYN_WARPS * 2 * NF * 4);
     }
 };
 struct PlanSynth {
     LaunchPlan& plan;
     const SynthParams& p;
-    int dep, node;
+    int dep, node, sm_count;
     template <int NF, bool MS10> void operator()() {
-        const int grid = (p.n_streams + SYN_WARPS - 1) / SYN_WARPS;
-        node = plan.add(synth_kernel<NF, MS10>, (unsigned)grid, SYN_WARPS * 32, SYN_WARPS * 2 * NF * 4, p, dep);
+        // persistent: at most as many CTAs as fit on the device at once (4 of 8 warps per SM by registers; shared memory may allow fewer)
+        const int full = (p.n_streams + SYN_WARPS - 1) / SYN_WARPS;
+        static const bool classic = [] { const char* e = getenv("LC3B_SYNTH"); return e && e[0] == 'c'; }();
+        if (classic) {
+            node = plan.add(synth_classic_kernel<NF, MS10>, (unsigned)full, SYN_WARPS * 32, SYN_WARPS * 2 * NF * 4, p, dep);
+            return;
+        }
+        const size_t smem = synth_smem_bytes(NF);
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        const int resident = sm_count * per_sm;
+        const int ctas = (p.n_streams + PIPE_WARPS - 1) / PIPE_WARPS;
+        node = plan.add(synth_kernel<NF, MS10>, (unsigned)(ctas < resident ? ctas : resident), PIPE_WARPS * 32, smem, p, dep);
     }
 };
 }  // namespace
@@ -369,8 +595,10 @@ int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_
     p.group = group;
     const size_t lw = ltpf_warp_bytes(st.cfg);
     p.smem_per_warp = (int)lw;
-    PlanSynth ps{plan, p, dep, -1};
+    p.no_ltpf = st.no_ltpf;
+    PlanSynth ps{plan, p, dep, -1, st.sm_count > 0 ? st.sm_count : 148};
     if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ps)) return -1;
+    if (st.no_ltpf) return ps.node;                           // the post filter can never be active: nothing to launch
     const int n_warps = (st.n_streams + group - 1) / group;
     return plan.add(ltpf_kernel, (unsigned)((n_warps + SYN_WARPS - 1) / SYN_WARPS), SYN_WARPS * 32, lw * SYN_WARPS, p, ps.node);
 }

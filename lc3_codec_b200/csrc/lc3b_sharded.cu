@@ -245,6 +245,17 @@ int lc3b_sharded_decode_frames_host(lc3b_sharded_decoder* h, int bits_per_sample
 
 int lc3b_sharded_decoder_wait(lc3b_sharded_decoder* h) { return h ? drain(h->pool) : LC3B_ERR_INVALID_ARG; }
 
+int lc3b_sharded_decoder_set_min_nbytes(lc3b_sharded_decoder* h, int min_nbytes) {
+    if (!h) return LC3B_ERR_INVALID_ARG;
+    const int rc0 = drain(h->pool);                       // no call in flight while the shards' settings change
+    if (rc0 != LC3B_OK) return rc0;
+    for (Shard* sh : h->pool->shards) {
+        const int rc = lc3b_decoder_set_min_nbytes(sh->dec, min_nbytes);
+        if (rc != LC3B_OK) return rc;
+    }
+    return LC3B_OK;
+}
+
 void lc3b_sharded_decoder_destroy(lc3b_sharded_decoder* h) {
     if (!h) return;
     destroy(h->pool);

@@ -164,6 +164,13 @@ class Lc3BatchDecoder:
         if rc:
             raise Lc3bError(rc, "lc3b_decoder_set_graph_mode")
 
+    def set_min_nbytes(self, min_nbytes: int) -> None:
+        """Promise that every submitted frame is at least min_nbytes long (or lost).  When that rules the long-term post filter
+        out for good (e.g. >= 110 bytes at 48 kHz / 10 ms) the decoder stops keeping the filter's output history; include/lc3b.h."""
+        rc = native.lib().lc3b_decoder_set_min_nbytes(self._h, int(min_nbytes))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_set_min_nbytes")
+
     def set_dequant_mode(self, mode: int) -> None:
         """0 = dequantisation kernel chosen by batch size, 1 = warp per frame, 2 = thread per frame (identical results)."""
         rc = native.lib().lc3b_decoder_set_dequant_mode(self._h, mode)

@@ -57,12 +57,12 @@ EXPORTS = ["lc3b_config_new", "lc3b_last_cuda_error", "lc3b_version", "lc3b_deco
            "lc3b_selftest_math_host",
            "lc3b_selftest_math_device", "lc3b_encoder_workspace_bytes", "lc3b_encoder_init", "lc3b_encode_frames",
            "lc3b_encode_frames_host", "lc3b_encoder_set_host_pipelining", "lc3b_encoder_debug_read", "lc3b_encoder_set_stage_mask",
-           "lc3b_encoder_destroy", "lc3b_decoder_set_graph_mode", "lc3b_decoder_graph_stats", "lc3b_decoder_set_dequant_mode", "lc3b_mixed_decoder_set_dequant_mode", "lc3b_encoder_set_graph_mode",
+           "lc3b_encoder_destroy", "lc3b_decoder_set_graph_mode", "lc3b_decoder_graph_stats", "lc3b_decoder_set_dequant_mode", "lc3b_mixed_decoder_set_dequant_mode", "lc3b_decoder_set_min_nbytes", "lc3b_encoder_set_graph_mode",
            "lc3b_mixed_decoder_layout", "lc3b_mixed_decoder_workspace_bytes", "lc3b_mixed_decoder_init", "lc3b_mixed_decode_frames",
            "lc3b_mixed_decode_frames_host", "lc3b_mixed_decoder_set_host_pipelining", "lc3b_mixed_decoder_host_fence",
            "lc3b_mixed_decoder_set_graph_mode", "lc3b_mixed_decoder_destroy",
            "lc3b_sharded_decoder_create", "lc3b_sharded_decoder_n_shards", "lc3b_sharded_decoder_shard",
-           "lc3b_sharded_decode_frames_host", "lc3b_sharded_decoder_wait", "lc3b_sharded_decoder_destroy",
+           "lc3b_sharded_decode_frames_host", "lc3b_sharded_decoder_wait", "lc3b_sharded_decoder_set_min_nbytes", "lc3b_sharded_decoder_destroy",
            "lc3b_sharded_encoder_create", "lc3b_sharded_encoder_n_shards", "lc3b_sharded_encoder_shard",
            "lc3b_sharded_encode_frames_host", "lc3b_sharded_encoder_wait", "lc3b_sharded_encoder_destroy",
            "lc3b_host_alloc", "lc3b_host_free"]
@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
         u64p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
         L.lc3b_decoder_set_graph_mode.argtypes = [vp, i32]
         L.lc3b_decoder_set_dequant_mode.argtypes = [vp, i32]
+        L.lc3b_decoder_set_min_nbytes.argtypes = [vp, i32]
         L.lc3b_mixed_decoder_set_dequant_mode.argtypes = [vp, i32]
         L.lc3b_decoder_graph_stats.argtypes = [vp, u64p, u64p, u64p]
         L.lc3b_encoder_set_graph_mode.argtypes = [vp, i32]
@@ -134,6 +135,7 @@ def lib() -> C.CDLL:
             getattr(L, f"lc3b_sharded_{kind}_wait").argtypes = [vp]
             getattr(L, f"lc3b_sharded_{kind}_destroy").argtypes = [vp]
             getattr(L, f"lc3b_sharded_{kind}_destroy").restype = None
+        L.lc3b_sharded_decoder_set_min_nbytes.argtypes = [vp, i32]
         L.lc3b_sharded_decode_frames_host.argtypes = [vp, i32, vp, vp, i32, sz, vp, sz, vp]
         L.lc3b_sharded_encode_frames_host.argtypes = [vp, vp, sz, vp, i32, sz]
         L.lc3b_host_alloc.argtypes = [C.POINTER(vp), sz]

@@ -91,6 +91,12 @@ class Lc3ShardedBatchDecoder(_Sharded):
     """decode_frame for every stream of a batch spread over several GPUs (lc3b_sharded_decoder_*)."""
     _kind = "decoder"
 
+    def set_min_nbytes(self, min_nbytes: int) -> None:
+        """lc3b_decoder_set_min_nbytes on every shard (joins outstanding calls first)."""
+        rc = native.lib().lc3b_sharded_decoder_set_min_nbytes(self._h, int(min_nbytes))
+        if rc:
+            raise Lc3bError(rc, "lc3b_sharded_decoder_set_min_nbytes")
+
     def decode_frames_host(self, num_bits_per_audio_sample: int, frames: torch.Tensor, pcm_out: torch.Tensor,
                            frame_nbytes: torch.Tensor | None = None, nbytes: int | None = None,
                            status_out: torch.Tensor | None = None) -> None:

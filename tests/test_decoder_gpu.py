@@ -399,3 +399,50 @@ def test_dequantisation_kernels_agree_bitwise_at_batch_sizes_around_the_switch()
     b = gpu_decode(48000, 10, frames, dequant_mode=2)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[3].view(np.uint32), b[3].view(np.uint32))
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[4], b[4])
+
+
+def test_min_nbytes_promise_drops_the_post_filter_history_without_changing_results():
+    """lc3b_decoder_set_min_nbytes: at >= 110 bytes (48 kHz / 10 ms: 880 bits = 560 + 80 * 4) the reference's gain table row
+    is (0.0, 0), so the post filter can never act and its history is dead state.  With the promise the decoder stops
+    keeping it; every parity gate still holds - fixed 150 B frames, lengths varying in [110, 150] per call and stream,
+    lost frames - and frames that break the promise are concealed / rejected."""
+    import torch
+
+    import lc3_codec_b200 as L
+    from oracle import pyoracle as O
+    _, f150 = corpus(48000, 10, 150, 96, 24)
+    assert_parity(48000, 10, f150, min_nbytes=110)
+    _, f110 = corpus(48000, 10, 110, 96, 24)
+    _, f128 = corpus(48000, 10, 128, 96, 24)
+    frames = f150.copy()
+    lens = np.full((96, 24), 150, np.int32)
+    pick = (np.arange(96)[:, None] * 7 + np.arange(24)[None, :] * 3) % 5
+    for val, src, nb in ((1, f110, 110), (2, f128, 128)):
+        sel = pick == val
+        frames[sel, :nb] = src[sel]
+        frames[sel, nb:] = 0x55
+        lens[sel] = nb
+    lens[pick == 3] = np.broadcast_to(np.where(np.arange(24)[None, :] % 4 == 0, 0, 150), (96, 24))[pick == 3]     # some lost frames
+    stats = assert_parity(48000, 10, frames, lens, min_nbytes=110)
+    assert stats["concealed"] > 0.0
+    # a frame shorter than the promise is treated as lost: same output as handing the decoder an empty slice
+    short = lens.copy()
+    short[pick == 1] = 60
+    as_lost = lens.copy()
+    as_lost[pick == 1] = 0
+    got = gpu_decode(48000, 10, frames, short, trace=False, min_nbytes=110)
+    exp = gpu_decode(48000, 10, frames, as_lost, trace=False, min_nbytes=110)
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[4], exp[4]) and got[4][pick == 1].all()
+    # a promise that does not rule the filter out changes nothing: LTPF stays on at 60 bytes
+    _, f60 = corpus(48000, 10, 60, 96, 40)
+    stats = assert_parity(48000, 10, f60, min_nbytes=60)
+    assert stats["ltpf_active"] > 0.1
+    # fixed frame length below the promise: rejected like any other bad argument
+    ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(4, L.FrameDuration.TenMs, L.SamplingFrequency.Hz48000, 150),
+                     dtype=torch.uint8, device="cuda:0")
+    dec = L.Lc3BatchDecoder(4, L.FrameDuration.TenMs, L.SamplingFrequency.Hz48000, ws, 150)
+    dec.set_min_nbytes(110)
+    with pytest.raises(L.Lc3bError):
+        dec.decode_frames(16, torch.zeros((4, 100), dtype=torch.uint8, device="cuda:0"), torch.zeros((4, 480), dtype=torch.int16, device="cuda:0"))
+    with pytest.raises(L.Lc3bError):
+        dec.set_min_nbytes(151)
