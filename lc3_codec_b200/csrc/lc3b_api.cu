@@ -327,6 +327,7 @@ int decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int samp
     st.trace_x = nullptr;
     st.fixed_slot = -1;
     st.dequant_mode = 0;
+    st.synth_mode = 0;
     st.no_ltpf = 0;
     st.min_nbytes = 0;
     st.sm_count = 148;
@@ -409,6 +410,12 @@ int lc3b_decoder_set_min_nbytes(lc3b_decoder* h, int min_nbytes) {
     if (!h || min_nbytes < 0 || min_nbytes > h->st.max_nbytes) return LC3B_ERR_INVALID_ARG;
     h->st.min_nbytes = min_nbytes;
     h->st.no_ltpf = (min_nbytes > 0 && ltpf_impossible(h->st.cfg, min_nbytes)) ? 1 : 0;
+    return LC3B_OK;
+}
+
+int lc3b_decoder_set_synth_mode(lc3b_decoder* h, int mode) {
+    if (!h || mode < 0 || mode > 1) return LC3B_ERR_INVALID_ARG;
+    h->st.synth_mode = mode;
     return LC3B_OK;
 }
 

@@ -70,6 +70,7 @@ struct DecoderState {
     int no_ltpf;         // 1: every frame the handle accepts is too long for the post filter to be active (gain row (0.0, 0))
     int min_nbytes;      // promised minimum frame length (0 = none), lc3b_decoder_set_min_nbytes
     int sm_count;        // multiprocessors of the handle's device (persistent kernels size their grids with it)
+    int synth_mode;      // 0 one warp per frame with ordinary loads (default), 1 persistent warps + TMA prefetch (lc3b_decoder_set_synth_mode)
     int dequant_mode;    // 0 auto, 1 warp-per-frame dequantisation kernel, 2 thread-per-frame (lc3b_decoder_set_dequant_mode)
     // device pointers (carved from the caller's workspace)
     DevConfig* dcfg;

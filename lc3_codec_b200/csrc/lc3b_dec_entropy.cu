@@ -977,7 +977,7 @@ __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_mixed_kernel(const __g
 
 // ---------------------------------------------------------------- kernels 1b' / 1b'': the small-batch dequantisation
 // The thread-per-frame dequant_kernel needs ~100 k frames to fill the GPU: every frame's ne lines are one thread's serial
-// loop (0.07 ms at 16 384 streams of 120 lines whatever the occupancy).  Below DQW_MAX_STREAMS streams the same work is
+// loop (0.07 ms at 16 384 streams of 120 lines whatever the occupancy).  Up to DQW_MAX_STREAMS streams the same work is
 // split along what is really serial:
 //   dequant_warp_kernel (one WARP per frame, a lane owns the lines k = lane, lane + 32, ...): everything but the lattice.
 //     * residual refinement and noise filling are per-line decisions whose only serial part is a COUNT (the i-th
@@ -1410,7 +1410,7 @@ void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frame
 // Which dequantisation kernel a batch of n streams gets: warp-per-frame below DQW_MAX_STREAMS (it finishes a small batch
 // in a fraction of the thread-per-frame kernel's serial latency but costs more issue slots per frame), thread-per-frame
 // above.  lc3b_decoder_set_dequant_mode (or LC3B_DEQUANT=warp|thread in the environment) forces one; tests run both.
-constexpr int DQW_MAX_STREAMS = 98304;
+constexpr int DQW_MAX_STREAMS = 12288;        // measured cross-over at 16 kHz / 7.5 ms: 12-16 k streams (profiles/r2_small_batch.json)
 bool use_dequant_warp(int n_streams, int mode) {
     static const int forced = [] {
         const char* e = getenv("LC3B_DEQUANT");

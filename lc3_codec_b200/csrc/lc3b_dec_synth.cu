@@ -60,8 +60,9 @@ __device__ __forceinline__ int32_t round_pcm_i32(float v) {          // output_s
     return q > 32767 ? 32767 : q < -32768 ? -32768 : q;
 }
 
-// The non-persistent form of the same kernel (one warp = one frame, spectrum through ordinary loads): kept selectable
-// (LC3B_SYNTH=classic) for A/B measurements against the TMA-pipelined persistent kernel below.
+// synth_classic_kernel: one warp = one frame, spectrum through ordinary loads.  The default: at 262 144 streams it runs in
+// 0.507 ms against 0.525 ms for the persistent TMA-pipelined kernel below (profiles/r2_synth_ab.json) - the kernel is bound
+// by instruction issue (about 1 500 warp instructions per frame at IPC 2.2), not by the latency the prefetch hides.
 template <int NF, bool MS10>
 __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __grid_constant__ SynthParams p) {
     using G = FrameGeo<NF, MS10>;
@@ -543,11 +544,11 @@ struct PlanSynth {
     LaunchPlan& plan;
     const SynthParams& p;
     int dep, node, sm_count;
+    bool pipelined;
     template <int NF, bool MS10> void operator()() {
         // persistent: at most as many CTAs as fit on the device at once (4 of 8 warps per SM by registers; shared memory may allow fewer)
         const int full = (p.n_streams + SYN_WARPS - 1) / SYN_WARPS;
-        static const bool classic = [] { const char* e = getenv("LC3B_SYNTH"); return e && e[0] == 'c'; }();
-        if (classic) {
+        if (!pipelined) {
             node = plan.add(synth_classic_kernel<NF, MS10>, (unsigned)full, SYN_WARPS * 32, SYN_WARPS * 2 * NF * 4, p, dep);
             return;
         }
@@ -596,7 +597,11 @@ int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_
     const size_t lw = ltpf_warp_bytes(st.cfg);
     p.smem_per_warp = (int)lw;
     p.no_ltpf = st.no_ltpf;
-    PlanSynth ps{plan, p, dep, -1, st.sm_count > 0 ? st.sm_count : 148};
+    // which synthesis kernel: 0 = one warp per frame, ordinary loads (default: measured faster, the kernel is issue bound);
+    // 1 = persistent warps with the next frame's spectrum prefetched by the TMA unit (lc3b_decoder_set_synth_mode / LC3B_SYNTH=pipe)
+    static const int env_mode = [] { const char* e = getenv("LC3B_SYNTH"); return !e ? -1 : (e[0] == 'p' ? 1 : 0); }();
+    const int mode = env_mode >= 0 ? env_mode : st.synth_mode;
+    PlanSynth ps{plan, p, dep, -1, st.sm_count > 0 ? st.sm_count : 148, mode == 1};
     if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ps)) return -1;
     if (st.no_ltpf) return ps.node;                           // the post filter can never be active: nothing to launch
     const int n_warps = (st.n_streams + group - 1) / group;

@@ -171,6 +171,12 @@ class Lc3BatchDecoder:
         if rc:
             raise Lc3bError(rc, "lc3b_decoder_set_min_nbytes")
 
+    def set_synth_mode(self, mode: int) -> None:
+        """0 = synthesis kernel with one warp per frame (default), 1 = persistent warps + TMA prefetch (identical results)."""
+        rc = native.lib().lc3b_decoder_set_synth_mode(self._h, mode)
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_set_synth_mode")
+
     def set_dequant_mode(self, mode: int) -> None:
         """0 = dequantisation kernel chosen by batch size, 1 = warp per frame, 2 = thread per frame (identical results)."""
         rc = native.lib().lc3b_decoder_set_dequant_mode(self._h, mode)

@@ -40,7 +40,7 @@ def corpus_clip(fs: int, ms: float, nbytes: int, n_streams: int, window: int = 0
 
 
 def gpu_decode(fs, ms, frames, nbytes_per_frame=None, host=False, trace=True, device="cuda:0", dequant_mode=0, graph=None,
-               min_nbytes=0):
+               min_nbytes=0, synth_mode=0):
     """Decode [S,F,nbytes] frame by frame through the C ABI; returns pcm [S,F,nf], trace [S,F,48], x [S,F,ne],
     spectrum [S,F,ne], status [S,F]."""
     import torch
@@ -55,6 +55,7 @@ def gpu_decode(fs, ms, frames, nbytes_per_frame=None, host=False, trace=True, de
     dec.set_dequant_mode(dequant_mode)                  # 0 auto, 1 warp-per-frame kernel, 2 thread-per-frame kernel
     if graph is not None:
         dec.set_graph_mode(graph)
+    dec.set_synth_mode(synth_mode)                      # 0 one warp per frame, 1 persistent + TMA prefetch
     if min_nbytes:
         dec.set_min_nbytes(min_nbytes)                  # the handle may drop the post filter's history (include/lc3b.h)
     nf, ne = dec.nf, dec.ne

@@ -136,3 +136,55 @@ def test_sharded_encoder_and_graph_executor():
         for f in range(F):
             e1.encode_frames(x[f], out[f])
         assert np.array_equal(out.cpu().numpy().transpose(1, 0, 2), o_frames), graph
+
+
+@pytest.mark.parametrize("fs,ms,nbytes", [(48000, 10, 150), (16000, 7.5, 30)])
+def test_stage_level_parity_through_debug_read(fs, ms, nbytes):
+    """lc3b_encoder_debug_read: the intermediates the kernels hand to each other, against the ORACLE'S STAGES chained by
+    hand on the same frames (the stage functions the reference's own #[test]s pin: modified_dct_encode, attack_detector_run,
+    long_term_post_filter_run, bandwidth_detector_run, sns_run, temporal_noise_shaping_run, spectral_quantization_run):
+      e_b   band energies after the MDCT                      bit exact
+      hand  near-Nyquist flag, attack flag, pitch index / present, LTPF active, LTPF bits
+      xf    spectrum after SNS and TNS (the quantiser's input) bit exact
+      xq    quantised spectrum                                 exact
+    A byte-identical frame could in principle hide two compensating errors; these cannot."""
+    import ctypes as C
+
+    from oracle import pyoracle as O
+    lib = O.lib()
+    lib.lc3o_quant_new.restype = C.c_void_p
+    sf, fd = O.SF[fs], O.FD[ms]
+    cfg = O.config(fs, ms)
+    nf, ne, fs_ind = cfg["nf"], cfg["ne"], cfg["fs_ind"]
+    S, F = 6, 8
+    pcm, _ = corpus(fs, ms, nbytes, S, F, first_stream=3)
+    _, dbg = gpu_encode(fs, ms, pcm, nbytes, debug=True)
+    nbits = nbytes * 8
+    for s_ in range(S):
+        mdct, att, ltpf = (C.c_void_p(getattr(lib, f"lc3o_{n}_new")(sf, fd)) for n in ("encmdct", "attack", "encltpf"))
+        quant = C.c_void_p(lib.lc3o_quant_new(ne, fs_ind))
+        for f in range(F):
+            x16 = np.ascontiguousarray(pcm[s_, f])
+            spec, eb = np.zeros(nf, np.float32), np.zeros(64, np.float32)
+            near_nyquist = lib.lc3o_encmdct_run(mdct, O.p(x16), O.p(spec), O.p(eb))
+            attack = lib.lc3o_attack_run(att, O.p(x16), nbytes)
+            lt = np.zeros(4, np.int32)
+            lib.lc3o_encltpf_run(ltpf, O.p(x16), near_nyquist, nbits, O.p(lt))
+            bw = np.zeros(2, np.int32)
+            lib.lc3o_bandwidth_detect(sf, fd, O.p(eb), O.p(bw))
+            sns = np.zeros(7, np.int64)
+            lib.lc3o_sns_encode(sf, fd, O.p(spec), O.p(eb), attack, O.p(sns))
+            ti, rq = np.zeros(21, np.int32), np.zeros(16, np.float32)
+            lib.lc3o_tns_encode(sf, fd, O.p(spec), int(bw[0]), nbits, near_nyquist, O.p(ti), O.p(rq))
+            xq, qi, gg = np.zeros(ne, np.int16), np.zeros(7, np.int32), C.c_float(0)
+            lib.lc3o_quant_run(quant, O.p(spec), O.p(xq), nbits, int(bw[1]), int(ti[0]), int(lt[3]), O.p(qi), C.byref(gg))
+            g_xf, g_eb, g_hand, g_xq = (a[s_] for a in dbg[f])
+            where = (fs, s_, f)
+            assert np.array_equal(g_eb.view(np.uint32), eb.view(np.uint32)), where
+            assert g_hand[:6].tolist() == [near_nyquist, attack, int(lt[0]), int(lt[1]), int(lt[2]), int(lt[3])], where
+            assert np.array_equal(g_xf.view(np.uint32), spec[:ne].view(np.uint32)), where
+            assert np.array_equal(g_xq, xq), where
+        lib.lc3o_encmdct_free(mdct)
+        lib.lc3o_attack_free(att)
+        lib.lc3o_encltpf_free(ltpf)
+        lib.lc3o_quant_free(quant)
