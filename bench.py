@@ -571,6 +571,7 @@ def main():
     ap.add_argument("--workload", default="decode48", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the named workload's)")
     ap.add_argument("--total-streams", type=int, default=0, help="strong scaling: this many streams in total, split over the GPUs")
+    ap.add_argument("--distinct", type=int, default=1024, help="distinct synthetic streams the batch is tiled from (PCM workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the small-batch workloads reported under `secondary`")
     ap.add_argument("--quick", action="store_true", help="device-resident loop only (for ncu captures; not a bench value)")
@@ -642,7 +643,7 @@ def run_codec(args, w, rank, local_rank, world, dev, dist, quick=False):
     S, NB, NF, mode = w["streams"], w["nbytes"], w["nf"], w["mode"]
     sf, fd = L.SamplingFrequency.from_hz(w["fs"]), L.FrameDuration.from_ms(w["ms"])
     stream = torch.cuda.current_stream(dev)
-    U, F, WARM = (256 if quick and w["name"] != "decode48" else 1024), 8, 4       # distinct streams, frames each, encoder lead-in
+    U, F, WARM = (256 if quick and w["name"] != "decode48" else (1024 if w["name"] == "decode48" else args.distinct)), 8, 4   # distinct streams, frames each, encoder lead-in
     # rank r owns streams [r*S, (r+1)*S) of the job; stream s replays corpus stream s mod U
     idx = torch.from_numpy((np.arange(S) + rank * S) % U).to(dev)
 

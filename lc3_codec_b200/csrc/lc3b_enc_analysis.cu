@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_mdct_kernel(AnalysisParams
     // the terms x^2 / width of all lines in parallel (the division is the expensive part), then one ordered sum per band
     float* tq = (float*)tb;                         // the time buffer is dead by now; ne floats fit in its 2 nf int16
     WARP_STRIDE(k, ne) {
-        const int b = c.band_of[k];
-        if (b != 255) tq[k] = wk[k] * wk[k] / (float)(c.band_idx[b + 1] - c.band_idx[b]);
+        const float width = c.band_width_of[k];                       // (band_idx[b + 1] - band_idx[b]) as f32, one load instead of three
+        if (width != 0.0f) tq[k] = wk[k] * wk[k] / width;
     }
     __syncwarp();
     WARP_STRIDE(b, c.nb) {

@@ -90,6 +90,7 @@ __global__ void enc_init_band_kernel(EncConfig* cfg) {
         int band = 255;
         for (int b = 0; b < cfg->nb; b++) if (k >= bi[b] && k < bi[b + 1]) band = b;
         cfg->band_of[k] = (uint8_t)band;
+        cfg->band_width_of[k] = band == 255 ? 0.0f : (float)(bi[band + 1] - bi[band]);
     }
 }
 

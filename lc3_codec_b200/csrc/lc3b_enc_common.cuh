@@ -16,6 +16,7 @@ struct EncConfig {
     int32_t fac_p[8], fac_m[8], fac_stride[8];   // kf_factor (kissfft.rs:47): radix, sub-length, fstride per level
     int32_t band_idx[65];
     uint8_t band_of[400];             // line -> band (255: beyond the last band)
+    float band_width_of[400];         // line -> width of its band as f32, 0 beyond the last band (energy estimation divides by it)
     // LTPF analysis (encoder/long_term_post_filter.rs:91-124)
     int32_t len12p8, len6p4, delay, up, x_s_ext_len, x12_len;
     float resamp_fac;
