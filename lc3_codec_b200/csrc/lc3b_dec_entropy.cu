@@ -327,7 +327,10 @@ __host__ __device__ inline size_t dequant_smem_bytes(int row_pitch) {
     return 16 * ENT_THREADS * 4 + 68 * 4 + (size_t)ENT_THREADS * row_pitch;
 }
 
-__device__ __forceinline__ void entropy_body(const EntropyParams& p, const int block, uint8_t* smem) {
+__device__ __forceinline__ void entropy_body(const EntropyParams& p, const int block) {
+    // declared here, not handed in as a pointer: the compiler then addresses shared memory directly instead of rebuilding the
+    // shared window base from a generic pointer inside the symbol loop
+    extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* s_lookup = smem;
     uint8_t* s_clut = smem + 4096;
     uint32_t* s_spec_cf = (uint32_t*)(smem + 4096 + 2048);
@@ -644,8 +647,7 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
 
 
 __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_kernel(const __grid_constant__ EntropyParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    entropy_body(p, blockIdx.x, smem);
+    entropy_body(p, blockIdx.x);
 }
 
 // Mixed-rate batches (BASELINE config 4; lc3b_mixed_*): ONE launch covers every (fs, duration) bucket.  A CTA finds its
@@ -670,18 +672,18 @@ __device__ __forceinline__ void mixed_select(const MixedParams& m, EntropyParams
 }
 
 __global__ void __launch_bounds__(ENT_THREADS, 6) entropy_mixed_kernel(const __grid_constant__ MixedParams m) {
-    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ EntropyParams s_p;
     __shared__ int s_block;
     mixed_select(m, &s_p, &s_block);
-    entropy_body(s_p, s_block, smem);
+    entropy_body(s_p, s_block);
 }
 
 // ---------------------------------------------------------------- kernel 1b: integers -> shaped spectrum
 // Dequantisation, residual refinement, noise filling, global gain, TNS lattice, SNS gains (reference D4-D8); one
 // thread per frame, every thread walks all ne lines, so the warp stays converged without any work sorting.
 template <int W /* noise-filling half width: 3 at 10 ms, 2 at 7.5 ms */>
-__device__ __forceinline__ void dequant_body(const EntropyParams& p, const int block, uint8_t* smem) {
+__device__ __forceinline__ void dequant_body(const EntropyParams& p, const int block) {
+    extern __shared__ __align__(16) uint8_t smem[];
     float* s_scf = (float*)smem;
     int32_t* s_band = (int32_t*)(s_scf + 16 * ENT_THREADS);
     uint8_t* s_rows = (uint8_t*)(s_band + 68);
@@ -962,17 +964,15 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
 
 template <int W>
 __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(const __grid_constant__ EntropyParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    dequant_body<W>(p, blockIdx.x, smem);
+    dequant_body<W>(p, blockIdx.x);
 }
 
 template <int W>
 __global__ void __launch_bounds__(ENT_THREADS, 5) dequant_mixed_kernel(const __grid_constant__ MixedParams m) {
-    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ EntropyParams s_p;
     __shared__ int s_block;
     mixed_select(m, &s_p, &s_block);
-    dequant_body<W>(s_p, s_block, smem);
+    dequant_body<W>(s_p, s_block);
 }
 
 // ---------------------------------------------------------------- kernels 1b' / 1b'': the small-batch dequantisation
@@ -1008,7 +1008,8 @@ __device__ __forceinline__ float sns_interp64(const float* scf, int j) {        
     return xa(fn, xm(w, d));
 }
 
-__device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const int block, uint8_t* smem) {
+__device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const int block) {
+    extern __shared__ __align__(16) uint8_t smem[];
     float* s_gband = (float*)smem;                                     // [DQW_WARPS][64]
     float* s_scf = s_gband + DQW_WARPS * 64;                           // [DQW_WARPS][16]
     float* s_y = s_scf + DQW_WARPS * 16;                               // [DQW_WARPS][16]
@@ -1301,8 +1302,7 @@ __device__ __forceinline__ void tns_list_body(const EntropyParams& p, const int 
 }
 
 __global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_kernel(const __grid_constant__ EntropyParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    dequant_warp_body(p, blockIdx.x, smem);
+    dequant_warp_body(p, blockIdx.x);
 }
 __global__ void __launch_bounds__(ENT_THREADS) tns_list_kernel(const __grid_constant__ EntropyParams p) {
     tns_list_body(p, blockIdx.x);
@@ -1328,11 +1328,10 @@ __device__ __forceinline__ void mixed_select_scaled(const MixedParams& m, Entrop
     __syncthreads();
 }
 __global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_mixed_kernel(const __grid_constant__ MixedParams m) {
-    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ EntropyParams s_p;
     __shared__ int s_block;
     mixed_select_scaled(m, &s_p, &s_block, ENT_THREADS / DQW_WARPS);
-    dequant_warp_body(s_p, s_block, smem);
+    dequant_warp_body(s_p, s_block);
 }
 __global__ void __launch_bounds__(ENT_THREADS) tns_list_mixed_kernel(const __grid_constant__ MixedParams m) {
     __shared__ EntropyParams s_p;

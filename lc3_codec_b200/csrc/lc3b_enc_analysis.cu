@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
 
     const int16_t* x = p.pcm + (size_t)stream * p.pcm_stride;     // this frame's input samples
     int32_t* es = p.estate + (size_t)stream * ES_WORDS;
+    const int n_live_c = min(ANA_WARPS, p.n_streams - (int)blockIdx.x * ANA_WARPS);   // warps of this CTA that have a frame
     const int near_nyquist = p.ehand[(size_t)stream * EH_WORDS + EH_NEAR_NYQUIST];
     const int up = c.up, ns_keep = 240 / up;
     {   // x_s_extended (long_term_post_filter.rs:217-224): last 240/up samples of the previous frame, then this frame
@@ -465,14 +466,23 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
         const int k_from = (K_MIN > t_prev - 4 ? K_MIN : t_prev - 4) - K_MIN;
         const int k_to = (K_MAX < t_prev + 4 ? K_MAX : t_prev + 4) - K_MIN + 1;
         const int lag_t2 = index_of_max_w(r6 + k_from, k_to - k_from) + k_from + K_MIN;
-        // the three norm values are independent ordered sums: lanes 0, 1, 2 take one each
-        const int my_lag = lane == 1 ? lag_t1 : lane == 2 ? lag_t2 : 0;
-        float nv = 0.0f;
-        {
-            const int from = K_MAX - my_lag;
-            for (int n = from; n < from + len6; n++) nv += x6[n] * x6[n];
+        // the three norm values are independent ordered sums of len6 terms.  Three busy lanes per warp would cost every
+        // frame a warp's issue slots for the whole loop: the sums of all frames of the CTA run on the lanes of warp 0
+        // (lane 3 w + j: frame of warp w, sum j), between two named barriers, like the biquad above.
+        if (lane == 0) { ((int*)wk)[256] = lag_t1; ((int*)wk)[257] = lag_t2; }
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live_c * 32) : "memory");
+        if (wid == 0 && lane < 3 * n_live_c) {
+            const int w = lane / 3, j = lane - 3 * w;
+            float* o_wk = (float*)(smem + (size_t)w * p.smem_per_warp);
+            const float* o_x6 = o_wk + 320 + 98 + 98 + 236 + c.x12_len;
+            const int lag = j == 0 ? 0 : ((const int*)o_wk)[255 + j];
+            const int from = K_MAX - lag;
+            float nv = 0.0f;
+            for (int n = from; n < from + len6; n++) nv += o_x6[n] * o_x6[n];
+            o_wk[258 + j] = nv;
         }
-        const float nv0 = __shfl_sync(0xffffffffu, nv, 0), nv1 = __shfl_sync(0xffffffffu, nv, 1), nv2 = __shfl_sync(0xffffffffu, nv, 2);
+        asm volatile("bar.sync 1, %0;" ::"r"(n_live_c * 32) : "memory");
+        const float nv0 = wk[258], nv1 = wk[259], nv2 = wk[260];
         const float normvalue1 = sqrtf(nv0 * nv1);
         const float normcorr1 = maxf_rs(0.0f, r6[lag_t1 - K_MIN] / normvalue1);
         float normcorr2;
@@ -549,13 +559,22 @@ __global__ void __launch_bounds__(ANA_WARPS * 32) enc_ltpf_kernel(AnalysisParams
         sh_a[n] = dot(n - pitch_int, pitch_fr);
     }
     __syncwarp();
-    float acc3 = 0.0f;
-    {   // the three running sums are independent ordered sums: lane 0 nd*sh, lane 1 nd*nd, lane 2 sh*sh
-        const float* pa = lane == 2 ? sh_a : nd_a;
-        const float* pb = lane == 1 ? nd_a : sh_a;
-        for (int n = 0; n < len12; n++) acc3 += pa[n] * pb[n];
+    // the three running sums (nd*sh, nd*nd, sh*sh) are independent ordered sums of len12 terms: again on warp 0 for all
+    // frames of the CTA (lane 3 w + j)
+    asm volatile("bar.sync 1, %0;" ::"r"(n_live_c * 32) : "memory");
+    if (wid == 0 && lane < 3 * n_live_c) {
+        const int w = lane / 3, j = lane - 3 * w;
+        float* o_wk = (float*)(smem + (size_t)w * p.smem_per_warp);
+        const float* o_nd = o_wk;
+        const float* o_sh = o_wk + 128;
+        const float* pa = j == 2 ? o_sh : o_nd;
+        const float* pb = j == 1 ? o_nd : o_sh;
+        float acc = 0.0f;
+        for (int n = 0; n < len12; n++) acc += pa[n] * pb[n];
+        o_wk[258 + j] = acc;
     }
-    const float nd_tot = __shfl_sync(0xffffffffu, acc3, 1), sh_tot = __shfl_sync(0xffffffffu, acc3, 2);
+    asm volatile("bar.sync 1, %0;" ::"r"(n_live_c * 32) : "memory");
+    const float acc3 = wk[258], nd_tot = wk[259], sh_tot = wk[260];
     if (lane == 0) {
         const float nc_num = acc3;
         const float nc_den = sqrtf(nd_tot * sh_tot);

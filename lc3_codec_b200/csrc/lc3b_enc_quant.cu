@@ -494,8 +494,7 @@ __device__ __noinline__ float fdiv_call(float a, float b) { return a / b; }
 
 // TemporalNoiseShaping::run :40-78.  Scratch: ac[2][27] at S, raw reflection coefficients at S+64,
 // results rc_i (int[16]) at S+256 and rc_q (float[16]) at S+272 (kept until the bitstream is written).
-__device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, int nbits, bool near_nyquist, TnsRes& r, int lane,
-                             int wib, int n_live) {
+__device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, int nbits, bool near_nyquist, TnsRes& r, int lane) {
     const TnsP& tp = (c.n_ms == LC3B_10MS ? TNS_T10 : TNS_T75)[p_bw];
     float* ac = S;
     float* rc_raw = S + 64;
@@ -516,19 +515,9 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         }
     }
     __syncwarp();
-    // Levinson-Durbin :204-232 and LPC weighting / LPC -> RC :234-257 are ~2 000 instructions of one serial chain per
-    // filter.  Run by every warp for its own frame they cost a warp's issue slots each; here the chains of all frames of
-    // the CTA run side by side on the lanes of warp 0 (lane 2 w + f: frame of warp w, filter f) between two named
-    // barriers, on the autocorrelations the warps left in their scratch areas.
-    if (lane == 0) { ((int*)S)[60] = p_bw; ((int*)S)[61] = near_nyquist ? 1 : 0; }
-    asm volatile("bar.sync 2, %0;" ::"r"(n_live * 32) : "memory");
-    if (wib == 0 && lane < 2 * n_live) {
-        const int w = lane >> 1, f = lane & 1;
-        float* oS = S + (size_t)w * (NE_MAX + S_FLOATS);                 // warp w's scratch (this is warp 0)
-        const TnsP& otp = (c.n_ms == LC3B_10MS ? TNS_T10 : TNS_T75)[((const int*)oS)[60]];
-        const bool o_near_nyquist = ((const int*)oS)[61] != 0;
-        if (f < otp.nf) {
-        const float* acf = oS + f * 27;
+    {   // Levinson-Durbin :204-232 and LPC weighting / LPC -> RC :234-257: lane f works on filter f
+        const int f = (lane & 1) < tp.nf ? (lane & 1) : 0;
+        const float* acf = ac + f * 27;
         float rr[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) {
@@ -562,7 +551,7 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         }
         const float pred_gain = e == 0.0f ? rr[0] : rr[0] / e;
         float rcq[8];
-        if (pred_gain > 1.5f && !o_near_nyquist) {
+        if (pred_gain > 1.5f && !near_nyquist) {
             float gamma = 1.0f;
             if (r.lpc_weighting > 0 && pred_gain < 2.0f) gamma -= (1.0f - 0.85f) * (2.0f - pred_gain) / (2.0f - 1.5f);
 #pragma unroll
@@ -584,12 +573,12 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
 #pragma unroll
             for (int k = 0; k < 8; k++) rcq[k] = 0.0f;
         }
-        float* o_rc_raw = oS + 64;
+        if (lane < tp.nf) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) o_rc_raw[f * 8 + k] = rcq[k];
+            for (int k = 0; k < 8; k++) rc_raw[lane * 8 + k] = rcq[k];
         }
     }
-    asm volatile("bar.sync 2, %0;" ::"r"(n_live * 32) : "memory");
+    __syncwarp();
     if (lane < 16) {                                         // quantisation :259-283: one coefficient per lane
         const float step = (float)M_PI / 17.0f;
         int qi = 8;
@@ -1477,8 +1466,7 @@ __global__ void __launch_bounds__(QNT_THREADS, 4) enc_tns_kernel(QuantParams p) 
     const int32_t* eh = p.ehand + (size_t)stream * EH_WORDS;
     int32_t* qh = p.qhand + (size_t)stream * QH_WORDS;
     TnsRes tns;
-    const int n_live_tns = min(QW, p.n_streams - blockIdx.x * QW);   // warps of this CTA that have a frame (the others returned)
-    tns_encode_w(c, xf, S, qh[QH_BW], p.nbytes * 8, eh[EH_NEAR_NYQUIST] != 0, tns, lane, wib, n_live_tns);
+    tns_encode_w(c, xf, S, qh[QH_BW], p.nbytes * 8, eh[EH_NEAR_NYQUIST] != 0, tns, lane);
     if (tns.rc_order[0] != 0 || tns.rc_order[1] != 0) {           // the spectrum only changes when a filter is active
         WARP_STRIDE(i, ne / 4) gx[i] = ((const float4*)xf)[i];
     }

@@ -1,21 +1,29 @@
 #!/bin/bash
-# Run on the GPU box (gpurun): every bench workload, the ncu launch list of the default bench command, and one
-# `ncu --set full` capture of all kernels.  Outputs land in gpurun_out/ and are summarised into profiles/ afterwards
-# with tools/ncu_summary.py and tools/ncu_lines.py.
+# Run on the GPU box (gpurun): every bench workload, the ncu launch list of the default bench command, and `ncu --set full`
+# captures of all kernels.  Outputs land in gpurun_out/ and are summarised into profiles/ afterwards with
+# tools/ncu_summary.py and tools/ncu_lines.py (bench JSONs are never taken under a profiler).
 set -u
-TAG=${1:-r1_final}
+TAG=${1:-r2_final}
 OUT=gpurun_out
 mkdir -p $OUT
-for w in decode48 encode48 decode16 mixed roundtrip48 file48; do
-  python bench.py --workload $w > $OUT/${TAG}_bench_$w.json 2> $OUT/${TAG}_bench_$w.err || echo "bench $w failed"
+python bench.py > $OUT/${TAG}_bench_decode48.json 2> $OUT/${TAG}_bench_decode48.err || echo "bench decode48 failed"
+tail -c 400 $OUT/${TAG}_bench_decode48.json; echo
+for w in encode48 decode16 mixed roundtrip48 file48; do
+  python bench.py --workload $w --distinct 512 > $OUT/${TAG}_bench_$w.json 2> $OUT/${TAG}_bench_$w.err || echo "bench $w failed"
   tail -c 300 $OUT/${TAG}_bench_$w.json | head -c 300; echo
 done
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference_decode48.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_decode48.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_launches_decode48.log 2>&1
-# one full step of the round trip = 8 encoder + 4 decoder kernels; 3 warm-up steps are skipped
-ncu --set full --clock-control none --import-source on -k regex:"enc_|entropy|dequant|synth|ltpf_kernel" -s 36 -c 12 -o $OUT/${TAG}_all \
-    python bench.py --workload roundtrip48 --steps 2 --warmup 3 --quick --no-cpu-baseline > $OUT/${TAG}_all.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/${TAG}_launches_decode48.log 2>&1
+# one full step of the round trip = 8 encoder + 3 decoder kernels (no post-filter launch at 150 B); 3 warm-up steps are skipped
+ncu --set full --clock-control none --import-source on -k regex:"enc_|entropy_kernel|dequant_kernel|synth_" -s 33 -c 11 -o $OUT/${TAG}_all \
+    python bench.py --workload roundtrip48 --steps 2 --warmup 3 --quick --no-cpu-baseline --distinct 256 > $OUT/${TAG}_all.log 2>&1
+# the small-batch path: BASELINE config 3 (16 384 streams): entropy, dequant_warp, tns_list, synth, ltpf
+ncu --set full --clock-control none --import-source on -k regex:"entropy_kernel|dequant_warp|tns_list|synth_|ltpf_kernel" -s 45 -c 5 -o $OUT/${TAG}_small \
+    python bench.py --workload decode16 --streams 8192 --steps 2 --warmup 3 --quick --no-cpu-baseline > $OUT/${TAG}_small.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"multi|plc_scan" -s 12 -c 4 -o $OUT/${TAG}_multi \
     python bench.py --workload file48 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_multi.log 2>&1
+# the TMA-pipelined synthesis kernel, for the A/B table
+LC3B_SYNTH=pipe ncu --set full --clock-control none --import-source on -k regex:"synth_kernel" -s 3 -c 1 -o $OUT/${TAG}_synth_pipe \
+    python bench.py --steps 2 --warmup 3 --quick --no-cpu-baseline > $OUT/${TAG}_synth_pipe.log 2>&1
 ls -la $OUT | tail -20
