@@ -90,6 +90,24 @@ def emit(obj):
         os.write(_JSON_FD, line)
 
 
+NCU_RANGE = os.environ.get("LC3B_NCU_RANGE") == "1"     # ncu --profile-from-start off: capture only the first timed loop
+_ncu_range_used = False
+
+
+def ncu_range(start: bool):
+    """cudaProfilerStart/Stop around the FIRST timed loop of the run, so that an ncu capture (tools/collect_round_profiles.sh)
+    sees steady-state launches of the workload itself and none of the corpus preparation."""
+    global _ncu_range_used
+    if not NCU_RANGE:
+        return
+    import torch
+    if start and not _ncu_range_used:
+        torch.cuda.profiler.start()
+    elif not start and not _ncu_range_used:
+        torch.cuda.profiler.stop()
+        _ncu_range_used = True
+
+
 def algo_bytes(w):
     return w["nbytes"] + 2 * w["nf"]                  # SURVEY.md 8d: bitstream bytes + 2 bytes per PCM sample, one direction
 
@@ -361,12 +379,14 @@ def run_mixed(args, w, rank, local_rank, world, dev, dist, quick=False):
         for i in range(warmup):
             fn(i)
         barrier()
+        ncu_range(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(steps):
             fn(warmup + i)
         e1.record(stream)
         barrier()
+        ncu_range(False)
         ms_ = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms_], device=dev)
@@ -458,12 +478,14 @@ def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
         for i in range(warmup):
             fn(i)
         barrier()
+        ncu_range(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(steps):
             fn(warmup + i)
         e1.record(stream)
         barrier()
+        ncu_range(False)
         ms_ = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms_], device=dev)
@@ -699,6 +721,7 @@ def run_codec(args, w, rank, local_rank, world, dev, dist, quick=False):
         if finish:
             finish()
         barrier()
+        ncu_range(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(steps):
@@ -707,6 +730,7 @@ def run_codec(args, w, rank, local_rank, world, dev, dist, quick=False):
             finish()                      # e.g. make the stream wait for the last pipelined device->host copy
         e1.record(stream)
         barrier()
+        ncu_range(False)
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device=dev)

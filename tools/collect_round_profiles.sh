@@ -15,15 +15,16 @@ done
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference_decode48.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_decode48.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/${TAG}_launches_decode48.log 2>&1
-# one full step of the round trip = 8 encoder + 3 decoder kernels (no post-filter launch at 150 B); 3 warm-up steps are skipped
-ncu --set full --clock-control none --import-source on -k regex:"enc_|entropy_kernel|dequant_kernel|synth_" -s 33 -c 11 -o $OUT/${TAG}_all \
-    python bench.py --workload roundtrip48 --steps 2 --warmup 3 --quick --no-cpu-baseline --distinct 256 > $OUT/${TAG}_all.log 2>&1
+# one full step of the round trip = 8 encoder + 3 decoder kernels (no post-filter launch at 150 B).  bench.py brackets its first
+# timed loop with cudaProfilerStart/Stop when LC3B_NCU_RANGE=1, so the captures hold steady-state launches only
+LC3B_NCU_RANGE=1 ncu --set full --clock-control none --import-source on --profile-from-start off -c 11 -o $OUT/${TAG}_all \
+    python bench.py --workload roundtrip48 --steps 1 --warmup 3 --quick --no-cpu-baseline --distinct 256 > $OUT/${TAG}_all.log 2>&1
 # the small-batch path: BASELINE config 3 (16 384 streams): entropy, dequant_warp, tns_list, synth, ltpf
-ncu --set full --clock-control none --import-source on -k regex:"entropy_kernel|dequant_warp|tns_list|synth_|ltpf_kernel" -s 45 -c 5 -o $OUT/${TAG}_small \
+LC3B_NCU_RANGE=1 LC3B_GRAPH=0 ncu --set full --clock-control none --import-source on --profile-from-start off -c 5 -o $OUT/${TAG}_small \
     python bench.py --workload decode16 --streams 8192 --steps 2 --warmup 3 --quick --no-cpu-baseline > $OUT/${TAG}_small.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"multi|plc_scan" -s 12 -c 4 -o $OUT/${TAG}_multi \
+LC3B_NCU_RANGE=1 ncu --set full --clock-control none --import-source on --profile-from-start off -c 6 -o $OUT/${TAG}_multi \
     python bench.py --workload file48 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_multi.log 2>&1
 # the TMA-pipelined synthesis kernel, for the A/B table
-LC3B_SYNTH=pipe ncu --set full --clock-control none --import-source on -k regex:"synth_kernel" -s 3 -c 1 -o $OUT/${TAG}_synth_pipe \
+LC3B_NCU_RANGE=1 LC3B_SYNTH=pipe ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"synth_kernel" -c 1 -o $OUT/${TAG}_synth_pipe \
     python bench.py --steps 2 --warmup 3 --quick --no-cpu-baseline > $OUT/${TAG}_synth_pipe.log 2>&1
 ls -la $OUT | tail -20
