@@ -62,7 +62,7 @@ struct Carve {
 };
 
 struct Layout {
-    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, gband, tns_list, ola, ltpf_y, ltpf_xtail, ltpf_x, side, sstate, stage_in, stage_out, stage_len,
+    size_t dcfg, win, dtw, ftw, sym_lut, spec, xq, handoff, gband, tns_list, nsym_prev, ola, ltpf_y, ltpf_xtail, ltpf_x, side, sstate, stage_in, stage_out, stage_len,
         stage_status, total;
 };
 
@@ -81,6 +81,7 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes, b
     L.handoff = cv.take(sizeof(int32_t) * ((ns + 127) / 128) * 128 * HO_WORDS);   // every thread slot of whole entropy CTAs
     L.gband = cv.take(sizeof(float) * ((ns + 127) / 128) * 128 * 64);
     L.tns_list = cv.take(sizeof(int32_t) * (1 + ((ns + 127) / 128) * 128));
+    L.nsym_prev = cv.take(sizeof(int32_t) * ns);
     L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
     L.ltpf_y = cv.take(sizeof(float) * ns * blocks * c.nf);
     L.ltpf_xtail = cv.take(sizeof(float) * ns * XTAIL_FLOATS);
@@ -313,6 +314,7 @@ int decoder_init(lc3b_decoder** out, int n_streams, int frame_duration, int samp
     st.handoff = (int32_t*)(base + L.handoff);
     st.gband = (float*)(base + L.gband);
     st.tns_list = (int32_t*)(base + L.tns_list);
+    st.nsym_prev = (int32_t*)(base + L.nsym_prev);
     st.ola = (float*)(base + L.ola);
     st.ltpf_y = (float*)(base + L.ltpf_y);
     st.ltpf_xtail = (float*)(base + L.ltpf_xtail);

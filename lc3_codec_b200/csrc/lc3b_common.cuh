@@ -83,6 +83,7 @@ struct DecoderState {
     int32_t* handoff;    // [n_blocks32 * 32][HO_WORDS] decoded side information etc. (entropy -> dequantisation kernel)
     float* gband;        // [thread slots][64] SNS band gains, dequant_warp_kernel -> tns_list_kernel
     int32_t* tns_list;   // [1 + thread slots] count + thread slots of the frames tns_list_kernel has to finish
+    int32_t* nsym_prev;  // [n_streams] symbols decoded in the stream's previous good frame: predicts this frame's work (entropy kernel's sort key)
     float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)
     float* ltpf_y;       // [n_streams][blocks*nf]  x_hat_ltpf_mem (long_term_post_filter.rs:30)
     float* ltpf_xtail;   // [n_streams][3][16]  last samples of x_hat_mem per ring block (only l_num <= 10 are ever read back)
@@ -130,6 +131,7 @@ struct EntropyParams {
     const uint8_t* sym_lut;   // [64][32] symbol at the start of each 32-quotient bucket (init_sym_lut_kernel)
     float* gband;         // [thread slots][64] SNS band gains of frames waiting for the lattice kernel
     int32_t* tns_list;    // [1 + thread slots]: count, then the thread slots of frames with an active TNS filter
+    int32_t* nsym_prev;   // [n_streams] arithmetic symbols the stream's previous good frame took (work-sorting key), nullable
     int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
     int min_nbytes;           // frames shorter than this (but not empty) break the handle's promise and are treated as lost
     int row_pitch;        // bytes per staged frame row in shared memory

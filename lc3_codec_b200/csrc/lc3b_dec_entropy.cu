@@ -363,9 +363,12 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
     }
     __syncthreads();
 
-    // ---- work sorting: the spectral loop runs lastnz/2 tuples, which varies widely between streams.  Frames of the
-    // CTA are handed to threads in order of decreasing lastnz so that the 32 lanes of a warp finish together
-    // (frames live in shared rows, so any thread can take any frame; per-thread scratch stays indexed by tid).
+    // ---- work sorting: the spectral loop runs one iteration per arithmetic symbol (lastnz/2 tuples plus their escape
+    // levels), which varies widely between streams.  Frames of the CTA are handed to threads in order of decreasing
+    // expected work so that the 32 lanes of a warp finish together (frames live in shared rows, so any thread can take
+    // any frame; per-thread scratch stays indexed by tid).  The predictor is the number of symbols the stream's PREVIOUS
+    // good frame took (audio is stationary over a frame: correlation 0.91 on the corpus, lanes busy 80 % of a warp's
+    // iterations); a stream without history falls back to lastnz from the side information (correlation 0.37, 70 %).
     {
         int key = -1;
         const int s_me = stream0 + tid;
@@ -381,6 +384,10 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
             bool good = true;
             if (c.nbits_bw > 0) good = pr.tail_uint(c.nbits_bw, v);
             if (good && pr.tail_uint(c.lastnz_bits, v)) key = (int)((v + 1) << 1);
+            if (p.nsym_prev && key > 0) {
+                const int prev = p.nsym_prev[s_me];
+                if (prev > 0) key = prev;
+            }
         }
         s_key[tid] = key;
         __syncthreads();
@@ -469,7 +476,9 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
         int k = 0, lev = 0, xa_ = 0, xb_ = 0;
         uint32_t lev_word = 0;                                          // save_lev flags of the current 32 tuples
         bool bad = false;
+        int nsym = 0;                                                   // iterations = arithmetic symbols of this frame
         while (k < ntup && !bad) {
+            nsym++;
             const int t0 = ctx + rate_flag + ((k * 2) > half_ne ? 256 : 0);
             const int pki = s_lookup[t0 + min(lev, 3) * 1024];
             const uint32_t* tab = s_spec_cf + pki * SPEC_CF_STRIDE;
@@ -540,6 +549,7 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
             lev = fin ? 0 : lev2;
         }
         ok = !bad;
+        if (ok && p.nsym_prev) p.nsym_prev[stream] = nsym;              // next frame's sort key
         ac.low = low;
         ac.range = range;
         rd.head = head;
@@ -1382,6 +1392,7 @@ EntropyParams entropy_params(const DecoderState& st, const uint8_t* frames, cons
     p.sym_lut = st.sym_lut;
     p.gband = st.gband;
     p.tns_list = st.tns_list;
+    p.nsym_prev = st.nsym_prev;
     p.fixed_slot = st.fixed_slot;
     p.min_nbytes = st.min_nbytes;
     p.row_pitch = entropy_row_pitch(nbytes);

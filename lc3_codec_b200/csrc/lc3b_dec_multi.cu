@@ -454,6 +454,7 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     vs.handoff = (int32_t*)(base + L.handoff);
     vs.gband = (float*)(base + L.gband);
     vs.tns_list = (int32_t*)(base + L.tns_list);
+    vs.nsym_prev = nullptr;                                       // units of one call are not consecutive frames of a stream slot
     vs.side = (int32_t*)(base + L.side);
     vs.fixed_slot = 0;
     vs.trace = nullptr;

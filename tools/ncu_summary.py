@@ -39,6 +39,8 @@ def main():
             "grid": [int(g("launch__grid_size"))], "block": [int(g("launch__block_size"))],
             "duration_us": dur_us,
             "dram_bytes": dram,
+            "dram_bytes_read": g("dram__bytes_read.sum"),
+            "dram_bytes_write": g("dram__bytes_write.sum"),
             "dram_gbs": dram / (dur_us * 1e-6) / 1e9 if dur_us > 0 else 0.0,
             "ipc_per_sm": g("sm__inst_executed.avg.per_cycle_elapsed"),
             "warps_active_pct": g("sm__warps_active.avg.pct_of_peak_sustained_active"),
