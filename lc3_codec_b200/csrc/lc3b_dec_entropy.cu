@@ -972,8 +972,8 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
     }
 }
 
-template <int W>
-__global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(const __grid_constant__ EntropyParams p) {
+template <int W, int OCC = 5>
+__global__ void __launch_bounds__(ENT_THREADS, OCC) dequant_kernel(const __grid_constant__ EntropyParams p) {
     dequant_body<W>(p, blockIdx.x);
 }
 
@@ -1363,6 +1363,8 @@ cudaError_t prepare_entropy(const DecoderState& st) {
     cudaError_t e = cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, es);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(entropy_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, es);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_mixed_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_mixed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
@@ -1411,8 +1413,12 @@ void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frame
             plan.add(tns_list_kernel, grid, ENT_THREADS, 0, p);
         } else {
             const size_t smem = dequant_smem_bytes(p.row_pitch);
-            if (st.cfg.n_ms == LC3B_10MS) plan.add(dequant_kernel<3>, grid, ENT_THREADS, smem, p);
-            else plan.add(dequant_kernel<2>, grid, ENT_THREADS, smem, p);
+            static const int occ = [] { const char* e = getenv("LC3B_DQ_OCC"); return e ? atoi(e) : 5; }();   // experiment: CTAs per SM
+            if (st.cfg.n_ms == LC3B_10MS) {
+                if (occ == 6) plan.add(dequant_kernel<3, 6>, grid, ENT_THREADS, smem, p);
+                else if (occ == 7) plan.add(dequant_kernel<3, 7>, grid, ENT_THREADS, smem, p);
+                else plan.add(dequant_kernel<3>, grid, ENT_THREADS, smem, p);
+            } else plan.add(dequant_kernel<2>, grid, ENT_THREADS, smem, p);
         }
     }
 }
