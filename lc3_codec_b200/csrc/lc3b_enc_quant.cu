@@ -515,9 +515,17 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
         }
     }
     __syncwarp();
+    // the 27 quotients ac[sb][k] / ac[sb][0] of a filter are independent: one per lane instead of 27 divisions in a row on
+    // every lane (the sums below still add them in the reference's order)
+    float* qv = S + 128;                                    // [2][27]
+    for (int f = 0; f < tp.nf; f++) {
+        if (lane < 27) qv[f * 27 + lane] = ac[f * 27 + lane] / ac[f * 27 + (lane / 9) * 9];
+    }
+    __syncwarp();
     {   // Levinson-Durbin :204-232 and LPC weighting / LPC -> RC :234-257: lane f works on filter f
         const int f = (lane & 1) < tp.nf ? (lane & 1) : 0;
         const float* acf = ac + f * 27;
+        const float* qf = qv + f * 27;
         float rr[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) {
@@ -526,7 +534,7 @@ __device__ void tns_encode_w(const EncConfig& c, float* x, float* S, int p_bw, i
 #pragma unroll
             for (int sb = 0; sb < 3; sb++) {
                 e_prod *= acf[sb * 9];
-                rk += fdiv_call(acf[sb * 9 + k], acf[sb * 9]);
+                rk += qf[sb * 9 + k];
             }
             rr[k] = (e_prod == 0.0f ? r0 : rk) * LAG[k];
         }
@@ -771,7 +779,8 @@ __device__ __noinline__ BitCons quantize_spectrum_w(const EncConfig& c, const fl
     const float gg = gain_of(c, gg_ind, gg_off);
     WARP_STRIDE(k, ne) {
         const float v = xf[k];
-        xq[k] = v >= 0.0f ? cast_i16(v / gg + 0.375f) : cast_i16(v / gg - 0.375f);
+        const float q = v / gg;                      // one division for both signs (the lanes of a warp mix them)
+        xq[k] = cast_i16(v >= 0.0f ? q + 0.375f : q - 0.375f);
     }
     __syncwarp();
     BitCons bc = compute_bit_consumption_w(ne, c.fs_ind, xq, pre, nbits, nbits_spec, lane);
@@ -828,17 +837,26 @@ __device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const f
     // only coupling is "has a louder block been seen above me", a ballot), then added from the top down by one chain.
     int fac = 256, gg_ind = 255;
     const int rounds = (ne4 + 31) >> 5;
+    // the block energies do not change over the eight bisection steps: their scaled forms (two f32 multiplications and
+    // two IEEE divisions per block, exactly the reference's expressions) are computed once, not once per step
+    float e28[4], e28x2[4], e28lo[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int i = r * 32 + lane;
+        const float ei = (r < rounds && i < ne4) ? e4[i] : -INFINITY;
+        e28[r] = ei * 28.0f / 20.0f;
+        e28lo[r] = ei * 28.0f / 20.0f - 43.0f * 28.0f / 20.0f;
+        e28x2[r] = 2.0f * ei * 28.0f / 20.0f;
+    }
     for (int it = 0; it < 8; it++) {
         fac >>= 1;
         gg_ind -= fac;
         const float g = (float)gg_ind + (float)gg_off;
         uint32_t ball[4];
-        float ev[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int i = r * 32 + lane;
-            ev[r] = (r < rounds && i < ne4) ? e4[i] : -INFINITY;
-            const bool loud = (r < rounds && i < ne4) && !(ev[r] * 28.0f / 20.0f < g);
+            const bool loud = (r < rounds && i < ne4) && !(e28[r] < g);
             ball[r] = __ballot_sync(FULL, loud);
         }
         bool any_loud = false;
@@ -846,12 +864,11 @@ __device__ QRes spectral_quantization_w(const EncConfig& c, int32_t* es, const f
         for (int r = 3; r >= 0; r--) {
             const int i = r * 32 + lane;
             if (r < rounds && i < ne4) {
-                const float ei = ev[r];
                 const bool above = any_loud || (lane < 31 && (ball[r] >> (lane + 1)) != 0);
                 float term;
-                if (ei * 28.0f / 20.0f < g) term = above ? 2.7f * 28.0f / 20.0f : 0.0f;
-                else if (g < (ei * 28.0f / 20.0f - 43.0f * 28.0f / 20.0f)) term = 2.0f * ei * 28.0f / 20.0f - 2.0f * g - 36.0f * 28.0f / 20.0f;
-                else term = ei * 28.0f / 20.0f - g + 7.0f * 28.0f / 20.0f;
+                if (e28[r] < g) term = above ? 2.7f * 28.0f / 20.0f : 0.0f;
+                else if (g < e28lo[r]) term = e28x2[r] - 2.0f * g - 36.0f * 28.0f / 20.0f;
+                else term = e28[r] - g + 7.0f * 28.0f / 20.0f;
                 T[i] = term;
             }
             any_loud = any_loud || ball[r] != 0;
