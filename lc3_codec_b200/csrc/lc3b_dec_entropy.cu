@@ -849,18 +849,16 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
         int res_used = 0;
-        // The integers come back four lines at a time (one 16-byte load per thread and group), several groups ahead of
-        // the group in use, so the memory round trip never sits on the serial per-line chain; the group in use is shifted
-        // down one element per line.  Groups beyond the frame's lastnz are not fetched (their lines read as zero).
+        // The integers come back four lines at a time (one 16-byte load per thread and group), one group ahead of the
+        // group in use, so the L2 round trip never sits on the serial per-line chain; the group in use is shifted down
+        // one element per line.  Groups beyond the frame's lastnz are not fetched (their lines read as zero).
         const int n_valid = ok ? lastnz : 0;
         const int4* xg = (const int4*)xq;                              // group g of this thread at xg[g * 32]
         const int4 zero4 = make_int4(0, 0, 0, 0);
-        // Prefetch depth: three groups beyond the one in use.  With one group ahead a warp had a single 512-byte load in
-        // flight and the kernel's whole DRAM traffic moved at exactly latency x (20 warps per SM): 978 MB in 0.67 ms.
+        // (Fetching three groups ahead instead of one changes nothing - 0.681 against 0.667 ms - so the kernel is not
+        // waiting for these loads.)
         int4 g = 0 < n_valid ? xg[0] : zero4;
         int4 gn = 4 < n_valid ? xg[32] : zero4;
-        int4 gn2 = 8 < n_valid ? xg[64] : zero4;
-        int4 gn3 = 12 < n_valid ? xg[96] : zero4;
         int jpos = 0;                                                  // next line to pop
         auto pop = [&]() -> int32_t {
             const int32_t v = jpos < n_valid ? g.x : 0;
@@ -868,10 +866,8 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
             jpos++;
             if ((jpos & 3) == 0) {                                     // warp-uniform: every lane pops the same line
                 g = gn;
-                gn = gn2;
-                gn2 = gn3;
-                const int nxt = jpos + 12;
-                gn3 = nxt < n_valid ? xg[(nxt >> 2) * 32] : zero4;
+                const int nxt = jpos + 4;
+                gn = nxt < n_valid ? xg[(nxt >> 2) * 32] : zero4;
             }
             return v;
         };
@@ -978,8 +974,9 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
     }
 }
 
-template <int W, int OCC = 5>
-__global__ void __launch_bounds__(ENT_THREADS, OCC) dequant_kernel(const __grid_constant__ EntropyParams p) {
+// 5 CTAs per SM (96 registers): measured against 4 (119 registers, 0.80 ms), 6 (80, 0.74 ms) and 7 (72, spills, 0.82 ms): 0.667 ms
+template <int W>
+__global__ void __launch_bounds__(ENT_THREADS, 5) dequant_kernel(const __grid_constant__ EntropyParams p) {
     dequant_body<W>(p, blockIdx.x);
 }
 
@@ -1369,7 +1366,6 @@ cudaError_t prepare_entropy(const DecoderState& st) {
     cudaError_t e = cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, es);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(entropy_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, es);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_mixed_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(dequant_mixed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds);
@@ -1418,11 +1414,8 @@ void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frame
             plan.add(tns_list_kernel, grid, ENT_THREADS, 0, p);
         } else {
             const size_t smem = dequant_smem_bytes(p.row_pitch);
-            static const int occ = [] { const char* e = getenv("LC3B_DQ_OCC"); return e ? atoi(e) : 5; }();   // experiment: CTAs per SM
-            if (st.cfg.n_ms == LC3B_10MS) {
-                if (occ == 4) plan.add(dequant_kernel<3, 4>, grid, ENT_THREADS, smem, p);
-                else plan.add(dequant_kernel<3>, grid, ENT_THREADS, smem, p);
-            } else plan.add(dequant_kernel<2>, grid, ENT_THREADS, smem, p);
+            if (st.cfg.n_ms == LC3B_10MS) plan.add(dequant_kernel<3>, grid, ENT_THREADS, smem, p);
+            else plan.add(dequant_kernel<2>, grid, ENT_THREADS, smem, p);
         }
     }
 }
