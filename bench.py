@@ -59,6 +59,11 @@ WORKLOADS = {
                    metric="decoded frames/sec (48kHz 10ms mono, whole files, time-parallel) per GPU",
                    desc="time-parallel file decode (SURVEY 8f-1): 64 streams x 4096 consecutive frames (41 s of audio each) in "
                         "ONE lc3b_decode_stream_frames call per step, 150 B/frame"),
+    "file16": dict(fs=16000, ms=7.5, nbytes=30, nf=120, streams=16384, frames=8, mode="file",
+                   metric="decoded frames/sec (16kHz 7.5ms mono, 30 B, 8 frames per call, time-parallel) per GPU",
+                   desc="BASELINE config 3's 16384 streams of 16 kHz / 7.5 ms / 30 B, decoded 8 consecutive frames per stream per call "
+                        "with lc3b_decode_stream_frames (60 ms of audio per call): how a throughput-bound caller feeds a small "
+                        "stream count"),
     "roundtrip48": dict(fs=48000, ms=10, nbytes=150, nf=480, streams=262144, mode="roundtrip",
                         metric="encode+decode round trips/sec (48kHz 10ms mono, 150 B) per GPU",
                         desc="encode then decode 48 kHz mono 10 ms at 150 B/frame, 262144 streams per GPU (BASELINE config 5)"),
@@ -461,7 +466,20 @@ def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
     ws = torch.empty(L.Lc3BatchDecoder.calc_working_buffer_lengths(S, fd, sf, NB), dtype=torch.uint8, device=dev)
     dec = L.Lc3BatchDecoder(S, fd, sf, ws, NB)
     scratch = torch.empty(dec.multi_scratch_bytes(F), dtype=torch.uint8, device=dev)
-    corpus = torch.from_numpy(load_frames()).to(dev)                                  # [1024, 8, 150]
+    if w["fs"] == 48000 and NB == 150:
+        corpus = torch.from_numpy(load_frames()).to(dev)                              # [1024, 8, 150]
+    else:                                                                             # bitstreams from the GPU encoder itself
+        from tools.corpus import make_pcm_window
+        U, WARM, FW = 256, 4, 8
+        pcm_u = torch.from_numpy(make_pcm_window(U, FW, w["fs"], NF, lead=WARM)).to(dev)
+        ews = torch.empty(L.Lc3BatchEncoder.calc_working_buffer_lengths(U, fd, sf, NB), dtype=torch.uint8, device=dev)
+        enc = L.Lc3BatchEncoder(U, fd, sf, ews, NB)
+        fr_all = torch.empty((WARM + FW, U, NB), dtype=torch.uint8, device=dev)
+        for f in range(WARM + FW):
+            enc.encode_frames(pcm_u[:, f].contiguous(), fr_all[f])
+        torch.cuda.synchronize(dev)
+        corpus = fr_all[WARM:].permute(1, 0, 2).contiguous()                          # [U, 8, NB]
+        del enc, ews
     sidx = (torch.arange(S, device=dev) + rank * S) % corpus.shape[0]
     fidx = torch.arange(F, device=dev) % corpus.shape[1]
     frames = corpus[sidx][:, fidx].contiguous()                                       # [S, F, 150]: stream s replays its 8 frames
@@ -496,9 +514,12 @@ def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
     with ClockSampler(local_rank) as clk:
         ms_total = timed(lambda i: dec.decode_stream_frames(16, frames, pcm, scratch), args.steps, args.warmup)
     ups = world * S * F * args.steps / (ms_total * 1e-3)
+    if quick:
+        return {"quick": True, "value": ups, "unit": "frames/s", "ms_per_step": ms_total / args.steps, "streams_per_gpu": S,
+                "frames_per_call": F}
     # the same files frame by frame (what the reference's loop shape gives a GPU): a 128-frame sample
     out1 = torch.empty((S, NF), dtype=torch.int16, device=dev)
-    fb_frames = 128
+    fb_frames = min(128, F)
     per_frame = frames.permute(1, 0, 2).contiguous()                                  # [F, S, 150]
 
     def fb(i):
@@ -565,7 +586,7 @@ def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
         "metric": w["metric"], "value": ups, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": w["desc"], "name": "file48", "streams_per_gpu": S, "frames_per_call": F,
+        "config": {"workload": w["desc"], "name": w["name"], "streams_per_gpu": S, "frames_per_call": F,
                    "frame_by_frame_value": fb_ups,
                    "frame_by_frame_note": f"same handle, {fb_frames} lc3b_decode_frames calls of {S} streams each",
                    "l2": f"per-unit scratch {scratch.numel() / 1e6:.0f} MB per call, far more than the 126 MB L2",
@@ -573,7 +594,7 @@ def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
         "clocks": clk.summary(),
         "e2e": {"value": world * S * F * e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * F * NB,
                 "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
-                "api": "pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames) on 4 chunks of 1024 "
+                "api": f"pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames) on {CH} chunks of {Fc} "
                        "frames, device -> pinned host copy of chunk c on a second stream overlapping chunk c+1"},
         "gpu_launches": 6 * args.steps,   # device-resident leg: one call (six kernels) per step
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -639,13 +660,15 @@ def main():
             sec = {}
             sargs = argparse.Namespace(**vars(args))
             sargs.steps, sargs.warmup = 200, 10
-            for name in ("decode16", "mixed", "encode48"):
+            for name in ("decode16", "mixed", "encode48", "file16"):
                 ws = dict(WORKLOADS[name])
-                fn = {"mixed": run_mixed}.get(ws["mode"], run_codec)
+                fn = {"mixed": run_mixed, "file": run_file}.get(ws["mode"], run_codec)
                 try:
                     r = fn(sargs, ws, rank, local_rank, world, dev, dist, quick=True)
                     sec[name] = {"workload": ws["desc"], "streams": ws["streams"], "ms_per_step": r["ms_per_step"],
                                  "value": r["value"], "unit": "channel-frames/s" if name == "encode48" else "frames/s"}
+                    if "frames_per_call" in r:
+                        sec[name]["frames_per_call"] = r["frames_per_call"]
                 except Exception as e:                      # the headline must not die with a secondary measurement
                     sec[name] = {"error": repr(e)}
             out["secondary"] = sec

@@ -80,7 +80,7 @@ static Layout make_layout(const lc3b_config& c, int n_streams, int max_nbytes, b
     L.xq = cv.take(sizeof(int32_t) * nblk * c.ne * 32);
     L.handoff = cv.take(sizeof(int32_t) * ((ns + 127) / 128) * 128 * HO_WORDS);   // every thread slot of whole entropy CTAs
     L.gband = cv.take(sizeof(float) * ((ns + 127) / 128) * 128 * 64);
-    L.tns_list = cv.take(sizeof(int32_t) * (1 + ((ns + 127) / 128) * 128));
+    L.tns_list = cv.take(sizeof(int32_t) * (2 + ((ns + 127) / 128) * 128));
     L.nsym_prev = cv.take(sizeof(int32_t) * ns);
     L.ola = cv.take(sizeof(float) * ns * (c.nf - c.z));
     L.ltpf_y = cv.take(sizeof(float) * ns * blocks * c.nf);

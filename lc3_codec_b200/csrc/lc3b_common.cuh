@@ -82,7 +82,7 @@ struct DecoderState {
     int32_t* xq;         // [n_blocks32][ne][32] entropy-decoded integers, lane-interleaved (entropy -> dequantisation kernel)
     int32_t* handoff;    // [n_blocks32 * 32][HO_WORDS] decoded side information etc. (entropy -> dequantisation kernel)
     float* gband;        // [thread slots][64] SNS band gains, dequant_warp_kernel -> tns_list_kernel
-    int32_t* tns_list;   // [1 + thread slots] count + thread slots of the frames tns_list_kernel has to finish
+    int32_t* tns_list;   // [2 + thread slots] count, CTAs done, thread slots of the frames tns_list_kernel has to finish (zero between calls)
     int32_t* nsym_prev;  // [n_streams] symbols decoded in the stream's previous good frame: predicts this frame's work (entropy kernel's sort key)
     float* ola;          // [n_streams][nf - z]  mem_ola_add (modified_dct.rs:16)
     float* ltpf_y;       // [n_streams][blocks*nf]  x_hat_ltpf_mem (long_term_post_filter.rs:30)
@@ -130,7 +130,7 @@ struct EntropyParams {
     int32_t* trace_x;     // nullable
     const uint8_t* sym_lut;   // [64][32] symbol at the start of each 32-quotient bucket (init_sym_lut_kernel)
     float* gband;         // [thread slots][64] SNS band gains of frames waiting for the lattice kernel
-    int32_t* tns_list;    // [1 + thread slots]: count, then the thread slots of frames with an active TNS filter
+    int32_t* tns_list;    // [2 + thread slots]: count, CTAs done, then the thread slots of frames with an active TNS filter
     int32_t* nsym_prev;   // [n_streams] arithmetic symbols the stream's previous good frame took (work-sorting key), nullable
     int fixed_slot;           // >= 0: spectrum always goes to this slot and sstate is left alone (time-parallel path)
     int min_nbytes;           // frames shorter than this (but not empty) break the handle's promise and are treated as lost

@@ -344,7 +344,6 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
     const int tid = threadIdx.x, lane = tid & 31;
     const int stream0 = block * ENT_THREADS;
     const int ne = c.ne;
-    if (block == 0 && tid == 0) p.tns_list[0] = 0;                     // list of TNS-active frames, filled by dequant_warp_kernel
 
     // ---- stage tables and frame bytes
     for (int i = tid; i < 4096 / 4; i += ENT_THREADS) ((uint32_t*)s_lookup)[i] = ((const uint32_t*)LC3T_AC_SPEC_LOOKUP)[i];
@@ -1190,7 +1189,7 @@ __device__ __forceinline__ void dequant_warp_body(const EntropyParams& p, const 
             float* gb = p.gband + (size_t)slot * 64;
             gb[lane] = lane < nb ? gband[lane] : 0.0f;
             gb[32 + lane] = 32 + lane < nb ? gband[32 + lane] : 0.0f;
-            if (lane == 0) p.tns_list[1 + atomicAdd(p.tns_list, 1)] = slot;
+            if (lane == 0) p.tns_list[2 + atomicAdd(p.tns_list, 1)] = slot;
         }
     }
     if (live && lane == 0) {
@@ -1214,10 +1213,17 @@ __device__ __forceinline__ void tns_list_body(const EntropyParams& p, const int 
     const DevConfig& c = *p.cfg;
     const int tid = (int)threadIdx.x;
     const int i = block * ENT_THREADS + tid;
+    // tns_list = [count, CTAs done, thread slots ...].  Every CTA reads the count first and reports when it is through; the
+    // last one to report empties the list for the next call (no kernel of the next call can be running yet).
     const int count = p.tns_list[0];
-    if (block * ENT_THREADS >= count) return;                          // whole CTA beyond the list
+    const int n_ctas = (p.n_streams + ENT_THREADS - 1) / ENT_THREADS;
+    auto report_done = [&]() {
+        __syncthreads();
+        if (tid == 0 && atomicAdd(p.tns_list + 1, 1) == n_ctas - 1) { p.tns_list[0] = 0; p.tns_list[1] = 0; }
+    };
+    if (block * ENT_THREADS >= count) { report_done(); return; }       // whole CTA beyond the list
     const bool mine = i < count;
-    const int slot = mine ? p.tns_list[1 + i] : 0;
+    const int slot = mine ? p.tns_list[2 + i] : 0;
     const int32_t* ho = p.handoff + (size_t)slot * HO_WORDS;
     const int ne = c.ne, nb = c.nb;
     for (int b = tid; b < 65; b += ENT_THREADS) s_edge[b] = b < nb ? c.band_idx[b] : 0x7fffffff;   // the last band runs to ne
@@ -1312,6 +1318,7 @@ __device__ __forceinline__ void tns_list_body(const EntropyParams& p, const int 
         cur4 = nxt4;
         nxt4 = nn4;
     }
+    report_done();
 }
 
 __global__ void __launch_bounds__(DQW_WARPS * 32) dequant_warp_kernel(const __grid_constant__ EntropyParams p) {

@@ -35,7 +35,7 @@ static MultiLayout multi_layout(const lc3b_config& c, int S, int F) {
     L.xq = take(sizeof(int32_t) * nblk * c.ne * 32);
     L.handoff = take(sizeof(int32_t) * nblk * 32 * HO_WORDS);
     L.gband = take(sizeof(float) * nblk * 32 * 64);             // small unit counts take the warp-per-frame dequantisation
-    L.tns_list = take(sizeof(int32_t) * (1 + nblk * 32));
+    L.tns_list = take(sizeof(int32_t) * (2 + nblk * 32));
     L.side = take(sizeof(int32_t) * V * SIDE_WORDS);
     L.head = take(sizeof(float) * V * c.nf);
     L.tail = take(sizeof(float) * V * (c.nf - c.z));
@@ -459,7 +459,8 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     vs.fixed_slot = 0;
     vs.trace = nullptr;
     vs.trace_x = nullptr;
-    cudaError_t e = launch_entropy(vs, frames, frame_nbytes, nbytes, frame_stride, status_out, 3, stream);
+    cudaError_t e = cudaMemsetAsync(vs.tns_list, 0, 2 * sizeof(int32_t), stream);   // caller-owned scratch: the list starts empty
+    if (e == cudaSuccess) e = launch_entropy(vs, frames, frame_nbytes, nbytes, frame_stride, status_out, 3, stream);
     if (e != cudaSuccess) return e;
     MultiParams p;
     p.cfg = st.dcfg; p.win = st.win; p.dtw = st.dtw; p.ftw = st.ftw;
