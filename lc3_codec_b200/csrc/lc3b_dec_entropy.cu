@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "lc3b_common.cuh"
 #include "lc3b_math.cuh"
 #include "lc3b_plan.cuh"
@@ -368,6 +370,14 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
     // any frame; per-thread scratch stays indexed by tid).  The predictor is the number of symbols the stream's PREVIOUS
     // good frame took (audio is stationary over a frame: correlation 0.91 on the corpus, lanes busy 80 % of a warp's
     // iterations); a stream without history falls back to lastnz from the side information (correlation 0.37, 70 %).
+    // Two flags of the side information class the frames first, because they switch on code only a few lanes run:
+    //   lsb_mode (7 % of frames: the refinement pass after the spectral loop) - these frames lead, so one warp of the
+    //     CTA walks that pass with several lanes instead of all four with one or two;
+    //   an active TNS filter (43 %: the TNS symbols here, the lattice in dequant_kernel, which runs at the warp's largest
+    //     order) - frames with TNS follow in decreasing order of work, frames without it close in INCREASING order, so
+    //     that the warp holding the class boundary gets the light frames of both sides.
+    // On the bench corpus: warps walking the refinement pass 88 % -> 25 %, warps running the lattice 93 % -> 52 %, for
+    // 3 % more iterations of the spectral loop.
     {
         int key = -1;
         const int s_me = stream0 + tid;
@@ -378,14 +388,21 @@ __device__ __forceinline__ void entropy_body(const EntropyParams& p, const int b
             Reader pr;
             pr.buf = s_rows + tid * p.row_pitch;
             pr.len = len; pr.head = 0; pr.tail = 0; pr.tw = 0; pr.tw_n = 0;
-            uint32_t v = 0;
+            uint32_t v = 0, bwv = 0;
             key = 0;
             bool good = true;
-            if (c.nbits_bw > 0) good = pr.tail_uint(c.nbits_bw, v);
-            if (good && pr.tail_uint(c.lastnz_bits, v)) key = (int)((v + 1) << 1);
-            if (p.nsym_prev && key > 0) {
-                const int prev = p.nsym_prev[s_me];
-                if (prev > 0) key = prev;
+            if (c.nbits_bw > 0) { good = pr.tail_uint(c.nbits_bw, v); bwv = v; }
+            if (good && pr.tail_uint(c.lastnz_bits, v)) {
+                int work = (int)((v + 1) << 1);
+                if (p.nsym_prev) {
+                    const int prev = p.nsym_prev[s_me];
+                    if (prev > 0) work = prev;
+                }
+                work = min(work, 0xffff);
+                uint32_t fl = 0;                                        // lsb_mode, 8 bits of gain, rc_order flags
+                int cls = 1;
+                if (pr.tail_uint(bwv < 3 ? 10 : 11, fl)) cls = (fl & 1u) ? 3 : ((fl >> 9) != 0u ? 2 : 1);
+                key = cls == 1 ? (1 << 16) + (0xffff - work) : (cls << 16) + work;
             }
         }
         s_key[tid] = key;
@@ -843,79 +860,130 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
         float rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // coefficient set in use
         int ord = 0, om = 0;                     // this lane's order in use, the warp's largest
         int tns_phase = 0, tns_next = ok ? tns_s0 : 0x7fffffff;   // next line at which this lane switches filters
-        float4 vq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // the finished lines of the current group of four
-        int32_t win[W + 1];                 // win[0] = x[k], win[j] = x[k + j]
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
         int res_used = 0;
-        // The integers come back four lines at a time (one 16-byte load per thread and group), one group ahead of the
-        // group in use, so the L2 round trip never sits on the serial per-line chain; the group in use is shifted down
-        // one element per line.  Groups beyond the frame's lastnz are not fetched (their lines read as zero).
+        // The integers come back four lines at a time (one 16-byte load per thread and group), two groups ahead of the
+        // group in use, so the L2 round trip never sits on the serial per-line chain.  The line loop is unrolled over a
+        // group: every lane walks the same line k, so k & 3 is static, a line and its look-ahead partner (k + W, for the
+        // noise-filling window) are fixed registers of the group in use and the next one, and four finished lines leave
+        // as one 16-byte store.  Groups beyond the frame's lastnz (even) are not fetched; their lines read as zero.
         const int n_valid = ok ? lastnz : 0;
-        const int4* xg = (const int4*)xq;                              // group g of this thread at xg[g * 32]
-        const int4 zero4 = make_int4(0, 0, 0, 0);
-        // (Fetching three groups ahead instead of one changes nothing - 0.681 against 0.667 ms - so the kernel is not
-        // waiting for these loads.)
-        int4 g = 0 < n_valid ? xg[0] : zero4;
-        int4 gn = 4 < n_valid ? xg[32] : zero4;
-        int jpos = 0;                                                  // next line to pop
-        auto pop = [&]() -> int32_t {
-            const int32_t v = jpos < n_valid ? g.x : 0;
-            g.x = g.y; g.y = g.z; g.z = g.w;
-            jpos++;
-            if ((jpos & 3) == 0) {                                     // warp-uniform: every lane pops the same line
-                g = gn;
-                const int nxt = jpos + 4;
-                gn = nxt < n_valid ? xg[(nxt >> 2) * 32] : zero4;
+        const int4* xg = (const int4*)xq;                              // group of lines b .. b + 3 of this thread at xg[(b / 4) * 32]
+        auto load_group = [&](int b) -> int4 {
+            int4 r = make_int4(0, 0, 0, 0);
+            if (b < n_valid) {
+                r = xg[(b >> 2) * 32];
+                if (b + 2 >= n_valid) { r.z = 0; r.w = 0; }
             }
-            return v;
+            return r;
         };
+        int4 g = load_group(0), gn = load_group(4);
+        {
+            const int32_t e[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-        for (int j = 0; j <= W; j++) win[j] = 0;
-#pragma unroll
-        for (int j = 0; j < W; j++) {
-            win[j + 1] = pop();
-            if (win[j + 1] != 0 && j < bw_stop) last_nz = j;
+            for (int j = 0; j < W; j++)
+                if (e[j] != 0 && j < bw_stop) last_nz = j;
         }
-        // lines are walked band by band (the last band runs to ne), so no per-line band-edge test is needed
-        int k = 0;
-        for (int band = 0; band < nb; band++) {
-        const float gband = ok ? band_gain(band) : 0.0f;
-        const int k_end = band + 1 < nb ? s_band[band + 1] : ne;
-        for (; k < k_end; k++) {
+        const bool res_on = ok && !si.lsb_mode;
+        const bool nf_on = ok && !is_zero_frame;
+        auto lines_fast = [&](auto omc, const int32_t (&e)[8], const float (&gl)[4], const int k4, float (&o)[4]) {
+            constexpr int OM = decltype(omc)::value;
 #pragma unroll
-            for (int j = 0; j < W; j++) win[j] = win[j + 1];
-            {
-                const int j = k + W;
-                win[W] = pop();
-                if (win[W] != 0 && j < bw_stop) last_nz = j;
+            for (int u = 0; u < 4; u++) {
+                const int k = k4 + u;
+                last_nz = (e[u + W] != 0 && k + W < bw_stop) ? k + W : last_nz;
+                const int32_t xi = e[u];
+                float v = (float)xi;
+                {   // residual bit (as below)
+                    const bool take = res_on && xi != 0 && res_used < nres;
+                    const int bidx = max(rd.len - 1 - (rd.tail >> 3), 0);
+                    const uint32_t bit = ((uint32_t)rd.buf[bidx] >> (rd.tail & 7)) & 1u;
+                    const float up = xi > 0 ? 0.3125f : 0.1875f, down = xi > 0 ? -0.1875f : -0.3125f;
+                    v = take ? xa(v, bit ? up : down) : v;
+                    rd.tail += take ? 1 : 0;
+                    res_used += take ? 1 : 0;
+                }
+                {   // noise filling (as below)
+                    const bool fill = nf_on && k >= nf_start && k < bw_stop && last_nz < k - W;
+                    const int nxt = (13849 + nf_state * 31821) & 0xFFFF;
+                    nf_state = fill ? nxt : nf_state;
+                    v = fill ? (nxt < 0x8000 ? nf_level : -nf_level) : v;
+                }
+                v = xm(v, gg);
+                if constexpr (OM > 0) {                                 // stages >= the lane's order are selects that keep
+                    float t = v;
+#pragma unroll
+                    for (int j = OM - 1; j >= 0; j--) {
+                        const float t2 = xs(t, xm(rc[j], st[j]));
+                        t = j < ord ? t2 : t;
+                        if (j + 1 < 8) {
+                            const float s2 = xa(xm(rc[j], t), st[j]);
+                            st[j + 1 < 8 ? j + 1 : 7] = j + 1 < ord ? s2 : st[j + 1 < 8 ? j + 1 : 7];
+                        }
+                    }
+                    st[0] = ord > 0 ? t : st[0];
+                    v = t;
+                }
+                o[u] = ok ? xm(v, gl[u]) : v;
             }
-            const int32_t xi = win[0];
-            float v = (float)xi;
-            {   // residual_spectrum.rs:13-39: one tail bit per non-zero line while the budget lasts (it cannot run past
-                // the frame here); read straight from the staged row, no window to refill
-                const bool take = ok && !si.lsb_mode && xi != 0 && res_used < nres;
-                const int bidx = max(rd.len - 1 - (rd.tail >> 3), 0);
-                const uint32_t bit = take ? ((uint32_t)rd.buf[bidx] >> (rd.tail & 7)) & 1u : 0u;
-                const float up = xi > 0 ? 0.3125f : 0.1875f, down = xi > 0 ? -0.1875f : -0.3125f;
-                v = take ? xa(v, bit ? up : down) : v;
-                rd.tail += take ? 1 : 0;
-                res_used += take ? 1 : 0;
+        };
+        // lines are walked band by band: the bands that start inside a group are entered (warp-uniformly) before its
+        // lines, each line then uses the gain of its own band
+        int band = -1, k_end = 0;
+        float gband = 0.0f;
+        float4* outp = (float4*)(p.spec + my_row_off_ll);
+        for (int k4 = 0; k4 < ne; k4 += 4) {
+            const int4 gnn = load_group(k4 + 8);
+            float gl[4] = {gband, gband, gband, gband};
+            while (k_end < k4 + 4) {
+                band++;
+                gband = ok ? band_gain(band) : 0.0f;
+                const int first = k_end - k4;
+                k_end = band + 1 < nb ? s_band[band + 1] : ne;
+#pragma unroll
+                for (int u = 0; u < 4; u++) gl[u] = u >= first ? gband : gl[u];
             }
-            {   // noise_filling.rs:37-55
-                const bool fill = ok && !is_zero_frame && k >= nf_start && k < bw_stop && last_nz < k - W;
-                const int nxt = (13849 + nf_state * 31821) & 0xFFFF;
-                nf_state = fill ? nxt : nf_state;
-                v = fill ? (nxt < 0x8000 ? nf_level : -nf_level) : v;
-            }
-            v = xm(v, gg);
-            // temporal_noise_shaping.rs:24-74.  Lanes sit in different filters (band edges depend on the bandwidth) with
-            // different orders; the coefficient set in use is switched per lane at its band edges, and the lattice runs
-            // the warp's largest order with per-lane selects, so the warp never splits over it.
-            {
-                const bool sw = k == tns_next;
-                if (__any_sync(0xffffffffu, sw)) {
-                    if (sw) {
+            const int32_t e[8] = {g.x, g.y, g.z, g.w, gn.x, gn.y, gn.z, gn.w};
+            const bool any_sw = __any_sync(0xffffffffu, (unsigned)(tns_next - k4) < 4u);
+            float o[4];
+            if (!any_sw) {
+                // No lane changes its TNS filter inside this group (all but two or three groups of a frame): the four
+                // lines are ONE basic block - selects only, the lattice at a compile-time depth that covers the warp's
+                // largest order - so the scheduler overlaps the lines' chains: stage j of a line needs the state stage
+                // j - 1 of the previous line left, i.e. consecutive lines run two lattice stages apart, not eight.
+                if (om == 0) lines_fast(std::integral_constant<int, 0>{}, e, gl, k4, o);
+                else if (om <= 4) lines_fast(std::integral_constant<int, 4>{}, e, gl, k4, o);
+                else lines_fast(std::integral_constant<int, 8>{}, e, gl, k4, o);
+            } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int k = k4 + u;
+                if (e[u + W] != 0 && k + W < bw_stop) last_nz = k + W;
+                const int32_t xi = e[u];
+                float v = (float)xi;
+                {   // residual_spectrum.rs:13-39: one tail bit per non-zero line while the budget lasts (it cannot run past
+                    // the frame here); read straight from the staged row, no window to refill
+                    const bool take = ok && !si.lsb_mode && xi != 0 && res_used < nres;
+                    const int bidx = max(rd.len - 1 - (rd.tail >> 3), 0);
+                    const uint32_t bit = take ? ((uint32_t)rd.buf[bidx] >> (rd.tail & 7)) & 1u : 0u;
+                    const float up = xi > 0 ? 0.3125f : 0.1875f, down = xi > 0 ? -0.1875f : -0.3125f;
+                    v = take ? xa(v, bit ? up : down) : v;
+                    rd.tail += take ? 1 : 0;
+                    res_used += take ? 1 : 0;
+                }
+                {   // noise_filling.rs:37-55
+                    const bool fill = ok && !is_zero_frame && k >= nf_start && k < bw_stop && last_nz < k - W;
+                    const int nxt = (13849 + nf_state * 31821) & 0xFFFF;
+                    nf_state = fill ? nxt : nf_state;
+                    v = fill ? (nxt < 0x8000 ? nf_level : -nf_level) : v;
+                }
+                v = xm(v, gg);
+                // temporal_noise_shaping.rs:24-74.  Lanes sit in different filters (band edges depend on the bandwidth)
+                // with different orders; the coefficient set in use is switched per lane at its band edges, and the
+                // lattice runs the warp's largest order with per-lane selects, so the warp never splits over it.
+                {
+                    if (k == tns_next) {
                         if (tns_phase == 0) {
 #pragma unroll
                             for (int i = 0; i < 8; i++) rc[i] = rc0[i];
@@ -951,13 +1019,15 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
                     st[0] = ord > 0 ? t : st[0];
                     v = t;
                 }
+                o[u] = ok ? xm(v, gl[u]) : v;
             }
-            v = ok ? xm(v, gband) : v;
+            }
             // four finished lines leave as one 16-byte store into the thread's own stream-major row (the two halves of
             // a 32-byte sector are written four lines apart and meet in L2)
-            if ((k & 3) == 0) vq.x = v; else if ((k & 3) == 1) vq.y = v; else if ((k & 3) == 2) vq.z = v; else vq.w = v;
-            if ((k & 3) == 3 && ok) *(float4*)(p.spec + my_row_off_ll + (k & ~3)) = vq;
-        }
+            if (ok) *outp = make_float4(o[0], o[1], o[2], o[3]);
+            outp++;
+            g = gn;
+            gn = gnn;
         }
     }
 

@@ -49,17 +49,29 @@ LC3B_HD float d2f(double d) { return (float)d; }
 LC3B_HD float trunc12(float v) { return u2f(f2u(v) & 0xfffff000u); }
 
 // Rust `as` casts: saturating, NaN -> 0
+// On the device these are single conversions: cvt.rzi.s32.f32 clamps to the integer range and turns NaN into 0 by
+// definition (PTX ISA, "cvt": float-to-integer conversions saturate; NaN -> 0), cvt.rzi.s16.f32 likewise.
 LC3B_HD int32_t cast_i32(float x) {
+#ifdef __CUDA_ARCH__
+    return __float2int_rz(x);
+#else
     if (x != x) return 0;
     if (x >= 2147483648.0f) return INT32_MAX;
     if (x <= -2147483648.0f) return INT32_MIN;
     return (int32_t)x;
+#endif
 }
 LC3B_HD int16_t cast_i16(float x) {
+#ifdef __CUDA_ARCH__
+    short r;
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return (int16_t)r;
+#else
     if (x != x) return 0;
     if (x >= 32767.0f) return INT16_MAX;
     if (x <= -32768.0f) return INT16_MIN;
     return (int16_t)x;
+#endif
 }
 LC3B_HD float maxf_rs(float a, float b) { return (a != a) ? b : (b != b) ? a : (a > b ? a : b); }
 LC3B_HD float minf_rs(float a, float b) { return (a != a) ? b : (b != b) ? a : (a < b ? a : b); }
