@@ -863,22 +863,24 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
         int last_nz = -1000;
         int nf_state = (int)(seed_acc & 0xffffu);
         int res_used = 0;
-        // The integers come back four lines at a time (one 16-byte load per thread and group), two groups ahead of the
+        // The integers come back four lines at a time (one 16-byte load per thread and group), three groups ahead of the
         // group in use, so the L2 round trip never sits on the serial per-line chain.  The line loop is unrolled over a
         // group: every lane walks the same line k, so k & 3 is static, a line and its look-ahead partner (k + W, for the
         // noise-filling window) are fixed registers of the group in use and the next one, and four finished lines leave
         // as one 16-byte store.  Groups beyond the frame's lastnz (even) are not fetched; their lines read as zero.
         const int n_valid = ok ? lastnz : 0;
         const int4* xg = (const int4*)xq;                              // group of lines b .. b + 3 of this thread at xg[(b / 4) * 32]
-        auto load_group = [&](int b) -> int4 {
+        auto fetch_group = [&](int b) -> int4 {                        // the load only: its result is not touched here
             int4 r = make_int4(0, 0, 0, 0);
-            if (b < n_valid) {
-                r = xg[(b >> 2) * 32];
-                if (b + 2 >= n_valid) { r.z = 0; r.w = 0; }
-            }
+            if (b < n_valid) r = xg[(b >> 2) * 32];
             return r;
         };
-        int4 g = load_group(0), gn = load_group(4);
+        auto trim_group = [&](int4 r, int b) -> int4 {                 // lines at and beyond lastnz hold stale integers
+            if (b + 2 >= n_valid) { r.z = 0; r.w = 0; }
+            return r;
+        };
+        int4 g = trim_group(fetch_group(0), 0), gn = trim_group(fetch_group(4), 4);
+        int4 gnn = fetch_group(8);
         {
             const int32_t e[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -934,7 +936,7 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
         float gband = 0.0f;
         float4* outp = (float4*)(p.spec + my_row_off_ll);
         for (int k4 = 0; k4 < ne; k4 += 4) {
-            const int4 gnn = load_group(k4 + 8);
+            const int4 g3 = fetch_group(k4 + 12);                       // three groups ahead; first touched a group later
             float gl[4] = {gband, gband, gband, gband};
             while (k_end < k4 + 4) {
                 band++;
@@ -1027,7 +1029,8 @@ __device__ __forceinline__ void dequant_body(const EntropyParams& p, const int b
             if (ok) *outp = make_float4(o[0], o[1], o[2], o[3]);
             outp++;
             g = gn;
-            gn = gnn;
+            gn = trim_group(gnn, k4 + 8);
+            gnn = g3;
         }
     }
 
