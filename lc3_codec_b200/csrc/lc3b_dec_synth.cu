@@ -61,8 +61,12 @@ __device__ __forceinline__ int32_t round_pcm_i32(float v) {          // output_s
 }
 
 // synth_classic_kernel: one warp = one frame, spectrum through ordinary loads.  The default: at 262 144 streams it runs in
-// 0.507 ms against 0.525 ms for the persistent TMA-pipelined kernel below (profiles/r2_synth_ab.json) - the kernel is bound
-// by instruction issue (about 1 500 warp instructions per frame at IPC 2.2), not by the latency the prefetch hides.
+// 0.50 ms against 0.525 ms for the persistent TMA-pipelined kernel below (profiles/r2_synth_ab.json).  What bounds it is
+// the SM's L1 / shared-memory data path, not instruction issue, DRAM or latency: dropping a quarter of its instructions
+// (the float -> int casts) changed nothing, the time per frame is the same at 16 384 streams (everything in L2) as at
+// 262 144, and MORE resident warps make it slower (8 / 10 / 12 CTAs per SM: 0.502 / 0.516 / 0.529 ms - the twiddle and
+// window tables share L1 with the shared-memory carve-out).  The per-frame streams (spectrum, overlap memory, PCM)
+// therefore use evict-first loads and stores, which leaves L1 to the tables (0.517 -> 0.500 ms).
 template <int NF, bool MS10>
 __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __grid_constant__ SynthParams p) {
     using G = FrameGeo<NF, MS10>;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
     float2 ola_r[NPT];
 #pragma unroll
     for (int j = 0; j < NPT; j++)
-        ola_r[j] = (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) ? ((const float2*)ola)[32 * j + lane] : make_float2(0.0f, 0.0f);
+        ola_r[j] = (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) ? __ldcs((const float2*)ola + 32 * j + lane) : make_float2(0.0f, 0.0f);
 
     // ---- spectrum load, with concealment (packet_loss_concealment.rs:63-85) when the frame was bad
     if (ok) {
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
         for (int k0 = 0; k0 < NF / 4; k0 += 32) {
             const int k4 = k0 + lane;
             if (k0 + 32 <= NF / 4 || k4 < NF / 4)
-                ((float4*)P)[k4] = 4 * k4 < NE ? ((const float4*)sp)[k4] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                ((float4*)P)[k4] = 4 * k4 < NE ? __ldcs((const float4*)sp + k4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         if (lane == 0) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
     } else {
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
         if (64 * j + 64 <= NF - Z || 64 * j + 2 * lane < NF - Z) {
             head[2 * j] = xa(ola_r[j].x, head[2 * j]);
             head[2 * j + 1] = xa(ola_r[j].y, head[2 * j + 1]);
-            ((float2*)ola)[32 * j + lane] = make_float2(tail[2 * j], tail[2 * j + 1]);
+            __stcs((float2*)ola + 32 * j + lane, make_float2(tail[2 * j], tail[2 * j + 1]));
         }
     }
 
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
                 if (n >= NF - 16) ((float2*)xtail)[(n - (NF - 16)) >> 1] = make_float2(a, b);   // x_hat tail for the next frame's filter
             }
             const int32_t qa = round_pcm_i32(a), qb = round_pcm_i32(b);
-            if (p.pcm_pairs) ((uint32_t*)out)[32 * j + lane] = ((uint32_t)qa & 0xffffu) | ((uint32_t)qb << 16);
+            if (p.pcm_pairs) __stcs((uint32_t*)out + 32 * j + lane, ((uint32_t)qa & 0xffffu) | ((uint32_t)qb << 16));
             else { out[n] = (int16_t)qa; out[n + 1] = (int16_t)qb; }
         }
     }
