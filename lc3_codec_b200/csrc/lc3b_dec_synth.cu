@@ -81,11 +81,16 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
 
     int32_t* sd = p.side + (size_t)stream * SIDE_WORDS;
     int32_t* ss = p.sstate + (size_t)stream * SS_WORDS;
-    const int ok = sd[SD_OK];
-    const int slot = sd[SD_SLOT];
-    const int active = sd[SD_LTPF_ACTIVE];
-    const int prev_active = ss[SS_LTPF_PREV] & 1;
-    const int blk_idx = ss[SS_LTPF_BLK];
+    // the two records as 16-byte loads (every lane reads the same words; each load is one slot of the memory pipe)
+    static_assert(SD_OK == 0 && SD_LTPF_ACTIVE == 1 && SD_SLOT == 6 && SS_PLC_LOST == 1 && SS_PLC_ALPHA == 2 && SS_LTPF_PREV == 4 && SS_LTPF_BLK == 7,
+                  "record layout");
+    const int4 sd_a = ((const int4*)sd)[0], sd_b = ((const int4*)sd)[1];
+    const int4 ss_a = ((const int4*)ss)[0], ss_b = ((const int4*)ss)[1];
+    const int ok = sd_a.x;
+    const int slot = sd_b.z;
+    const int active = sd_a.y;
+    const int prev_active = ss_b.x & 1;
+    const int blk_idx = ss_b.w;
     const float* sp = p.spec + ((size_t)slot * p.n_streams + stream) * NE;
 
     // overlap memory: requested now, consumed after the FFT
@@ -103,11 +108,11 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
             if (k0 + 32 <= NF / 4 || k4 < NF / 4)
                 ((float4*)P)[k4] = 4 * k4 < NE ? __ldcs((const float4*)sp + k4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        if (lane == 0) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
+        if (lane == 0 && (ss_a.y != 0 || ss_a.z != (int32_t)f2u(1.0f))) { ss[SS_PLC_LOST] = 0; ss[SS_PLC_ALPHA] = (int32_t)f2u(1.0f); }
     } else {
-        int lost = ss[SS_PLC_LOST];
-        float alpha = u2f((uint32_t)ss[SS_PLC_ALPHA]);
-        uint32_t seed = (uint32_t)ss[SS_PLC_SEED];
+        int lost = ss_a.y;
+        float alpha = u2f((uint32_t)ss_a.z);
+        uint32_t seed = (uint32_t)ss_a.w;
         __syncwarp();                                            // every lane has read the state before any lane updates it
         if (lost >= 4) alpha = xm(alpha, lost < 8 ? 0.9f : 0.85f);
         // lane's first line is k = lane: LCG advanced lane+1 times; then jump 32 steps at a time

@@ -154,31 +154,50 @@ __device__ __forceinline__ float* dct_iv_warp(float* P, float* Q, const float2* 
 }
 
 // Unfold (modified_dct.rs:97-136) and window: D holds the DCT-IV output; win[m] = gain * w[2nf-1-m].
+// A lane's two consecutive samples (m, m + 1 with m even) are neighbours in D in all four segments of the unfolding
+// (the segment borders nf/2, nf, 3nf/2 are even) and neighbours in the window, so each pair is one 8-byte shared-memory
+// load and one 8-byte table load: the kernel is bound by the L1 / shared-memory path (MIO), not by arithmetic.
 template <int NF, bool MS10>
 __device__ __forceinline__ void imdct_unfold(const float* __restrict__ D, const float* __restrict__ win, int lane,
                                              float (&head)[2 * FrameGeo<NF, MS10>::NP], float (&tail)[2 * FrameGeo<NF, MS10>::NPT]) {
     using G = FrameGeo<NF, MS10>;
     constexpr int H = NF / 2, Z = G::Z;
-    auto t_at = [&](int m) -> float {                                   // t[m] / gain
-        if (m < H) return D[H + m];
-        if (m < NF) return -D[NF - 1 - (m - H)];
-        if (m < NF + H) return -D[H - 1 - (m - NF)];
-        return -D[m - 3 * H];
+    static_assert((H & 1) == 0 && (Z & 1) == 0 && (NF & 1) == 0, "pairs must not straddle a segment of the unfolding");
+    auto t_pair = [&](int m) -> float2 {                                // (t[m], t[m + 1]) / gain, m even
+        if (m < H) return *(const float2*)(D + H + m);
+        if (m < NF) {
+            const float2 q = *(const float2*)(D + (NF - 1 - (m - H)) - 1);
+            return make_float2(-q.y, -q.x);
+        }
+        if (m < NF + H) {
+            const float2 q = *(const float2*)(D + (H - 1 - (m - NF)) - 1);
+            return make_float2(-q.y, -q.x);
+        }
+        const float2 q = *(const float2*)(D + (m - 3 * H));
+        return make_float2(-q.x, -q.y);
     };
 #pragma unroll
     for (int j = 0; j < G::NP; j++) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int n = 64 * j + 2 * lane + e;
-            head[2 * j + e] = (64 * j + 64 <= NF || n < NF) ? __fmul_rn(t_at(Z + n), win[Z + n]) : 0.0f;
+        const int n = 64 * j + 2 * lane;
+        if (64 * j + 64 <= NF || n < NF) {
+            const float2 t = t_pair(Z + n), w = *(const float2*)(win + Z + n);
+            head[2 * j] = __fmul_rn(t.x, w.x);
+            head[2 * j + 1] = __fmul_rn(t.y, w.y);
+        } else {
+            head[2 * j] = 0.0f;
+            head[2 * j + 1] = 0.0f;
         }
     }
 #pragma unroll
     for (int j = 0; j < G::NPT; j++) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int n = 64 * j + 2 * lane + e;
-            tail[2 * j + e] = (64 * j + 64 <= NF - Z || n < NF - Z) ? __fmul_rn(t_at(NF + Z + n), win[NF + Z + n]) : 0.0f;
+        const int n = 64 * j + 2 * lane;
+        if (64 * j + 64 <= NF - Z || n < NF - Z) {
+            const float2 t = t_pair(NF + Z + n), w = *(const float2*)(win + NF + Z + n);
+            tail[2 * j] = __fmul_rn(t.x, w.x);
+            tail[2 * j + 1] = __fmul_rn(t.y, w.y);
+        } else {
+            tail[2 * j] = 0.0f;
+            tail[2 * j + 1] = 0.0f;
         }
     }
 }
