@@ -8,7 +8,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 python bench.py > $OUT/${TAG}_bench_decode48.json 2> $OUT/${TAG}_bench_decode48.err || echo "bench decode48 failed"
 tail -c 400 $OUT/${TAG}_bench_decode48.json; echo
-for w in encode48 decode16 mixed roundtrip48 file48; do
+for w in encode48 decode16 mixed roundtrip48 file48 file16; do
   python bench.py --workload $w --distinct 512 > $OUT/${TAG}_bench_$w.json 2> $OUT/${TAG}_bench_$w.err || echo "bench $w failed"
   tail -c 300 $OUT/${TAG}_bench_$w.json | head -c 300; echo
 done
