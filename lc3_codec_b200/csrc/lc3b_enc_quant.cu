@@ -1375,12 +1375,24 @@ __device__ void ac_run_thread(const uint32_t* symq, uint8_t* out, int nbytes, Ac
     if (nsym < 0) return;
     FwdSink w{out, nbytes, 0, 0};
     AcEnc st{0, 0x00ffffffu, -1, 0, 0};
-    uint32_t cf = symq[0];
-    for (int i = 0; i < nsym; i++) {
-        const uint32_t nxt = symq[i + 1];                 // the queue has one spare entry
-        ac_encode(st, w, (int)(cf & 0xffffu), (int)(cf >> 16));
-        cf = nxt;
+    // Four symbols per round, the next four requested before the round starts: a frame's queue is this thread's own
+    // stretch of global memory, so every load is a round trip of its own, and a one-symbol prefetch is consumed by the
+    // register copy at the end of the very iteration that issued it (60 % of the kernel's stall samples sat there).
+    // Reads run at most three entries past the queue's end, into the frame's forward-bytes area (values unused).
+    uint32_t c0 = symq[0], c1 = symq[1], c2 = symq[2], c3 = symq[3];
+    int i = 0;
+#pragma unroll 1
+    for (; i + 4 <= nsym; i += 4) {
+        const uint32_t n0 = symq[i + 4], n1 = symq[i + 5], n2 = symq[i + 6], n3 = symq[i + 7];
+        ac_encode(st, w, (int)(c0 & 0xffffu), (int)(c0 >> 16));
+        ac_encode(st, w, (int)(c1 & 0xffffu), (int)(c1 >> 16));
+        ac_encode(st, w, (int)(c2 & 0xffffu), (int)(c2 >> 16));
+        ac_encode(st, w, (int)(c3 & 0xffffu), (int)(c3 >> 16));
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     }
+    if (i < nsym) ac_encode(st, w, (int)(c0 & 0xffffu), (int)(c0 >> 16));
+    if (i + 1 < nsym) ac_encode(st, w, (int)(c1 & 0xffffu), (int)(c1 >> 16));
+    if (i + 2 < nsym) ac_encode(st, w, (int)(c2 & 0xffffu), (int)(c2 >> 16));
     int nbits_ari = w.bp * 8;
     nbits_ari += 25 - (31 - __clz(st.range));
     nbits_ari += 8;                                   // QUIRK: `carry >= 0` is always true (:67)
@@ -1637,8 +1649,8 @@ __global__ void __launch_bounds__(QNT_THREADS) enc_bs_finish_kernel(QuantParams 
     int* rc_i = (int*)(wbase + L.symq + p.out_words);
     int16_t* xq = (int16_t*)(rc_i + 16);
     const uint32_t* g = p.bs_scratch + (size_t)stream * p.bs_words;
-    WARP_STRIDE_R(i, L.symq) wbase[i] = g[i];
-    WARP_STRIDE_R(i, p.out_words) ((uint32_t*)out)[i] = g[L.fwd + i];
+    WARP_STRIDE(i, L.symq) wbase[i] = g[i];                          // unrolled: the loads of a slice go out together
+    WARP_STRIDE(i, p.out_words) ((uint32_t*)out)[i] = g[L.fwd + i];
     BwRes bw;
     SnsRes sns;
     TnsRes tns;
