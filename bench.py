@@ -596,7 +596,7 @@ def run_file(args, w, rank, local_rank, world, dev, dist, quick=False):
                 "d2h_bytes_per_step": S * F * NF * 2, "ms_per_step": ms_e2e / e2e_steps,
                 "api": f"pinned host -> device copy, lc3b_decode_stream_frames (Lc3BatchDecoder.decode_stream_frames) on {CH} chunks of {Fc} "
                        "frames, device -> pinned host copy of chunk c on a second stream overlapping chunk c+1"},
-        "gpu_launches": 6 * args.steps,   # device-resident leg: one call (six kernels) per step
+        "gpu_launches": (6 + (3 * 2 if S * F >= 65536 else 0)) * args.steps,   # device-resident leg: one call (six kernels; entropy and dequantisation as four sub-batches each from 65 536 units) per step
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "whole call (entropy, dequant, plc_scan, imdct_multi, ola_multi, ltpf_multi)", "kernel_ms": step_ms,
                      "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes(w),
@@ -772,7 +772,12 @@ def run_codec(args, w, rank, local_rank, world, dev, dist, quick=False):
 
     # decoder: entropy, dequant, synth, ltpf; encoder: mdct, ltpf, sns, tns, quantize, bs_prepare, [range_coder], bs_finish
     enc_launches = 8 if S >= 12288 else 7          # small batches run the range coder inside bs_finish (lc3b_enc_quant.cu)
-    launches_per_step = {"decode": 4, "encode": enc_launches, "roundtrip": 4 + enc_launches}[mode]
+    # decoder: the post-filter kernel is not launched when the min_nbytes promise rules the filter out (48 kHz: >= 110 B per
+    # 10 ms); from 65 536 streams a call is issued as four sub-batches, each with its own launches (lc3b_decoder_set_split);
+    # 12 288 streams and fewer take the two-kernel small-batch dequantisation
+    ltpf_ruled_out = mode != "encode" and NB * 8 * (10.0 / w["ms"]) >= 560 + 80 * {8000: 0, 16000: 1, 24000: 2, 32000: 3, 44100: 4, 48000: 4}[w["fs"]]
+    dec_launches = ((3 if ltpf_ruled_out else 4) + (1 if S <= 12288 else 0)) * (4 if S >= 65536 else 1)
+    launches_per_step = {"decode": dec_launches, "encode": enc_launches, "roundtrip": dec_launches + enc_launches}[mode]
 
     # ---- device-resident throughput (value) with clocks sampled during the timed region
     with ClockSampler(local_rank) as clk:

@@ -115,6 +115,8 @@ class Lc3BatchDecoder {
     }
     // extension: issue every call as one cached CUDA graph (true) or one launch per kernel (false); same results
     void set_graph_mode(bool on) { detail::check(lc3b_decoder_set_graph_mode(h_, on ? 1 : 0), "lc3b_decoder_set_graph_mode"); }
+    // extension: cut every call into k independent sub-batches whose kernels overlap (0 = by batch size, 1, 2, 4); same results
+    void set_split(int k) { detail::check(lc3b_decoder_set_split(h_, k), "lc3b_decoder_set_split"); }
     // extension: overlap the PCM read-back of call i with the kernels of call i+1 (host residency)
     void set_host_pipelining(bool on) { detail::check(lc3b_decoder_set_host_pipelining(h_, on ? 1 : 0), "lc3b_decoder_set_host_pipelining"); }
     void host_fence() { detail::check(lc3b_decoder_host_fence(h_, stream_), "lc3b_decoder_host_fence"); }

@@ -400,6 +400,12 @@ int lc3b_decoder_set_graph_mode(lc3b_decoder* h, int mode) {
     return LC3B_OK;
 }
 
+int lc3b_decoder_set_split(lc3b_decoder* h, int k) {
+    if (!h || !(k == 0 || k == 1 || k == 2 || k == 4)) return LC3B_ERR_INVALID_ARG;
+    h->split = k;
+    return LC3B_OK;
+}
+
 // long_term_post_filter.rs:142-161: the filter's gain is the table row (0.0, 0) once the (10 ms-equivalent) frame bits reach
 // 560 + 80 * fs_ind - from there on is_active can be set in the bitstream but the filter passes its input through
 static bool ltpf_impossible(const lc3b_config& c, int nbytes) {
@@ -458,7 +464,7 @@ int lc3b_decode_stream_frames(lc3b_decoder* h, int bits_per_sample, const uint8_
     if ((long long)st.n_streams * n_frames > 0x7fffffffLL / 512) return LC3B_ERR_INVALID_ARG;
     if (scratch_bytes < multi_scratch_bytes(st, n_frames) || ((uintptr_t)scratch & 255) != 0) return LC3B_ERR_WORKSPACE;
     CU(launch_decode_multi(st, frames, frame_nbytes, nbytes, frame_stride, n_frames, pcm_out, status_out, scratch,
-                           (cudaStream_t)cuda_stream));
+                           (cudaStream_t)cuda_stream, h->split == 1 ? nullptr : &h->lanes));
     return LC3B_OK;
 }
 
@@ -473,11 +479,33 @@ int lc3b_decoder_set_trace(lc3b_decoder* h, int32_t* trace, int32_t* x) {
 static cudaError_t run_decode(lc3b_decoder* h, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes, size_t frame_stride,
                               int16_t* pcm_out, size_t pcm_stride, int32_t* status_out, int stage_mask, cudaStream_t stream) {
     LaunchPlan plan;
-    if (stage_mask & 3) plan_entropy(plan, h->st, frames, frame_nbytes, nbytes, frame_stride, status_out, stage_mask & 3);
-    if (stage_mask & 4) {
-        if (plan_synth(plan, h->st, pcm_out, pcm_stride, plan.n - 1) < 0) return cudaErrorInvalidValue;
+    // Sub-batches.  The three kernels are bound by different things (integer ALU / dependent-instruction latency / the
+    // memory-instruction path) and each ends in a ragged last wave of CTAs that are serial chains as long as a full
+    // wave's; issued as K independent sub-batches - K chains of kernels that only meet at the end of the call - one
+    // sub-batch's kernels fill the SMs the other's tail leaves idle and share them with a kernel that wants a different
+    // pipe.  Measured at 262 144 streams of 48 kHz / 150 B: 1.87 ms as one batch, 1.70 ms as two, 1.69 ms as four
+    // (tools/exp_split_overlap.py); 131 072 streams 1.11 -> 0.91 ms, 65 536 streams 0.57 -> 0.53 ms, no difference at 32 768 and
+    // below.  Streams are independent (lc3_decoder.rs:62-69), so any split computes the same bits.
+    const int n = h->st.n_streams;
+    int k_sub = h->split;
+    if (k_sub == 0) {
+        static const int env = [] { const char* e = getenv("LC3B_SPLIT"); return e ? atoi(e) : 0; }();
+        k_sub = env > 0 ? env : (n >= decode_split_min_streams() ? PLAN_MAX_LANES : 1);
     }
-    return h->graph_mode ? plan_launch_graph(h->graphs, plan, stream) : plan_launch_direct(plan, stream);
+    if (k_sub > PLAN_MAX_LANES) k_sub = PLAN_MAX_LANES;
+    if (use_dequant_warp(n, h->st.dequant_mode)) k_sub = 1;            // the small-batch kernels share one list per handle
+    int part = ((n + k_sub - 1) / k_sub + 127) & ~127;                // whole entropy CTAs
+    if (k_sub <= 1 || part >= n) { k_sub = 1; part = n; }
+    for (int k = 0, base = 0; k < k_sub && base < n; k++, base += part) {
+        const int count = k_sub == 1 ? -1 : (n - base < part ? n - base : part);
+        plan.lane = k;
+        const int first = plan.n;
+        if (stage_mask & 3) plan_entropy(plan, h->st, frames, frame_nbytes, nbytes, frame_stride, status_out, stage_mask & 3, base, count, -1);
+        if (stage_mask & 4) {
+            if (plan_synth(plan, h->st, pcm_out, pcm_stride, plan.n > first ? plan.n - 1 : -1, base, count) < 0) return cudaErrorInvalidValue;
+        }
+    }
+    return h->graph_mode ? plan_launch_graph(h->graphs, plan, stream) : plan_launch_direct(plan, stream, &h->lanes);
 }
 
 int lc3b_decode_frames(lc3b_decoder* h, int bits_per_sample, const uint8_t* frames, const int32_t* frame_nbytes,

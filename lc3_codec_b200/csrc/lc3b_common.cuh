@@ -119,8 +119,9 @@ struct EntropyParams {
     const int32_t* frame_nbytes;
     int nbytes;
     size_t frame_stride;
-    int n_streams;
-    float* spec;          // [2][n_streams][ne]
+    int n_streams;        // streams of THIS launch (a sub-batch of the handle's streams when a call is split)
+    int slot_streams;     // streams per spectrum slot = the handle's stream count (stride between the two slots)
+    float* spec;          // [2][slot_streams][ne], offset to the launch's first stream
     int32_t* xq;          // [n_blocks32][ne][32]
     int32_t* handoff;     // [n_blocks32 * 32][HO_WORDS] entropy kernel -> dequantisation kernel
     int32_t* side;        // [n_streams][SIDE_WORDS]
@@ -164,13 +165,15 @@ struct MixedTables {              // device tables + launch sizes: every bucket,
 struct LaunchPlan;
 int entropy_row_pitch(int nbytes);
 bool use_dequant_warp(int n_streams, int mode);   // mode: 0 auto (by batch size), 1 warp-per-frame, 2 thread-per-frame
+// base / count: the sub-batch of the handle's streams the launches cover (base a multiple of 128; count < 0 = all);
+// first_dep: what the first node added waits for (-2 = the node added just before, -1 = nothing)
 EntropyParams entropy_params(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
-                             size_t frame_stride, int32_t* status_out);
+                             size_t frame_stride, int32_t* status_out, int base = 0, int count = -1);
 void plan_entropy(LaunchPlan& plan, const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
-                  size_t frame_stride, int32_t* status_out, int stages);
+                  size_t frame_stride, int32_t* status_out, int stages, int base = 0, int count = -1, int first_dep = -2);
 void plan_entropy_mixed(LaunchPlan& plan, const MixedTables& t, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
                         size_t frame_stride, int32_t* status_out, int* node_d10, int* node_d75);
-int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, int dep);
+int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, int dep, int base = 0, int count = -1);
 
 cudaError_t prepare_entropy(const DecoderState& st);   // shared-memory limits of the kernels, once per handle
 cudaError_t prepare_synth(const DecoderState& st);
@@ -184,6 +187,7 @@ size_t multi_scratch_bytes(const DecoderState& st, int n_frames);
 cudaError_t prepare_multi(const DecoderState& st);
 cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
                                 size_t frame_stride, int n_frames, int16_t* pcm_out, int32_t* status_out, void* scratch,
-                                cudaStream_t stream);
+                                cudaStream_t stream, struct PlanLanes* lanes = nullptr);
+int decode_split_min_streams();    // from this many streams (or units) a decode call is cut into sub-batches
 
 }  // namespace lc3b

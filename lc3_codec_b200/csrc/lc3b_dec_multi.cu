@@ -19,6 +19,7 @@
 // Arithmetic is the frame-by-frame path's, operation for operation, so both paths produce identical PCM.
 #include "lc3b_common.cuh"
 #include "lc3b_imdct.cuh"
+#include "lc3b_plan.cuh"
 #include "lc3b_math.cuh"
 
 namespace lc3b {
@@ -440,7 +441,7 @@ cudaError_t prepare_multi(const DecoderState& st) {
 
 cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, const int32_t* frame_nbytes, int nbytes,
                                 size_t frame_stride, int n_frames, int16_t* pcm_out, int32_t* status_out, void* scratch,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, PlanLanes* lanes) {
     const int S = st.n_streams, F = n_frames;
     if (F <= 0) return cudaSuccess;
     const MultiLayout L = multi_layout(st.cfg, S, F);
@@ -460,7 +461,19 @@ cudaError_t launch_decode_multi(const DecoderState& st, const uint8_t* frames, c
     vs.trace = nullptr;
     vs.trace_x = nullptr;
     cudaError_t e = cudaMemsetAsync(vs.tns_list, 0, 2 * sizeof(int32_t), stream);   // caller-owned scratch: the list starts empty
-    if (e == cudaSuccess) e = launch_entropy(vs, frames, frame_nbytes, nbytes, frame_stride, status_out, 3, stream);
+    if (e == cudaSuccess) {
+        // large calls: the units as four independent sub-batches whose kernels overlap (run_decode in lc3b_api.cu)
+        LaunchPlan plan;
+        const int n = vs.n_streams;
+        const int k_sub = (lanes && n >= decode_split_min_streams() && !use_dequant_warp(n, vs.dequant_mode)) ? PLAN_MAX_LANES : 1;
+        int part = ((n + k_sub - 1) / k_sub + 127) & ~127;
+        if (k_sub == 1) part = n;
+        for (int k = 0, b = 0; k < k_sub && b < n; k++, b += part) {
+            plan.lane = k;
+            plan_entropy(plan, vs, frames, frame_nbytes, nbytes, frame_stride, status_out, 3, b, k_sub == 1 ? -1 : (n - b < part ? n - b : part), -1);
+        }
+        e = plan_launch_direct(plan, stream, lanes);
+    }
     if (e != cudaSuccess) return e;
     MultiParams p;
     p.cfg = st.dcfg; p.win = st.win; p.dtw = st.dtw; p.ftw = st.ftw;

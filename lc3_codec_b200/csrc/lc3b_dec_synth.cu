@@ -41,7 +41,8 @@ struct SynthParams {
     int32_t* sstate;
     int16_t* pcm_out;
     size_t pcm_stride;
-    int n_streams;
+    int n_streams;       // streams of this launch (a sub-batch when a call is split)
+    int slot_streams;    // streams per spectrum slot = the handle's stream count
     int hist_len;        // ltpf_blocks * nf
     int pcm_pairs;       // PCM rows are 4-byte aligned: samples leave two at a time
     int group;           // ltpf_kernel: streams looked after by one warp
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(SYN_WARPS * 32) synth_classic_kernel(const __g
     const int active = sd_a.y;
     const int prev_active = ss_b.x & 1;
     const int blk_idx = ss_b.w;
-    const float* sp = p.spec + ((size_t)slot * p.n_streams + stream) * NE;
+    const float* sp = p.spec + ((size_t)slot * p.slot_streams + stream) * NE;
 
     // overlap memory: requested now, consumed after the FFT
     float* ola = p.ola + (size_t)stream * (NF - Z);
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32, 4) synth_kernel(const __grid_
 
     auto fetch = [&](int st, int s, const FrameHead& h) {         // spectrum of stream s -> stage st
         if (lane == 0) {
-            const float* sp = p.spec + ((size_t)h.slot * p.n_streams + s) * NE;
+            const float* sp = p.spec + ((size_t)h.slot * p.slot_streams + s) * NE;
             mbar_expect_tx(&bars[st], NE * 4);
             bulk_g2s(S0 + st * NF, sp, NE * 4, &bars[st]);
         }
@@ -580,28 +581,32 @@ cudaError_t prepare_synth(const DecoderState& st) {
 }
 
 // Adds the synthesis kernel (after node `dep`, -1 = none) and the post-filter kernel behind it; returns the last node.
-int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, int dep) {
+int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_t pcm_stride, int dep, int base, int count) {
     SynthParams p;
     memset(&p, 0, sizeof(p));
     p.cfg = st.dcfg;
     p.win = st.win;
     p.dtw = st.dtw;
     p.ftw = st.ftw;
-    p.spec = st.spec;
-    p.ola = st.ola;
-    p.ltpf_y = st.ltpf_y;
-    p.ltpf_xtail = st.ltpf_xtail;
-    p.ltpf_x = st.ltpf_x;
-    p.side = st.side;
-    p.sstate = st.sstate;
-    p.pcm_out = pcm_out;
-    p.pcm_stride = pcm_stride;
-    p.n_streams = st.n_streams;
+    // a sub-batch: every per-stream pointer moved to its first stream (see entropy_params)
+    const size_t b = (size_t)base;
+    const int n = count < 0 ? st.n_streams : count;
     p.hist_len = (st.cfg.n_ms == LC3B_10MS ? 2 : 3) * st.cfg.nf;
-    p.pcm_pairs = (((uintptr_t)pcm_out & 3) == 0 && (pcm_stride & 1) == 0) ? 1 : 0;
+    p.spec = st.spec + b * st.cfg.ne;
+    p.ola = st.ola + b * (size_t)(st.cfg.nf - st.cfg.z);
+    p.ltpf_y = st.ltpf_y + b * (size_t)p.hist_len;
+    p.ltpf_xtail = st.ltpf_xtail + b * XTAIL_FLOATS;
+    p.ltpf_x = st.ltpf_x + b * (size_t)st.cfg.nf;
+    p.side = st.side + b * SIDE_WORDS;
+    p.sstate = st.sstate + b * SS_WORDS;
+    p.pcm_out = pcm_out + b * pcm_stride;
+    p.pcm_stride = pcm_stride;
+    p.n_streams = n;
+    p.slot_streams = st.n_streams;
+    p.pcm_pairs = (((uintptr_t)p.pcm_out & 3) == 0 && (pcm_stride & 1) == 0) ? 1 : 0;
     // ltpf_kernel: one warp per stream while that keeps the grid small, else a warp walks a group of streams
     int group = 1;
-    while (group < 32 && st.n_streams / group > 16384) group *= 2;
+    while (group < 32 && n / group > 16384) group *= 2;
     p.group = group;
     const size_t lw = ltpf_warp_bytes(st.cfg);
     p.smem_per_warp = (int)lw;
@@ -613,7 +618,7 @@ int plan_synth(LaunchPlan& plan, const DecoderState& st, int16_t* pcm_out, size_
     PlanSynth ps{plan, p, dep, -1, st.sm_count > 0 ? st.sm_count : 148, mode == 1};
     if (!dispatch_frame_geo(st.cfg.nf, st.cfg.n_ms == LC3B_10MS, ps)) return -1;
     if (st.no_ltpf) return ps.node;                           // the post filter can never be active: nothing to launch
-    const int n_warps = (st.n_streams + group - 1) / group;
+    const int n_warps = (n + group - 1) / group;
     return plan.add(ltpf_kernel, (unsigned)((n_warps + SYN_WARPS - 1) / SYN_WARPS), SYN_WARPS * 32, lw * SYN_WARPS, p, ps.node);
 }
 

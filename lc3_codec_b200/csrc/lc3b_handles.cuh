@@ -9,6 +9,9 @@ struct lc3b_decoder {
     // how a call's kernels are issued: 0 = one launch each on the caller's stream, 1 = one cached CUDA graph per call
     int graph_mode = 0;
     lc3b::GraphCache graphs;
+    // a large batch is issued as up to four independent sub-batches on auxiliary streams (run_decode in lc3b_api.cu)
+    int split = 0;                        // 0 = by batch size, 1 = never, 2 / 4 = that many sub-batches
+    lc3b::PlanLanes lanes;
     // optional pipelining of the host entry point: PCM leaves on an internal copy stream from a double-buffered
     // staging area, so the device->host copy of call i overlaps the kernels of call i+1
     int pipelined = 0;

@@ -3,11 +3,45 @@
 
 namespace lc3b {
 
-cudaError_t plan_launch_direct(const LaunchPlan& plan, cudaStream_t stream) {
+cudaError_t PlanLanes::ensure() {
+    if (fork) return cudaSuccess;
+    cudaError_t e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    for (int i = 0; i < PLAN_MAX_LANES - 1 && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming);
+    }
+    return e;
+}
+
+PlanLanes::~PlanLanes() {
+    for (int i = 0; i < PLAN_MAX_LANES - 1; i++) {
+        if (aux[i]) { cudaStreamSynchronize(aux[i]); cudaStreamDestroy(aux[i]); }
+        if (join[i]) cudaEventDestroy(join[i]);
+    }
+    if (fork) cudaEventDestroy(fork);
+}
+
+cudaError_t plan_launch_direct(const LaunchPlan& plan, cudaStream_t stream, PlanLanes* lanes) {
+    int max_lane = 0;
+    for (int i = 0; i < plan.n; i++) max_lane = plan.nodes[i].lane > max_lane ? plan.nodes[i].lane : max_lane;
+    if (!lanes || max_lane >= PLAN_MAX_LANES) max_lane = 0;           // no auxiliary streams: everything in order on one
+    cudaError_t e = cudaSuccess;
+    if (max_lane > 0) {
+        e = lanes->ensure();
+        if (e == cudaSuccess) e = cudaEventRecord(lanes->fork, stream);
+        for (int l = 1; l <= max_lane && e == cudaSuccess; l++) e = cudaStreamWaitEvent(lanes->aux[l - 1], lanes->fork, 0);
+        if (e != cudaSuccess) return e;
+    }
     for (int i = 0; i < plan.n; i++) {
         const PlanNode& k = plan.nodes[i];
         void* args[1] = {(void*)k.param};
-        cudaError_t e = cudaLaunchKernel(k.func, dim3(k.grid), dim3(k.block), args, k.smem, stream);
+        cudaStream_t s = (max_lane > 0 && k.lane > 0) ? lanes->aux[k.lane - 1] : stream;
+        e = cudaLaunchKernel(k.func, dim3(k.grid), dim3(k.block), args, k.smem, s);
+        if (e != cudaSuccess) return e;
+    }
+    for (int l = 1; l <= max_lane; l++) {
+        e = cudaEventRecord(lanes->join[l - 1], lanes->aux[l - 1]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, lanes->join[l - 1], 0);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

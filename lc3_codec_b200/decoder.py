@@ -164,6 +164,12 @@ class Lc3BatchDecoder:
         if rc:
             raise Lc3bError(rc, "lc3b_decoder_set_graph_mode")
 
+    def set_split(self, k: int) -> None:
+        """Cut every call into k independent sub-batches whose kernels overlap (0 = by batch size, 1 = never, 2, 4); include/lc3b.h."""
+        rc = native.lib().lc3b_decoder_set_split(self._h, int(k))
+        if rc:
+            raise Lc3bError(rc, "lc3b_decoder_set_split")
+
     def set_min_nbytes(self, min_nbytes: int) -> None:
         """Promise that every submitted frame is at least min_nbytes long (or lost).  When that rules the long-term post filter
         out for good (e.g. >= 110 bytes at 48 kHz / 10 ms) the decoder stops keeping the filter's output history; include/lc3b.h."""

@@ -57,7 +57,7 @@ EXPORTS = ["lc3b_config_new", "lc3b_last_cuda_error", "lc3b_version", "lc3b_deco
            "lc3b_selftest_math_host",
            "lc3b_selftest_math_device", "lc3b_encoder_workspace_bytes", "lc3b_encoder_init", "lc3b_encode_frames",
            "lc3b_encode_frames_host", "lc3b_encoder_set_host_pipelining", "lc3b_encoder_debug_read", "lc3b_encoder_set_stage_mask",
-           "lc3b_encoder_destroy", "lc3b_decoder_set_graph_mode", "lc3b_decoder_graph_stats", "lc3b_decoder_set_dequant_mode", "lc3b_mixed_decoder_set_dequant_mode", "lc3b_decoder_set_min_nbytes", "lc3b_decoder_set_synth_mode", "lc3b_encoder_set_graph_mode",
+           "lc3b_encoder_destroy", "lc3b_decoder_set_graph_mode", "lc3b_decoder_set_split", "lc3b_decoder_graph_stats", "lc3b_decoder_set_dequant_mode", "lc3b_mixed_decoder_set_dequant_mode", "lc3b_decoder_set_min_nbytes", "lc3b_decoder_set_synth_mode", "lc3b_encoder_set_graph_mode",
            "lc3b_mixed_decoder_layout", "lc3b_mixed_decoder_workspace_bytes", "lc3b_mixed_decoder_init", "lc3b_mixed_decode_frames",
            "lc3b_mixed_decode_frames_host", "lc3b_mixed_decoder_set_host_pipelining", "lc3b_mixed_decoder_host_fence",
            "lc3b_mixed_decoder_set_graph_mode", "lc3b_mixed_decoder_destroy",
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         L.lc3b_encoder_destroy.restype = None
         u64p, i32p = C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
         L.lc3b_decoder_set_graph_mode.argtypes = [vp, i32]
+        L.lc3b_decoder_set_split.argtypes = [vp, i32]
         L.lc3b_decoder_set_dequant_mode.argtypes = [vp, i32]
         L.lc3b_decoder_set_min_nbytes.argtypes = [vp, i32]
         L.lc3b_decoder_set_synth_mode.argtypes = [vp, i32]

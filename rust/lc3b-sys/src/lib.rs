@@ -90,6 +90,7 @@ extern "C" {
                                      cuda_stream: *mut c_void) -> c_int;
     /// 0 = one launch per kernel, 1 = one cached CUDA graph per call
     pub fn lc3b_decoder_set_graph_mode(h: *mut lc3b_decoder, mode: c_int) -> c_int;
+    pub fn lc3b_decoder_set_split(h: *mut lc3b_decoder, k: c_int) -> c_int;
     /// 0 = by batch size, 1 = warp-per-frame dequantisation kernel, 2 = thread-per-frame
     pub fn lc3b_decoder_set_dequant_mode(h: *mut lc3b_decoder, mode: c_int) -> c_int;
     /// promise: every frame is at least `min_nbytes` long or lost; lets the decoder drop dead LTPF history (include/lc3b.h)

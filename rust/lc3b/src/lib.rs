@@ -161,6 +161,11 @@ impl<'a> Lc3BatchDecoder<'a> {
         check(unsafe { sys::lc3b_decoder_set_graph_mode(self.h, on as i32) }, "lc3b_decoder_set_graph_mode");
     }
 
+    /// Cut every call into `k` independent sub-batches whose kernels overlap (0 = by batch size, 1 = never, 2, 4).
+    pub fn set_split(&mut self, k: i32) {
+        check(unsafe { sys::lc3b_decoder_set_split(self.h, k) }, "lc3b_decoder_set_split");
+    }
+
     /// Raw handle, for the inspection hooks of `lc3b_sys` (tests).
     pub fn raw(&mut self) -> *mut sys::lc3b_decoder { self.h }
 

@@ -40,7 +40,7 @@ def corpus_clip(fs: int, ms: float, nbytes: int, n_streams: int, window: int = 0
 
 
 def gpu_decode(fs, ms, frames, nbytes_per_frame=None, host=False, trace=True, device="cuda:0", dequant_mode=0, graph=None,
-               min_nbytes=0, synth_mode=0):
+               min_nbytes=0, synth_mode=0, split=None):
     """Decode [S,F,nbytes] frame by frame through the C ABI; returns pcm [S,F,nf], trace [S,F,48], x [S,F,ne],
     spectrum [S,F,ne], status [S,F]."""
     import torch
@@ -56,6 +56,8 @@ def gpu_decode(fs, ms, frames, nbytes_per_frame=None, host=False, trace=True, de
     if graph is not None:
         dec.set_graph_mode(graph)
     dec.set_synth_mode(synth_mode)                      # 0 one warp per frame, 1 persistent + TMA prefetch
+    if split is not None:
+        dec.set_split(split)                            # sub-batches per call (include/lc3b.h)
     if min_nbytes:
         dec.set_min_nbytes(min_nbytes)                  # the handle may drop the post filter's history (include/lc3b.h)
     nf, ne = dec.nf, dec.ne
@@ -88,11 +90,11 @@ def gpu_decode(fs, ms, frames, nbytes_per_frame=None, host=False, trace=True, de
 
 
 def assert_parity(fs, ms, frames, nbytes_per_frame=None, host=False, exact_spectrum=True, dequant_mode=0, graph=None,
-                  min_nbytes=0):
+                  min_nbytes=0, split=None):
     """The three decoder parity gates of SURVEY.md 8d against the oracle on the same bytes."""
     o_pcm, o_tr, o_x, o_sp = O.decode_streams(frames, fs, ms, nbytes_per_frame, trace=True)
     g_pcm, g_tr, g_x, g_sp, g_status = gpu_decode(fs, ms, frames, nbytes_per_frame, host=host, dequant_mode=dequant_mode, graph=graph,
-                                                    min_nbytes=min_nbytes)
+                                                    min_nbytes=min_nbytes, split=split)
     # (i) side info, TNS data, integer spectrum, residual-bit count, seed, zero-frame flag: bit exact
     bad = np.argwhere(o_tr != g_tr)
     assert bad.size == 0, f"trace mismatch at (stream, frame, word) {bad[:8].tolist()}: " \

@@ -173,6 +173,7 @@ def test_mixed_layout_is_bucket_ordered(L):
 def test_new_entry_points_reject_null_handles(L):
     lib = L.lib()
     assert lib.lc3b_decoder_set_graph_mode(None, 1) == 2
+    assert lib.lc3b_decoder_set_split(None, 2) == 2
     assert lib.lc3b_encoder_set_graph_mode(None, 1) == 2
     assert lib.lc3b_mixed_decode_frames(None, 16, None, None, 10, 10, None, 480, None, None) == 2
     assert lib.lc3b_mixed_decoder_host_fence(None, None) == 2

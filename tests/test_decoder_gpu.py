@@ -9,7 +9,7 @@ Run on the B200 box: python -m pytest tests -m gpu
 import numpy as np
 import pytest
 
-from common import ALL_CONFIGS, assert_parity, corpus, gpu_decode
+from common import ALL_CONFIGS, assert_parity, corpus, corpus_clip, gpu_decode
 from conftest import load_golden
 from tools.corpus import MIXED_NBYTES
 
@@ -466,3 +466,31 @@ def test_tma_pipelined_synthesis_kernel_is_bit_identical():
     g = gpu_decode(48000, 10, frames, trace=False, synth_mode=1)
     from oracle import pyoracle as O
     assert np.abs(g[0].astype(np.int32) - O.decode_streams(frames, 48000, 10).astype(np.int32)).max() <= PCM_TOL
+
+
+
+@pytest.mark.parametrize("fs,ms,nbytes,split,graph,host", [
+    (48000, 10.0, 150, 4, False, False), (48000, 10.0, 150, 2, True, False), (16000, 7.5, 30, 4, False, True),
+    (16000, 7.5, 30, 2, True, True)])
+def test_sub_batches_match_the_oracle(fs, ms, nbytes, split, graph, host):
+    """lc3b_decoder_set_split: a call cut into 2 / 4 sub-batches whose kernels run on the handle's auxiliary streams (or as
+    parallel branches of the call's graph).  Ragged on purpose: 700 streams are sub-batches of 256 + 256 + 188 (+ none) or
+    384 + 316 - the last one ends in a partly filled CTA.  All three gates against the oracle, lost and short frames
+    included, through the device and the host entry points; the thread-per-frame dequantisation kernel is forced because
+    the small-batch kernels are never split."""
+    _, frames = corpus_clip(fs, ms, nbytes, 700, window=6)
+    lens = np.full(frames.shape[:2], nbytes, np.int32)
+    rng = np.random.default_rng(5)
+    lens[rng.random(lens.shape) < 0.03] = 0                                # lost frames
+    stats = assert_parity(fs, ms, frames, lens, host=host, dequant_mode=2, graph=graph, split=split)
+    assert stats["concealed"] > 0.0
+
+
+def test_sub_batches_are_bit_identical_to_one_batch():
+    """Same handle configuration, split 1 against split 4, device entry point: PCM, status and the inspection records agree
+    bit for bit over consecutive frames (per-stream state carries over between calls in every sub-batch)."""
+    _, frames = corpus_clip(48000, 10.0, 150, 1100, window=5)
+    a = gpu_decode(48000, 10.0, frames, dequant_mode=2, split=1)
+    b = gpu_decode(48000, 10.0, frames, dequant_mode=2, split=4)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
