@@ -120,8 +120,8 @@ int lc3b_decoder_get_spectrum(lc3b_decoder* h, float* out, void* cuda_stream);
  * 131 072 streams (launch-sensitive), else 0; LC3B_GRAPH=0/1 in the environment overrides the default.  Results are
  * identical either way.  graph_stats: cache hits / in-place updates / instantiations so far (any pointer may be NULL). */
 int lc3b_decoder_set_graph_mode(lc3b_decoder* h, int mode);
-/* Into how many independent sub-batches of streams a call is cut: 0 = by batch size (the default: 2 from 65 536 streams,
- * 4 from 131 072), 1 = never, 2 or 4 = always.  The sub-batches' kernels run on auxiliary streams of the handle, forked from
+/* Into how many independent sub-batches of streams a call is cut: 0 = by batch size (the default: 4 from 65 536 streams,
+ * 1 below), 1 = never, 2 or 4 = always.  The sub-batches' kernels run on auxiliary streams of the handle, forked from
  * and joined back into `cuda_stream` inside the call (or as parallel branches of the call's graph), so that one
  * sub-batch's kernels fill the SMs another's last wave leaves idle.  Streams are independent, so results are identical
  * for every setting.  LC3B_SPLIT=k in the environment overrides the default. */
